@@ -1,0 +1,198 @@
+/*
+ * kmpx.h - C ABI of libkmpx.so: the sm_100a (B200) CUDA implementation of the KMP learn-and-adapt
+ * hot path of lbusellato/KMP_demos.
+ *
+ * The reference has no FFI of its own (it is pure Python); the boundary it offers is its Python class
+ * API.  Each entry point below replaces the numerical body of one reference method and is what a
+ * ctypes binding placed inside that method would call (INTEGRATION.md shows the stubs).  Citations are
+ * file:line in /root/reference.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 for a bad argument (-k = k-th argument), >0 for a CUDA
+ *    error code; kmpx_last_error() returns a thread-local message.  Nothing throws across the boundary.
+ *  - all array arguments are DEVICE pointers to caller-owned buffers unless the name ends in _host;
+ *    fp64 everywhere, labels int32 (sklearn path) or int64 (reference KMeans path).
+ *  - the library allocates nothing persistent; scratch is passed in (`ws`, `ws_bytes`, sized by the
+ *    matching *_workspace_bytes function).  No call synchronises the host.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - batched problems are ragged: `n_pts[b]` (device int32, may be NULL => n_max for every problem) is
+ *    the number of stored reference points of problem b; buffers are strided by the *_max sizes.
+ *
+ * KMP data layouts on the device ("point-major" = the reference's vec order, KMP.py:151,185-186)
+ *    s      [batch][n_max][I]        inputs            (reference keeps (I,N); host transposes)
+ *    y      [batch][n_max][O]        outputs mu        (reference (O,N))
+ *    sigma  [batch][n_max][O][O]     covariances       (reference (O,O,N))
+ *  System matrices A (n_b x n_b, n_b = n_pts[b]*O, row-major, leading dimension lda, batch stride
+ *  strideA elements) use one of two index orders:
+ *    KMPX_LAYOUT_POINT      row = i*O + a   - the reference's order (KMP.py:151)
+ *    KMPX_LAYOUT_COMPONENT  row = a*N_b + i - component-major; what the factorisation / predict
+ *                                             kernels consume (every GEMM operand is a contiguous panel)
+ */
+#ifndef KMPX_H
+#define KMPX_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMPX_VERSION 100
+#define KMPX_LAYOUT_POINT 0
+#define KMPX_LAYOUT_COMPONENT 1
+#define KMPX_UPLO_FULL 0
+#define KMPX_UPLO_LOWER 1
+#define KMPX_SMALL_MAX 512 /* largest system handled by the one-CTA-per-problem kernels */
+
+int kmpx_version(void);
+const char* kmpx_last_error(void);
+/* Number of kernels launched by this library in the calling process since load (bench.py's gpu_launches). */
+long long kmpx_launch_count(void);
+
+/* ---- K1: kernel-matrix builder.  Replaces the N^2 Python loop of KMP.fit, KMP.py:146-156, with
+ *      KMP.__kernel_matrix (KMP.py:93-128) evaluated in-kernel (plain RBF block or the finite-difference
+ *      time-driven 2x2 block form).  A = K (x) I + lambda*blockdiag(Sigma), written once, 16-byte stores.
+ *      uplo = KMPX_UPLO_LOWER writes only row >= col (what potrf consumes). */
+int kmpx_kernel_build(const double* s, const double* sigma, const int* n_pts, double* A,
+                      int batch, int n_max, int I, int O, int lda, long long strideA,
+                      double sigma_f, double lambda, int time_driven, int layout, int uplo, void* stream);
+
+/* ---- K2: batched fp64 Cholesky A = L L^T, lower, in place (replaces numpy.linalg.inv at KMP.py:157
+ *      for symmetric systems).  n_sys[b] = system size (NULL => n_max).  info[b] = 0 or the 1-based
+ *      index of the first non-positive pivot (LAPACK convention).  n_max <= KMPX_SMALL_MAX: one CTA per
+ *      problem; larger: blocked right-looking on DMMA GEMMs (needs ws). */
+long long kmpx_potrf_workspace_bytes(int n_max, int batch);
+int kmpx_potrf(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch,
+               int* info, void* ws, long long ws_bytes, void* stream);
+
+/* ---- K3: in-place inverse of the lower-triangular factor, L <- L^{-1} (same dispatch as potrf). */
+long long kmpx_trtri_workspace_bytes(int n_max, int batch);
+int kmpx_trtri(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch,
+               void* ws, long long ws_bytes, void* stream);
+
+/* ---- K3a: w = Linv * P y and alpha = P^T Linv^T w  (= (K+lambda Sigma)^{-1} mu, the reference's
+ *      `_estimator @ Y`, KMP.py:185-187).  y, alpha are point-major [batch][n_max][O]; P is the permutation
+ *      to `layout`; w [batch][ldw] is kept in system order for the predict kernel. */
+int kmpx_solve_alpha(const double* Linv, int lda, long long strideA, const int* n_pts, int n_max, int O,
+                     int batch, int layout, const double* y, double* w, int ldw, double* alpha, void* stream);
+
+/* ---- general (non-symmetric) path: in-place Gauss-Jordan inverse with partial pivoting, one CTA per
+ *      problem.  Needed because demos.py:251,285 hands set_waypoint an un-listed covariance, which makes the
+ *      stored block non-symmetric; the reference's LU inverse digests it.  info[b] > 0 =>
+ *      singular (the reference raises LinAlgError).  ws: batch*n_max int32 (pivot rows). */
+long long kmpx_inverse_workspace_bytes(int n_max, int batch);
+int kmpx_inverse(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch,
+                 int* info, void* ws, long long ws_bytes, void* stream);
+/* alpha' = Ainv * P y for the general path (same argument meaning as kmpx_solve_alpha); here w receives
+ * alpha' in system order (what kmpx_kmp_predict with factor_kind 1 expects) and alpha the point-major copy. */
+int kmpx_apply_inverse(const double* Ainv, int lda, long long strideA, const int* n_pts, int n_max, int O,
+                       int batch, int layout, const double* y, double* w, int ldw, double* alpha, void* stream);
+
+/* Size of the linear system for N stored points: N*O (point-major) or O*roundup(N,2) (component-major:
+ * each component block is padded to an even length with identity rows so that it starts 16-byte aligned).
+ * kmpx_sys_sizes fills a device array for a ragged batch. */
+int kmpx_sys_size(int N, int O, int layout);
+int kmpx_sys_sizes(const int* n_pts, int O, int layout, int batch, int* n_sys, void* stream);
+
+/* ---- K4: predict.  Replaces the per-query loop of KMP.predict, KMP.py:178-190.
+ *      xi    [batch][O][M]     = k* (K+lambda Sigma)^{-1} Y
+ *      sigma [batch][O][O][M]  = alpha_kmp * (kernel(s*,s*) - k* (K+lambda Sigma)^{-1} k*^T)
+ *      (the reference's output layout, query index last).
+ *      factor_kind 0: F = Linv (component-major, from potrf+trtri), w from kmpx_solve_alpha:
+ *                     V = Linv k*^T on DMMA, xi = V^T w, sigma = alpha (k** - V^T V), fused, V never stored.
+ *      factor_kind 1: F = Ainv (component-major, general path): U = Ainv k*^T, xi = U^T y', sigma uses k* U.
+ *      queries sq [batch or 1][M][I]; stride_sq = 0 shares one query grid between all problems.
+ *      want_cov = 0 skips the covariance (mean only, from alpha: cheap path). */
+int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kind,
+                     const double* w, int ldw, const double* s, const int* n_pts, int n_max, int I, int O,
+                     int batch, const double* sq, long long stride_sq, int M,
+                     double sigma_f, double alpha_kmp, int time_driven,
+                     double* xi, double* sigma_out, void* stream);
+/* mean-only predict from alpha (point-major [batch][n_max][O]): xi[a][m] = sum_i k(s*_m,s_i) alpha_i. */
+int kmpx_kmp_predict_mean(const double* alpha, const double* s, const int* n_pts, int n_max, int I, int O,
+                          int batch, const double* sq, long long stride_sq, int M,
+                          double sigma_f, int time_driven, double* xi, void* stream);
+
+/* ---- a4: KMP.set_waypoint's database update (KMP.py:72-89) for a batch of problems that share base
+ *      trajectories.  For via-point j = 0..P-1 in order: nearest stored input by L2, strict `< tol` =>
+ *      overwrite in place, else append.  base_of[b] selects the base trajectory of problem b. */
+int kmpx_waypoint_insert(const double* s_base, const double* y_base, const double* sigma_base,
+                         const int* n_base, int n_base_max, const int* base_of,
+                         const double* via_s, const double* via_y, const double* via_sigma, int P, double tol,
+                         double* s, double* y, double* sigma, int* n_pts, int n_max, int I, int O, int batch,
+                         void* stream);
+
+/* ---- K8: GMR conditioning.  Replaces GaussianMixtureModel.predict, GaussianMixtureModel.py:83-105.
+ *      priors [K], means [d][K], covs [d][d][K] (the reference's feature-major attributes), x [I][M];
+ *      out mu [O][M], sigma [O][O][M].  Keeps the REALMIN normaliser (:90) and reg*I - mu mu^T (:104-105). */
+int kmpx_gmr(const double* priors, const double* means, const double* covs, int K, int I, int O,
+             const double* x, int M, double reg, double* mu, double* sigma_out, void* stream);
+
+/* ---- K5/K6: one fused EM pass.  Replaces sklearn's _e_step + _m_step
+ *      (sklearn/mixture/_base.py:265-278, _gaussian_mixture.py:282-320,490-553) behind
+ *      GaussianMixtureModel.fit, GaussianMixtureModel.py:53.
+ *      X [n][d] row-major samples; `shift` [d] is subtracted from every sample before the moments are
+ *      accumulated (EM is shift-invariant).  Parameters: log_weights [K], means [K][d],
+ *      prec_chol [K][d][d] (upper-triangular P_k = chol(Sigma_k)^{-T}), log_det [K].
+ *      stats [K*F + 1], F = 1 + d + d(d+1)/2: per component {sum r, sum r x', sum r x' x'^T (upper, row order)}
+ *      with x' = x - shift, then sum_n log p(x_n).  This is the buffer the NCCL all-reduce sums when the
+ *      samples are partitioned across GPUs.  labels (int32 [n], argmax responsibility) and lse [n] optional. */
+long long kmpx_gmm_workspace_bytes(int n, int d, int K);
+int kmpx_gmm_em_pass(const double* X, long long n, int d, int K, const double* shift,
+                     const double* log_weights, const double* means, const double* prec_chol,
+                     const double* log_det, double* stats, int* labels, double* lse,
+                     void* ws, long long ws_bytes, void* stream);
+/* Same sufficient statistics from hard labels (one-hot responsibilities): the initial M-step after the
+ * k-means initialisation (sklearn/mixture/_base.py:119-128) and the Lloyd centre update. */
+int kmpx_gmm_label_stats(const double* X, long long n, int d, int K, const double* shift,
+                         const int* labels, double* stats, void* ws, long long ws_bytes, void* stream);
+/* M-step finalisation from (all-reduced) statistics: nk = sum r + 10 eps, means, covariances + reg*I,
+ * weights = nk / n_total (first = 1) or nk / sum nk, precision Cholesky, log-dets
+ * (sklearn/mixture/_gaussian_mixture.py:312-320,358-370,883-901).  info[k] != 0 => covariance not SPD. */
+int kmpx_gmm_finalize(const double* stats, double n_total, int first, int d, int K, double reg,
+                      const double* shift, double* weights, double* log_weights, double* means,
+                      double* covs, double* prec_chol, double* log_det, int* info, void* stream);
+
+/* ---- K7 (sklearn mode): the k-means initialisation of the GMM
+ *      (sklearn/cluster/_kmeans.py:180-278,630-758, _k_means_lloyd.pyx:23-230).  The RandomState stream and
+ *      the cumulative-sum sampling stay on the host; distances, minima, potentials, assignment and centre
+ *      sums are device kernels. */
+int kmpx_rows_center_sqnorm(double* X, long long n, int d, const double* mean, double* x_sq, void* stream);
+/* dist[t][i] = min(closest[i], max(0, |c_t|^2 - 2 c_t.x_i + |x_i|^2)), pot[t] = sum_i dist[t][i];
+ * closest may be NULL (first centre).  cand [T] are row indices into X. */
+int kmpx_kpp_candidates(const double* X, const double* x_sq, long long n, int d, const int* cand, int T,
+                        const double* closest, double* dist, double* pot, void* ws, long long ws_bytes,
+                        void* stream);
+/* labels[i] = argmin_j(|c_j|^2 - 2 x_i.c_j) (first minimum); n_changed += (labels != labels_prev). */
+int kmpx_kmeans_assign(const double* X, long long n, int d, int K, const double* centers,
+                       const int* labels_prev, int* labels, int* n_changed, void* stream);
+
+/* ---- K7 (reference mode): kmp.cluster.KMeans, Cluster.py:88-102, bit-exact: feature-major X [d][n],
+ *      distances = sqrt of a left-to-right sum of separately rounded squares (no FMA), first-index argmin
+ *      with numpy's NaN rule, labels int64; update = sequential sum in sample order then one division,
+ *      NaN for an empty cluster. */
+int kmpx_refkmeans_assign(const double* X, long long n, int d, int K, const double* centroids,
+                          long long* labels, void* stream);
+int kmpx_refkmeans_update(const double* X, long long n, int d, int K, const long long* labels,
+                          double* centroids, void* stream);
+
+/* ---- K9: quaternion maps, kmp/types/quaternion.py (scalar-first [v,u0,u1,u2], every result re-normalised
+ *      as the reference constructor does, :18-21).  M elements; for kmpx_quat_mul the second operand is
+ *      broadcast when q_bcast != 0. */
+int kmpx_quat_normalize(const double* q, double* out, long long M, void* stream);
+int kmpx_quat_exp(const double* w, double* q, long long M, void* stream);            /* :60-80  */
+int kmpx_quat_log(const double* q, double* w, long long M, void* stream);            /* :82-96  */
+int kmpx_quat_mul(const double* p, const double* q, int q_bcast, int conj_q, double* out, long long M,
+                  void* stream);                                                     /* :182-202, :219-227 */
+int kmpx_quat_from_rotvec(const double* r, double* q, long long M, void* stream);    /* :23-42  */
+
+/* ---- dense fp64 GEMM on DMMA (the building block of the blocked factorisations; exported for tests and
+ *      for the lazily materialised `_estimator`).  C = alpha*op(A)*op(B) + beta*C, row-major, strided batch.
+ *      tri: 0 none; 1 compute only tiles with row >= col of C (SYRK-like); 2 op(A) is lower-triangular
+ *      (skip k > row); 3 op(B) is lower-triangular (skip k < col).  */
+int kmpx_dgemm(int transA, int transB, int m, int n, int k, double alpha, const double* A, int lda,
+               long long strideA, const double* B, int ldb, long long strideB, double beta, double* C,
+               int ldc, long long strideC, int batch, int tri, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMPX_H */

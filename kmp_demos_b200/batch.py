@@ -1,0 +1,153 @@
+"""Batched KMP adaptation: many independent (base trajectory, via-point set) problems through one
+set_waypoint -> fit -> predict pipeline on the device (SURVEY.md 8d cfg 3).
+
+One problem = what the reference does with
+    kmp.fit(t, mu, sigma); kmp.set_waypoint(via_t, via_p, via_var); kmp.predict(queries)
+(KMP.py:57-91,130-194); here B of them run per kernel launch:
+    kmpx_waypoint_insert -> kmpx_kernel_build -> kmpx_potrf -> kmpx_trtri -> kmpx_solve_alpha -> kmpx_kmp_predict
+Problems are independent, so a multi-GPU run just gives every rank a contiguous slice (no collective).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def _roundup(v, m):
+    return (v + m - 1) // m * m
+
+
+class KMPBatch:
+    """Batched fit+predict of KMP problems that share base trajectories and a query grid.
+
+    Parameters mirror ``KMP`` (l, alpha, sigma_f, adaptation_tol, time_driven_kernel).  ``chunk`` bounds the
+    number of systems resident at once (each is n^2 doubles)."""
+
+    def __init__(self, l=0.5, alpha=40.0, sigma_f=1.0, adaptation_tol=0.0005, time_driven_kernel=False, chunk=2048):
+        self.l, self.alpha, self.sigma_f = float(l), float(alpha), float(sigma_f)
+        self.tol, self.time_driven_kernel, self.chunk = float(adaptation_tol), bool(time_driven_kernel), int(chunk)
+        self._bufs = {}
+        self._base = None
+        self.events = None        # set to a list to collect (kernel name, start, end) CUDA events per launch
+
+    # ------------------------------------------------------------------ data staging
+    def set_base(self, s_base, xi_base, sigma_base):
+        """Base trajectories: s_base (L,I,N0), xi_base (L,O,N0), sigma_base (L,O,O,N0) host arrays in the
+        reference's layouts (sample index last); copied to the device once."""
+        torch = _lib.require_cuda()
+        dev = torch.device('cuda')
+        s_base = np.asarray(s_base, dtype=np.float64)
+        xi_base = np.asarray(xi_base, dtype=np.float64)
+        sigma_base = np.asarray(sigma_base, dtype=np.float64)
+        L, I, N0 = s_base.shape
+        O = xi_base.shape[1]
+        self._base = dict(
+            L=L, I=I, O=O, N0=N0,
+            s=torch.as_tensor(np.ascontiguousarray(np.transpose(s_base, (0, 2, 1))), device=dev),          # (L,N0,I)
+            y=torch.as_tensor(np.ascontiguousarray(np.transpose(xi_base, (0, 2, 1))), device=dev),         # (L,N0,O)
+            g=torch.as_tensor(np.ascontiguousarray(np.transpose(sigma_base, (0, 3, 1, 2))), device=dev),   # (L,N0,O,O)
+        )
+
+    def _launch(self, name, *args):
+        if self.events is None:
+            _lib.call(name, *args)
+            return
+        torch = _lib.require_cuda()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call(name, *args)
+        e1.record()
+        self.events.append((name, e0, e1))
+
+    def _buf(self, name, shape, dtype):
+        torch = _lib.require_cuda()
+        key = (name, tuple(shape), dtype)
+        if key not in self._bufs:
+            self._bufs[key] = torch.empty(shape, dtype=dtype, device='cuda')
+        return self._bufs[key]
+
+    # ------------------------------------------------------------------ device pipeline
+    def run_device(self, base_of, via_s, via_xi, via_sigma, queries, want_cov=True, out_xi=None, out_sigma=None):
+        """All arguments are device tensors: base_of int32 (B,), via_s (B,P,I), via_xi (B,P,O), via_sigma (B,P,O,O),
+        queries (M,I).  Returns (xi (B,O,M), sigma (B,O,O,M) or None, info (B,) int32, n_pts (B,) int32)."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        b = self._base
+        if b is None:
+            raise RuntimeError('KMPBatch.set_base must be called first')
+        I, O, N0 = b['I'], b['O'], b['N0']
+        B, P = via_s.shape[0], via_s.shape[1]
+        M = queries.shape[0]
+        n_max_pts = N0 + P
+        n_max = int(lib.kmpx_sys_size(n_max_pts, O, _lib.LAYOUT_COMPONENT))
+        if n_max > _lib.SMALL_MAX:
+            raise ValueError(f'batched path handles systems up to {_lib.SMALL_MAX}, got {n_max}')
+        lda = _roundup(n_max, 8)
+        f64, i32 = torch.float64, torch.int32
+        xi = out_xi if out_xi is not None else torch.empty((B, O, M), dtype=f64, device='cuda')
+        sg = None
+        if want_cov:
+            sg = out_sigma if out_sigma is not None else torch.empty((B, O, O, M), dtype=f64, device='cuda')
+        info = self._buf('info', (B,), i32)
+        n_pts = self._buf('n_pts', (B,), i32)
+        Bc = min(self.chunk, B)
+        A = self._buf('A', (Bc, n_max, lda), f64)
+        s = self._buf('s', (Bc, n_max_pts, I), f64)
+        y = self._buf('y', (Bc, n_max_pts, O), f64)
+        g = self._buf('g', (Bc, n_max_pts, O, O), f64)
+        w = self._buf('w', (Bc, lda), f64)
+        al = self._buf('alpha', (Bc, n_max_pts, O), f64)
+        n_sys = self._buf('n_sys', (Bc,), i32)
+        st = _lib.stream()
+        td = int(self.time_driven_kernel)
+        strideA = n_max * lda
+        for c0 in range(0, B, Bc):
+            bc = min(Bc, B - c0)
+            npc = n_pts[c0:c0 + bc]
+            self._launch('kmpx_waypoint_insert', _lib.ptr(b['s']), _lib.ptr(b['y']), _lib.ptr(b['g']), None, N0,
+                      _lib.ptr(base_of[c0:]), _lib.ptr(via_s[c0:]), _lib.ptr(via_xi[c0:]), _lib.ptr(via_sigma[c0:]), P,
+                      self.tol, _lib.ptr(s), _lib.ptr(y), _lib.ptr(g), _lib.ptr(npc), n_max_pts, I, O, bc, st)
+            self._launch('kmpx_sys_sizes', _lib.ptr(npc), O, _lib.LAYOUT_COMPONENT, bc, _lib.ptr(n_sys), st)
+            self._launch('kmpx_kernel_build', _lib.ptr(s), _lib.ptr(g), _lib.ptr(npc), _lib.ptr(A), bc, n_max_pts, I, O, lda,
+                      strideA, self.sigma_f, self.l, td, _lib.LAYOUT_COMPONENT, _lib.UPLO_LOWER, st)
+            self._launch('kmpx_potrf', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, _lib.ptr(info[c0:]), None, 0, st)
+            self._launch('kmpx_trtri', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, None, 0, st)
+            self._launch('kmpx_solve_alpha', _lib.ptr(A), lda, strideA, _lib.ptr(npc), n_max_pts, O, bc,
+                      _lib.LAYOUT_COMPONENT, _lib.ptr(y), _lib.ptr(w), lda, _lib.ptr(al), st)
+            if want_cov:
+                self._launch('kmpx_kmp_predict', _lib.ptr(A), lda, strideA, 0, _lib.ptr(w), lda, _lib.ptr(s), _lib.ptr(npc),
+                          n_max_pts, I, O, bc, _lib.ptr(queries), 0, M, self.sigma_f, self.alpha, td,
+                          _lib.ptr(xi[c0:]), _lib.ptr(sg[c0:]), st)
+            else:
+                self._launch('kmpx_kmp_predict_mean', _lib.ptr(al), _lib.ptr(s), _lib.ptr(npc), n_max_pts, I, O, bc,
+                          _lib.ptr(queries), 0, M, self.sigma_f, td, _lib.ptr(xi[c0:]), st)
+        return xi, sg, info, n_pts
+
+    # ------------------------------------------------------------------ host-facing call
+    def fit_predict(self, base_of, via_s, via_xi, via_sigma, queries, want_cov=True):
+        """Host arrays in, host arrays out (the reference-facing call):
+        base_of (B,), via_s (B,P) or (B,P,I), via_xi (B,P,O), via_sigma (B,P,O,O), queries (I,M).
+        Returns xi (B,O,M), sigma (B,O,O,M)."""
+        torch = _lib.require_cuda()
+        dev = torch.device('cuda')
+        via_s = np.asarray(via_s, dtype=np.float64)
+        if via_s.ndim == 2:
+            via_s = via_s[:, :, None]
+        d_base = torch.as_tensor(np.asarray(base_of, dtype=np.int32), device=dev)
+        d_vs = torch.as_tensor(np.ascontiguousarray(via_s), device=dev)
+        d_vx = torch.as_tensor(np.ascontiguousarray(via_xi, dtype=np.float64), device=dev)
+        d_vg = torch.as_tensor(np.ascontiguousarray(via_sigma, dtype=np.float64), device=dev)
+        d_q = torch.as_tensor(np.ascontiguousarray(np.asarray(queries, dtype=np.float64).T), device=dev)
+        xi, sg, info, _ = self.run_device(d_base, d_vs, d_vx, d_vg, d_q, want_cov)
+        bad = int((info != 0).sum().item())
+        if bad:
+            raise np.linalg.LinAlgError(f'{bad} of {len(base_of)} systems are not positive definite')
+        return xi.cpu().numpy(), (sg.cpu().numpy() if sg is not None else None)
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous static split of n_items units over `world` ranks: [lo, hi) of `rank`."""
+    per, rem = divmod(n_items, world)
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)

@@ -1,0 +1,101 @@
+// Shared device/host helpers for libkmpx (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include "../../include/kmpx.h"
+
+namespace kmpx {
+
+// ---------------------------------------------------------------- host side: errors, launch counting
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail_arg(int k, const char* what) {
+    snprintf(g_err, sizeof(g_err), "kmpx: bad argument %d: %s", k, what);
+    return -k;
+}
+inline int check_launch(const char* name) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "kmpx: launch of %s failed: %s", name, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+inline int check_cuda(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "kmpx: %s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+#define KMPX_TRY(expr) do { int _rc = (expr); if (_rc != 0) return _rc; } while (0)
+
+constexpr int kNumSMs = 148;   // B200
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------- device side
+constexpr double kFdDt = 0.001;   // finite-difference step of the time-driven kernel, KMP.py:113
+
+// FP64 tensor-core MMA: D(8x8) += A(8x4,row) * B(4x8,col).  Lowers to DMMA.8x8x4 on sm_100a.
+//   a: A[row = lane/4][k = lane%4]     b: B[k = lane%4][col = lane/4]
+//   c[0..1]: C[row = lane/4][col = (lane%4)*2 + {0,1}]
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// 16-byte async global->shared copy; src_bytes in {0,8,16}: the remainder is zero-filled.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, int src_bytes) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" :: "r"(d), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+// RBF coefficient k = exp(-sigma_f * ||s1-s2||^2), norm first then squared (KMP.py:109-110).
+template <typename P1, typename P2>
+__device__ __forceinline__ double rbf(P1 s1, P2 s2, int I, double sigma_f, double d1, double d2) {
+    double r;
+    if (I == 1) {
+        r = fabs((s1[0] + d1) - (s2[0] + d2));
+    } else {
+        double acc = 0.0;
+        for (int t = 0; t < I; ++t) { double d = (s1[t] + d1) - (s2[t] + d2); acc += d * d; }
+        r = sqrt(acc);
+    }
+    return exp(-sigma_f * (r * r));
+}
+
+// The coefficient block of one kernel evaluation: plain -> c[0]; time-driven -> c = {ktt, ktdt, kdtt, kdtdt}
+// by forward differences with dt = 1e-3 added to every input coordinate (KMP.py:113-123).
+template <typename P1, typename P2>
+__device__ __forceinline__ void kernel_coeffs(P1 s1, P2 s2, int I, double sigma_f, bool time_driven, double (&c)[4]) {
+    double ktt = rbf(s1, s2, I, sigma_f, 0.0, 0.0);
+    c[0] = ktt;
+    if (!time_driven) { c[1] = c[2] = c[3] = 0.0; return; }
+    double a = rbf(s1, s2, I, sigma_f, 0.0, kFdDt);
+    double b = rbf(s1, s2, I, sigma_f, kFdDt, 0.0);
+    double d = rbf(s1, s2, I, sigma_f, kFdDt, kFdDt);
+    c[1] = (a - ktt) / kFdDt;
+    c[2] = (b - ktt) / kFdDt;
+    c[3] = (d - a - b + ktt) / (kFdDt * kFdDt);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace kmpx

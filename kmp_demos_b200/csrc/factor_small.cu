@@ -1,0 +1,424 @@
+// K2/K3 for small systems (n <= KMPX_SMALL_MAX): one CTA per problem, persistent over the batch.
+//
+//   k_potrf_small   left-looking blocked Cholesky, block columns of 32.  The update of block column k0
+//                   (rows k0..n-1) by all previous columns is the only dense contraction:
+//                   C(m x 32) += L[k0:n, 0:k0] * L[k0:k0+32, 0:k0]^T  on DMMA, the operand streamed once
+//                   per block column through a 3-stage cp.async ring (the B operand is the first 32 rows
+//                   of the same tile).  Diagonal block: one warp, shared memory.  Panel solve: one thread
+//                   per row, registers.
+//   k_trtri_small   in-place inverse of the lower factor, right to left:
+//                   X = -Linv22 * (L21 * Dinv)   with the (m x m, lower) Linv22 streamed on DMMA.
+//   k_solve_alpha   w = Linv * y', alpha' = Linv^T * w   (two passes over Linv, bandwidth-bound).
+//
+// Algorithmic flops: n^3/3 each for potrf and trtri; bytes: the matrix is read and written once.
+#include "dmma_tile.cuh"
+#include "kmpx_internal.cuh"
+
+namespace kmpx {
+
+constexpr int NB = 32;       // block-column width
+constexpr int FBK = 8;       // k-step of the streamed operand
+constexpr int FLDT = 12;     // leading dimension of a stage tile [rows][8]   (12 = conflict-free, see dmma_tile.cuh)
+constexpr int FLDP = 36;     // leading dimension of the panel / diagonal blocks [rows][32]  (4 mod 16)
+constexpr int FLDB = 36;     // leading dimension of the k-major B stage tile [8][32]
+constexpr int FSTAGES = 3;
+constexpr int FTHREADS = 256;
+constexpr int FWARPS = FTHREADS / 32;
+
+__host__ __device__ inline size_t potrf_small_smem(int n_max) {
+    const size_t rows = (size_t)((n_max + 31) / 32) * 32;
+    const size_t stages = (size_t)FSTAGES * rows * FLDT * sizeof(double);
+    const size_t panel = rows * FLDP * sizeof(double);
+    return (stages > panel ? stages : panel) + (size_t)32 * FLDP * sizeof(double);
+}
+__host__ __device__ inline size_t trtri_small_smem(int n_max) {
+    const size_t rows = (size_t)((n_max + 31) / 32) * 32;
+    return (size_t)FSTAGES * (rows * FLDT + FBK * FLDB) * sizeof(double) + 2 * 32 * FLDP * sizeof(double);
+}
+
+// Cholesky of the kb x kb block at P (leading dimension FLDP) by one warp, lane = row.
+// Returns the 1-based index of the first non-positive pivot, 0 if none.
+__device__ __forceinline__ int warp_potf2(double* P, int kb, int lane) {
+    int bad = 0;
+    for (int j = 0; j < kb; ++j) {
+        const double d = P[j * FLDP + j];
+        if (!(d > 0.0) && bad == 0) bad = j + 1;
+        const double sd = sqrt(d);
+        __syncwarp();
+        double lij = 0.0;
+        if (lane == j) P[j * FLDP + j] = sd;
+        if (lane > j && lane < kb) { lij = P[lane * FLDP + j] / sd; P[lane * FLDP + j] = lij; }
+        __syncwarp();
+        if (lane > j && lane < kb) {
+            for (int c = j + 1; c <= lane; ++c) P[lane * FLDP + c] -= lij * P[c * FLDP + j];
+        }
+        __syncwarp();
+    }
+    return bad;
+}
+
+// Inverse of the kb x kb lower-triangular block D into Di (both leading dimension FLDP), lane = column.
+__device__ __forceinline__ void warp_trtri32(const double* D, double* Di, int kb, int lane) {
+    if (lane < kb) {
+        const int c = lane;
+        for (int i = 0; i < c; ++i) Di[i * FLDP + c] = 0.0;
+        Di[c * FLDP + c] = 1.0 / D[c * FLDP + c];
+        for (int i = c + 1; i < kb; ++i) {
+            double acc = 0.0;
+            for (int t = c; t < i; ++t) acc += D[i * FLDP + t] * Di[t * FLDP + c];
+            Di[i * FLDP + c] = -acc / D[i * FLDP + i];
+        }
+    }
+}
+
+
+// X(32 x 32) = A(32 x 32) * op(D) on DMMA for one warp.  A rows come from `src` (row-major, leading dimension
+// lds, shared or global), D is a 32x32 block in shared memory (leading dimension FLDP); X goes to `dst`
+// (may alias src: every A fragment is in registers before the first store).  Rows >= rows_valid are skipped.
+//   D_TRANS: X = A * D^T   (B[k][n] = D[n][k])        else: X = A * D   (B[k][n] = D[k][n])
+template <bool D_TRANS>
+__device__ __forceinline__ void warp_chunk_mul32(const double* src, int lds, double* dst, int ldd, const double* D,
+                                                 int rows_valid, double scale, int lane) {
+    const int g = lane >> 2, t4 = lane & 3;
+    double a[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + g;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) a[i][ks] = (r < rows_valid) ? src[(size_t)r * lds + ks * 4 + t4] : 0.0;
+    }
+    double acc[4][4][2];
+    zero_acc(acc);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        double bf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = D_TRANS ? D[(j * 8 + g) * FLDP + ks * 4 + t4] : D[(ks * 4 + t4) * FLDP + j * 8 + g];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j], a[i][ks], bf[j]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + g;
+        if (r < rows_valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                dst[(size_t)r * ldd + j * 8 + 2 * t4] = scale * acc[i][j][0];
+                dst[(size_t)r * ldd + j * 8 + 2 * t4 + 1] = scale * acc[i][j][1];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FTHREADS) k_potrf_small(FactorArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int rows_max = ((p.n_max + 31) / 32) * 32;
+    const size_t stage_elems = (size_t)rows_max * FLDT;
+    const size_t stages_bytes = (size_t)FSTAGES * stage_elems;
+    const size_t panel_elems = (size_t)rows_max * FLDP;
+    double* stage0 = smem;
+    double* panel = smem;                                                     // aliases the stage ring
+    double* Dinv = smem + (stages_bytes > panel_elems ? stages_bytes : panel_elems);    // [32][FLDP] inverse of the diagonal block
+    __shared__ int sh_bad;
+
+    for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+        const int n = p.n_sys ? p.n_sys[b] : p.n_max;
+        double* A = p.A + (size_t)b * p.strideA;
+        int bad_total = 0;
+        for (int k0 = 0; k0 < n; k0 += NB) {
+            const int kb = min(NB, n - k0);
+            const int m = n - k0;
+            const int nch = (m + 31) >> 5;
+            const int rows_t = nch * 32;
+            double acc[2][4][4][2];
+            zero_acc(acc[0]);
+            zero_acc(acc[1]);
+            const int nk = k0 / FBK;
+            if (nk > 0) {
+                const double* gA = A + (size_t)k0 * p.lda;
+#pragma unroll
+                for (int s = 0; s < FSTAGES - 1; ++s) {
+                    if (s < nk) load_tile_async<FBK, FLDT, false>(stage0 + s * stage_elems, gA + s * FBK, p.lda, rows_t, m,
+                                                                  k0, s * FBK, k0, tid, FTHREADS);
+                    cp_async_commit();
+                }
+                for (int kt = 0; kt < nk; ++kt) {
+                    cp_async_wait<FSTAGES - 2>();
+                    __syncthreads();
+                    const int nxt = kt + FSTAGES - 1;
+                    if (nxt < nk) load_tile_async<FBK, FLDT, false>(stage0 + (nxt % FSTAGES) * stage_elems, gA + nxt * FBK, p.lda,
+                                                                    rows_t, m, k0, nxt * FBK, k0, tid, FTHREADS);
+                    cp_async_commit();
+                    const double* tile = stage0 + (kt % FSTAGES) * stage_elems;
+#pragma unroll
+                    for (int kk = 0; kk < FBK; kk += 4) {
+                        if (warp < nch) warp_mma_k4<4, 4, false>(acc[0], tile + (warp * 32) * FLDT + kk, FLDT, tile + kk, FLDT, lane);
+                        if (warp + FWARPS < nch)
+                            warp_mma_k4<4, 4, false>(acc[1], tile + ((warp + FWARPS) * 32) * FLDT + kk, FLDT, tile + kk, FLDT, lane);
+                    }
+                }
+                cp_async_wait<0>();
+            }
+            __syncthreads();   // the stage ring is dead from here on: the panel may overwrite it
+            // panel = A[k0:n, k0:k0+kb] - acc
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int ch = warp + c * FWARPS;
+                if (ch < nch) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = ch * 32 + i * 8 + g;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int col = j * 8 + 2 * t4 + e;
+                                if (r < m && col < kb && (r >= NB || col <= r))
+                                    panel[r * FLDP + col] = A[(size_t)(k0 + r) * p.lda + k0 + col] - acc[c][i][j][e];
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const int bad = warp_potf2(panel, kb, lane);
+                __syncwarp();
+                if (m > NB) warp_trtri32(panel, Dinv, kb, lane);
+                if (lane == 0) sh_bad = bad;
+            }
+            __syncthreads();
+            if (sh_bad != 0 && bad_total == 0) bad_total = k0 + sh_bad;
+            // panel rows below the diagonal block:  X = A21 * L_kk^{-T}   (only exists when kb == 32)
+            if (m > NB) {
+                for (int ch = 1 + warp; ch < nch; ch += FWARPS)
+                    warp_chunk_mul32<true>(panel + (size_t)ch * 32 * FLDP, FLDP, panel + (size_t)ch * 32 * FLDP, FLDP, Dinv,
+                                           m - ch * 32, 1.0, lane);
+            }
+            __syncthreads();
+            for (int idx = tid; idx < m * NB; idx += FTHREADS) {
+                const int r = idx >> 5, c = idx & 31;
+                if (c < kb && (r >= NB || c <= r)) A[(size_t)(k0 + r) * p.lda + k0 + c] = panel[r * FLDP + c];
+            }
+            __threadfence();   // the block column is read back through cp.async (L2) by later iterations
+            __syncthreads();
+        }
+        if (tid == 0 && p.info) {
+            if (!p.info_accumulate) p.info[b] = bad_total;
+            else if (bad_total != 0 && p.info[b] == 0) p.info[b] = p.info_offset + bad_total;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int rows_max = ((p.n_max + 31) / 32) * 32;
+    const size_t stage_elems = (size_t)rows_max * FLDT + FBK * FLDB;
+    double* stage0 = smem;
+    double* Dsm = smem + FSTAGES * stage_elems;
+    double* Dinv = Dsm + 32 * FLDP;
+
+    for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+        const int n = p.n_sys ? p.n_sys[b] : p.n_max;
+        double* L = p.A + (size_t)b * p.strideA;
+        const int nblk = (n + NB - 1) / NB;
+        for (int jb = nblk - 1; jb >= 0; --jb) {
+            const int k0 = jb * NB;
+            const int kb = min(NB, n - k0);
+            const int m = n - k0 - kb;            // rows below the diagonal block
+            for (int idx = tid; idx < NB * NB; idx += FTHREADS) {
+                const int r = idx >> 5, c = idx & 31;
+                Dsm[r * FLDP + c] = (r < kb && c <= r) ? L[(size_t)(k0 + r) * p.lda + k0 + c] : 0.0;
+            }
+            __syncthreads();
+            if (warp == 0) warp_trtri32(Dsm, Dinv, kb, lane);
+            __syncthreads();
+            if (m > 0) {
+                // T = L21 * Dinv, in place in global memory, one 32-row chunk per warp (kb == 32 here)
+                {
+                    const int nch_t = (m + 31) >> 5;
+                    for (int ch = warp; ch < nch_t; ch += FWARPS) {
+                        double* rows = L + (size_t)(k0 + NB + ch * 32) * p.lda + k0;
+                        warp_chunk_mul32<false>(rows, p.lda, rows, p.lda, Dinv, m - ch * 32, 1.0, lane);
+                    }
+                }
+                __threadfence();
+                __syncthreads();
+                // X = -Linv22 * T   (Linv22 lower-triangular m x m, streamed; T streamed k-major)
+                const int nch = (m + 31) >> 5;
+                const int rows_t = nch * 32;
+                const int nk = (m + FBK - 1) / FBK;
+                const int r_g0 = k0 + NB;                                  // first trailing row / column
+                const double* gA = L + (size_t)r_g0 * p.lda + r_g0;          // Linv22
+                const double* gT = L + (size_t)r_g0 * p.lda + k0;            // T (m x 32)
+                double acc[2][4][4][2];
+                zero_acc(acc[0]);
+                zero_acc(acc[1]);
+                auto issue = [&](int kt) {
+                    double* st = stage0 + (kt % FSTAGES) * stage_elems;
+                    load_tile_async<FBK, FLDT, true>(st, gA + kt * FBK, p.lda, rows_t, m, r_g0, r_g0 + kt * FBK, r_g0 + m,
+                                                     tid, FTHREADS);
+                    // B tile: rows kt*8 .. +8 of T, 32 columns -> [8][FLDB]
+                    double* bt = st + (size_t)rows_max * FLDT;
+                    for (int idx = tid; idx < FBK * (NB / 2); idx += FTHREADS) {
+                        const int r = idx / (NB / 2), q = idx - r * (NB / 2);
+                        const int tr = kt * FBK + r;
+                        cp_async16(bt + r * FLDB + 2 * q, tr < m ? gT + (size_t)tr * p.lda + 2 * q : gT, tr < m ? 16 : 0);
+                    }
+                };
+#pragma unroll
+                for (int s = 0; s < FSTAGES - 1; ++s) { if (s < nk) issue(s); cp_async_commit(); }
+                for (int kt = 0; kt < nk; ++kt) {
+                    cp_async_wait<FSTAGES - 2>();
+                    __syncthreads();
+                    if (kt + FSTAGES - 1 < nk) issue(kt + FSTAGES - 1);
+                    cp_async_commit();
+                    const double* tile = stage0 + (kt % FSTAGES) * stage_elems;
+                    const double* bt = tile + (size_t)rows_max * FLDT;
+#pragma unroll
+                    for (int kk = 0; kk < FBK; kk += 4) {
+                        // a 32-row chunk ch only needs k < 32*(ch+1)
+                        if (warp < nch && kt * FBK + kk < 32 * (warp + 1))
+                            warp_mma_k4<4, 4, true>(acc[0], tile + (warp * 32) * FLDT + kk, FLDT, bt + kk * FLDB, FLDB, lane);
+                        if (warp + FWARPS < nch && kt * FBK + kk < 32 * (warp + FWARPS + 1))
+                            warp_mma_k4<4, 4, true>(acc[1], tile + ((warp + FWARPS) * 32) * FLDT + kk, FLDT, bt + kk * FLDB, FLDB, lane);
+                    }
+                }
+                cp_async_wait<0>();
+                __syncthreads();   // every read of T is complete: X may overwrite it
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int ch = warp + c * FWARPS;
+                    if (ch < nch) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = ch * 32 + i * 8 + g;
+                            if (r < m) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    double2 v = make_double2(-acc[c][i][j][0], -acc[c][i][j][1]);
+                                    *reinterpret_cast<double2*>(L + (size_t)(r_g0 + r) * p.lda + k0 + j * 8 + 2 * t4) = v;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            for (int idx = tid; idx < NB * NB; idx += FTHREADS) {
+                const int r = idx >> 5, c = idx & 31;
+                if (r < kb && c <= r) L[(size_t)(k0 + r) * p.lda + k0 + c] = Dinv[r * FLDP + c];
+            }
+            __threadfence();
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// symmetric: w = Linv*y', alpha' = Linv^T*w.   general: alpha' = Ainv*y' (w untouched).
+__global__ void __launch_bounds__(256) k_solve_alpha(AlphaArgs p) {
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nmax_sys = sys_size(p.n_max, p.O, p.layout);
+    double* ys = smem;                 // y' in system order
+    double* ws = smem + nmax_sys;      // w
+    for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+        const int N = p.n_pts ? p.n_pts[b] : p.n_max;
+        const int O = p.O;
+        const int Ns = (p.layout == KMPX_LAYOUT_POINT) ? N : comp_stride(N);
+        const int n = sys_size(N, O, p.layout);
+        const double* F = p.F + (size_t)b * p.strideA;
+        const double* y = p.y + (size_t)b * p.n_max * O;
+        for (int r = tid; r < n; r += blockDim.x) ys[r] = 0.0;     // identity padding rows carry y' = 0
+        __syncthreads();
+        for (int idx = tid; idx < N * O; idx += blockDim.x) {
+            const int i = idx / O, a = idx - i * O;
+            const int r = (p.layout == KMPX_LAYOUT_POINT) ? idx : a * Ns + i;
+            ys[r] = y[idx];
+        }
+        __syncthreads();
+        for (int r = warp; r < n; r += 8) {
+            const double* row = F + (size_t)r * p.lda;
+            const int cend = p.general ? n : r + 1;
+            double acc = 0.0;
+            for (int c = lane; c < cend; c += 32) acc += row[c] * ys[c];
+            acc = warp_sum(acc);
+            if (lane == 0) ws[r] = acc;
+        }
+        __syncthreads();
+        if (!p.general) {
+            if (p.w) for (int r = tid; r < n; r += blockDim.x) p.w[(size_t)b * p.ldw + r] = ws[r];
+            for (int c = tid; c < n; c += blockDim.x) {
+                double acc = 0.0;
+                for (int r = c; r < n; ++r) acc += F[(size_t)r * p.lda + c] * ws[r];
+                ys[c] = acc;       // each thread owns entry c
+            }
+            __syncthreads();
+        }
+        const double* res = p.general ? ws : ys;
+        if (p.alpha) {
+            double* al = p.alpha + (size_t)b * p.n_max * O;
+            for (int idx = tid; idx < N * O; idx += blockDim.x) {
+                const int i = idx / O, a = idx - i * O;
+                const int r = (p.layout == KMPX_LAYOUT_POINT) ? idx : a * Ns + i;
+                al[idx] = res[r];
+            }
+        }
+        if (p.general && p.w) for (int r = tid; r < n; r += blockDim.x) p.w[(size_t)b * p.ldw + r] = ws[r];
+        __syncthreads();
+    }
+}
+
+int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
+                       int info_offset, int info_accumulate, cudaStream_t st) {
+    const size_t smem = potrf_small_smem(n_max);
+    static bool attr_done = false;
+    if (!attr_done) {
+        KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_potrf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                            "cudaFuncSetAttribute(k_potrf_small)"));
+        attr_done = true;
+    }
+    FactorArgs p{A, lda, strideA, n_sys, n_max, batch, info, info_offset, info_accumulate};
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int grid = batch < kNumSMs * per_sm ? batch : kNumSMs * per_sm;
+    k_potrf_small<<<grid, FTHREADS, smem, st>>>(p);
+    return check_launch("k_potrf_small");
+}
+
+int launch_trtri_small(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, cudaStream_t st) {
+    const size_t smem = trtri_small_smem(n_max);
+    static bool attr_done = false;
+    if (!attr_done) {
+        KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_trtri_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                            "cudaFuncSetAttribute(k_trtri_small)"));
+        attr_done = true;
+    }
+    FactorArgs p{L, lda, strideA, n_sys, n_max, batch, nullptr, 0, 0};
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int grid = batch < kNumSMs * per_sm ? batch : kNumSMs * per_sm;
+    k_trtri_small<<<grid, FTHREADS, smem, st>>>(p);
+    return check_launch("k_trtri_small");
+}
+
+int launch_solve_alpha(const AlphaArgs& p, cudaStream_t st) {
+    const size_t smem = (size_t)2 * sys_size(p.n_max, p.O, p.layout) * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_solve_alpha, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                            "cudaFuncSetAttribute(k_solve_alpha)"));
+        attr_done = true;
+    }
+    if (smem > 227 * 1024) { snprintf(g_err, sizeof(g_err), "kmpx: system too large for k_solve_alpha"); return -5; }
+    const int grid = p.batch < kNumSMs * 4 ? p.batch : kNumSMs * 4;
+    k_solve_alpha<<<grid, 256, smem, st>>>(p);
+    return check_launch("k_solve_alpha");
+}
+
+}  // namespace kmpx

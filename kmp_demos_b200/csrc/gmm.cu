@@ -1,0 +1,360 @@
+// K5/K6: fused EM pass of the full-covariance Gaussian mixture behind GaussianMixtureModel.fit
+// (GaussianMixtureModel.py:53 -> sklearn/mixture/_base.py:265-278; E-step _gaussian_mixture.py:490-553,
+// M-step :282-320) and the M-step finalisation (:312-320, :358-370, :883-901).
+//
+// One pass over the samples produces the sufficient statistics {sum r, sum r x', sum r x' x'^T} per
+// component and sum log p(x); responsibilities are never written to HBM.
+//   E-step : one (sample, half of the components) per thread; parameters broadcast from shared memory;
+//            y = (x - mu_k) P_k with P_k upper-triangular, log-sum-exp over the components.
+//   M-step : stats[k][f] += sum_s R[s][k] * Phi[s][f] with Phi = [1, x', vech(x' x'^T)]  -- a
+//            (K x TS) x (TS x F) contraction per tile on DMMA, accumulators persistent in registers.
+//   Per-CTA partial sums are combined in CTA order by a second kernel => bitwise reproducible.
+//
+// Roofline: 8*n*d bytes per pass but ~180*n*K flops => FP64-bound for K >= 2.
+#include "dmma_tile.cuh"
+
+namespace kmpx {
+
+constexpr int ETS = 128;          // samples per tile
+constexpr int ETHREADS = 256;
+constexpr double kLog2Pi = 1.8378770664093454835606594728112;
+
+__host__ __device__ inline int gmm_F(int d) { return 1 + d + d * (d + 1) / 2; }
+__host__ __device__ inline int pad8(int v) { return (v + 7) & ~7; }
+// leading dimensions = 4 or 12 (mod 16) for conflict-free k-major fragment reads
+__host__ __device__ inline int ld_conflict_free(int v) { int l = v + 4; while ((l & 15) != 4 && (l & 15) != 12) ++l; return l; }
+
+struct EmArgs {
+    const double* X; long long n; int d, K; const double* shift;
+    const double* log_weights; const double* means; const double* prec_chol; const double* log_det;
+    const int* hard_labels;           // != NULL: one-hot responsibilities from labels (no E-step)
+    double* partials; int* labels; double* lse;
+};
+
+template <int D, int KB>   // KB = 8-component blocks per warp (K_pad <= 64*KB)
+__global__ void __launch_bounds__(ETHREADS) k_gmm_em(EmArgs p) {
+    constexpr int F = 1 + D + D * (D + 1) / 2;
+    constexpr int FP = (F + 7) & ~7;
+    constexpr int NF = FP / 8;
+    constexpr int TRI = D * (D + 1) / 2;
+    extern __shared__ __align__(16) double smem[];
+    const int K = p.K, KP = pad8(K);
+    const int ldr = ld_conflict_free(KP), ldf = ld_conflict_free(FP);
+    double* s_mu = smem;                          // [K][D]
+    double* s_pc = s_mu + (size_t)K * D;          // [K][TRI] packed upper triangle, row order
+    double* s_c = s_pc + (size_t)K * TRI;         // [K] log_det + log_weight - D/2 log(2 pi)
+    double* s_shift = s_c + K;                    // [D]
+    double* s_x = s_shift + D;                    // [ETS][D]
+    double* s_R = s_x + (size_t)ETS * D;          // [ETS][ldr]
+    double* s_Phi = s_R + (size_t)ETS * ldr;      // [ETS][ldf]
+    double* s_red = s_Phi + (size_t)ETS * ldf;    // [2][ETS] max / sum exchange
+    int* s_arg = reinterpret_cast<int*>(s_red + 2 * ETS);   // [2][ETS]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const bool hard = p.hard_labels != nullptr;
+
+    if (!hard) {
+        for (int idx = tid; idx < K * D; idx += ETHREADS) s_mu[idx] = p.means[idx];
+        for (int idx = tid; idx < K * TRI; idx += ETHREADS) {
+            const int k = idx / TRI; int t = idx - k * TRI, i = 0;
+            while (t >= D - i) { t -= D - i; ++i; }
+            s_pc[idx] = p.prec_chol[((size_t)k * D + i) * D + i + t];
+        }
+        for (int k = tid; k < K; k += ETHREADS) s_c[k] = p.log_det[k] + p.log_weights[k] - 0.5 * D * kLog2Pi;
+    }
+    for (int i = tid; i < D; i += ETHREADS) s_shift[i] = p.shift ? p.shift[i] : 0.0;
+    __syncthreads();
+
+    double acc[KB][NF][2];
+#pragma unroll
+    for (int q = 0; q < KB; ++q)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) { acc[q][j][0] = 0.0; acc[q][j][1] = 0.0; }
+    double ll_acc = 0.0;
+
+    const int s_loc = tid & (ETS - 1), half = tid >> 7;       // sample in tile, component half
+    const int kh = (K + 1) >> 1;
+    const int kbeg = half ? kh : 0, kend = half ? K : kh;
+    const long long ntiles = (p.n + ETS - 1) / ETS;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * ETS;
+        const int cnt = (int)((p.n - base) < ETS ? (p.n - base) : ETS);
+        __syncthreads();                                        // previous tile's M-step is done with s_R / s_Phi
+        for (int idx = tid; idx < ETS * D; idx += ETHREADS) s_x[idx] = idx < cnt * D ? p.X[base * D + idx] : 0.0;
+        __syncthreads();
+        const bool live = s_loc < cnt;
+        double x[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) x[i] = s_x[s_loc * D + i];
+        if (half == 0) {                                         // Phi row = [1, x', vech(x' x'^T)]
+            double xs[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) xs[i] = x[i] - s_shift[i];
+            double* ph = s_Phi + (size_t)s_loc * ldf;
+            ph[0] = live ? 1.0 : 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) ph[1 + i] = live ? xs[i] : 0.0;
+            int t = 1 + D;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = i; j < D; ++j) ph[t++] = live ? xs[i] * xs[j] : 0.0;
+            for (; t < FP; ++t) ph[t] = 0.0;
+        }
+        double* Rrow = s_R + (size_t)s_loc * ldr;
+        if (hard) {
+            const int lab = live ? p.hard_labels[base + s_loc] : -1;
+            for (int k = kbeg; k < kend; ++k) Rrow[k] = (k == lab) ? 1.0 : 0.0;
+            if (half) for (int k = K; k < KP; ++k) Rrow[k] = 0.0;
+        } else {
+            double mx = -INFINITY; int am = kbeg;
+            for (int k = kbeg; k < kend; ++k) {
+                const double* mu = s_mu + (size_t)k * D;
+                const double* pc = s_pc + (size_t)k * TRI;
+                double df[D], y[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) { df[i] = x[i] - mu[i]; y[i] = 0.0; }
+                int t = 0;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = i; j < D; ++j) y[j] += df[i] * pc[t++];
+                double q = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) q += y[j] * y[j];
+                const double wlp = s_c[k] - 0.5 * q;
+                Rrow[k] = wlp;
+                if (wlp > mx) { mx = wlp; am = k; }
+            }
+            s_red[half * ETS + s_loc] = mx; s_arg[half * ETS + s_loc] = am;
+            __syncthreads();
+            const double m0 = s_red[s_loc], m1 = s_red[ETS + s_loc];
+            const double m = m0 > m1 ? m0 : m1;                  // (K >= 2: both halves are non-empty)
+            const int amax = (m1 > m0) ? s_arg[ETS + s_loc] : s_arg[s_loc];   // first maximum wins
+            __syncthreads();
+            double se = 0.0;
+            for (int k = kbeg; k < kend; ++k) { const double e = exp(Rrow[k] - m); Rrow[k] = e; se += e; }
+            s_red[half * ETS + s_loc] = se;
+            __syncthreads();
+            const double tot = s_red[s_loc] + s_red[ETS + s_loc];
+            const double inv = live ? 1.0 / tot : 0.0;
+            for (int k = kbeg; k < kend; ++k) Rrow[k] *= inv;
+            if (half) for (int k = K; k < KP; ++k) Rrow[k] = 0.0;
+            if (half == 0 && live) {
+                const double l = m + log(tot);
+                ll_acc += l;
+                if (p.lse) p.lse[base + s_loc] = l;
+                if (p.labels) p.labels[base + s_loc] = amax;
+            }
+        }
+        __syncthreads();
+        // M-step tile: stats[k][f] += sum_s R[s][k] Phi[s][f]
+#pragma unroll
+        for (int q = 0; q < KB; ++q) {
+            const int kb = warp + q * 8;                          // 8-component block of this warp
+            if (kb * 8 < KP) {
+                for (int s0 = 0; s0 < ETS; s0 += 4) {
+                    const double a = s_R[(size_t)(s0 + t4) * ldr + kb * 8 + g];
+#pragma unroll
+                    for (int j = 0; j < NF; ++j) {
+                        const double bv = s_Phi[(size_t)(s0 + t4) * ldf + j * 8 + g];
+                        dmma884(acc[q][j], a, bv);
+                    }
+                }
+            }
+        }
+    }
+    // per-CTA partials: [KP][FP] then the log-likelihood
+    double* part = p.partials + (size_t)blockIdx.x * ((size_t)KP * FP + 1);
+#pragma unroll
+    for (int q = 0; q < KB; ++q) {
+        const int kb = warp + q * 8;
+        if (kb * 8 < KP) {
+#pragma unroll
+            for (int j = 0; j < NF; ++j) {
+                const int k = kb * 8 + g, f = j * 8 + 2 * t4;
+                part[(size_t)k * FP + f] = acc[q][j][0];
+                part[(size_t)k * FP + f + 1] = acc[q][j][1];
+            }
+        }
+    }
+    __syncthreads();
+    s_red[tid & 255] = 0.0;
+    __syncthreads();
+    if (half == 0) s_red[s_loc] = ll_acc;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int i = 0; i < ETS; ++i) t += s_red[i]; part[(size_t)KP * FP] = t; }
+}
+
+// stats[k*F + f] = sum over CTAs (fixed order) of partials; stats[K*F] = log-likelihood sum
+__global__ void k_gmm_reduce(const double* partials, int nctas, int K, int KP, int F, int FP, double* stats) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)KP * FP + 1;
+    if (idx < K * F) {
+        const int k = idx / F, f = idx - k * F;
+        double s = 0.0;
+        for (int c = 0; c < nctas; ++c) s += partials[c * stride + (size_t)k * FP + f];
+        stats[idx] = s;
+    } else if (idx == K * F) {
+        double s = 0.0;
+        for (int c = 0; c < nctas; ++c) s += partials[c * stride + (size_t)KP * FP];
+        stats[idx] = s;
+    }
+}
+
+struct FinArgs {
+    const double* stats; double n_total; int first, d, K; double reg; const double* shift;
+    double *weights, *log_weights, *means, *covs, *prec_chol, *log_det; int* info;
+};
+
+// One thread per component (K <= 1024, d <= 16).
+__global__ void k_gmm_finalize(FinArgs p) {
+    __shared__ double s_nk[1024];
+    const int k = threadIdx.x, d = p.d, K = p.K, F = gmm_F(d);
+    double nk = 0.0;
+    if (k < K) { nk = p.stats[(size_t)k * F] + 10.0 * 2.220446049250313e-16; s_nk[k] = nk; }
+    __syncthreads();
+    if (k >= K) return;
+    double tot = 0.0;
+    if (p.first) tot = p.n_total; else for (int j = 0; j < K; ++j) tot += s_nk[j];
+    const double wk = nk / tot;
+    p.weights[k] = wk;
+    p.log_weights[k] = log(wk);
+    const double* st = p.stats + (size_t)k * F;
+    double mu[16], cov[16][16], L[16][16], Li[16][16];
+    for (int i = 0; i < d; ++i) mu[i] = st[1 + i] / nk;
+    int t = 1 + d;
+    for (int i = 0; i < d; ++i)
+        for (int j = i; j < d; ++j) {
+            double c = st[t++] / nk - mu[i] * mu[j];
+            if (i == j) c += p.reg;
+            cov[i][j] = c; cov[j][i] = c;
+        }
+    for (int i = 0; i < d; ++i) p.means[(size_t)k * d + i] = mu[i] + (p.shift ? p.shift[i] : 0.0);
+    for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) p.covs[((size_t)k * d + i) * d + j] = cov[i][j];
+    // Cholesky cov = L L^T
+    int bad = 0;
+    for (int j = 0; j < d; ++j) {
+        double s = cov[j][j];
+        for (int c = 0; c < j; ++c) s -= L[j][c] * L[j][c];
+        if (!(s > 0.0) && bad == 0) bad = j + 1;
+        const double dj = sqrt(s);
+        L[j][j] = dj;
+        for (int i = j + 1; i < d; ++i) {
+            double v = cov[i][j];
+            for (int c = 0; c < j; ++c) v -= L[i][c] * L[j][c];
+            L[i][j] = v / dj;
+        }
+    }
+    // Li = L^{-1} (lower); precisions_chol = Li^T (upper)
+    double ld = 0.0;
+    for (int c = 0; c < d; ++c) {
+        for (int i = 0; i < c; ++i) Li[i][c] = 0.0;
+        Li[c][c] = 1.0 / L[c][c];
+        for (int i = c + 1; i < d; ++i) {
+            double s = 0.0;
+            for (int tt = c; tt < i; ++tt) s += L[i][tt] * Li[tt][c];
+            Li[i][c] = -s / L[i][i];
+        }
+    }
+    for (int i = 0; i < d; ++i) {
+        for (int j = 0; j < d; ++j) p.prec_chol[((size_t)k * d + i) * d + j] = (j >= i) ? Li[j][i] : 0.0;
+        ld += log(Li[i][i]);
+    }
+    p.log_det[k] = ld;
+    if (p.info) p.info[k] = bad;
+}
+
+static int em_grid(long long n) {
+    const long long tiles = (n + ETS - 1) / ETS;
+    const long long g = tiles < kNumSMs ? tiles : kNumSMs;
+    return (int)(g < 1 ? 1 : g);
+}
+static size_t em_smem(int d, int K) {
+    const int F = gmm_F(d), FP = pad8(F), KP = pad8(K), TRI = d * (d + 1) / 2;
+    size_t dbl = (size_t)K * d + (size_t)K * TRI + K + d + (size_t)ETS * d + (size_t)ETS * ld_conflict_free(KP) +
+                 (size_t)ETS * ld_conflict_free(FP) + 2 * ETS + 2 * ETS;
+    return dbl * sizeof(double);
+}
+
+template <int D>
+static int launch_em_d(const EmArgs& p, int grid, size_t smem, cudaStream_t st) {
+    const int KP = pad8(p.K);
+    if (KP <= 64) {
+        KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_gmm_em<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr k_gmm_em"));
+        k_gmm_em<D, 1><<<grid, ETHREADS, smem, st>>>(p);
+    } else {
+        KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_gmm_em<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr k_gmm_em"));
+        k_gmm_em<D, 2><<<grid, ETHREADS, smem, st>>>(p);
+    }
+    return check_launch("k_gmm_em");
+}
+
+static int run_em(EmArgs p, double* stats, void* ws, long long ws_bytes, cudaStream_t st) {
+    if (!p.X) return fail_arg(1, "X is NULL");
+    if (p.n <= 0) return fail_arg(2, "n must be > 0");
+    if (p.d < 1 || p.d > 8) return fail_arg(3, "d must be in 1..8");
+    if (p.K < 1 || p.K > 128) return fail_arg(4, "K must be in 1..128");
+    if (!stats) return fail_arg(10, "stats is NULL");
+    const int F = gmm_F(p.d), FP = pad8(F), KP = pad8(p.K);
+    const int grid = em_grid(p.n);
+    const long long need = (long long)grid * ((long long)KP * FP + 1) * (long long)sizeof(double);
+    if (!ws || ws_bytes < need) return fail_arg(13, "workspace too small (kmpx_gmm_workspace_bytes)");
+    p.partials = (double*)ws;
+    const size_t smem = em_smem(p.d, p.K);
+    if (smem > 227 * 1024) return fail_arg(4, "K*d too large for the shared-memory tile");
+    int rc;
+    switch (p.d) {
+        case 1: rc = launch_em_d<1>(p, grid, smem, st); break;
+        case 2: rc = launch_em_d<2>(p, grid, smem, st); break;
+        case 3: rc = launch_em_d<3>(p, grid, smem, st); break;
+        case 4: rc = launch_em_d<4>(p, grid, smem, st); break;
+        case 5: rc = launch_em_d<5>(p, grid, smem, st); break;
+        case 6: rc = launch_em_d<6>(p, grid, smem, st); break;
+        case 7: rc = launch_em_d<7>(p, grid, smem, st); break;
+        default: rc = launch_em_d<8>(p, grid, smem, st); break;
+    }
+    KMPX_TRY(rc);
+    k_gmm_reduce<<<ceil_div(p.K * F + 1, 128), 128, 0, st>>>(p.partials, grid, p.K, KP, F, FP, stats);
+    return check_launch("k_gmm_reduce");
+}
+
+}  // namespace kmpx
+
+using namespace kmpx;
+
+extern "C" long long kmpx_gmm_workspace_bytes(int n, int d, int K) {
+    (void)n;
+    const int F = gmm_F(d), FP = pad8(F), KP = pad8(K);
+    return (long long)kNumSMs * ((long long)KP * FP + 1) * (long long)sizeof(double);
+}
+
+extern "C" int kmpx_gmm_em_pass(const double* X, long long n, int d, int K, const double* shift,
+                                const double* log_weights, const double* means, const double* prec_chol,
+                                const double* log_det, double* stats, int* labels, double* lse,
+                                void* ws, long long ws_bytes, void* stream) {
+    if (!log_weights || !means || !prec_chol || !log_det) return fail_arg(6, "mixture parameters are NULL");
+    if (K < 2) return fail_arg(4, "K must be >= 2");
+    EmArgs p{X, n, d, K, shift, log_weights, means, prec_chol, log_det, nullptr, nullptr, labels, lse};
+    return run_em(p, stats, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int kmpx_gmm_label_stats(const double* X, long long n, int d, int K, const double* shift,
+                                    const int* labels, double* stats, void* ws, long long ws_bytes, void* stream) {
+    if (!labels) return fail_arg(6, "labels is NULL");
+    EmArgs p{X, n, d, K, shift, nullptr, nullptr, nullptr, nullptr, labels, nullptr, nullptr, nullptr};
+    return run_em(p, stats, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int kmpx_gmm_finalize(const double* stats, double n_total, int first, int d, int K, double reg,
+                                 const double* shift, double* weights, double* log_weights, double* means,
+                                 double* covs, double* prec_chol, double* log_det, int* info, void* stream) {
+    if (!stats) return fail_arg(1, "stats is NULL");
+    if (d < 1 || d > 16) return fail_arg(4, "d must be in 1..16");
+    if (K < 1 || K > 1024) return fail_arg(5, "K must be in 1..1024");
+    if (!weights || !log_weights || !means || !covs || !prec_chol || !log_det) return fail_arg(8, "output arrays are NULL");
+    FinArgs p{stats, n_total, first, d, K, reg, shift, weights, log_weights, means, covs, prec_chol, log_det, info};
+    k_gmm_finalize<<<1, ((K + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("k_gmm_finalize");
+}

@@ -1,0 +1,160 @@
+// K8: Gaussian mixture regression  (GaussianMixtureModel.predict, GaussianMixtureModel.py:59-107)
+//
+//   h_k = pi_k N(x; mu_k^I, S_k^II);  h /= sum_k (h_k + REALMIN)                        (:85-90)
+//   m_k = mu_k^O + S_k^OI (S_k^II)^-1 (x - mu_k^I);  mean = sum h_k m_k                  (:92-96)
+//   cov = sum h_k (S_k^OO - S_k^OI (S_k^II)^-1 S_k^IO + m_k m_k^T) + reg I - mean mean^T (:98-105)
+//
+// Per-component constants (gain G_k, conditional covariance, log-normaliser, chol(S^II)^-1) are hoisted
+// into shared memory by the first K threads of every CTA; then one thread per query.  Inputs x [I][M] and
+// outputs mu [O][M], sigma [O][O][M] keep the reference's query-last layout, so every access is coalesced.
+// Bytes per query: 8 (I + O + O^2); flops ~ K (30 + 2 I O + 2 O + 3 O (O+1)): at the ridge for K=8, O=2.
+#include "common.cuh"
+
+namespace kmpx {
+
+constexpr int GMR_MAXI = 4;
+constexpr double kRealMin = 2.2250738585072014e-308;
+constexpr double kLog2PiG = 1.8378770664093454835606594728112;
+
+struct GmrArgs {
+    const double* priors; const double* means; const double* covs; int K, I, O;
+    const double* x; long long M; double reg; double* mu; double* sigma;
+};
+
+// shared layout per component: [prior, logc, muI (I), Linv (I*I), muO (O), G (O*I), Sc (O*O)]
+__host__ __device__ inline int gmr_stride(int I, int O) { return 2 + I + I * I + O + O * I + O * O; }
+
+template <int O>
+__global__ void __launch_bounds__(128) k_gmr(GmrArgs p) {
+    extern __shared__ double sh[];
+    const int I = p.I, K = p.K, d = I + O;
+    const int stride = gmr_stride(I, O);
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        double* c = sh + (size_t)k * stride;
+        double S[GMR_MAXI][GMR_MAXI], L[GMR_MAXI][GMR_MAXI], Li[GMR_MAXI][GMR_MAXI], Sinv[GMR_MAXI][GMR_MAXI];
+        for (int i = 0; i < I; ++i) for (int j = 0; j < I; ++j) S[i][j] = p.covs[((size_t)i * d + j) * K + k];
+        // Cholesky of S^II and its inverse
+        for (int j = 0; j < I; ++j) {
+            double s = S[j][j];
+            for (int t = 0; t < j; ++t) s -= L[j][t] * L[j][t];
+            const double dj = sqrt(s);
+            L[j][j] = dj;
+            for (int i = j + 1; i < I; ++i) {
+                double v = S[i][j];
+                for (int t = 0; t < j; ++t) v -= L[i][t] * L[j][t];
+                L[i][j] = v / dj;
+            }
+        }
+        double logdet = 0.0;
+        for (int cc = 0; cc < I; ++cc) {
+            for (int i = 0; i < cc; ++i) Li[i][cc] = 0.0;
+            Li[cc][cc] = 1.0 / L[cc][cc];
+            for (int i = cc + 1; i < I; ++i) {
+                double s = 0.0;
+                for (int t = cc; t < i; ++t) s += L[i][t] * Li[t][cc];
+                Li[i][cc] = -s / L[i][i];
+            }
+            logdet += log(L[cc][cc]);
+        }
+        for (int i = 0; i < I; ++i)
+            for (int j = 0; j < I; ++j) {
+                double s = 0.0;
+                for (int t = 0; t < I; ++t) s += Li[t][i] * Li[t][j];
+                Sinv[i][j] = (I == 1) ? 1.0 / S[0][0] : s;
+            }
+        c[0] = p.priors[k];
+        c[1] = -0.5 * I * kLog2PiG - logdet;
+        double* muI = c + 2; double* Lv = muI + I; double* muO = Lv + I * I; double* G = muO + O; double* Sc = G + O * I;
+        for (int i = 0; i < I; ++i) muI[i] = p.means[(size_t)i * K + k];
+        for (int i = 0; i < I; ++i) for (int j = 0; j < I; ++j) Lv[i * I + j] = Li[i][j];
+        for (int a = 0; a < O; ++a) muO[a] = p.means[(size_t)(I + a) * K + k];
+        for (int a = 0; a < O; ++a)
+            for (int j = 0; j < I; ++j) {
+                double s = 0.0;
+                for (int t = 0; t < I; ++t) s += p.covs[((size_t)(I + a) * d + t) * K + k] * Sinv[t][j];
+                G[a * I + j] = s;
+            }
+        for (int a = 0; a < O; ++a)
+            for (int b = 0; b < O; ++b) {
+                double s = 0.0;
+                for (int t = 0; t < I; ++t) s += G[a * I + t] * p.covs[((size_t)t * d + I + b) * K + k];
+                Sc[a * O + b] = p.covs[((size_t)(I + a) * d + I + b) * K + k] - s;
+            }
+    }
+    __syncthreads();
+    for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < p.M; m += (long long)gridDim.x * blockDim.x) {
+        double x[GMR_MAXI];
+        for (int i = 0; i < I; ++i) x[i] = p.x[(size_t)i * p.M + m];
+        double mean[O], sec[O][O];
+#pragma unroll
+        for (int a = 0; a < O; ++a) { mean[a] = 0.0;
+#pragma unroll
+            for (int b = 0; b < O; ++b) sec[a][b] = 0.0; }
+        double hsum = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double* c = sh + (size_t)k * stride;
+            const double* muI = c + 2; const double* Lv = muI + I; const double* muO = Lv + I * I;
+            const double* G = muO + O; const double* Sc = G + O * I;
+            double dev[GMR_MAXI], q = 0.0;
+            for (int i = 0; i < I; ++i) dev[i] = x[i] - muI[i];
+            for (int i = 0; i < I; ++i) { double z = 0.0; for (int t = 0; t <= i; ++t) z += Lv[i * I + t] * dev[t]; q += z * z; }
+            const double h = c[0] * exp(c[1] - 0.5 * q);
+            hsum += h + kRealMin;
+            double mk[O];
+#pragma unroll
+            for (int a = 0; a < O; ++a) { double s = muO[a]; for (int t = 0; t < I; ++t) s += G[a * I + t] * dev[t]; mk[a] = s; mean[a] += h * s; }
+#pragma unroll
+            for (int a = 0; a < O; ++a)
+#pragma unroll
+                for (int b = 0; b < O; ++b) sec[a][b] += h * (Sc[a * O + b] + mk[a] * mk[b]);
+        }
+        const double inv = 1.0 / hsum;
+#pragma unroll
+        for (int a = 0; a < O; ++a) mean[a] *= inv;
+#pragma unroll
+        for (int a = 0; a < O; ++a) {
+            p.mu[(size_t)a * p.M + m] = mean[a];
+#pragma unroll
+            for (int b = 0; b < O; ++b)
+                p.sigma[((size_t)a * O + b) * p.M + m] = sec[a][b] * inv + (a == b ? p.reg : 0.0) - mean[a] * mean[b];
+        }
+    }
+}
+
+template <int O>
+static int launch_gmr(const GmrArgs& p, cudaStream_t st) {
+    const size_t smem = (size_t)p.K * gmr_stride(p.I, O) * sizeof(double);
+    if (smem > 200 * 1024) { snprintf(g_err, sizeof(g_err), "kmpx: too many mixture components for k_gmr"); return -4; }
+    KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_gmr<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr k_gmr"));
+    const long long blocks = (p.M + 127) / 128;
+    const int grid = (int)(blocks < kNumSMs * 16 ? blocks : kNumSMs * 16);
+    k_gmr<O><<<grid, 128, smem, st>>>(p);
+    return check_launch("k_gmr");
+}
+
+}  // namespace kmpx
+
+using namespace kmpx;
+
+extern "C" int kmpx_gmr(const double* priors, const double* means, const double* covs, int K, int I, int O,
+                        const double* x, int M, double reg, double* mu, double* sigma_out, void* stream) {
+    if (!priors || !means || !covs) return fail_arg(1, "mixture parameters are NULL");
+    if (K < 1) return fail_arg(4, "K must be > 0");
+    if (I < 1 || I > GMR_MAXI) return fail_arg(5, "I must be in 1..4");
+    if (O < 1 || O > 8) return fail_arg(6, "O must be in 1..8");
+    if (!x) return fail_arg(7, "x is NULL");
+    if (M <= 0) return fail_arg(8, "M must be > 0");
+    if (!mu || !sigma_out) return fail_arg(10, "outputs are NULL");
+    GmrArgs p{priors, means, covs, K, I, O, x, M, reg, mu, sigma_out};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (O) {
+        case 1: return launch_gmr<1>(p, st);
+        case 2: return launch_gmr<2>(p, st);
+        case 3: return launch_gmr<3>(p, st);
+        case 4: return launch_gmr<4>(p, st);
+        case 5: return launch_gmr<5>(p, st);
+        case 6: return launch_gmr<6>(p, st);
+        case 7: return launch_gmr<7>(p, st);
+        default: return launch_gmr<8>(p, st);
+    }
+}

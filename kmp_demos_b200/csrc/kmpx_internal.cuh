@@ -1,0 +1,34 @@
+// Argument structs and launchers shared between the translation units of libkmpx.
+#pragma once
+#include "common.cuh"
+
+namespace kmpx {
+
+// Component-major system order: row = a*Ns + i with Ns = N rounded up to even, so that every component
+// block starts on a 16-byte boundary (cp.async granularity).  Padding rows/columns (i >= N) are identity.
+__host__ __device__ inline int comp_stride(int N) { return (N + 1) & ~1; }
+__host__ __device__ inline int sys_size(int N, int O, int layout) {
+    return layout == KMPX_LAYOUT_POINT ? N * O : comp_stride(N) * O;
+}
+
+struct FactorArgs {
+    double* A; int lda; long long strideA; const int* n_sys; int n_max; int batch; int* info;
+    int info_offset;       // added to a non-zero local pivot index (blocked large-n driver)
+    int info_accumulate;   // keep an already recorded failure instead of overwriting it
+};
+struct GemmArgs {
+    int m, n, k; double alpha; const double* A; int lda; long long strideA;
+    const double* B; int ldb; long long strideB; double beta; double* C; int ldc; long long strideC; int tri;
+};
+struct AlphaArgs {
+    const double* F; int lda; long long strideA; const int* n_pts; int n_max, O, batch, layout;
+    const double* y; double* w; int ldw; double* alpha; int general;
+};
+
+int launch_dgemm(int transA, int transB, const GemmArgs& p, int batch, cudaStream_t st);
+int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
+                       int info_offset, int info_accumulate, cudaStream_t st);
+int launch_trtri_small(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, cudaStream_t st);
+int launch_solve_alpha(const AlphaArgs& p, cudaStream_t st);
+
+}  // namespace kmpx

@@ -1,0 +1,265 @@
+"""``KMP`` - drop-in for the reference's ``kmp.model.KMP`` (kmp/model/KMP.py) whose numerical bodies are
+calls into libkmpx.so (sm_100a CUDA kernels, include/kmpx.h).
+
+Same constructor, methods, argument shapes and host-visible attributes as the reference:
+``KMP(l, alpha, sigma_f, adaptation_tol, time_driven_kernel, verbose)``, ``fit(X (I,N), mu (O,N), var (O,O,N))``,
+``predict(s (I,M)) -> (xi (O,M), sigma (O,O,M))``, ``set_waypoint(s, xi, sigma)``; attributes ``s, xi, sigma, N, O,
+l, alpha, sigma_f, tol, time_driven_kernel, kl_divergence, _estimator``.
+
+How the path maps to kernels (reference file:line -> entry point):
+  KMP.py:146-156  N^2 Python loop building K (x) I + l*Sigma   -> kmpx_kernel_build   (K1)
+  KMP.py:157      numpy.linalg.inv (LU)                        -> kmpx_potrf + kmpx_trtri (K2/K3); non-symmetric
+                                                                  Sigma blocks (demos.py:251,285) -> kmpx_inverse
+  KMP.py:178-190  per-query loop, k@inv@Y, k@inv@k.T           -> kmpx_solve_alpha + kmpx_kmp_predict (K4)
+"""
+from __future__ import annotations
+
+import copy
+import logging
+from typing import Tuple
+
+import numpy as np
+
+from . import _lib
+
+logging.basicConfig(
+    level=logging.INFO,
+    format="%(asctime)s.%(msecs)03d %(levelname)s %(message)s",
+    datefmt="%Y-%m-%d,%H:%M:%S",
+)
+
+
+def _roundup(v, m):
+    return (v + m - 1) // m * m
+
+
+class _Factorisation:
+    """Device state of one fitted system in the component-major order."""
+
+    def __init__(self, F, lda, kind, w, alpha, s_dev, N, I, O):
+        self.F, self.lda, self.kind, self.w, self.alpha = F, lda, kind, w, alpha
+        self.s_dev, self.N, self.I, self.O = s_dev, N, I, O
+
+
+def factorise(s, xi, sigma, lam, sigma_f, time_driven, layout=_lib.LAYOUT_COMPONENT, force_general=False):
+    """Builds and factorises one KMP system on the device.  s (I,N), xi (O,N), sigma (O,O,N) host arrays.
+    Returns a _Factorisation with F = L^{-1} (kind 0) or A^{-1} (kind 1, non-symmetric blocks)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device('cuda')
+    I, N = s.shape
+    O = xi.shape[0]
+    if time_driven and O % 2:
+        raise ValueError('time_driven_kernel needs an even number of outputs (KMP.py:125)')
+    n = int(lib.kmpx_sys_size(N, O, layout))
+    lda = _roundup(n, 8)
+    s_dev = torch.as_tensor(np.ascontiguousarray(s.T), dtype=torch.float64, device=dev)                     # (N,I)
+    y_dev = torch.as_tensor(np.ascontiguousarray(xi.T), dtype=torch.float64, device=dev)                    # (N,O)
+    g_host = np.ascontiguousarray(np.transpose(sigma, (2, 0, 1)))                                            # (N,O,O)
+    g_dev = torch.as_tensor(g_host, dtype=torch.float64, device=dev)
+    # material asymmetry of the stored covariance blocks => general (LU-like) path, SURVEY.md H2
+    scale = float(np.max(np.abs(g_host))) if g_host.size else 0.0
+    asym = float(np.max(np.abs(g_host - np.transpose(g_host, (0, 2, 1))))) if g_host.size else 0.0
+    general = force_general or (asym > 1e-12 * scale)
+    A = torch.empty((n, lda), dtype=torch.float64, device=dev)
+    st = _lib.stream()
+    _lib.call('kmpx_kernel_build', _lib.ptr(s_dev), _lib.ptr(g_dev), None, _lib.ptr(A), 1, N, I, O, lda, n * lda,
+              float(sigma_f), float(lam), int(bool(time_driven)), layout,
+              _lib.UPLO_FULL if general else _lib.UPLO_LOWER, st)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    w = torch.zeros(lda, dtype=torch.float64, device=dev)
+    alpha = torch.empty((N, O), dtype=torch.float64, device=dev)
+    if not general:
+        nbytes = int(lib.kmpx_potrf_workspace_bytes(n, 1))
+        ws = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=dev)
+        _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
+        if int(info.item()) != 0:
+            # not positive definite: the reference's LU inverse would still go through -> general path
+            return factorise(s, xi, sigma, lam, sigma_f, time_driven, layout, force_general=True)
+        _lib.call('kmpx_trtri', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(ws), nbytes, st)
+        _lib.call('kmpx_solve_alpha', _lib.ptr(A), lda, n * lda, None, N, O, 1, layout, _lib.ptr(y_dev),
+                  _lib.ptr(w), lda, _lib.ptr(alpha), st)
+        kind = 0
+    else:
+        nbytes = int(lib.kmpx_inverse_workspace_bytes(n, 1))
+        ws = torch.empty(max(nbytes, 8) // 8 + 1, dtype=torch.float64, device=dev)
+        _lib.call('kmpx_inverse', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError('Singular matrix')      # what numpy.linalg.inv raises at KMP.py:157
+        _lib.call('kmpx_apply_inverse', _lib.ptr(A), lda, n * lda, None, N, O, 1, layout, _lib.ptr(y_dev),
+                  _lib.ptr(w), lda, _lib.ptr(alpha), st)
+        kind = 1
+    return _Factorisation(A, lda, kind, w, alpha, s_dev, N, I, O)
+
+
+class KMP:
+    """Trajectory imitation and adaptation using Kernelized Movement Primitives (B200 implementation).
+
+    Parameters (identical to the reference, KMP.py:39-47)
+    ----------
+    l : float, default=0.5            lambda regularisation factor.
+    alpha : float, default=40         coefficient of the covariance prediction.
+    sigma_f : float, default=1        kernel coefficient.
+    adaptation_tol : float, default=0.0005   distance below which a via-point replaces a stored point.
+    time_driven_kernel : bool, default=True  finite-difference position/velocity kernel.
+    verbose : bool, default=False
+    """
+
+    def __init__(self, l: float = 0.5, alpha: float = 40, sigma_f: float = 1.0, adaptation_tol: float = 0.0005,
+                 time_driven_kernel: bool = True, verbose: bool = False) -> None:
+        self.l = l
+        self.alpha = alpha
+        self.sigma_f = sigma_f
+        self.kl_divergence = None
+        self.tol = adaptation_tol
+        self.time_driven_kernel = time_driven_kernel
+        self._logger = logging.getLogger(__name__)
+        self._logger.setLevel(level=logging.DEBUG if verbose else logging.INFO)
+        self._fact = None
+        self._estimator_cache = None
+
+    # ------------------------------------------------------------------ fit (KMP.py:130-158)
+    def fit(self, X: np.ndarray, mu: np.ndarray, var: np.ndarray) -> None:
+        """Builds K (x) I + l*Sigma on the device and factorises it.  X (I,N), mu (O,N), var (O,O,N);
+        the inputs are deep-copied like the reference does (KMP.py:142-144)."""
+        self.s = copy.deepcopy(X)
+        self.xi = copy.deepcopy(mu)
+        self.sigma = copy.deepcopy(var)
+        self.O, self.N = self.xi.shape
+        self._fact = factorise(np.asarray(self.s, dtype=np.float64), np.asarray(self.xi, dtype=np.float64),
+                               np.asarray(self.sigma, dtype=np.float64), self.l, self.sigma_f,
+                               self.time_driven_kernel)
+        self._estimator_cache = None
+        self._logger.info("KMP fit done.")
+
+    # ------------------------------------------------------------------ predict (KMP.py:160-194)
+    def predict(self, s: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """Mean (O,M) and covariance (O,O,M) for the inputs s (I,M)."""
+        torch = _lib.require_cuda()
+        if self._fact is None:
+            raise AttributeError("KMP.predict called before fit")
+        f = self._fact
+        s = np.asarray(s, dtype=np.float64)
+        M = s.shape[1]
+        dev = torch.device('cuda')
+        sq = torch.as_tensor(np.ascontiguousarray(s.T), dtype=torch.float64, device=dev)
+        xi = torch.empty((f.O, M), dtype=torch.float64, device=dev)
+        sg = torch.empty((f.O, f.O, M), dtype=torch.float64, device=dev)
+        n = f.F.shape[0]
+        _lib.call('kmpx_kmp_predict', _lib.ptr(f.F), f.lda, n * f.lda, f.kind, _lib.ptr(f.w), f.lda,
+                  _lib.ptr(f.s_dev), None, f.N, f.I, f.O, 1, _lib.ptr(sq), 0, M, float(self.sigma_f),
+                  float(self.alpha), int(bool(self.time_driven_kernel)), _lib.ptr(xi), _lib.ptr(sg), _lib.stream())
+        self._logger.info("KMP predict done.")
+        return xi.cpu().numpy(), sg.cpu().numpy()
+
+    def predict_mean(self, s: np.ndarray) -> np.ndarray:
+        """Mean only, from alpha = (K + l*Sigma)^-1 mu: O(N*M) kernel evaluations instead of the GEMM."""
+        torch = _lib.require_cuda()
+        f = self._fact
+        s = np.asarray(s, dtype=np.float64)
+        M = s.shape[1]
+        dev = torch.device('cuda')
+        sq = torch.as_tensor(np.ascontiguousarray(s.T), dtype=torch.float64, device=dev)
+        xi = torch.empty((f.O, M), dtype=torch.float64, device=dev)
+        _lib.call('kmpx_kmp_predict_mean', _lib.ptr(f.alpha), _lib.ptr(f.s_dev), None, f.N, f.I, f.O, 1, _lib.ptr(sq), 0, M,
+                  float(self.sigma_f), int(bool(self.time_driven_kernel)), _lib.ptr(xi), _lib.stream())
+        return xi.cpu().numpy()
+
+    # ------------------------------------------------------------------ set_waypoint (KMP.py:57-91)
+    def set_waypoint(self, s, xi, sigma) -> None:
+        """Inserts via-points: the nearest stored input (L2, first minimum, only among the ``self.N`` points of
+        the last fit) is overwritten when closer than ``tol`` (strict), otherwise the point is appended; then
+        the model is refitted.  ``s[j]``, ``xi[j]`` and ``sigma[j]`` are used exactly as indexed by the caller,
+        so the reference's un-listed forms (demos.py:251,285) broadcast the same way."""
+        for j in range(len(s)):
+            d = np.linalg.norm(self.s[:, :self.N] - np.asarray(s[j], dtype=float).reshape(-1, 1), axis=0) \
+                if self.s.shape[0] > 1 else np.abs(self.s[0, :self.N] - s[j])
+            idx = int(np.argmin(d)) if self.N > 0 else -1
+            if idx >= 0 and d[idx] < self.tol:
+                self.s[:, idx] = s[j]
+                self.xi[:, idx] = xi[j]
+                self.sigma[:, :, idx] = sigma[j]
+            else:
+                self.s = np.concatenate((self.s, np.array(s[j]).reshape(1, -1)), axis=1)
+                self.xi = np.concatenate((self.xi, xi[j].T), axis=1)
+                self.sigma = np.concatenate((self.sigma, np.expand_dims(sigma[j], 2)), axis=2)
+        self.fit(self.s, self.xi, self.sigma)
+
+    # ------------------------------------------------------------------ _estimator (KMP.py:157), lazily
+    @property
+    def _estimator(self) -> np.ndarray:
+        """inv(K (x) I + l*Sigma) in the reference's point-major order, materialised on first access
+        (the prediction path never needs it)."""
+        if self._estimator_cache is None:
+            self._estimator_cache = explicit_inverse(np.asarray(self.s, float), np.asarray(self.sigma, float), self.l,
+                                                     self.sigma_f, self.time_driven_kernel)
+        return self._estimator_cache
+
+    def system_matrix(self, layout=_lib.LAYOUT_POINT) -> np.ndarray:
+        """K (x) I + l*Sigma as built by kmpx_kernel_build (point-major = the reference's ``k``, KMP.py:146-156)."""
+        return build_matrix(np.asarray(self.s, float), np.asarray(self.sigma, float), self.l, self.sigma_f,
+                            self.time_driven_kernel, layout)
+
+    def KL_divergence(self, xi, sigma, xi_ref, sigma_ref) -> float:
+        raise NotImplementedError("KL_divergence is unused by the reference (call commented out at KMP.py:192)")
+
+
+def build_matrix(s, sigma, lam, sigma_f, time_driven, layout=_lib.LAYOUT_POINT):
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device('cuda')
+    I, N = s.shape
+    O = sigma.shape[0]
+    n = int(lib.kmpx_sys_size(N, O, layout))
+    lda = _roundup(n, 8)
+    s_dev = torch.as_tensor(np.ascontiguousarray(s.T), dtype=torch.float64, device=dev)
+    g_dev = torch.as_tensor(np.ascontiguousarray(np.transpose(sigma, (2, 0, 1))), dtype=torch.float64, device=dev)
+    A = torch.empty((n, lda), dtype=torch.float64, device=dev)
+    _lib.call('kmpx_kernel_build', _lib.ptr(s_dev), _lib.ptr(g_dev), None, _lib.ptr(A), 1, N, I, O, lda, n * lda,
+              float(sigma_f), float(lam), int(bool(time_driven)), layout, _lib.UPLO_FULL, _lib.stream())
+    return A[:, :n].cpu().numpy()
+
+
+def explicit_inverse(s, sigma, lam, sigma_f, time_driven):
+    """Point-major inverse on the device: potrf + trtri + Linv^T Linv (DMMA GEMM), or Gauss-Jordan when the
+    covariance blocks are not symmetric."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device('cuda')
+    I, N = s.shape
+    O = sigma.shape[0]
+    n = N * O
+    lda = _roundup(n, 8)
+    s_dev = torch.as_tensor(np.ascontiguousarray(s.T), dtype=torch.float64, device=dev)
+    g_host = np.ascontiguousarray(np.transpose(sigma, (2, 0, 1)))
+    g_dev = torch.as_tensor(g_host, dtype=torch.float64, device=dev)
+    A = torch.empty((n, lda), dtype=torch.float64, device=dev)
+    st = _lib.stream()
+    _lib.call('kmpx_kernel_build', _lib.ptr(s_dev), _lib.ptr(g_dev), None, _lib.ptr(A), 1, N, I, O, lda, n * lda,
+              float(sigma_f), float(lam), int(bool(time_driven)), _lib.LAYOUT_POINT, _lib.UPLO_FULL, st)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    scale = float(np.max(np.abs(g_host)))
+    asym = float(np.max(np.abs(g_host - np.transpose(g_host, (0, 2, 1)))))
+    if asym <= 1e-12 * scale:
+        nbytes = int(lib.kmpx_potrf_workspace_bytes(n, 1))
+        ws = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=dev)
+        A0 = A.clone()
+        _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
+        if int(info.item()) == 0:
+            _lib.call('kmpx_trtri', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(ws), nbytes, st)
+            Linv = torch.tril(A[:, :n]).contiguous()
+            ldl = Linv.stride(0)
+            if ldl % 2:
+                Linv = torch.nn.functional.pad(Linv, (0, 1)).contiguous()
+                ldl = Linv.stride(0)
+            out = torch.empty((n, lda), dtype=torch.float64, device=dev)
+            _lib.call('kmpx_dgemm', 1, 0, n, n, n, 1.0, _lib.ptr(Linv), ldl, 0, _lib.ptr(Linv), ldl, 0, 0.0,
+                      _lib.ptr(out), lda, 0, 1, 0, st)
+            return out[:, :n].cpu().numpy()
+        A = A0
+    nbytes = int(lib.kmpx_inverse_workspace_bytes(n, 1))
+    ws = torch.empty(max(nbytes, 8) // 8 + 1, dtype=torch.float64, device=dev)
+    _lib.call('kmpx_inverse', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError('Singular matrix')
+    return A[:, :n].cpu().numpy()

@@ -180,11 +180,14 @@ def kmp_predict(estimator, s_train, xi_train, s_query, alpha, sigma_f, time_driv
 # ----------------------------------------------------------------------------------------------
 def kmp_set_waypoint(s_db, xi_db, sigma_db, s, xi, sigma, tol):
     """Nearest stored input by L2, strict ``< tol`` => overwrite, else append (KMP.py:72-89).
-    Returns the new (s, xi, sigma) database; the caller refits (KMP.py:91)."""
+    Returns the new (s, xi, sigma) database; the caller refits (KMP.py:91).
+    The scan covers only the points present at the last fit (``self.N`` is not updated between
+    via-points of one call, KMP.py:74), so a point appended earlier in the same call is never matched."""
     s_db, xi_db, sigma_db = s_db.copy(), xi_db.copy(), sigma_db.copy()
+    n_at_entry = s_db.shape[1]
     for j in range(len(s)):
         min_dist, idx = np.inf, None
-        for i in range(s_db.shape[1]):
+        for i in range(n_at_entry):
             dist = np.linalg.norm(s_db[:, i] - s[j])
             if dist < min_dist:
                 min_dist, idx = dist, i

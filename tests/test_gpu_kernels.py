@@ -1,0 +1,319 @@
+"""GPU parity of the individual kernels, called through the C ABI (kmp_demos_b200._lib), against numpy and the
+CPU oracle.  Tolerances: bit-exact for labels/indices; fp64 kernels within the stated relative error."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def T():
+    import torch
+    from kmp_demos_b200 import _lib
+    _lib.load()
+    return torch
+
+
+def dev(torch, a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), device='cuda') if dtype is None else \
+        torch.as_tensor(np.ascontiguousarray(a), device='cuda', dtype=dtype)
+
+
+def comp_perm(N, O):
+    """index map point-major (i*O+a) -> component-major (a*Ns+i) and the padded size"""
+    Ns = (N + 1) // 2 * 2
+    idx = np.array([[a * Ns + i for a in range(O)] for i in range(N)]).reshape(-1)
+    return idx, O * Ns
+
+
+def test_kernel_build_matches_reference_matrix(T, golden):
+    from kmp_demos_b200 import model, _lib
+    z = golden('small_cases.npz')
+    for c in range(int(z['kmp_cases'])):
+        I, O, N, td, sf, lam, alpha = z[f'kmp{c}_cfg']
+        O, N, td = int(O), int(N), bool(td)
+        s, sig, Aref = z[f'kmp{c}_s'], z[f'kmp{c}_sigma'], z[f'kmp{c}_A']
+        A = model.build_matrix(s, sig, lam, sf, td, _lib.LAYOUT_POINT)
+        tol = 1e-10 if td else 1e-15      # FD blocks amplify 1-ulp exp differences by 1/dt^2
+        assert rel_err(A, Aref) < tol, f'case {c} point-major'
+        Ac = model.build_matrix(s, sig, lam, sf, td, _lib.LAYOUT_COMPONENT)
+        idx, n = comp_perm(N, O)
+        assert Ac.shape == (n, n)
+        assert rel_err(Ac[np.ix_(idx, idx)], Aref) < tol, f'case {c} component-major'
+        pad = np.setdiff1d(np.arange(n), idx)
+        if pad.size:
+            assert np.array_equal(Ac[np.ix_(pad, pad)], np.eye(pad.size)) and np.all(Ac[np.ix_(pad, idx)] == 0)
+
+
+def test_kernel_build_lower_only_and_batch(T):
+    from kmp_demos_b200 import _lib
+    rng = np.random.default_rng(0)
+    B, Nmax, O, I = 5, 37, 2, 1
+    npts = np.array([37, 36, 1, 20, 33], dtype=np.int32)
+    s = np.sort(rng.random((B, Nmax, I)), axis=1)
+    Bm = rng.normal(size=(B, Nmax, O, O))
+    sig = np.einsum('bnij,bnkj->bnik', Bm, Bm) + 0.1 * np.eye(O)
+    n = O * ((Nmax + 1) // 2 * 2)
+    lda = (n + 7) // 8 * 8
+    A_full = T.full((B, n, lda), -7.0, dtype=T.float64, device='cuda')
+    A_low = T.full((B, n, lda), -7.0, dtype=T.float64, device='cuda')
+    for A, uplo in ((A_full, _lib.UPLO_FULL), (A_low, _lib.UPLO_LOWER)):
+        _lib.call('kmpx_kernel_build', _lib.ptr(dev(T, s)), _lib.ptr(dev(T, sig)), _lib.ptr(dev(T, npts)), _lib.ptr(A), B, Nmax,
+                  I, O, lda, n * lda, 200.0, 0.5, 0, _lib.LAYOUT_COMPONENT, uplo, _lib.stream())
+    Af, Al = A_full.cpu().numpy(), A_low.cpu().numpy()
+    from oracle import kmp_oracle as orc
+    for b in range(B):
+        N = int(npts[b])
+        idx, nb = comp_perm(N, O)
+        ref = orc.kmp_matrix(s[b, :N].T, np.transpose(sig[b, :N], (1, 2, 0)), 0.5, 200.0, False)
+        assert rel_err(Af[b][np.ix_(idx, idx)], ref) < 1e-15
+        low = np.tril(Af[b][:nb, :nb])
+        assert np.array_equal(np.tril(Al[b][:nb, :nb]), low)
+        assert np.all(np.triu(Al[b][:nb, :nb], 1) == -7.0), 'LOWER must not touch the strict upper triangle'
+        assert np.all(Af[b][nb:, :] == -7.0), 'rows beyond the system must stay untouched'
+
+
+@pytest.mark.parametrize('ta,tb', [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_dgemm(T, ta, tb):
+    from kmp_demos_b200 import _lib
+    rng = np.random.default_rng(1)
+    for (m, n, k) in [(128, 128, 64), (130, 70, 33), (257, 300, 129), (1, 5, 3)]:
+        A = rng.normal(size=(k, m) if ta else (m, k))
+        Bm = rng.normal(size=(n, k) if tb else (k, n))
+        C0 = rng.normal(size=(m, n))
+        lda = (A.shape[1] + 1) // 2 * 2
+        ldb = (Bm.shape[1] + 1) // 2 * 2
+        ldc = (n + 1) // 2 * 2
+        Ad = T.zeros((A.shape[0], lda), dtype=T.float64, device='cuda'); Ad[:, :A.shape[1]] = dev(T, A)
+        Bd = T.zeros((Bm.shape[0], ldb), dtype=T.float64, device='cuda'); Bd[:, :Bm.shape[1]] = dev(T, Bm)
+        Cd = T.zeros((m, ldc), dtype=T.float64, device='cuda'); Cd[:, :n] = dev(T, C0)
+        _lib.call('kmpx_dgemm', ta, tb, m, n, k, 1.5, _lib.ptr(Ad), lda, 0, _lib.ptr(Bd), ldb, 0, -0.5, _lib.ptr(Cd), ldc, 0, 1, 0,
+                  _lib.stream())
+        ref = 1.5 * (A.T if ta else A) @ (Bm.T if tb else Bm) - 0.5 * C0
+        assert rel_err(Cd[:, :n].cpu().numpy(), ref) < 1e-13, (m, n, k)
+
+
+def test_dgemm_triangular_modes(T):
+    from kmp_demos_b200 import _lib
+    rng = np.random.default_rng(2)
+    m = 300
+    A = rng.normal(size=(m, 64)); C0 = rng.normal(size=(m, m))
+    Ad, Cd = dev(T, A), dev(T, C0)
+    _lib.call('kmpx_dgemm', 0, 1, m, m, 64, -1.0, _lib.ptr(Ad), 64, 0, _lib.ptr(Ad), 64, 0, 1.0, _lib.ptr(Cd), m, 0, 1, 1, _lib.stream())
+    out = Cd.cpu().numpy()
+    assert rel_err(np.tril(out), np.tril(C0 - A @ A.T)) < 1e-13
+    Lw = np.tril(rng.normal(size=(m, m))); Bm = rng.normal(size=(m, 40))
+    Cd = T.zeros((m, 40), dtype=T.float64, device='cuda')
+    _lib.call('kmpx_dgemm', 0, 0, m, 40, m, 1.0, _lib.ptr(dev(T, Lw)), m, 0, _lib.ptr(dev(T, Bm)), 40, 0, 0.0, _lib.ptr(Cd), 40, 0, 1, 2,
+              _lib.stream())
+    assert rel_err(Cd.cpu().numpy(), Lw @ Bm) < 1e-13
+    Bl = np.tril(rng.normal(size=(m, m)))
+    Cd = T.zeros((40, m), dtype=T.float64, device='cuda')
+    A2 = rng.normal(size=(40, m))
+    _lib.call('kmpx_dgemm', 0, 0, 40, m, m, 1.0, _lib.ptr(dev(T, A2)), m, 0, _lib.ptr(dev(T, Bl)), m, 0, 0.0, _lib.ptr(Cd), m, 0, 1, 3,
+              _lib.stream())
+    assert rel_err(Cd.cpu().numpy(), A2 @ Bl) < 1e-13
+
+
+def _spd(rng, n):
+    M = rng.normal(size=(n, n))
+    return M @ M.T / n + np.eye(n)
+
+
+def test_potrf_trtri_small_ragged_batch(T):
+    from kmp_demos_b200 import _lib
+    rng = np.random.default_rng(3)
+    sizes = [1, 5, 31, 32, 33, 64, 100, 257, 402, 404, 453, 512]
+    nmax = 512
+    lda = nmax
+    A = T.full((len(sizes), nmax, lda), float('nan'), dtype=T.float64, device='cuda')
+    mats = []
+    for b, n in enumerate(sizes):
+        S = _spd(rng, n)
+        mats.append(S)
+        low = np.tril(S) + np.triu(np.full((n, n), np.nan), 1)     # strict upper = NaN: must never be read
+        A[b, :n, :n] = dev(T, low)
+    n_sys = dev(T, np.array(sizes, dtype=np.int32))
+    info = T.full((len(sizes),), -1, dtype=T.int32, device='cuda')
+    _lib.call('kmpx_potrf', _lib.ptr(A), lda, nmax * lda, _lib.ptr(n_sys), nmax, len(sizes), _lib.ptr(info), None, 0, _lib.stream())
+    L = A.cpu().numpy()
+    assert np.all(info.cpu().numpy() == 0)
+    for b, n in enumerate(sizes):
+        assert rel_err(np.tril(L[b, :n, :n]), np.linalg.cholesky(mats[b])) < 1e-13, n
+    _lib.call('kmpx_trtri', _lib.ptr(A), lda, nmax * lda, _lib.ptr(n_sys), nmax, len(sizes), None, 0, _lib.stream())
+    Li = A.cpu().numpy()
+    for b, n in enumerate(sizes):
+        ref = np.linalg.inv(np.linalg.cholesky(mats[b]))
+        assert rel_err(np.tril(Li[b, :n, :n]), ref) < 1e-12, n
+
+
+def test_potrf_reports_first_bad_pivot(T):
+    from kmp_demos_b200 import _lib
+    rng = np.random.default_rng(4)
+    n = 70
+    S = _spd(rng, n)
+    S[40, 40] = -1.0
+    A = dev(T, np.stack([S, _spd(rng, n)]))
+    info = T.zeros(2, dtype=T.int32, device='cuda')
+    _lib.call('kmpx_potrf', _lib.ptr(A), n, n * n, None, n, 2, _lib.ptr(info), None, 0, _lib.stream())
+    assert info.cpu().numpy().tolist() == [41, 0]
+
+
+@pytest.mark.parametrize('n', [600, 1100, 1536])
+def test_potrf_trtri_large_blocked(T, n):
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    S = _spd(rng, n)
+    lda = (n + 7) // 8 * 8
+    A = T.zeros((n, lda), dtype=T.float64, device='cuda')
+    A[:, :n] = dev(T, S)
+    nbytes = int(lib.kmpx_potrf_workspace_bytes(n, 1))
+    ws = T.empty(nbytes // 8, dtype=T.float64, device='cuda')
+    info = T.full((1,), -1, dtype=T.int32, device='cuda')
+    _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, _lib.stream())
+    assert int(info.item()) == 0
+    Lref = np.linalg.cholesky(S)
+    assert rel_err(np.tril(A[:, :n].cpu().numpy()), Lref) < 1e-12
+    _lib.call('kmpx_trtri', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(ws), nbytes, _lib.stream())
+    assert rel_err(np.tril(A[:, :n].cpu().numpy()), np.linalg.inv(Lref)) < 1e-11
+
+
+def test_inverse_gauss_jordan(T):
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    sizes = [1, 7, 64, 150, 300]
+    nmax = 300
+    A = T.zeros((len(sizes), nmax, nmax), dtype=T.float64, device='cuda')
+    mats = []
+    for b, n in enumerate(sizes):
+        M = rng.normal(size=(n, n)) + 0.5 * np.eye(n)
+        M[0, 0] = 0.0        # forces a row interchange in the first step
+        mats.append(M)
+        A[b, :n, :n] = dev(T, M)
+    nbytes = int(lib.kmpx_inverse_workspace_bytes(nmax, len(sizes)))
+    ws = T.empty(nbytes // 8 + 1, dtype=T.float64, device='cuda')
+    info = T.zeros(len(sizes), dtype=T.int32, device='cuda')
+    _lib.call('kmpx_inverse', _lib.ptr(A), nmax, nmax * nmax, _lib.ptr(dev(T, np.array(sizes, dtype=np.int32))), nmax, len(sizes),
+              _lib.ptr(info), _lib.ptr(ws), nbytes, _lib.stream())
+    out = A.cpu().numpy()
+    assert np.all(info.cpu().numpy() == 0)
+    for b, n in enumerate(sizes):
+        ref = np.linalg.inv(mats[b])
+        assert rel_err(out[b, :n, :n], ref) < 1e-9 * np.linalg.cond(mats[b]) / 1e3 + 1e-11, n
+    sing = T.zeros((1, 4, 4), dtype=T.float64, device='cuda')
+    _lib.call('kmpx_inverse', _lib.ptr(sing), 4, 16, None, 4, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, _lib.stream())
+    assert int(info[0].item()) > 0
+
+
+def test_gmr_matches_reference(T, golden):
+    from kmp_demos_b200.mixture import GaussianMixtureModel
+    z = golden('small_cases.npz')
+    for c in range(int(z['gmr_cases'])):
+        I, O, K, M, reg = z[f'gmr{c}_cfg']
+        g = GaussianMixtureModel(n_components=int(K), diag_reg_factor=float(reg))
+        g.n_features = int(I + O)
+        g.priors, g.means, g.covariances = z[f'gmr{c}_priors'], z[f'gmr{c}_means'], z[f'gmr{c}_covs']
+        mu, sg = g.predict(z[f'gmr{c}_x'])
+        assert rel_err(mu, z[f'gmr{c}_mu']) < 1e-12 and rel_err(sg, z[f'gmr{c}_sigma']) < 1e-11, c
+        assert np.all(mu[:, -1] == 0) and rel_err(sg[:, :, -1], float(reg) * np.eye(int(O))) < 1e-15   # all-underflow query
+
+
+def test_reference_kmeans_labels_bit_exact(T, golden):
+    from kmp_demos_b200.cluster import KMeans, Uniform
+    z = golden('small_cases.npz')
+    for c in range(int(z['km_cases'])):
+        np.random.seed(int(z[f'km{c}_seed']))
+        labels = KMeans(int(z[f'km{c}_K'])).fit_predict(z[f'km{c}_X'])
+        assert labels.dtype == np.int64 and np.array_equal(labels, z[f'km{c}_labels']), c
+    assert np.array_equal(Uniform(8, 5).fit_predict(np.zeros((3, 1000))), z['uniform_1000_8_5'])
+    with pytest.raises(ValueError):
+        KMeans(0)
+
+
+def test_reference_kmeans_empty_cluster_nan_rule(T):
+    """An empty cluster gives a NaN centroid and numpy's argmin then sends every sample to it (Cluster.py:91-95)."""
+    from kmp_demos_b200.cluster import KMeans
+    from oracle import kmp_oracle as orc
+    X = np.array([[0.0, 0.0, 0.0, 10.0, 10.0, 10.0], [0.0, 0.0, 0.0, 1.0, 1.0, 1.0]])   # duplicates => empty cluster
+    np.random.seed(0)
+    init = np.random.choice(6, 3, replace=False)
+    np.random.seed(0)
+    got = KMeans(3, n_iter=5).fit_predict(X)
+    ref, _ = orc.ref_kmeans(X, 3, 5, 1e-4, init)
+    assert np.array_equal(got, ref)
+
+
+def test_quaternion_maps(T, golden):
+    from kmp_demos_b200.types import quaternion as qm
+    from kmp_demos_b200.types.quaternion import quaternion
+    z = golden('small_cases.npz')
+    Q, P, W = z['quat_Q'], z['quat_P'], z['quat_W']
+    qn = qm.normalize_batch(Q)
+    pn = qm.normalize_batch(P)
+    assert rel_err(qn, z['quat_norm']) < 1e-15
+    assert np.max(np.abs(qm.log_batch(qn) - z['quat_log'])) < 1e-14
+    assert np.max(np.abs(qm.exp_batch(W) - z['quat_exp'])) < 1e-15
+    assert np.max(np.abs(qm.mul_batch(qn, pn) - z['quat_mul'])) < 1e-15
+    assert np.max(np.abs(qm.log_batch(qm.mul_batch(qn, pn, conj_q=True)) - z['quat_mulconj_log'])) < 1e-13
+    rv = qm.from_rotvec_batch(W)
+    assert np.allclose(rv, z['quat_rotvec'], rtol=0, atol=1e-15, equal_nan=True) and np.all(np.isnan(rv[0]))
+    # scalar class, SURVEY.md 8c known answers
+    q = quaternion(-0.2, np.array([0.8, -0.7, -1.6]))
+    assert np.allclose(q.as_array(), [-0.10355607461569954, 0.4142242984627982, -0.3624462611549484, -0.8284485969255964], atol=1e-16)
+    assert np.allclose(q.log(), [-0.610974356491441, 0.5346025619300109, 1.221948712982882], atol=1e-15)
+    assert np.array_equal(quaternion.exp(np.array([1e-9] * 3)).as_array(), [1, 0, 0, 0])
+    assert np.allclose(quaternion.exp(np.array([2e-8, 0, 0])).as_array(), [0.9999999999999998, 2e-8, 0, 0], atol=1e-16)
+    assert np.array_equal(quaternion(0, np.array([1.0, 0, 0])).log(), [0, 0, 0])
+    r = quaternion(1, np.array([2., 3, 4])) * quaternion(.5, np.array([-1, .2, .3]))
+    assert np.allclose(r.as_array(), [0.10879222762803663, 0.01554174680400521, -0.45071065731615173, 0.8858795678282981], atol=1e-15)
+    w = np.array([0.508369, 0.857956, -0.167863])
+    assert np.allclose(quaternion.exp(w).log(), w, atol=1e-15)
+    assert np.allclose((~q).as_array(), q.as_array() * [1, -1, -1, -1], atol=1e-16)
+    assert np.allclose(quaternion.from_rotation_vector(np.array([3., 2, 1])).as_array(),
+                       [0.29555112749297824, 0.7659655801357929, 0.5106437200905286, 0.2553218600452643], atol=1e-15)
+
+
+def test_em_statistics_partition_sum_equals_whole(T):
+    """Data partitioned in two: the summed statistics (what the NCCL all-reduce produces) give the same M-step
+    as the unpartitioned pass (<= 1e-12)."""
+    from kmp_demos_b200.mixture import EMEngine
+    from kmp_demos_b200 import workloads as wl
+    from oracle import kmp_oracle as orc
+    X, means, _ = wl.cfg5_samples(30000, K=12, d=7, seed=1)
+    lab = np.argmin(((X[:, None, :] - means[None]) ** 2).sum(-1), axis=1).astype(np.int32)
+    Xd = dev(T, X)
+    shift = dev(T, X.mean(axis=0))
+    whole = EMEngine(Xd, 12, 1e-6, shift=shift)
+    whole.init_from_labels(dev(T, lab))
+    # oracle M-step from the same labels
+    resp = np.zeros((X.shape[0], 12)); resp[np.arange(X.shape[0]), lab] = 1
+    nk, mu, cov = orc.gmm_m_step(X, resp, 1e-6)
+    assert rel_err(whole.means.cpu().numpy(), mu) < 1e-12 and rel_err(whole.covs.cpu().numpy(), cov) < 1e-10
+    assert rel_err(whole.prec_chol.cpu().numpy(), orc.gmm_precisions_chol(cov)) < 1e-9
+    whole.em_pass()
+    lse, log_resp = orc.gmm_e_step(X, nk / X.shape[0], mu, orc.gmm_precisions_chol(cov))
+    assert abs(float(whole.stats[-1].item()) - lse.sum()) < 1e-9 * abs(lse.sum())
+    nk2, mu2, cov2 = orc.gmm_m_step(X, np.exp(log_resp), 1e-6)
+    assert rel_err(whole.means.cpu().numpy(), mu2) < 1e-11 and rel_err(whole.covs.cpu().numpy(), cov2) < 1e-9
+    half = X.shape[0] // 2 + 37
+    parts = [EMEngine(dev(T, X[:half]), 12, 1e-6, shift=shift, n_total=X.shape[0]),
+             EMEngine(dev(T, X[half:]), 12, 1e-6, shift=shift, n_total=X.shape[0])]
+    labs = [dev(T, lab[:half]), dev(T, lab[half:])]
+    from kmp_demos_b200 import _lib
+    for p, l in zip(parts, labs):
+        _lib.call('kmpx_gmm_label_stats', _lib.ptr(p.X), p.n, p.d, p.K, _lib.ptr(p.shift), _lib.ptr(l), _lib.ptr(p.stats),
+                  _lib.ptr(p.ws), p.ws_bytes, _lib.stream())
+    tot = parts[0].stats + parts[1].stats
+    for p in parts:
+        p.stats.copy_(tot); p._finalize(first=True)
+    for p in parts:
+        _lib.call('kmpx_gmm_em_pass', _lib.ptr(p.X), p.n, p.d, p.K, _lib.ptr(p.shift), _lib.ptr(p.log_weights), _lib.ptr(p.means),
+                  _lib.ptr(p.prec_chol), _lib.ptr(p.log_det), _lib.ptr(p.stats), None, None, _lib.ptr(p.ws), p.ws_bytes, _lib.stream())
+    tot = parts[0].stats + parts[1].stats
+    parts[0].stats.copy_(tot); parts[0]._finalize(first=False)
+    assert rel_err(parts[0].means.cpu().numpy(), whole.means.cpu().numpy()) < 1e-12
+    assert rel_err(parts[0].covs.cpu().numpy(), whole.covs.cpu().numpy()) < 1e-12

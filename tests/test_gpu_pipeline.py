@@ -1,0 +1,255 @@
+"""GPU parity of the reference-facing classes (kmp.model.KMP, kmp.mixture.GaussianMixtureModel, KMPBatch) against
+golden outputs of the reference itself (tests/golden/*.npz) and the CPU oracle.
+
+Tolerances (BASELINE.json north star): means <= 1e-9, covariances <= 1e-7 (norm-wise relative);
+time-driven kernel <= 1e-7 on both."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from kmp_demos_b200 import workloads as wl
+
+pytestmark = pytest.mark.gpu
+MEAN_TOL, COV_TOL = 1e-9, 1e-7
+
+
+def test_kmp_small_cases_vs_reference(golden):
+    from kmp.model import KMP
+    z = golden('small_cases.npz')
+    for c in range(int(z['kmp_cases'])):
+        I, O, N, td, sf, lam, alpha = z[f'kmp{c}_cfg']
+        td = bool(td)
+        k = KMP(l=lam, alpha=alpha, sigma_f=sf, time_driven_kernel=td)
+        k.fit(z[f'kmp{c}_s'], z[f'kmp{c}_mu'], z[f'kmp{c}_sigma'])
+        assert (k.O, k.N) == (int(O), int(N))
+        xi, sg = k.predict(z[f'kmp{c}_q'])
+        mt, ct = (1e-7, 1e-7) if td else (MEAN_TOL, COV_TOL)
+        assert rel_err(xi, z[f'kmp{c}_xi']) < mt and rel_err(sg, z[f'kmp{c}_sg']) < ct, c
+        assert rel_err(k.predict_mean(z[f'kmp{c}_q']), z[f'kmp{c}_xi']) < mt
+        est = k._estimator
+        assert rel_err(est, z[f'kmp{c}_estimator']) < (1e-6 if td else 1e-9), c
+        assert rel_err(k.system_matrix(), z[f'kmp{c}_A']) < (1e-10 if td else 1e-15)
+
+
+def test_cfg1_full_pipeline(golden):
+    """cfg 1: G.mat -> GMM(8) -> GMR -> KMP(N=200) -> 2 via-points -> predict 1000."""
+    from kmp.model import KMP
+    from kmp.mixture import GaussianMixtureModel
+    zl, z = golden('letters_ref.npz'), golden('cfg1_G.npz')
+    gi = wl.LETTERS.index('G')
+    X = wl.cfg1_design_matrix(zl['pos'][gi])
+    gmm = GaussianMixtureModel(n_components=8, diag_reg_factor=1e-6)
+    gmm.fit(X)
+    assert gmm.model.n_iter_ == int(zl['n_iter'][gi])
+    assert abs(gmm.model.lower_bound_ - float(zl['lower_bound'][gi])) < 1e-10
+    assert rel_err(gmm.priors, zl['priors'][gi]) < MEAN_TOL and rel_err(gmm.means, zl['means'][gi]) < MEAN_TOL
+    assert rel_err(gmm.covariances, zl['covariances'][gi]) < COV_TOL
+    assert np.array_equal(gmm.model.predict(X), zl['labels'][gi])                 # argmax assignments: bit-exact
+    mu, sig = gmm.predict(wl.cfg1_gmr_grid(200))
+    assert rel_err(mu, zl['gmr_mu'][gi]) < MEAN_TOL and rel_err(sig, zl['gmr_sigma'][gi]) < COV_TOL
+    c = wl.CFG1
+    kmp = KMP(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False)
+    kmp.fit(wl.cfg1_kmp_grid(200), mu, sig)
+    q = wl.cfg1_query_grid(1000)
+    xi, sg = kmp.predict(q)
+    assert rel_err(xi, z['n200_pred_xi']) < MEAN_TOL and rel_err(sg, z['n200_pred_sigma']) < COV_TOL
+    kmp.set_waypoint(list(z['n200_via_t']), [p for p in z['n200_via_p']], [v for v in z['n200_via_var']])
+    assert kmp.N == int(z['n200_adapt_N']) and np.array_equal(kmp.s, z['n200_adapt_s'])
+    xi, sg = kmp.predict(q)
+    assert rel_err(xi, z['n200_adapt_xi']) < MEAN_TOL and rel_err(sg, z['n200_adapt_sigma']) < COV_TOL
+
+
+def test_demo1_subsampled_variant(golden):
+    from kmp.model import KMP
+    from kmp.mixture import GaussianMixtureModel
+    z = golden('cfg1_G.npz')
+    gmm = GaussianMixtureModel(n_components=8, diag_reg_factor=1e-6)
+    gmm.fit(z['d1_X'])
+    assert gmm.model.n_iter_ == int(z['d1_n_iter']) == 33
+    assert rel_err(gmm.means, z['d1_means']) < MEAN_TOL and rel_err(gmm.covariances, z['d1_covs']) < COV_TOL
+    T = z['d1_gmr_mu'].shape[1]
+    mu, sig = gmm.predict(0.01 * np.arange(T).reshape(1, -1))
+    assert rel_err(mu, z['d1_gmr_mu']) < MEAN_TOL and rel_err(sig, z['d1_gmr_sigma']) < COV_TOL
+    tk = 0.01 * np.arange(1, T + 1).reshape(1, -1)
+    k = KMP(l=0.5, alpha=40, sigma_f=200, time_driven_kernel=False)
+    k.fit(tk, z['d1_gmr_mu'], z['d1_gmr_sigma'])
+    xi, sg = k.predict(tk)
+    assert rel_err(xi, z['d1_pred_xi']) < MEAN_TOL and rel_err(sg, z['d1_pred_sigma']) < COV_TOL
+    assert rel_err(k._estimator, z['d1_estimator']) < 1e-9
+    k.set_waypoint([0.25], [np.array([[2.0, -1.0]])], [1e-4 * np.eye(2)])
+    xi, sg = k.predict(tk)
+    assert rel_err(xi, z['d1_adapt_xi']) < MEAN_TOL and rel_err(sg, z['d1_adapt_sigma']) < COV_TOL
+
+
+@pytest.mark.parametrize('letter', ['A', 'M', 'S', 'Z'])
+def test_gmm_fit_other_letters(golden, letter):
+    from kmp.mixture import GaussianMixtureModel
+    zl = golden('letters_ref.npz')
+    li = wl.LETTERS.index(letter)
+    X = wl.cfg1_design_matrix(zl['pos'][li])
+    gmm = GaussianMixtureModel(n_components=8, diag_reg_factor=1e-6)
+    gmm.fit(X)
+    assert gmm.model.n_iter_ == int(zl['n_iter'][li])
+    assert rel_err(gmm.means, zl['means'][li]) < MEAN_TOL and rel_err(gmm.covariances, zl['covariances'][li]) < COV_TOL
+    assert np.array_equal(gmm.model.predict(X), zl['labels'][li])
+
+
+def test_gmm_fit_synthetic_7d_and_bic(golden):
+    from kmp.mixture import GaussianMixtureModel
+    z = golden('gmm_synth.npz')
+    X, _, _ = wl.cfg5_samples(int(z['n']), K=int(z['K']), d=7, seed=int(z['seed']))
+    gmm = GaussianMixtureModel(n_components=int(z['K']), diag_reg_factor=1e-6)
+    gmm.fit(X)
+    assert gmm.model.n_iter_ == int(z['n_iter'])
+    assert rel_err(gmm.priors, z['priors']) < MEAN_TOL and rel_err(gmm.means, z['means']) < MEAN_TOL
+    assert rel_err(gmm.covariances, z['covs']) < COV_TOL
+    assert np.array_equal(gmm.model.predict(X), z['labels'])
+    assert abs(gmm.bic(X) - float(z['bic'])) < 1e-9 * abs(float(z['bic']))
+
+
+def test_cfg3_batch_vs_reference_and_vs_single(golden):
+    """cfg 3 sample: batched adaptation == the reference's per-problem results; batch == one-by-one bit for bit."""
+    from kmp_demos_b200.batch import KMPBatch
+    from kmp.model import KMP
+    zl, z = golden('letters_ref.npz'), golden('cfg3_sample.npz')
+    c = wl.CFG1
+    t = wl.cfg1_kmp_grid(200)
+    L = 26
+    kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=16)
+    kb.set_base(np.broadcast_to(t, (L, 1, 200)), zl['gmr_mu'], zl['gmr_sigma'])
+    base_of, vs, vp, vv = [], [], [], []
+    for r in range(len(z['letter'])):
+        li, si = int(z['letter'][r]), int(z['set_idx'][r])
+        a, b, cc = wl.cfg3_via_sets(li, zl['gmr_mu'][li], si + 1)
+        base_of.append(li); vs.append(a[si]); vp.append(b[si]); vv.append(cc[si])
+    xi, sg = kb.fit_predict(np.array(base_of), np.array(vs), np.array(vp), np.array(vv), z['queries'])
+    for r in range(len(z['letter'])):
+        assert rel_err(xi[r], z['xi'][r]) < MEAN_TOL and rel_err(sg[r], z['sigma'][r]) < COV_TOL, r
+    # same problems through the single-problem class: same kernels => identical bits
+    for r in (0, 7, 20):
+        li = base_of[r]
+        k = KMP(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False)
+        k.fit(t, zl['gmr_mu'][li], zl['gmr_sigma'][li])
+        k.set_waypoint(list(vs[r]), [vp[r][j].reshape(1, -1) for j in range(2)], [vv[r][j] for j in range(2)])
+        assert k.N == int(z['N'][r])
+        x1, s1 = k.predict(z['queries'])
+        assert np.array_equal(x1, xi[r]) and np.array_equal(s1, sg[r])
+    # sharding the batch (what a multi-GPU run does) leaves every problem's result bit-identical
+    from kmp_demos_b200.dist import shard_range
+    lo, hi = shard_range(len(base_of), 1, 2)
+    x2, s2 = kb.fit_predict(np.array(base_of)[lo:hi], np.array(vs)[lo:hi], np.array(vp)[lo:hi], np.array(vv)[lo:hi], z['queries'])
+    assert np.array_equal(x2, xi[lo:hi]) and np.array_equal(s2, sg[lo:hi])
+
+
+def test_demo2_pose_and_unlisted_sigma_quirk(golden):
+    """cfg 2 (reference-faithful): O=3 KMPs on pose_data, un-listed covariance => non-symmetric system (H2)."""
+    from kmp.model import KMP
+    from kmp.mixture import GaussianMixtureModel
+    from kmp.types.quaternion import quaternion
+    from kmp_demos_b200.types import quaternion as qm
+    z = golden('demo2_pose.npz')
+    time = z['time']
+    ts = time[:, :150]
+    for name, Y in (('pos', z['pos']), ('quat', z['quat_eucl'])):
+        X = np.vstack((time, Y)).T
+        gmm = GaussianMixtureModel(n_demos=6)
+        gmm.fit(X)
+        assert gmm.model.n_iter_ == int(z[f'{name}_n_iter'])
+        assert rel_err(gmm.means, z[f'{name}_means']) < MEAN_TOL and rel_err(gmm.covariances, z[f'{name}_covs']) < COV_TOL
+        mu, sig = gmm.predict(ts)
+        assert rel_err(mu, z[f'{name}_gmr_mu']) < MEAN_TOL and rel_err(sig, z[f'{name}_gmr_sigma']) < COV_TOL
+        k = KMP(l=0.5, alpha=60, sigma_f=4, time_driven_kernel=False)
+        k.fit(ts, z[f'{name}_gmr_mu'], z[f'{name}_gmr_sigma'])
+        xi, sg = k.predict(ts)
+        assert rel_err(xi, z[f'{name}_pred_xi']) < MEAN_TOL and rel_err(sg, z[f'{name}_pred_sigma']) < COV_TOL
+        if name == 'pos':
+            wp = np.array([0.0, 0.85, 0.3])
+        else:
+            qa = quaternion.from_array(z['qa'])
+            des = quaternion(-0.2, np.array([0.8, -0.7, -1.6]))
+            wp = (des * (~qa)).log()
+            assert np.allclose(wp, z['quat_wp'], atol=1e-13)
+        k.set_waypoint([1], wp.reshape(1, -1), np.eye(3) * 1e-6)          # demos.py:251,285
+        assert np.array_equal(k.sigma, z[f'{name}_adapt_sigma_db'])
+        assert k._fact.kind == 1, 'non-symmetric blocks must take the general path'
+        xi, sg = k.predict(ts)
+        assert rel_err(xi, z[f'{name}_adapt_xi']) < MEAN_TOL and rel_err(sg, z[f'{name}_adapt_sigma']) < COV_TOL
+    back = qm.mul_batch(qm.exp_batch(z['quat_adapt_xi'][:3].T), z['qa'].reshape(1, 4))
+    assert rel_err(back.T, z['quat_adapt_back']) < 1e-9
+    # named variant: joint 7-D mixture, O = 6
+    X = np.vstack((time, z['pos'], z['quat_eucl'])).T
+    gmm = GaussianMixtureModel(n_demos=6)
+    gmm.fit(X)
+    assert gmm.model.n_iter_ == int(z['joint_n_iter'])
+    tq = np.linspace(0.01, 1.5, 400).reshape(1, -1)
+    mu, sig = gmm.predict(tq)
+    assert rel_err(mu, z['joint_gmr_mu']) < MEAN_TOL and rel_err(sig, z['joint_gmr_sigma']) < COV_TOL
+    k = KMP(l=0.5, alpha=60, sigma_f=4, time_driven_kernel=False)
+    k.fit(tq[:, ::8], z['joint_gmr_mu'][:, ::8], z['joint_gmr_sigma'][:, :, ::8])
+    xi, sg = k.predict(tq[:, ::16])
+    assert rel_err(xi, z['joint_sub_pred_xi']) < MEAN_TOL and rel_err(sg, z['joint_sub_pred_sigma']) < COV_TOL
+
+
+def test_cfg2_named_variant_large_system():
+    """O=6, N=400 (n = 2400 > KMPX_SMALL_MAX): the blocked large-n path against the vectorised oracle."""
+    from kmp.model import KMP
+    from oracle import kmp_oracle as orc
+    rng = np.random.default_rng(11)
+    N, O = 400, 6
+    t = np.linspace(0.01, 1.5, N).reshape(1, -1)
+    mu = np.stack([np.sin((o + 1) * t[0]) for o in range(O)])
+    Bm = rng.normal(size=(N, O, O)) * 0.1
+    sig = np.transpose(np.einsum('nab,ncb->nac', Bm, Bm) + 1e-3 * np.eye(O), (1, 2, 0)).copy()
+    k = KMP(l=0.5, alpha=60, sigma_f=4, time_driven_kernel=False)
+    k.fit(t, mu, sig)
+    q = np.linspace(0.0, 1.6, 77).reshape(1, -1)
+    xi, sg = k.predict(q)
+    est = orc.kmp_fit(t, sig, 0.5, 4.0, False)
+    xr, sr = orc.kmp_predict(est, t, mu, q, 60.0, 4.0, False)
+    assert rel_err(xi, xr) < MEAN_TOL and rel_err(sg, sr) < COV_TOL
+
+
+def test_demo3_time_driven(golden):
+    from kmp.model import KMP
+    from kmp.mixture import GaussianMixtureModel
+    z = golden('demo3_vel.npz')
+    gmm = GaussianMixtureModel(n_demos=5)
+    gmm.fit(z['X'])
+    assert gmm.model.n_iter_ == int(z['n_iter'])
+    assert rel_err(gmm.means, z['means']) < MEAN_TOL and rel_err(gmm.covariances, z['covs']) < COV_TOL
+    mu, sig = gmm.predict(0.01 * np.arange(200).reshape(1, -1))
+    assert rel_err(mu, z['gmr_mu']) < MEAN_TOL and rel_err(sig, z['gmr_sigma']) < COV_TOL
+    tk = 0.01 * np.arange(1, 201).reshape(1, -1)
+    k = KMP(l=1, sigma_f=6)
+    k.fit(tk, z['gmr_mu'], z['gmr_sigma'])
+    xi, sg = k.predict(tk[:, ::4])
+    assert rel_err(xi, z['pred_xi']) < 1e-7 and rel_err(sg, z['pred_sigma']) < 1e-7       # H3 tolerance
+    k.set_waypoint(list(z['via_t']), [p for p in z['via_p']], [np.eye(4) * 1e-6] * 4)
+    assert k.N == int(z['adapt_N'])
+    xi, sg = k.predict(tk)
+    assert rel_err(xi, z['adapt_xi']) < 1e-7 and rel_err(sg, z['adapt_sigma']) < 1e-7
+
+
+def test_cfg4_shape_reduced_and_properties():
+    """cfg 4 at N=1024 (n=2048, blocked path, on-the-fly predict) against the oracle, plus size-independent
+    properties at N=4096: zero posterior covariance is never negative, prediction at stored inputs with tiny
+    lambda*Sigma reproduces mu."""
+    from kmp.model import KMP
+    from oracle import kmp_oracle as orc
+    c = wl.CFG1
+    t, mu, sig = wl.cfg4_problem(N=1024, seed=0)
+    k = KMP(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False)
+    k.fit(t, mu, sig)
+    q = np.linspace(0.0, 2.0, 513).reshape(1, -1)
+    xi, sg = k.predict(q)
+    est = orc.kmp_fit(t, sig, c['lam'], c['sigma_f'], False)
+    xr, sr = orc.kmp_predict(est, t, mu, q, c['alpha'], c['sigma_f'], False)
+    assert rel_err(xi, xr) < MEAN_TOL and rel_err(sg, sr) < COV_TOL
+    assert rel_err(k.predict_mean(q), xr) < MEAN_TOL
+    t, mu, sig = wl.cfg4_problem(N=4096, seed=1)
+    k = KMP(l=1e-3, alpha=1.0, sigma_f=c['sigma_f'], time_driven_kernel=False)
+    k.fit(t, mu, sig)
+    xi, sg = k.predict(t[:, ::16])
+    assert rel_err(xi, mu[:, ::16]) < 1e-4                      # interpolation property as lambda -> 0
+    d0, d1 = sg[0, 0], sg[1, 1]
+    assert np.all(d0 > -1e-6) and np.all(d1 > -1e-6) and np.all(d0 < 1.0 + 1e-6)

@@ -1,0 +1,133 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/kmpx.h declares (no compute calls),
+host-side logic (sharding, workloads, argument validation that happens before any launch), and the N>1 path on a
+world_size-2 gloo group."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kmp_demos_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        from kmp_demos_b200.csrc import build
+        build.build()
+    header = open(os.path.join(ROOT, 'include', 'kmpx.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(kmpx_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in include/kmpx.h but not exported'
+    assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)
+    assert _lib.load().kmpx_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected on the host before any launch: negative status + message."""
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    rc = lib.kmpx_kernel_build(None, None, None, None, 1, 4, 1, 2, 8, 64, 1.0, 0.5, 0, 0, 0, None)
+    assert rc == -1 and b'NULL' in lib.kmpx_last_error()
+    rc = lib.kmpx_dgemm(0, 0, 4, 4, 4, 1.0, ctypes.c_void_p(16), 3, 0, ctypes.c_void_p(16), 4, 0, 0.0, ctypes.c_void_p(16), 4, 0, 1, 0, None)
+    assert rc == -8
+    assert lib.kmpx_sys_size(201, 2, _lib.LAYOUT_COMPONENT) == 404 and lib.kmpx_sys_size(201, 2, _lib.LAYOUT_POINT) == 402
+    assert lib.kmpx_potrf_workspace_bytes(512, 1) == 0 and lib.kmpx_potrf_workspace_bytes(16384, 1) > 0
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from kmp.model import KMP
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        KMP().fit(np.zeros((1, 3)), np.zeros((2, 3)), np.zeros((2, 2, 3)))
+    from kmp.types.quaternion import quaternion
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        quaternion(1.0, np.zeros(3))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'kmp_demos_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in src.replace('no oracle import', ''), f'{f} mentions the oracle'
+
+
+def test_shard_range_partitions_exactly():
+    from kmp_demos_b200.dist import shard_range
+    for n in (0, 1, 7, 26624, 26625):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_workloads_are_deterministic_and_shaped():
+    from kmp_demos_b200 import workloads as wl
+    mu, sig, src = wl.load_letter_references()
+    assert mu.shape == (26, 2, 200) and sig.shape == (26, 2, 2, 200)
+    t1, p1, v1 = wl.cfg3_via_sets(3, mu[3], 5)
+    t2, p2, v2 = wl.cfg3_via_sets(3, mu[3], 9)
+    assert np.array_equal(t1, t2[:5]) and np.array_equal(p1, p2[:5])
+    assert np.all(t1 >= 0.01) and np.all(t1 <= 2.0) and v1.shape == (5, 2, 2, 2)
+    t, m, s = wl.cfg4_problem(N=64)
+    assert np.all(np.linalg.eigvalsh(np.transpose(s, (2, 0, 1))) > 0.04)
+    X, _, _ = wl.cfg5_samples(1000, K=8, d=7)
+    assert X.shape == (1000, 7) and X.flags.c_contiguous
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["KMP_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from kmp_demos_b200 import dist as kd, workloads as wl
+from kmp_demos_b200.mixture import stats_len
+from oracle import kmp_oracle as orc
+rank, world, _ = kd.init_process_group("gloo")
+X, means, _ = wl.cfg5_samples(4000, K=6, d=4, seed=2)
+lab = np.argmin(((X[:, None, :] - means[None]) ** 2).sum(-1), axis=1)
+lo, hi = kd.shard_range(X.shape[0], rank, world)
+# per-rank sufficient statistics of the one-hot M-step in the packed layout of kmpx_gmm_label_stats
+K, d = 6, 4
+F = 1 + d + d * (d + 1) // 2
+st = np.zeros(stats_len(K, d))
+iu = np.triu_indices(d)
+for k in range(K):
+    xs = X[lo:hi][lab[lo:hi] == k]
+    st[k * F] = len(xs)
+    st[k * F + 1:k * F + 1 + d] = xs.sum(0)
+    st[k * F + 1 + d:(k + 1) * F] = (xs[:, :, None] * xs[:, None, :]).sum(0)[iu]
+t = torch.from_numpy(st)
+kd.allreduce_stats(t)
+tot = t.numpy().reshape(-1)[:-1].reshape(K, F)
+nk = tot[:, 0]
+mu = tot[:, 1:1 + d] / nk[:, None]
+resp = np.zeros((X.shape[0], K)); resp[np.arange(X.shape[0]), lab] = 1
+nk_ref, mu_ref, _ = orc.gmm_m_step(X, resp, 1e-6)
+assert np.allclose(nk, nk_ref - 10 * np.finfo(float).eps) and np.allclose(mu, mu_ref, rtol=1e-12, atol=1e-12)
+ms = kd.max_over_ranks(10.0 + rank, torch.device("cpu"))
+assert ms == 10.0 + world - 1
+dist.barrier()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gloo_allreduce_of_statistics(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, KMP_ROOT=ROOT, MASTER_ADDR='127.0.0.1', MASTER_PORT='29613', PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', '29613', str(script)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count('ok') == 2
