@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the KMP learn-and-adapt hot path (BASELINE.json metric: KMP fit+predict problems/sec, batched).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): cfg 3 of BASELINE.json - all 26 2Dletters reference trajectories (the reference's own
+GMM+GMR output, tests/golden/letters_ref.npz) x 1024 seeded random via-point sets = 26 624 independent problems per
+GPU; one problem = set_waypoint (2 via-points) -> fit (n = 400..404 fp64 system) -> predict mean + covariance at 1000
+queries.  One "step" = one pass over the 26 624 problems of a rank.  Weak scaling: every rank gets its own 26 624
+problems (different via-point seeds), no data-path collective.
+
+`value`  : problems/s with inputs resident in HBM.
+`e2e`    : the same through KMPBatch with HOST (pinned) buffers: via-points copied in, means+covariances copied out,
+           every step, inside the timed region.
+`roofline`: the dominant kernel (k_kmp_predict, FP64 tensor pipe) timed per launch with CUDA events inside the
+           timed region; peak = cuBLAS DGEMM 8192^3 measured in the same run (MEASURED_PEAKS.json has no FP64 figure).
+`--impl reference`: the reference's own algorithm (literal loop nest of kmp/model/KMP.py, oracle port) on all host
+           cores, a bounded sample of the same problems per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from kmp_demos_b200 import workloads as wl  # noqa: E402
+
+METRIC = 'KMP fit+predict problems/sec (batched)'
+UNIT = 'problems/s'
+N_SETS = 1024
+M_QUERIES = 1000
+
+
+def build_problem_set(mu, sig, n_sets, seed_offset):
+    L = mu.shape[0]
+    ts, ps, vs = [], [], []
+    for li in range(L):
+        t, p, v = wl.cfg3_via_sets(li, mu[li], n_sets, seed_offset=seed_offset)
+        ts.append(t); ps.append(p); vs.append(v)
+    base_of = np.repeat(np.arange(L, dtype=np.int32), n_sets)
+    return base_of, np.concatenate(ts)[:, :, None], np.concatenate(ps), np.concatenate(vs)
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_one_problem(args):
+    """One cfg-3 problem the way the reference computes it (literal loops), oracle port."""
+    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+    from oracle import kmp_oracle as orc
+    t, mu, sig, vt, vp, vv, q = args
+    c = wl.CFG1
+    s2, y2, g2 = orc.kmp_set_waypoint(t, mu, sig, list(vt), [vp[j].reshape(1, -1) for j in range(len(vt))],
+                                      [vv[j] for j in range(len(vt))], 5e-4)
+    est = orc.kmp_fit(s2, g2, c['lam'], c['sigma_f'], False, literal=True)
+    xi, sg = orc.kmp_predict_literal(est, s2, y2, q, c['alpha'], c['sigma_f'], False)
+    return float(xi[0, 0])
+
+
+def cpu_sample_args(mu, sig, base_of, via_s, via_p, via_v, count):
+    t = wl.cfg1_kmp_grid(mu.shape[2])
+    q = wl.cfg1_query_grid(M_QUERIES)
+    idx = np.linspace(0, len(base_of) - 1, count).astype(int)       # stratified over the letters
+    return [(t, mu[base_of[i]], sig[base_of[i]], via_s[i, :, 0], via_p[i], via_v[i], q) for i in idx]
+
+
+def time_cpu(pool, sample):
+    t0 = time.perf_counter()
+    pool.map(_cpu_one_problem, sample, chunksize=1)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    mu, sig, src = wl.load_letter_references()
+    base_of, via_s, via_p, via_v = build_problem_set(mu, sig, 8, 0)
+    per_step = cores
+    sample = cpu_sample_args(mu, sig, base_of, via_s, via_p, via_v, per_step)
+    os.environ['OPENBLAS_NUM_THREADS'] = '1'
+    with mp.get_context('fork').Pool(cores) as pool:
+        for _ in range(args.warmup):
+            time_cpu(pool, sample)
+        t = [time_cpu(pool, sample) for _ in range(args.steps)]
+    sec = float(np.mean(t))
+    value = per_step / sec
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64', 'data': src,
+        'config': {'workload': 'cfg3: 26 letters x via-point sets, N=200..202, O=2, M=1000 queries, mean+covariance',
+                   'step': f'{per_step} problems (one per host core) through the literal KMP.py loop nest'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': f'{per_step} cfg-3 problems per step x {args.steps} steps, oracle port of KMP.fit/predict '
+                                   f'(literal loops), one process per core'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    def __init__(self, index):
+        self.path = tempfile.mktemp(suffix='.csv')
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = []
+        for ln in open(self.path).read().splitlines():
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) >= 7:
+                try:
+                    rows.append((float(f[0]), float(f[1]), float(f[2]), f[3:7]))
+                except ValueError:
+                    pass
+        if rows:
+            busy = [r for r in rows if r[2] > 0.5 * max(x[2] for x in rows)] or rows
+            out['sm_mhz'] = float(np.median([r[0] for r in busy]))
+            out['sm_max_mhz'] = rows[0][1]
+            out['power_w_max'] = max(r[2] for r in rows)
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            out['reasons'] = [n for i, n in enumerate(names) if any(r[3][i].lower().startswith('active') for r in rows)]
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def measure_dgemm_peak(torch, n=8192, seconds=1.5):
+    a = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    b = torch.randn(n, n, dtype=torch.float64, device='cuda')
+    c = torch.empty_like(a)
+    for _ in range(2):
+        torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); torch.matmul(a, b, out=c); e1.record(); e1.synchronize()
+    reps = max(3, int(seconds * 1e3 / e0.elapsed_time(e1)))
+    e0.record()
+    for _ in range(reps):
+        torch.matmul(a, b, out=c)
+    e1.record(); e1.synchronize()
+    return 2.0 * n ** 3 * reps / e0.elapsed_time(e1) * 1e-9
+
+
+def extras_single_gpu(torch, dgemm_tflops):
+    """Second headline of BASELINE.json (fp64 Cholesky TFLOP/s at N*O = 16384) and the HBM-bound kernel build,
+    on the cfg-4 system, timed with CUDA events (best of 3 after a warm-up)."""
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    N, O = 8192, 2
+    t, mu, sig = wl.cfg4_problem(N=N, seed=0)
+    n = int(lib.kmpx_sys_size(N, O, _lib.LAYOUT_COMPONENT))
+    lda = n
+    dev = torch.device('cuda')
+    s_d = torch.as_tensor(np.ascontiguousarray(t.T), device=dev)
+    g_d = torch.as_tensor(np.ascontiguousarray(np.transpose(sig, (2, 0, 1))), device=dev)
+    A = torch.empty((n, lda), dtype=torch.float64, device=dev)
+    nbytes = int(lib.kmpx_potrf_workspace_bytes(n, 1))
+    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = _lib.stream()
+    c = wl.CFG1
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    best_build, best_potrf = 1e30, 1e30
+    for rep in range(4):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        _lib.call('kmpx_kernel_build', _lib.ptr(s_d), _lib.ptr(g_d), None, _lib.ptr(A), 1, N, 1, O, lda, n * lda,
+                  c['sigma_f'], c['lam'], 0, _lib.LAYOUT_COMPONENT, _lib.UPLO_FULL, st)
+        e1.record()
+        _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
+        e2.record(); e2.synchronize()
+        if rep > 0:
+            best_build = min(best_build, e0.elapsed_time(e1))
+            best_potrf = min(best_potrf, e1.elapsed_time(e2))
+    assert int(info.item()) == 0
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.isfile(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    potrf_tf = n ** 3 / 3.0 / best_potrf * 1e-9
+    build_gbs = 8.0 * n * n / best_build * 1e-6
+    return {
+        'potrf_n16384': {'ms': best_potrf, 'tflops': potrf_tf, 'frac_of_dgemm': potrf_tf / dgemm_tflops},
+        'kernel_build_n16384': {'ms': best_build, 'gbs': build_gbs, 'frac_of_hbm': build_gbs / hbm,
+                                'hbm_peak_gbs': hbm, 'hbm_peak_source': 'measured' if peaks else 'fallback'},
+    }
+
+
+def run_ours(args):
+    import torch
+    from kmp_demos_b200 import _lib, dist as kd
+    from kmp_demos_b200.batch import KMPBatch
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
+    rank, world, local = kd.init_process_group()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    _lib.load()
+    mu, sig, src = wl.load_letter_references()
+    L, O, T = mu.shape
+    base_of, via_s, via_p, via_v = build_problem_set(mu, sig, args.sets, seed_offset=rank)
+    B = len(base_of)
+    c = wl.CFG1
+    kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=args.chunk)
+    kb.set_base(np.broadcast_to(wl.cfg1_kmp_grid(T), (L, 1, T)), mu, sig)
+    q_host = np.ascontiguousarray(wl.cfg1_query_grid(M_QUERIES).T)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    h_base, h_vs, h_vp, h_vv, h_q = pin(base_of), pin(via_s), pin(via_p), pin(via_v), pin(q_host)
+    d_base, d_vs, d_vp, d_vv, d_q = (x.to(dev) for x in (h_base, h_vs, h_vp, h_vv, h_q))
+    xi = torch.empty((B, O, M_QUERIES), dtype=torch.float64, device=dev)
+    sg = torch.empty((B, O, O, M_QUERIES), dtype=torch.float64, device=dev)
+    h_xi = torch.empty(xi.shape, dtype=torch.float64).pin_memory()
+    h_sg = torch.empty(sg.shape, dtype=torch.float64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return kb.run_device(d_base, d_vs, d_vp, d_vv, d_q, True, xi, sg)
+
+    def step_e2e():
+        for dst, srcb in ((d_base, h_base), (d_vs, h_vs), (d_vp, h_vp), (d_vv, h_vv), (d_q, h_q)):
+            dst.copy_(srcb, non_blocking=True)
+        kb.run_device(d_base, d_vs, d_vp, d_vv, d_q, True, xi, sg)
+        h_xi.copy_(xi, non_blocking=True)
+        h_sg.copy_(sg, non_blocking=True)
+
+    def timed(fn, collect_events):
+        for _ in range(args.warmup):
+            fn()
+        barrier()
+        sampler = ClockSampler(local) if collect_events else None
+        kb.events = [] if collect_events else None
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        launches = _lib.launch_count() - n0
+        clocks = sampler.stop() if sampler else None
+        events, kb.events = kb.events, None
+        return kd.max_over_ranks(ms, dev), launches, clocks, events
+
+    ms_dev, launches, clocks, events = timed(step_device, True)
+    _, _, info, n_pts = step_device()
+    torch.cuda.synchronize()
+    assert int((info != 0).sum().item()) == 0, 'a system was not positive definite'
+    n_host = n_pts.cpu().numpy().astype(np.float64)
+    ms_e2e, _, _, _ = timed(step_e2e, False)
+    # sanity on the copied-out results: finite, covariance diagonals non-negative up to rounding
+    assert bool(torch.isfinite(h_xi[:64]).all()) and float(h_sg[:64, 0, 0].min()) > -1e-6
+
+    value = world * B / (ms_dev * 1e-3)
+    e2e_value = world * B / (ms_e2e * 1e-3)
+    h2d = sum(x.numel() * x.element_size() for x in (h_base, h_vs, h_vp, h_vv, h_q))
+    d2h = h_xi.numel() * 8 + h_sg.numel() * 8
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': src + '; via-point sets seeded per (letter, rank, set)',
+        'config': {'workload': 'cfg3: 26 letters x 1024 via-point sets, N=200..202, O=2, M=1000 queries, mean+covariance',
+                   'problems_per_gpu': B, 'chunk': args.chunk,
+                   'l2': 'inputs larger than L2: each step streams ~35 GB of system matrices per GPU (126 MB L2)'},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': launches,
+        'clocks': clocks,
+    }
+    if rank == 0:
+        # per-kernel device time inside the timed region
+        per = {}
+        for name, a, b in events:
+            per.setdefault(name, []).append(a.elapsed_time(b))
+        kern = {k: {'ms_per_step': sum(v) / args.steps, 'launches_per_step': len(v) // args.steps} for k, v in per.items()}
+        tot = sum(v['ms_per_step'] for v in kern.values())
+        for v in kern.values():
+            v['share'] = v['ms_per_step'] / tot
+        line['kernels'] = kern
+        dgemm_tf = measure_dgemm_peak(torch)
+        pred = per['kmpx_kmp_predict']
+        n_launch = len(pred)
+        # algorithmic flops of the fused predict: triangular V = Linv k*^T (O^2 Ns^2 M) + Gram/mean reduction
+        Ns = np.ceil(n_host / 2) * 2
+        flops_step = float(np.sum(O * O * Ns * Ns * M_QUERIES + 2.0 * O * Ns * (O * (O + 1) / 2 + O) * M_QUERIES))
+        avg_ms = sum(pred) / n_launch
+        achieved = flops_step * args.steps / n_launch / avg_ms * 1e-9
+        line['roofline'] = {'kernel': 'k_kmp_predict', 'bound': 'tensor', 'achieved': achieved, 'peak': dgemm_tf, 'unit': 'TFLOP/s',
+                            'frac': achieved / dgemm_tf, 'traffic': None, 'avg_launch_ms': avg_ms,
+                            'flops_per_launch': flops_step * args.steps / n_launch,
+                            'peak_source': 'cuBLAS DGEMM 8192^3 sustained, measured in this run (FP64 tensor pipe)'}
+        if world == 1:
+            import multiprocessing as mp
+            cores = len(os.sched_getaffinity(0))
+            sample = cpu_sample_args(mu, sig, base_of, via_s, via_p, via_v, 2 * cores)
+            os.environ['OPENBLAS_NUM_THREADS'] = '1'
+            with mp.get_context('fork').Pool(cores) as pool:
+                sec = time_cpu(pool, sample)
+            line['cpu_baseline'] = {'value': len(sample) / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': f'{len(sample)} cfg-3 problems, oracle port of KMP.set_waypoint/fit/predict with the '
+                                              f"reference's literal loop nest, one process per core, {sec:.1f} s wall"}
+            if not args.no_extras:
+                line['extras'] = extras_single_gpu(torch, dgemm_tf)
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--sets', type=int, default=N_SETS, help='via-point sets per letter (1024 = the named config)')
+    ap.add_argument('--chunk', type=int, default=2048)
+    ap.add_argument('--no-extras', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -33,6 +33,20 @@ inline int check_cuda(cudaError_t e, const char* what) {
     }
     return 0;
 }
+// Opt-in to more than 48 KB of dynamic shared memory; `cur` caches the largest size requested so far for this
+// kernel (the limit is 227 KB minus the kernel's static shared memory).
+template <typename Kern>
+inline int ensure_dyn_smem(Kern kernel, size_t bytes, size_t& cur, const char* name) {
+    if (bytes <= cur) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        snprintf(g_err, sizeof(g_err), "kmpx: %s needs %zu bytes of shared memory: %s", name, bytes, cudaGetErrorString(e));
+        return (int)e;
+    }
+    cur = bytes;
+    return 0;
+}
 #define KMPX_TRY(expr) do { int _rc = (expr); if (_rc != 0) return _rc; } while (0)
 
 constexpr int kNumSMs = 148;   // B200

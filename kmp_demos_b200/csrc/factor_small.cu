@@ -379,12 +379,8 @@ __global__ void __launch_bounds__(256) k_solve_alpha(AlphaArgs p) {
 int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
                        int info_offset, int info_accumulate, cudaStream_t st) {
     const size_t smem = potrf_small_smem(n_max);
-    static bool attr_done = false;
-    if (!attr_done) {
-        KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_potrf_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                            "cudaFuncSetAttribute(k_potrf_small)"));
-        attr_done = true;
-    }
+    static size_t smem_set = 48 * 1024;
+    KMPX_TRY(ensure_dyn_smem(k_potrf_small, smem, smem_set, "k_potrf_small"));
     FactorArgs p{A, lda, strideA, n_sys, n_max, batch, info, info_offset, info_accumulate};
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;
     const int grid = batch < kNumSMs * per_sm ? batch : kNumSMs * per_sm;
@@ -394,12 +390,8 @@ int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, 
 
 int launch_trtri_small(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, cudaStream_t st) {
     const size_t smem = trtri_small_smem(n_max);
-    static bool attr_done = false;
-    if (!attr_done) {
-        KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_trtri_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                            "cudaFuncSetAttribute(k_trtri_small)"));
-        attr_done = true;
-    }
+    static size_t smem_set = 48 * 1024;
+    KMPX_TRY(ensure_dyn_smem(k_trtri_small, smem, smem_set, "k_trtri_small"));
     FactorArgs p{L, lda, strideA, n_sys, n_max, batch, nullptr, 0, 0};
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;
     const int grid = batch < kNumSMs * per_sm ? batch : kNumSMs * per_sm;
@@ -409,13 +401,8 @@ int launch_trtri_small(double* L, int lda, long long strideA, const int* n_sys, 
 
 int launch_solve_alpha(const AlphaArgs& p, cudaStream_t st) {
     const size_t smem = (size_t)2 * sys_size(p.n_max, p.O, p.layout) * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
-        KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_solve_alpha, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                            "cudaFuncSetAttribute(k_solve_alpha)"));
-        attr_done = true;
-    }
-    if (smem > 227 * 1024) { snprintf(g_err, sizeof(g_err), "kmpx: system too large for k_solve_alpha"); return -5; }
+    static size_t smem_set = 48 * 1024;
+    KMPX_TRY(ensure_dyn_smem(k_solve_alpha, smem, smem_set, "k_solve_alpha"));
     const int grid = p.batch < kNumSMs * 4 ? p.batch : kNumSMs * 4;
     k_solve_alpha<<<grid, 256, smem, st>>>(p);
     return check_launch("k_solve_alpha");

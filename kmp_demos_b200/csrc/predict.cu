@@ -327,13 +327,9 @@ static int launch_predict(PredictArgs& p, cudaStream_t st) {
     p.resident = (!p.time_driven && sm_res <= 220 * 1024) ? 1 : 0;
     p.ldp = ldp;
     const size_t smem = PredictSmem<MT>::total(p.O, p.I, p.resident, ldp);
-    if (smem > 227 * 1024) { snprintf(g_err, sizeof(g_err), "kmpx: predict tile does not fit shared memory (O=%d)", p.O); return -11; }
-    static bool attr_done = false;
-    if (!attr_done) {
-        KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_kmp_predict<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                            "cudaFuncSetAttribute(k_kmp_predict)"));
-        attr_done = true;
-    }
+    if (smem > 226 * 1024) { snprintf(g_err, sizeof(g_err), "kmpx: predict tile does not fit shared memory (O=%d)", p.O); return -11; }
+    static size_t smem_set = 48 * 1024;
+    KMPX_TRY(ensure_dyn_smem(k_kmp_predict<MT>, smem, smem_set, "k_kmp_predict"));
     dim3 grid(ceil_div(p.M, MT), p.batch);
     k_kmp_predict<MT><<<grid, PTHREADS, smem, st>>>(p);
     return check_launch("k_kmp_predict");

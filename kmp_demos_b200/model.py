@@ -81,15 +81,36 @@ def factorise(s, xi, sigma, lam, sigma_f, time_driven, layout=_lib.LAYOUT_COMPON
                   _lib.ptr(w), lda, _lib.ptr(alpha), st)
         kind = 0
     else:
-        nbytes = int(lib.kmpx_inverse_workspace_bytes(n, 1))
-        ws = torch.empty(max(nbytes, 8) // 8 + 1, dtype=torch.float64, device=dev)
-        _lib.call('kmpx_inverse', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
-        if int(info.item()) != 0:
-            raise np.linalg.LinAlgError('Singular matrix')      # what numpy.linalg.inv raises at KMP.py:157
+        A = general_inverse(A, n, lda)
         _lib.call('kmpx_apply_inverse', _lib.ptr(A), lda, n * lda, None, N, O, 1, layout, _lib.ptr(y_dev),
                   _lib.ptr(w), lda, _lib.ptr(alpha), st)
         kind = 1
     return _Factorisation(A, lda, kind, w, alpha, s_dev, N, I, O)
+
+
+def general_inverse(A, n, lda, newton_steps=2):
+    """In-place inverse of a general (non-symmetric) n x n device matrix: Gauss-Jordan with partial pivoting
+    (kmpx_inverse) followed by Newton-Schulz refinement X <- X + X (I - A X) on the DMMA GEMM, which brings the
+    result to the accuracy of a backward-stable LU inverse (what numpy.linalg.inv delivers at KMP.py:157)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = A.device
+    st = _lib.stream()
+    A0 = A.clone()
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = int(lib.kmpx_inverse_workspace_bytes(n, 1))
+    ws = torch.empty(max(nbytes, 8) // 8 + 1, dtype=torch.float64, device=dev)
+    _lib.call('kmpx_inverse', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
+    if int(info.item()) != 0:
+        raise np.linalg.LinAlgError('Singular matrix')      # what numpy.linalg.inv raises
+    R = torch.empty_like(A)
+    for _ in range(newton_steps):
+        R.zero_()
+        R[:, :n].fill_diagonal_(1.0)
+        _lib.call('kmpx_dgemm', 0, 0, n, n, n, -1.0, _lib.ptr(A0), lda, 0, _lib.ptr(A), lda, 0, 1.0, _lib.ptr(R), lda, 0, 1, 0, st)
+        X = A.clone()
+        _lib.call('kmpx_dgemm', 0, 0, n, n, n, 1.0, _lib.ptr(X), lda, 0, _lib.ptr(R), lda, 0, 1.0, _lib.ptr(A), lda, 0, 1, 0, st)
+    return A
 
 
 class KMP:
@@ -257,9 +278,5 @@ def explicit_inverse(s, sigma, lam, sigma_f, time_driven):
                       _lib.ptr(out), lda, 0, 1, 0, st)
             return out[:, :n].cpu().numpy()
         A = A0
-    nbytes = int(lib.kmpx_inverse_workspace_bytes(n, 1))
-    ws = torch.empty(max(nbytes, 8) // 8 + 1, dtype=torch.float64, device=dev)
-    _lib.call('kmpx_inverse', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
-    if int(info.item()) != 0:
-        raise np.linalg.LinAlgError('Singular matrix')
+    A = general_inverse(A, n, lda)
     return A[:, :n].cpu().numpy()

@@ -1,2 +1,1 @@
 from .point import Point
-from .quaternion import quaternion

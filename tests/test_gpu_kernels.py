@@ -59,8 +59,9 @@ def test_kernel_build_lower_only_and_batch(T):
     lda = (n + 7) // 8 * 8
     A_full = T.full((B, n, lda), -7.0, dtype=T.float64, device='cuda')
     A_low = T.full((B, n, lda), -7.0, dtype=T.float64, device='cuda')
+    s_d, sig_d, n_d = dev(T, s), dev(T, sig), dev(T, npts)       # keep the device tensors alive across the launches
     for A, uplo in ((A_full, _lib.UPLO_FULL), (A_low, _lib.UPLO_LOWER)):
-        _lib.call('kmpx_kernel_build', _lib.ptr(dev(T, s)), _lib.ptr(dev(T, sig)), _lib.ptr(dev(T, npts)), _lib.ptr(A), B, Nmax,
+        _lib.call('kmpx_kernel_build', _lib.ptr(s_d), _lib.ptr(sig_d), _lib.ptr(n_d), _lib.ptr(A), B, Nmax,
                   I, O, lda, n * lda, 200.0, 0.5, 0, _lib.LAYOUT_COMPONENT, uplo, _lib.stream())
     Af, Al = A_full.cpu().numpy(), A_low.cpu().numpy()
     from oracle import kmp_oracle as orc
@@ -71,7 +72,7 @@ def test_kernel_build_lower_only_and_batch(T):
         assert rel_err(Af[b][np.ix_(idx, idx)], ref) < 1e-15
         low = np.tril(Af[b][:nb, :nb])
         assert np.array_equal(np.tril(Al[b][:nb, :nb]), low)
-        assert np.all(np.triu(Al[b][:nb, :nb], 1) == -7.0), 'LOWER must not touch the strict upper triangle'
+        assert np.all(Al[b][:nb, :nb][np.triu_indices(nb, 1)] == -7.0), 'LOWER must not touch the strict upper triangle'
         assert np.all(Af[b][nb:, :] == -7.0), 'rows beyond the system must stay untouched'
 
 
@@ -106,13 +107,15 @@ def test_dgemm_triangular_modes(T):
     assert rel_err(np.tril(out), np.tril(C0 - A @ A.T)) < 1e-13
     Lw = np.tril(rng.normal(size=(m, m))); Bm = rng.normal(size=(m, 40))
     Cd = T.zeros((m, 40), dtype=T.float64, device='cuda')
-    _lib.call('kmpx_dgemm', 0, 0, m, 40, m, 1.0, _lib.ptr(dev(T, Lw)), m, 0, _lib.ptr(dev(T, Bm)), 40, 0, 0.0, _lib.ptr(Cd), 40, 0, 1, 2,
+    Lw_d, Bm_d = dev(T, Lw), dev(T, Bm)
+    _lib.call('kmpx_dgemm', 0, 0, m, 40, m, 1.0, _lib.ptr(Lw_d), m, 0, _lib.ptr(Bm_d), 40, 0, 0.0, _lib.ptr(Cd), 40, 0, 1, 2,
               _lib.stream())
     assert rel_err(Cd.cpu().numpy(), Lw @ Bm) < 1e-13
     Bl = np.tril(rng.normal(size=(m, m)))
     Cd = T.zeros((40, m), dtype=T.float64, device='cuda')
     A2 = rng.normal(size=(40, m))
-    _lib.call('kmpx_dgemm', 0, 0, 40, m, m, 1.0, _lib.ptr(dev(T, A2)), m, 0, _lib.ptr(dev(T, Bl)), m, 0, 0.0, _lib.ptr(Cd), m, 0, 1, 3,
+    A2_d, Bl_d = dev(T, A2), dev(T, Bl)
+    _lib.call('kmpx_dgemm', 0, 0, 40, m, m, 1.0, _lib.ptr(A2_d), m, 0, _lib.ptr(Bl_d), m, 0, 0.0, _lib.ptr(Cd), m, 0, 1, 3,
               _lib.stream())
     assert rel_err(Cd.cpu().numpy(), A2 @ Bl) < 1e-13
 
@@ -191,13 +194,15 @@ def test_inverse_gauss_jordan(T):
     mats = []
     for b, n in enumerate(sizes):
         M = rng.normal(size=(n, n)) + 0.5 * np.eye(n)
-        M[0, 0] = 0.0        # forces a row interchange in the first step
+        if n > 1:
+            M[0, 0] = 0.0    # forces a row interchange in the first step
         mats.append(M)
         A[b, :n, :n] = dev(T, M)
     nbytes = int(lib.kmpx_inverse_workspace_bytes(nmax, len(sizes)))
     ws = T.empty(nbytes // 8 + 1, dtype=T.float64, device='cuda')
     info = T.zeros(len(sizes), dtype=T.int32, device='cuda')
-    _lib.call('kmpx_inverse', _lib.ptr(A), nmax, nmax * nmax, _lib.ptr(dev(T, np.array(sizes, dtype=np.int32))), nmax, len(sizes),
+    n_d = dev(T, np.array(sizes, dtype=np.int32))
+    _lib.call('kmpx_inverse', _lib.ptr(A), nmax, nmax * nmax, _lib.ptr(n_d), nmax, len(sizes),
               _lib.ptr(info), _lib.ptr(ws), nbytes, _lib.stream())
     out = A.cpu().numpy()
     assert np.all(info.cpu().numpy() == 0)
@@ -248,7 +253,7 @@ def test_reference_kmeans_empty_cluster_nan_rule(T):
 
 
 def test_quaternion_maps(T, golden):
-    from kmp_demos_b200.types import quaternion as qm
+    import kmp_demos_b200.types.quaternion as qm
     from kmp_demos_b200.types.quaternion import quaternion
     z = golden('small_cases.npz')
     Q, P, W = z['quat_Q'], z['quat_P'], z['quat_W']
