@@ -33,6 +33,15 @@ if ROOT not in sys.path:
 
 from kmp_demos_b200 import workloads as wl  # noqa: E402
 
+T0 = time.perf_counter()
+
+
+def log(msg):
+    """Progress on stderr (stdout carries exactly one JSON line)."""
+    sys.stderr.write(f'[bench +{time.perf_counter() - T0:7.1f}s] {msg}\n')
+    sys.stderr.flush()
+
+
 METRIC = 'KMP fit+predict problems/sec (batched)'
 UNIT = 'problems/s'
 N_SETS = 1024
@@ -87,7 +96,7 @@ def run_reference(args):
     per_step = cores
     sample = cpu_sample_args(mu, sig, base_of, via_s, via_p, via_v, per_step)
     os.environ['OPENBLAS_NUM_THREADS'] = '1'
-    with mp.get_context('fork').Pool(cores) as pool:
+    with mp.get_context('spawn').Pool(cores) as pool:
         for _ in range(args.warmup):
             time_cpu(pool, sample)
         t = [time_cpu(pool, sample) for _ in range(args.steps)]
@@ -223,8 +232,25 @@ def run_ours(args):
     _lib.load()
     mu, sig, src = wl.load_letter_references()
     L, O, T = mu.shape
+    log(f'rank {rank}/{world}: building {L} x {args.sets} via-point sets')
     base_of, via_s, via_p, via_v = build_problem_set(mu, sig, args.sets, seed_offset=rank)
     B = len(base_of)
+    cpu_line = None
+    if rank == 0 and world == 1:
+        # CPU baseline first (before the CUDA context exists in this process): oracle port on all host cores
+        import multiprocessing as mp
+        cores = len(os.sched_getaffinity(0))
+        sample = cpu_sample_args(mu, sig, base_of, via_s, via_p, via_v, 2 * cores)
+        os.environ['OPENBLAS_NUM_THREADS'] = '1'
+        log(f'cpu_baseline: {len(sample)} problems on {cores} processes')
+        with mp.get_context('spawn').Pool(cores) as pool:
+            pool.map(_cpu_one_problem, sample[:cores], chunksize=1)          # warm-up: imports, page-in
+            sec = time_cpu(pool, sample)
+        os.environ.pop('OPENBLAS_NUM_THREADS', None)
+        cpu_line = {'value': len(sample) / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                    'sample': f'{len(sample)} cfg-3 problems, oracle port of KMP.set_waypoint/fit/predict with the '
+                              f"reference's literal loop nest, one process per core, {sec:.1f} s wall"}
+        log(f'cpu_baseline done: {cpu_line["value"]:.2f} problems/s')
     c = wl.CFG1
     kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=args.chunk)
     kb.set_base(np.broadcast_to(wl.cfg1_kmp_grid(T), (L, 1, T)), mu, sig)
@@ -253,8 +279,11 @@ def run_ours(args):
         h_sg.copy_(sg, non_blocking=True)
 
     def timed(fn, collect_events):
-        for _ in range(args.warmup):
+        for i in range(args.warmup):
+            t1 = time.perf_counter()
             fn()
+            torch.cuda.synchronize()
+            log(f'{fn.__name__} warm-up {i}: {(time.perf_counter() - t1) * 1e3:.1f} ms')
         barrier()
         sampler = ClockSampler(local) if collect_events else None
         kb.events = [] if collect_events else None
@@ -271,12 +300,15 @@ def run_ours(args):
         events, kb.events = kb.events, None
         return kd.max_over_ranks(ms, dev), launches, clocks, events
 
+    log(f'{B} problems per GPU resident; timing')
     ms_dev, launches, clocks, events = timed(step_device, True)
+    log(f'device-resident: {ms_dev:.1f} ms/step')
     _, _, info, n_pts = step_device()
     torch.cuda.synchronize()
     assert int((info != 0).sum().item()) == 0, 'a system was not positive definite'
     n_host = n_pts.cpu().numpy().astype(np.float64)
     ms_e2e, _, _, _ = timed(step_e2e, False)
+    log(f'end-to-end: {ms_e2e:.1f} ms/step')
     # sanity on the copied-out results: finite, covariance diagonals non-negative up to rounding
     assert bool(torch.isfinite(h_xi[:64]).all()) and float(h_sg[:64, 0, 0].min()) > -1e-6
 
@@ -307,6 +339,7 @@ def run_ours(args):
             v['share'] = v['ms_per_step'] / tot
         line['kernels'] = kern
         dgemm_tf = measure_dgemm_peak(torch)
+        log(f'cuBLAS DGEMM peak {dgemm_tf:.2f} TFLOP/s')
         pred = per['kmpx_kmp_predict']
         n_launch = len(pred)
         # algorithmic flops of the fused predict: triangular V = Linv k*^T (O^2 Ns^2 M) + Gram/mean reduction
@@ -319,16 +352,9 @@ def run_ours(args):
                             'flops_per_launch': flops_step * args.steps / n_launch,
                             'peak_source': 'cuBLAS DGEMM 8192^3 sustained, measured in this run (FP64 tensor pipe)'}
         if world == 1:
-            import multiprocessing as mp
-            cores = len(os.sched_getaffinity(0))
-            sample = cpu_sample_args(mu, sig, base_of, via_s, via_p, via_v, 2 * cores)
-            os.environ['OPENBLAS_NUM_THREADS'] = '1'
-            with mp.get_context('fork').Pool(cores) as pool:
-                sec = time_cpu(pool, sample)
-            line['cpu_baseline'] = {'value': len(sample) / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                    'sample': f'{len(sample)} cfg-3 problems, oracle port of KMP.set_waypoint/fit/predict with the '
-                                              f"reference's literal loop nest, one process per core, {sec:.1f} s wall"}
+            line['cpu_baseline'] = cpu_line
             if not args.no_extras:
+                log('extras: cfg-4 kernel build + Cholesky at n=16384')
                 line['extras'] = extras_single_gpu(torch, dgemm_tf)
         print(json.dumps(line))
     if world > 1:
