@@ -50,8 +50,8 @@ inline int ensure_dyn_smem(Kern kernel, size_t bytes, size_t& cur, const char* n
 #define KMPX_TRY(expr) do { int _rc = (expr); if (_rc != 0) return _rc; } while (0)
 
 constexpr int kNumSMs = 148;   // B200
-inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
-inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+__host__ __device__ inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
 // ---------------------------------------------------------------- device side
 constexpr double kFdDt = 0.001;   // finite-difference step of the time-driven kernel, KMP.py:113

@@ -36,41 +36,85 @@ __host__ __device__ inline size_t trtri_small_smem(int n_max) {
     return (size_t)FSTAGES * (rows * FLDT + FBK * FLDB) * sizeof(double) + 2 * 32 * FLDP * sizeof(double);
 }
 
-// Cholesky of the kb x kb block at P (leading dimension FLDP) by one warp, lane = row.
-// Returns the 1-based index of the first non-positive pivot, 0 if none.
-__device__ __forceinline__ int warp_potf2(double* P, int kb, int lane) {
+// ---- 32 x 32 diagonal blocks, one warp, everything in registers -------------------------------------------
+// Lane i keeps row i of the block (a[c], c <= i); rows/columns >= kb are padded with the identity.
+// Values travel between lanes with shuffles, so the only shared-memory traffic is the load and the store.
+__device__ __forceinline__ void diag_load_rows(const double* P, int kb, int lane, double (&a)[32]) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        double v = (c == lane) ? 1.0 : 0.0;
+        if (lane < kb && c < kb && c <= lane) v = P[lane * FLDP + c];
+        a[c] = v;
+    }
+}
+
+// In-register Cholesky (right-looking).  Returns the 1-based index of the first non-positive pivot, 0 if none.
+__device__ __forceinline__ int diag_potf2(double (&a)[32], int kb, int lane) {
     int bad = 0;
-    for (int j = 0; j < kb; ++j) {
-        const double d = P[j * FLDP + j];
-        if (!(d > 0.0) && bad == 0) bad = j + 1;
-        const double sd = sqrt(d);
-        __syncwarp();
-        double lij = 0.0;
-        if (lane == j) P[j * FLDP + j] = sd;
-        if (lane > j && lane < kb) { lij = P[lane * FLDP + j] / sd; P[lane * FLDP + j] = lij; }
-        __syncwarp();
-        if (lane > j && lane < kb) {
-            for (int c = j + 1; c <= lane; ++c) P[lane * FLDP + c] -= lij * P[c * FLDP + j];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(d > 0.0) && bad == 0 && j < kb) bad = j + 1;
+        const double rs = rsqrt(d);
+        const double lij = (lane == j) ? d * rs : a[j] * rs;     // lanes < j hold nothing meaningful in column j
+        a[j] = lij;
+#pragma unroll
+        for (int c = j + 1; c < 32; ++c) {
+            const double lcj = __shfl_sync(0xffffffffu, lij, c);
+            if (lane >= c) a[c] -= lij * lcj;
         }
-        __syncwarp();
     }
     return bad;
 }
 
-// Inverse of the kb x kb lower-triangular block D into Di (both leading dimension FLDP), lane = column.
-__device__ __forceinline__ void warp_trtri32(const double* D, double* Di, int kb, int lane) {
-    if (lane < kb) {
-        const int c = lane;
-        for (int i = 0; i < c; ++i) Di[i * FLDP + c] = 0.0;
-        Di[c * FLDP + c] = 1.0 / D[c * FLDP + c];
-        for (int i = c + 1; i < kb; ++i) {
-            double acc = 0.0;
-            for (int t = c; t < i; ++t) acc += D[i * FLDP + t] * Di[t * FLDP + c];
-            Di[i * FLDP + c] = -acc / D[i * FLDP + i];
+// Inverse of the lower-triangular block held as rows in a[]: lane c ends up with column c of the inverse in x[].
+__device__ __forceinline__ void diag_trtri(const double (&a)[32], int lane, double (&x)[32]) {
+    double dg = 1.0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) if (c == lane) dg = a[c];
+    const double rd = 1.0 / dg;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = 0.0;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+        const double rdt = __shfl_sync(0xffffffffu, rd, t);
+        const double xt = (t == lane) ? rdt : ((t > lane) ? -x[t] * rdt : 0.0);
+        x[t] = xt;
+#pragma unroll
+        for (int i = t + 1; i < 32; ++i) {
+            const double lit = __shfl_sync(0xffffffffu, a[t], i);
+            x[i] += lit * xt;
         }
     }
 }
 
+// potf2 of the kb x kb block at P (in place, lower part) and, if Di != nullptr, its inverse into Di (full 32 x 32,
+// zeros above the diagonal).
+__device__ __forceinline__ int warp_potf2(double* P, double* Di, int kb, int lane) {
+    double a[32];
+    diag_load_rows(P, kb, lane, a);
+    const int bad = diag_potf2(a, kb, lane);
+    if (lane < kb) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) if (c <= lane && c < kb) P[lane * FLDP + c] = a[c];
+    }
+    if (Di) {
+        double x[32];
+        diag_trtri(a, lane, x);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) Di[i * FLDP + lane] = x[i];
+    }
+    return bad;
+}
+
+// Inverse of the kb x kb lower-triangular block D into Di (both leading dimension FLDP).
+__device__ __forceinline__ void warp_trtri32(const double* D, double* Di, int kb, int lane) {
+    double a[32], x[32];
+    diag_load_rows(D, kb, lane, a);
+    diag_trtri(a, lane, x);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) Di[i * FLDP + lane] = x[i];
+}
 
 // X(32 x 32) = A(32 x 32) * op(D) on DMMA for one warp.  A rows come from `src` (row-major, leading dimension
 // lds, shared or global), D is a 32x32 block in shared memory (leading dimension FLDP); X goes to `dst`
@@ -187,9 +231,7 @@ __global__ void __launch_bounds__(FTHREADS) k_potrf_small(FactorArgs p) {
             }
             __syncthreads();
             if (warp == 0) {
-                const int bad = warp_potf2(panel, kb, lane);
-                __syncwarp();
-                if (m > NB) warp_trtri32(panel, Dinv, kb, lane);
+                const int bad = warp_potf2(panel, m > NB ? Dinv : nullptr, kb, lane);
                 if (lane == 0) sh_bad = bad;
             }
             __syncthreads();

@@ -25,6 +25,17 @@ struct AlphaArgs {
     const double* y; double* w; int ldw; double* alpha; int general;
 };
 
+struct PredictArgs {
+    const double* F; int lda; long long strideA; int general;
+    const double* w; int ldw; const double* s; const int* n_pts; int n_max, I, O, batch;
+    const double* sq; long long stride_sq; int M;
+    double sigma_f, alpha_kmp; int time_driven;
+    double* xi; double* sigma_out;
+    int resident; int ldp;   // panel leading dimension (resident mode)
+};
+bool predict_fast_applicable(const PredictArgs& p);
+int launch_predict_fast(PredictArgs& p, cudaStream_t st);
+
 int launch_dgemm(int transA, int transB, const GemmArgs& p, int batch, cudaStream_t st);
 int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
                        int info_offset, int info_accumulate, cudaStream_t st);

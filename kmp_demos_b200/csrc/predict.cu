@@ -28,15 +28,6 @@ constexpr int PSTAGES = 3;
 constexpr int PTHREADS = 256;
 constexpr int PMAXSEG = 16;    // O*C <= 16
 
-struct PredictArgs {
-    const double* F; int lda; long long strideA; int general;
-    const double* w; int ldw; const double* s; const int* n_pts; int n_max, I, O, batch;
-    const double* sq; long long stride_sq; int M;
-    double sigma_f, alpha_kmp; int time_driven;
-    double* xi; double* sigma_out;
-    int resident; int ldp;   // panel leading dimension (resident mode)
-};
-
 template <int MT>
 struct PredictSmem {
     // all offsets in doubles
@@ -361,6 +352,7 @@ extern "C" int kmpx_kmp_predict(const double* F, int lda, long long strideA, int
     if ((reinterpret_cast<uintptr_t>(F) & 15) != 0) return fail_arg(1, "F must be 16-byte aligned");
     PredictArgs p{F, lda, strideA, factor_kind, w, ldw, s, n_pts, n_max, I, O, batch, sq, stride_sq, M,
                   sigma_f, alpha_kmp, time_driven, xi, sigma_out, 0, 0};
+    if (predict_fast_applicable(p)) return launch_predict_fast(p, (cudaStream_t)stream);
     if (O <= 2) return launch_predict<64>(p, (cudaStream_t)stream);
     return launch_predict<32>(p, (cudaStream_t)stream);
 }

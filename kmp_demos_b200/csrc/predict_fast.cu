@@ -1,0 +1,259 @@
+// K4 fast path: plain RBF kernel, O <= 2, symmetric factor (the cfg-1/3/4 shape of BASELINE.json).
+//
+// Same mathematics as predict.cu (V_a = Linv[:, block a] * kappa; Gram / mean reductions over the rows of V),
+// organised so that the FP64 tensor pipe never waits on a CTA-wide barrier:
+//   * a CTA owns 64 queries of one problem; kappa[m][j] (64 x N) is evaluated once and stays in shared memory;
+//   * each of the 8 warps owns a static list of 16-row chunks of Linv (longest-processing-time schedule over
+//     the triangular costs) and streams them through a PRIVATE 3-stage cp.async ring - only __syncwarp inside
+//     the main loop;
+//   * warp tile = 16 rows x 64 queries x both outputs: 16 independent DMMA.8x8x4 per k-step of 4 and output,
+//     10 LDS.64 per 16 DMMA;
+//   * the V tile is reduced straight from the accumulator registers (products, 3 xor-shuffles over the 8 row
+//     lanes) into a per-warp slice of shared memory; slices are summed in warp order at the end, so results are
+//     bitwise reproducible and independent of the batch a problem sits in.
+// Algorithmic flops per problem: O^2 Ns^2 M (+ lower-order reductions); F is streamed from L2 once per CTA.
+#include "dmma_tile.cuh"
+#include "kmpx_internal.cuh"
+
+namespace kmpx {
+
+constexpr int QT = 64;          // queries per CTA
+constexpr int RC = 16;          // rows of Linv per chunk
+constexpr int QK = 16;          // k per stage
+constexpr int QLD = 20;         // ring tile leading dimension (4 mod 16)
+constexpr int QST = 3;          // ring stages per warp
+constexpr int QWARPS = 8;
+constexpr int QTHREADS = QWARPS * 32;
+constexpr int QMAXCH = 80;      // chunks per problem: n_sys <= 1280
+
+template <int O> struct FastCfg { static constexpr int NT = O * (O + 1) / 2 + O; };
+
+__host__ __device__ inline size_t fast_smem_bytes(int O, int I, int n_max_pts, int ldp) {
+    const int nt = O * (O + 1) / 2 + O;
+    const int n_sys_max = O * comp_stride(n_max_pts);
+    size_t d = (size_t)QT * ldp + (size_t)QWARPS * QST * RC * QLD + (size_t)QWARPS * nt * QT + round_up(n_sys_max, 2) + (size_t)QT * I;
+    return d * sizeof(double) + (size_t)(QWARPS * QMAXCH + QWARPS + 2 * QMAXCH) * sizeof(int);
+}
+
+struct Cursor {   // position of a warp in its flattened list of (chunk, output a, k-block) items
+    int ci, a, kb, nk, r0, col0, jmax;
+    bool valid;
+};
+
+template <int O>
+__global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p) {
+    constexpr int NT = FastCfg<O>::NT;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int b = blockIdx.y, m0 = blockIdx.x * QT;
+    const int I = p.I;
+    const int N = p.n_pts ? p.n_pts[b] : p.n_max;
+    const int Ns = comp_stride(N);
+    const int n = O * Ns;
+    const int ldp = p.ldp;
+    const int n_sys_max = O * comp_stride(p.n_max);
+
+    double* panel = smem;                                               // [QT][ldp]
+    double* rings = panel + (size_t)QT * ldp;                           // [QWARPS][QST][RC*QLD]
+    double* racc = rings + (size_t)QWARPS * QST * RC * QLD;              // [QWARPS][NT][QT]
+    double* wsh = racc + (size_t)QWARPS * NT * QT;                       // [n_sys_max]
+    double* sqs = wsh + round_up(n_sys_max, 2);                          // [QT][I]
+    int* sched = reinterpret_cast<int*>(sqs + (size_t)QT * I);          // [QWARPS][QMAXCH]
+    int* sched_n = sched + QWARPS * QMAXCH;                              // [QWARPS]
+    int* cost = sched_n + QWARPS;                                        // [QMAXCH]
+    int* order = cost + QMAXCH;                                          // [QMAXCH]
+
+    const double* F = p.F + (size_t)b * p.strideA;
+    const double* s = p.s + (size_t)b * p.n_max * I;
+    const double* sq = p.sq + (size_t)b * p.stride_sq;
+    const double* w = p.w + (size_t)b * p.ldw;
+
+    for (int idx = tid; idx < QT * I; idx += QTHREADS) {
+        const int m = idx / I;
+        sqs[idx] = (m0 + m < p.M) ? sq[(size_t)(m0 + m) * I + (idx - m * I)] : 0.0;
+    }
+    for (int idx = tid; idx < n_sys_max; idx += QTHREADS) wsh[idx] = idx < n ? w[idx] : 0.0;
+    for (int idx = tid; idx < QWARPS * NT * QT; idx += QTHREADS) racc[idx] = 0.0;
+    const int nchunks = (n + RC - 1) / RC;
+    // static longest-processing-time schedule of the chunks over the warps (depends on n only)
+    if (tid == 0) {
+        for (int c = 0; c < nchunks; ++c) {
+            int cs = 0;
+            for (int a = 0; a < O; ++a) {
+                int jm = c * RC + RC - a * Ns;
+                jm = jm < 0 ? 0 : (jm > N ? N : jm);
+                cs += (jm + QK - 1) / QK;
+            }
+            cost[c] = cs; order[c] = c;
+        }
+        for (int i = 1; i < nchunks; ++i) {              // insertion sort by descending cost (stable)
+            const int o = order[i]; int j = i - 1;
+            while (j >= 0 && cost[order[j]] < cost[o]) { order[j + 1] = order[j]; --j; }
+            order[j + 1] = o;
+        }
+        int load[QWARPS];
+        for (int q = 0; q < QWARPS; ++q) { load[q] = 0; sched_n[q] = 0; }
+        for (int i = 0; i < nchunks; ++i) {
+            int best = 0;
+            for (int q = 1; q < QWARPS; ++q) if (load[q] < load[best]) best = q;
+            sched[best * QMAXCH + sched_n[best]++] = order[i];
+            load[best] += cost[order[i]];
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < QT * ldp; idx += QTHREADS) {
+        const int m = idx / ldp, j = idx - m * ldp;
+        double v = 0.0;
+        if (j < N && m0 + m < p.M) v = rbf(sqs + m * I, s + (size_t)j * I, I, p.sigma_f, 0.0, 0.0);
+        panel[idx] = v;
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- per-warp streaming loop
+    double* ring = rings + (size_t)warp * QST * RC * QLD;
+    double* my_racc = racc + (size_t)warp * NT * QT;
+    const int my_n = sched_n[warp];
+    const int* my_chunks = sched + warp * QMAXCH;
+
+    auto seek = [&](Cursor& c) {          // make (ci, a) point at the next segment with work, or invalidate
+        while (c.ci < my_n) {
+            c.r0 = my_chunks[c.ci] * RC;
+            while (c.a < O) {
+                c.col0 = c.a * Ns;
+                int jm = c.r0 + RC - c.col0;
+                jm = jm < 0 ? 0 : (jm > N ? N : jm);
+                c.jmax = jm;
+                c.nk = (jm + QK - 1) / QK;
+                if (c.nk > 0) { c.valid = true; return; }
+                ++c.a;
+            }
+            ++c.ci; c.a = 0;
+        }
+        c.valid = false;
+    };
+    auto advance = [&](Cursor& c) {
+        if (++c.kb >= c.nk) { c.kb = 0; ++c.a; seek(c); }
+    };
+    auto issue = [&](const Cursor& c, int slot) {
+        const int cg0 = c.col0 + c.kb * QK;
+        int rows_valid = n - c.r0; rows_valid = rows_valid > RC ? RC : rows_valid;
+        load_tile_async<QK, QLD, true>(ring + slot * RC * QLD, F + (size_t)c.r0 * p.lda + cg0, p.lda, RC, rows_valid,
+                                       c.r0, cg0, c.col0 + c.jmax, lane, 32);
+    };
+
+    Cursor prod{0, 0, 0, 0, 0, 0, 0, false}, cons{0, 0, 0, 0, 0, 0, 0, false};
+    seek(prod);
+    seek(cons);
+    int issued = 0, consumed = 0;
+#pragma unroll
+    for (int st = 0; st < QST - 1; ++st) {
+        if (prod.valid) { issue(prod, issued % QST); advance(prod); ++issued; }
+        cp_async_commit();
+    }
+    double acc0[2][8][2], acc1[2][8][2];
+    zero_acc(acc0);
+    zero_acc(acc1);
+    while (cons.valid) {
+        cp_async_wait<QST - 2>();
+        __syncwarp();
+        if (prod.valid) { issue(prod, issued % QST); advance(prod); ++issued; }
+        cp_async_commit();
+        const double* tile = ring + (consumed % QST) * RC * QLD;
+        const double* Bs = panel + cons.kb * QK;
+        if (O == 1 || cons.a == 0) {
+#pragma unroll
+            for (int kk = 0; kk < QK; kk += 4) warp_mma_k4<2, 8, false>(acc0, tile + kk, QLD, Bs + kk, ldp, lane);
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < QK; kk += 4) warp_mma_k4<2, 8, false>(acc1, tile + kk, QLD, Bs + kk, ldp, lane);
+        }
+        ++consumed;
+        const int cur_ci = cons.ci, cur_r0 = cons.r0;
+        advance(cons);
+        if (!cons.valid || cons.ci != cur_ci) {
+            // chunk complete: reduce the V tile over its 16 rows straight from the accumulators
+            double wv[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { const int r = cur_r0 + i * 8 + g; wv[i] = r < n ? wsh[r] : 0.0; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double red[NT][2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double q00 = 0.0, q01 = 0.0, q11 = 0.0, mu0 = 0.0, mu1 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const double v0 = acc0[i][j][e];
+                        q00 += v0 * v0; mu0 += v0 * wv[i];
+                        if (O == 2) { const double v1 = acc1[i][j][e]; q01 += v0 * v1; q11 += v1 * v1; mu1 += v1 * wv[i]; }
+                    }
+                    if (O == 1) { red[0][e] = q00; red[1][e] = mu0; }
+                    else { red[0][e] = q00; red[1][e] = q01; red[2][e] = q11; red[3][e] = mu0; red[NT - 1][e] = mu1; }
+                }
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double v = red[t][e];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if (g == 0) my_racc[t * QT + j * 8 + 2 * t4 + e] += v;
+                    }
+            }
+            zero_acc(acc0);
+            zero_acc(acc1);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // ---------------------------------------------------------------- outputs (reference layout, query last)
+    double* xi = p.xi + (size_t)b * O * p.M;
+    double* sg_out = p.sigma_out ? p.sigma_out + (size_t)b * O * O * p.M : nullptr;
+    constexpr int NPAIR = O * (O + 1) / 2;
+    for (int idx = tid; idx < NT * QT; idx += QTHREADS) {
+        const int t = idx / QT, m = idx - t * QT;
+        if (m0 + m >= p.M) continue;
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < QWARPS; ++q) v += racc[((size_t)q * NT + t) * QT + m];
+        if (t >= NPAIR) {
+            xi[(size_t)(t - NPAIR) * p.M + m0 + m] = v;
+        } else if (sg_out) {
+            // pair index -> (a <= bb): O == 1: (0,0);  O == 2: 0 -> (0,0), 1 -> (0,1), 2 -> (1,1)
+            const int a = (O == 2 && t == 2) ? 1 : 0;
+            const int bb = (O == 2 && t >= 1) ? 1 : 0;
+            const double val = p.alpha_kmp * ((a == bb ? 1.0 : 0.0) - v);
+            sg_out[((size_t)a * O + bb) * p.M + m0 + m] = val;
+            if (a != bb) sg_out[((size_t)bb * O + a) * p.M + m0 + m] = val;
+        }
+    }
+}
+
+bool predict_fast_applicable(const PredictArgs& p) {
+    if (p.time_driven || p.general || p.O > 2) return false;
+    const int ldp = (int)round_up(p.n_max, 16) + 4;
+    if ((long long)p.O * comp_stride(p.n_max) > (long long)QMAXCH * RC) return false;
+    return fast_smem_bytes(p.O, p.I, p.n_max, ldp) <= 226 * 1024;
+}
+
+int launch_predict_fast(PredictArgs& p, cudaStream_t st) {
+    p.ldp = (int)round_up(p.n_max, 16) + 4;
+    p.resident = 1;
+    const size_t smem = fast_smem_bytes(p.O, p.I, p.n_max, p.ldp);
+    dim3 grid(ceil_div(p.M, QT), p.batch);
+    if (p.O == 1) {
+        static size_t set1 = 48 * 1024;
+        KMPX_TRY(ensure_dyn_smem(k_kmp_predict_fast<1>, smem, set1, "k_kmp_predict_fast<1>"));
+        k_kmp_predict_fast<1><<<grid, QTHREADS, smem, st>>>(p);
+    } else {
+        static size_t set2 = 48 * 1024;
+        KMPX_TRY(ensure_dyn_smem(k_kmp_predict_fast<2>, smem, set2, "k_kmp_predict_fast<2>"));
+        k_kmp_predict_fast<2><<<grid, QTHREADS, smem, st>>>(p);
+    }
+    return check_launch("k_kmp_predict_fast");
+}
+
+}  // namespace kmpx
