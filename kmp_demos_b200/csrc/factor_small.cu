@@ -29,91 +29,95 @@ __host__ __device__ inline size_t potrf_small_smem(int n_max) {
     const size_t rows = (size_t)((n_max + 31) / 32) * 32;
     const size_t stages = (size_t)FSTAGES * rows * FLDT * sizeof(double);
     const size_t panel = rows * FLDP * sizeof(double);
-    return (stages > panel ? stages : panel) + (size_t)32 * FLDP * sizeof(double);
+    return (stages > panel ? stages : panel) + (size_t)2 * 32 * FLDP * sizeof(double);
 }
 __host__ __device__ inline size_t trtri_small_smem(int n_max) {
     const size_t rows = (size_t)((n_max + 31) / 32) * 32;
     return (size_t)FSTAGES * (rows * FLDT + FBK * FLDB) * sizeof(double) + 2 * 32 * FLDP * sizeof(double);
 }
 
-// ---- 32 x 32 diagonal blocks, one warp, everything in registers -------------------------------------------
-// Lane i keeps row i of the block (a[c], c <= i); rows/columns >= kb are padded with the identity.
-// Values travel between lanes with shuffles, so the only shared-memory traffic is the load and the store.
-__device__ __forceinline__ void diag_load_rows(const double* P, int kb, int lane, double (&a)[32]) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        double v = (c == lane) ? 1.0 : 0.0;
-        if (lane < kb && c < kb && c <= lane) v = P[lane * FLDP + c];
-        a[c] = v;
+// ---- 32 x 32 diagonal blocks, whole CTA, shared memory, small loops (a fully unrolled single-warp version
+//      was measured to be instruction-cache bound) ------------------------------------------------------------
+// Right-looking Cholesky of the kb x kb block in P (leading dimension FLDP).  The factor goes to Ld (lower
+// triangle; rows/columns >= kb are set to the identity), P's trailing part is consumed.  One barrier per
+// column: column j of P stays unscaled while the trailing update of step j reads it.
+// *bad receives the 1-based index of the first non-positive pivot (0 if none).
+__device__ __forceinline__ void cta_potf2(double* P, double* Ld, int kb, int tid, int* bad) {
+    if (tid == 0) *bad = 0;
+    for (int idx = tid; idx < 32 * 32; idx += FTHREADS) {
+        const int r = idx >> 5, c = idx & 31;
+        if (r >= kb || c >= kb || c > r) Ld[r * FLDP + c] = (r == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < kb; ++j) {
+        const double pjj = P[j * FLDP + j];
+        const double rs = rsqrt(pjj);
+        const double rinv = rs * rs;
+        if (tid == 0 && !(pjj > 0.0) && *bad == 0) *bad = j + 1;
+        if (tid >= j && tid < kb) Ld[tid * FLDP + j] = (tid == j) ? pjj * rs : P[tid * FLDP + j] * rs;
+        for (int idx = tid; idx < 32 * 32; idx += FTHREADS) {
+            const int r = idx >> 5, c = idx & 31;
+            if (r > j && c > j && c <= r && r < kb) P[r * FLDP + c] -= (P[r * FLDP + j] * rinv) * P[c * FLDP + j];
+        }
+        __syncthreads();
     }
 }
 
-// In-register Cholesky (right-looking).  Returns the 1-based index of the first non-positive pivot, 0 if none.
-__device__ __forceinline__ int diag_potf2(double (&a)[32], int kb, int lane) {
-    int bad = 0;
+// X = L^{-1} for the 32 x 32 lower-triangular L (identity-padded), recursive 8 -> 16 -> 32 blocking:
+// [[L00,0],[L10,L11]]^{-1} = [[X00,0],[-X11 L10 X00, X11]].  S: 256 doubles of scratch.  Five barriers.
+__device__ __forceinline__ void cta_trtri32(const double* L, double* X, double* S, int tid) {
+    for (int idx = tid; idx < 32 * 32; idx += FTHREADS) X[(idx >> 5) * FLDP + (idx & 31)] = 0.0;
+    __syncthreads();
+    if (tid < 32) {                                   // four 8x8 diagonal blocks, one thread per column
+        const int base = (tid >> 3) * 8, c = tid & 7;
+        double x[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(d > 0.0) && bad == 0 && j < kb) bad = j + 1;
-        const double rs = rsqrt(d);
-        const double lij = (lane == j) ? d * rs : a[j] * rs;     // lanes < j hold nothing meaningful in column j
-        a[j] = lij;
+        for (int i = 0; i < 8; ++i) {
+            double v = 0.0;
+            if (i == c) v = 1.0 / L[(base + i) * FLDP + base + i];
+            else if (i > c) {
+                double sum = 0.0;
 #pragma unroll
-        for (int c = j + 1; c < 32; ++c) {
-            const double lcj = __shfl_sync(0xffffffffu, lij, c);
-            if (lane >= c) a[c] -= lij * lcj;
+                for (int t = 0; t < 8; ++t) if (t >= c && t < i) sum += L[(base + i) * FLDP + base + t] * x[t];
+                v = -sum / L[(base + i) * FLDP + base + i];
+            }
+            x[i] = v;
+            X[(base + i) * FLDP + base + c] = v;
         }
     }
-    return bad;
-}
-
-// Inverse of the lower-triangular block held as rows in a[]: lane c ends up with column c of the inverse in x[].
-__device__ __forceinline__ void diag_trtri(const double (&a)[32], int lane, double (&x)[32]) {
-    double dg = 1.0;
+    __syncthreads();
+    if (tid < 128) {                                  // level 16: T = L10 X00 for both 16-blocks
+        const int pb = (tid >> 6) * 16, r = (tid >> 3) & 7, c = tid & 7;
+        double sum = 0.0;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) if (c == lane) dg = a[c];
-    const double rd = 1.0 / dg;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = 0.0;
-#pragma unroll
-    for (int t = 0; t < 32; ++t) {
-        const double rdt = __shfl_sync(0xffffffffu, rd, t);
-        const double xt = (t == lane) ? rdt : ((t > lane) ? -x[t] * rdt : 0.0);
-        x[t] = xt;
-#pragma unroll
-        for (int i = t + 1; i < 32; ++i) {
-            const double lit = __shfl_sync(0xffffffffu, a[t], i);
-            x[i] += lit * xt;
-        }
+        for (int t = 0; t < 8; ++t) sum += L[(pb + 8 + r) * FLDP + pb + t] * X[(pb + t) * FLDP + pb + c];
+        S[tid] = sum;
     }
-}
-
-// potf2 of the kb x kb block at P (in place, lower part) and, if Di != nullptr, its inverse into Di (full 32 x 32,
-// zeros above the diagonal).
-__device__ __forceinline__ int warp_potf2(double* P, double* Di, int kb, int lane) {
-    double a[32];
-    diag_load_rows(P, kb, lane, a);
-    const int bad = diag_potf2(a, kb, lane);
-    if (lane < kb) {
+    __syncthreads();
+    if (tid < 128) {                                  // X10 = -X11 T
+        const int q = tid >> 6, pb = q * 16, r = (tid >> 3) & 7, c = tid & 7;
+        double sum = 0.0;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) if (c <= lane && c < kb) P[lane * FLDP + c] = a[c];
+        for (int t = 0; t < 8; ++t) sum += X[(pb + 8 + r) * FLDP + pb + 8 + t] * S[q * 64 + t * 8 + c];
+        X[(pb + 8 + r) * FLDP + pb + c] = -sum;
     }
-    if (Di) {
-        double x[32];
-        diag_trtri(a, lane, x);
+    __syncthreads();
+    {                                                 // level 32: T = L10 X00 (16 x 16), one output per thread
+        const int r = tid >> 4, c = tid & 15;
+        double sum = 0.0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) Di[i * FLDP + lane] = x[i];
+        for (int t = 0; t < 16; ++t) sum += L[(16 + r) * FLDP + t] * X[t * FLDP + c];
+        S[tid] = sum;
     }
-    return bad;
-}
-
-// Inverse of the kb x kb lower-triangular block D into Di (both leading dimension FLDP).
-__device__ __forceinline__ void warp_trtri32(const double* D, double* Di, int kb, int lane) {
-    double a[32], x[32];
-    diag_load_rows(D, kb, lane, a);
-    diag_trtri(a, lane, x);
+    __syncthreads();
+    {
+        const int r = tid >> 4, c = tid & 15;
+        double sum = 0.0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) Di[i * FLDP + lane] = x[i];
+        for (int t = 0; t < 16; ++t) sum += X[(16 + r) * FLDP + 16 + t] * S[t * 16 + c];
+        X[(16 + r) * FLDP + c] = -sum;
+    }
+    __syncthreads();
 }
 
 // X(32 x 32) = A(32 x 32) * op(D) on DMMA for one warp.  A rows come from `src` (row-major, leading dimension
@@ -168,7 +172,9 @@ __global__ void __launch_bounds__(FTHREADS) k_potrf_small(FactorArgs p) {
     double* stage0 = smem;
     double* panel = smem;                                                     // aliases the stage ring
     double* Dinv = smem + (stages_bytes > panel_elems ? stages_bytes : panel_elems);    // [32][FLDP] inverse of the diagonal block
+    double* Ld = Dinv + 32 * FLDP;                                                          // [32][FLDP] factor of the diagonal block
     __shared__ int sh_bad;
+    __shared__ double scratch[256];
 
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
         const int n = p.n_sys ? p.n_sys[b] : p.n_max;
@@ -230,9 +236,11 @@ __global__ void __launch_bounds__(FTHREADS) k_potrf_small(FactorArgs p) {
                 }
             }
             __syncthreads();
-            if (warp == 0) {
-                const int bad = warp_potf2(panel, m > NB ? Dinv : nullptr, kb, lane);
-                if (lane == 0) sh_bad = bad;
+            cta_potf2(panel, Ld, kb, tid, &sh_bad);
+            if (m > NB) cta_trtri32(Ld, Dinv, scratch, tid);
+            for (int idx = tid; idx < NB * NB; idx += FTHREADS) {
+                const int r = idx >> 5, c = idx & 31;
+                if (r < kb && c <= r) panel[r * FLDP + c] = Ld[r * FLDP + c];
             }
             __syncthreads();
             if (sh_bad != 0 && bad_total == 0) bad_total = k0 + sh_bad;
@@ -266,6 +274,7 @@ __global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
     double* stage0 = smem;
     double* Dsm = smem + FSTAGES * stage_elems;
     double* Dinv = Dsm + 32 * FLDP;
+    __shared__ double scratch[256];
 
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
         const int n = p.n_sys ? p.n_sys[b] : p.n_max;
@@ -277,11 +286,10 @@ __global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
             const int m = n - k0 - kb;            // rows below the diagonal block
             for (int idx = tid; idx < NB * NB; idx += FTHREADS) {
                 const int r = idx >> 5, c = idx & 31;
-                Dsm[r * FLDP + c] = (r < kb && c <= r) ? L[(size_t)(k0 + r) * p.lda + k0 + c] : 0.0;
+                Dsm[r * FLDP + c] = (r < kb && c <= r) ? L[(size_t)(k0 + r) * p.lda + k0 + c] : ((r == c) ? 1.0 : 0.0);
             }
             __syncthreads();
-            if (warp == 0) warp_trtri32(Dsm, Dinv, kb, lane);
-            __syncthreads();
+            cta_trtri32(Dsm, Dinv, scratch, tid);
             if (m > 0) {
                 // T = L21 * Dinv, in place in global memory, one 32-row chunk per warp (kb == 32 here)
                 {

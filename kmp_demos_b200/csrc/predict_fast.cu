@@ -3,9 +3,9 @@
 // Same mathematics as predict.cu (V_a = Linv[:, block a] * kappa; Gram / mean reductions over the rows of V),
 // organised so that the FP64 tensor pipe never waits on a CTA-wide barrier:
 //   * a CTA owns 64 queries of one problem; kappa[m][j] (64 x N) is evaluated once and stays in shared memory;
-//   * each of the 8 warps owns a static list of 16-row chunks of Linv (longest-processing-time schedule over
-//     the triangular costs) and streams them through a PRIVATE 3-stage cp.async ring - only __syncwarp inside
-//     the main loop;
+//   * each of the 8 warps owns a static list of 16-row chunks of Linv (the triangular costs grow with the row
+//     index, so the chunks are dealt from the bottom up in boustrophedon order) and streams them through a
+//     PRIVATE 3-stage cp.async ring - only __syncwarp inside the main loop;
 //   * warp tile = 16 rows x 64 queries x both outputs: 16 independent DMMA.8x8x4 per k-step of 4 and output,
 //     10 LDS.64 per 16 DMMA;
 //   * the V tile is reduced straight from the accumulator registers (products, 3 xor-shuffles over the 8 row
@@ -32,7 +32,7 @@ __host__ __device__ inline size_t fast_smem_bytes(int O, int I, int n_max_pts, i
     const int nt = O * (O + 1) / 2 + O;
     const int n_sys_max = O * comp_stride(n_max_pts);
     size_t d = (size_t)QT * ldp + (size_t)QWARPS * QST * RC * QLD + (size_t)QWARPS * nt * QT + round_up(n_sys_max, 2) + (size_t)QT * I;
-    return d * sizeof(double) + (size_t)(QWARPS * QMAXCH + QWARPS + 2 * QMAXCH) * sizeof(int);
+    return d * sizeof(double);
 }
 
 struct Cursor {   // position of a warp in its flattened list of (chunk, output a, k-block) items
@@ -59,10 +59,6 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
     double* racc = rings + (size_t)QWARPS * QST * RC * QLD;              // [QWARPS][NT][QT]
     double* wsh = racc + (size_t)QWARPS * NT * QT;                       // [n_sys_max]
     double* sqs = wsh + round_up(n_sys_max, 2);                          // [QT][I]
-    int* sched = reinterpret_cast<int*>(sqs + (size_t)QT * I);          // [QWARPS][QMAXCH]
-    int* sched_n = sched + QWARPS * QMAXCH;                              // [QWARPS]
-    int* cost = sched_n + QWARPS;                                        // [QMAXCH]
-    int* order = cost + QMAXCH;                                          // [QMAXCH]
 
     const double* F = p.F + (size_t)b * p.strideA;
     const double* s = p.s + (size_t)b * p.n_max * I;
@@ -76,49 +72,18 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
     for (int idx = tid; idx < n_sys_max; idx += QTHREADS) wsh[idx] = idx < n ? w[idx] : 0.0;
     for (int idx = tid; idx < QWARPS * NT * QT; idx += QTHREADS) racc[idx] = 0.0;
     const int nchunks = (n + RC - 1) / RC;
-    // static longest-processing-time schedule of the chunks over the warps (depends on n only)
-    if (tid == 0) {
-        for (int c = 0; c < nchunks; ++c) {
-            int cs = 0;
-            for (int a = 0; a < O; ++a) {
-                int jm = c * RC + RC - a * Ns;
-                jm = jm < 0 ? 0 : (jm > N ? N : jm);
-                cs += (jm + QK - 1) / QK;
-            }
-            cost[c] = cs; order[c] = c;
-        }
-        for (int i = 1; i < nchunks; ++i) {              // insertion sort by descending cost (stable)
-            const int o = order[i]; int j = i - 1;
-            while (j >= 0 && cost[order[j]] < cost[o]) { order[j + 1] = order[j]; --j; }
-            order[j + 1] = o;
-        }
-        int load[QWARPS];
-        for (int q = 0; q < QWARPS; ++q) { load[q] = 0; sched_n[q] = 0; }
-        for (int i = 0; i < nchunks; ++i) {
-            int best = 0;
-            for (int q = 1; q < QWARPS; ++q) if (load[q] < load[best]) best = q;
-            sched[best * QMAXCH + sched_n[best]++] = order[i];
-            load[best] += cost[order[i]];
-        }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < QT * ldp; idx += QTHREADS) {
-        const int m = idx / ldp, j = idx - m * ldp;
-        double v = 0.0;
-        if (j < N && m0 + m < p.M) v = rbf(sqs + m * I, s + (size_t)j * I, I, p.sigma_f, 0.0, 0.0);
-        panel[idx] = v;
-    }
     __syncthreads();
 
     // ---------------------------------------------------------------- per-warp streaming loop
     double* ring = rings + (size_t)warp * QST * RC * QLD;
     double* my_racc = racc + (size_t)warp * NT * QT;
-    const int my_n = sched_n[warp];
-    const int* my_chunks = sched + warp * QMAXCH;
+    // k-th chunk of this warp: position k*8 + (k even ? warp : 7 - warp) in the list of chunks sorted by
+    // descending cost (= descending row index)
+    auto chunk_of = [&](int k) { const int pos = k * QWARPS + ((k & 1) ? (QWARPS - 1 - warp) : warp); return nchunks - 1 - pos; };
 
     auto seek = [&](Cursor& c) {          // make (ci, a) point at the next segment with work, or invalidate
-        while (c.ci < my_n) {
-            c.r0 = my_chunks[c.ci] * RC;
+        while (chunk_of(c.ci) >= 0) {
+            c.r0 = chunk_of(c.ci) * RC;
             while (c.a < O) {
                 c.col0 = c.a * Ns;
                 int jm = c.r0 + RC - c.col0;
@@ -151,6 +116,17 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
         if (prod.valid) { issue(prod, issued % QST); advance(prod); ++issued; }
         cp_async_commit();
     }
+    // kappa panel (the B operand), evaluated while the first Linv tiles are in flight: warp-strided over the
+    // queries, lane-strided over the stored points
+    for (int m = warp; m < QT; m += QWARPS) {
+        const bool live = m0 + m < p.M;
+        for (int j = lane; j < ldp; j += 32) {
+            double v = 0.0;
+            if (j < N && live) v = rbf(sqs + m * I, s + (size_t)j * I, I, p.sigma_f, 0.0, 0.0);
+            panel[(size_t)m * ldp + j] = v;
+        }
+    }
+    __syncthreads();
     double acc0[2][8][2], acc1[2][8][2];
     zero_acc(acc0);
     zero_acc(acc1);
