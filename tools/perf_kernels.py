@@ -1,0 +1,166 @@
+"""Per-kernel throughput on the B200: DGEMM, large Cholesky / triangular inverse, kernel build,
+fused EM pass, GMR, quaternion maps, cfg-4 predict.  CUDA-event timing, best of `reps` after a warm-up.
+Prints one JSON object; `bench.py` reports the cfg-3 headline, this script the rest.
+
+    python tools/perf_kernels.py [--quick] [--only dgemm,potrf,...]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from kmp_demos_b200 import _lib, workloads as wl  # noqa: E402
+
+f64 = torch.float64
+
+
+def timeit(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    return json.load(open(p)).get('hbm_gbs', 6650.0) if os.path.isfile(p) else 6650.0
+
+
+def dgemm_cublas(n=8192):
+    a = torch.randn(n, n, dtype=f64, device='cuda'); b = torch.randn(n, n, dtype=f64, device='cuda'); c = torch.empty_like(a)
+    ms = timeit(lambda: torch.matmul(a, b, out=c), reps=3, warm=2)
+    return 2.0 * n ** 3 / ms * 1e-9
+
+
+def dgemm_ours(n=8192, ta=0, tb=1, tri=0):
+    a = torch.randn(n, n, dtype=f64, device='cuda'); b = torch.randn(n, n, dtype=f64, device='cuda'); c = torch.zeros(n, n, dtype=f64, device='cuda')
+    st = _lib.stream()
+    ms = timeit(lambda: _lib.call('kmpx_dgemm', ta, tb, n, n, n, 1.0, _lib.ptr(a), n, 0, _lib.ptr(b), n, 0, 0.0, _lib.ptr(c), n, 0, 1, tri, st))
+    fl = 2.0 * n ** 3 * (0.5 if tri == 1 else 1.0)
+    return fl / ms * 1e-9, ms
+
+
+def cfg4(N, dg):
+    lib = _lib.load()
+    O = 2
+    t, mu, sig = wl.cfg4_problem(N=N, seed=0)
+    n = int(lib.kmpx_sys_size(N, O, _lib.LAYOUT_COMPONENT)); lda = n
+    s_d = torch.as_tensor(np.ascontiguousarray(t.T), device='cuda')
+    g_d = torch.as_tensor(np.ascontiguousarray(np.transpose(sig, (2, 0, 1))), device='cuda')
+    y_d = torch.as_tensor(np.ascontiguousarray(mu.T), device='cuda')
+    A = torch.empty((n, lda), dtype=f64, device='cuda')
+    nbytes = int(lib.kmpx_potrf_workspace_bytes(n, 1)); ws = torch.empty(max(nbytes, 8) // 8, dtype=f64, device='cuda')
+    info = torch.zeros(1, dtype=torch.int32, device='cuda'); st = _lib.stream(); c = wl.CFG1
+    build = lambda uplo: _lib.call('kmpx_kernel_build', _lib.ptr(s_d), _lib.ptr(g_d), None, _lib.ptr(A), 1, N, 1, O, lda, n * lda,  # noqa: E731
+                                   c['sigma_f'], c['lam'], 0, _lib.LAYOUT_COMPONENT, uplo, st)
+    out = {}
+    ms = timeit(lambda: build(_lib.UPLO_FULL))
+    out['kernel_build_full'] = {'ms': ms, 'gbs': 8.0 * n * n / ms * 1e-6, 'frac_hbm': 8.0 * n * n / ms * 1e-6 / peaks()}
+    ms = timeit(lambda: build(_lib.UPLO_LOWER))
+    out['kernel_build_lower'] = {'ms': ms, 'gbs': 4.0 * n * (n + 1) / ms * 1e-6, 'frac_hbm': 4.0 * n * (n + 1) / ms * 1e-6 / peaks()}
+    best = 1e30
+    for _ in range(3):
+        build(_lib.UPLO_LOWER)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
+        e1.record(); e1.synchronize(); best = min(best, e0.elapsed_time(e1))
+    assert int(info.item()) == 0
+    out['potrf'] = {'n': n, 'ms': best, 'tflops': n ** 3 / 3 / best * 1e-9, 'frac_dgemm': n ** 3 / 3 / best * 1e-9 / dg}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call('kmpx_trtri', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(ws), nbytes, st)
+    e1.record(); e1.synchronize(); ms = e0.elapsed_time(e1)
+    out['trtri'] = {'ms': ms, 'tflops': n ** 3 / 3 / ms * 1e-9, 'frac_dgemm': n ** 3 / 3 / ms * 1e-9 / dg}
+    w = torch.zeros(lda, dtype=f64, device='cuda'); al = torch.empty((N, O), dtype=f64, device='cuda')
+    ms = timeit(lambda: _lib.call('kmpx_solve_alpha', _lib.ptr(A), lda, n * lda, None, N, O, 1, _lib.LAYOUT_COMPONENT, _lib.ptr(y_d),
+                                  _lib.ptr(w), lda, _lib.ptr(al), st), reps=2, warm=1)
+    out['solve_alpha'] = {'ms': ms, 'gbs': 8.0 * n * n / ms * 1e-6}
+    M = 8192
+    q = torch.as_tensor(np.linspace(0, 2, M).reshape(-1, 1), device='cuda')
+    xi = torch.empty((O, M), dtype=f64, device='cuda'); sg = torch.empty((O, O, M), dtype=f64, device='cuda')
+    ms = timeit(lambda: _lib.call('kmpx_kmp_predict', _lib.ptr(A), lda, n * lda, 0, _lib.ptr(w), lda, _lib.ptr(s_d), None, N, 1, O, 1,
+                                  _lib.ptr(q), 0, M, c['sigma_f'], c['alpha'], 0, _lib.ptr(xi), _lib.ptr(sg), st), reps=1, warm=1)
+    fl = float(O * O) * N * N * M
+    out['predict_cov'] = {'M': M, 'ms': ms, 'tflops': fl / ms * 1e-9, 'frac_dgemm': fl / ms * 1e-9 / dg, 'ms_per_100k_queries': ms * 1e5 / M}
+    ms = timeit(lambda: _lib.call('kmpx_kmp_predict_mean', _lib.ptr(al), _lib.ptr(s_d), None, N, 1, O, 1, _lib.ptr(q), 0, M, c['sigma_f'], 0,
+                                  _lib.ptr(xi), st), reps=2, warm=1)
+    out['predict_mean'] = {'M': M, 'ms': ms, 'gexp_per_s': N * M / ms * 1e-6}
+    return out
+
+
+def em(n, K=64, d=7):
+    from kmp_demos_b200.mixture import EMEngine
+    X, means, _ = wl.cfg5_samples(min(n, 2_000_000), K=K, d=d, seed=0)
+    Xd = torch.as_tensor(X, device='cuda')
+    if n > Xd.shape[0]:
+        Xd = Xd.repeat((n + Xd.shape[0] - 1) // Xd.shape[0], 1)[:n].contiguous()
+    lab = torch.as_tensor(np.argmin(((X[:200000, None, :] - means[None]) ** 2).sum(-1), axis=1).astype(np.int32), device='cuda')
+    lab = lab.repeat((n + lab.shape[0] - 1) // lab.shape[0])[:n].contiguous()
+    eng = EMEngine(Xd, K, 1e-6, shift=Xd[:100000].mean(dim=0))
+    eng.init_from_labels(lab)
+    ms = timeit(lambda: eng.em_pass(), reps=3, warm=1)
+    F = 1 + d + d * (d + 1) // 2
+    flops = float(n) * K * ((d * (d + 1) / 2 + 2 * d) * 2 + 60 + 2 * F)
+    return {'n': n, 'K': K, 'd': d, 'ms_per_iter': ms, 'gbs': 8.0 * n * d / ms * 1e-6, 'frac_hbm': 8.0 * n * d / ms * 1e-6 / peaks(),
+            'tflops_est': flops / ms * 1e-9}
+
+
+def gmr(M, K=8, O=2):
+    rng = np.random.default_rng(0)
+    d = 1 + O
+    pri = torch.as_tensor(np.full(K, 1.0 / K), device='cuda')
+    mea = torch.as_tensor(rng.normal(size=(d, K)), device='cuda')
+    Bm = rng.normal(size=(K, d, d))
+    cov = torch.as_tensor(np.ascontiguousarray(np.transpose(np.einsum('kab,kcb->kac', Bm, Bm) + 0.1 * np.eye(d), (1, 2, 0))), device='cuda')
+    x = torch.randn(1, M, dtype=f64, device='cuda'); mu = torch.empty((O, M), dtype=f64, device='cuda'); sg = torch.empty((O, O, M), dtype=f64, device='cuda')
+    ms = timeit(lambda: _lib.call('kmpx_gmr', _lib.ptr(pri), _lib.ptr(mea), _lib.ptr(cov), K, 1, O, _lib.ptr(x), M, 1e-6, _lib.ptr(mu), _lib.ptr(sg), _lib.stream()))
+    by = 8.0 * M * (1 + O + O * O)
+    return {'M': M, 'K': K, 'O': O, 'ms': ms, 'gbs': by / ms * 1e-6, 'frac_hbm': by / ms * 1e-6 / peaks()}
+
+
+def quat(M):
+    w = torch.randn(M, 3, dtype=f64, device='cuda'); q = torch.empty(M, 4, dtype=f64, device='cuda'); w2 = torch.empty_like(w)
+    ms_e = timeit(lambda: _lib.call('kmpx_quat_exp', _lib.ptr(w), _lib.ptr(q), M, _lib.stream()))
+    ms_l = timeit(lambda: _lib.call('kmpx_quat_log', _lib.ptr(q), _lib.ptr(w2), M, _lib.stream()))
+    return {'M': M, 'exp_gbs': 56.0 * M / ms_e * 1e-6, 'log_gbs': 56.0 * M / ms_l * 1e-6, 'exp_frac_hbm': 56.0 * M / ms_e * 1e-6 / peaks(),
+            'log_frac_hbm': 56.0 * M / ms_l * 1e-6 / peaks()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--quick', action='store_true')
+    ap.add_argument('--only', default='')
+    a = ap.parse_args()
+    only = set(a.only.split(',')) if a.only else None
+    want = lambda k: only is None or k in only  # noqa: E731
+    _lib.load()
+    out = {'gpu': torch.cuda.get_device_name(0), 'hbm_peak_gbs': peaks()}
+    dg = dgemm_cublas(4096 if a.quick else 8192)
+    out['dgemm_cublas_tflops'] = dg
+    if want('dgemm'):
+        for name, (ta, tb, tri) in {'NT': (0, 1, 0), 'NN': (0, 0, 0), 'NT_lower': (0, 1, 1)}.items():
+            tf, ms = dgemm_ours(4096 if a.quick else 8192, ta, tb, tri)
+            out[f'dgemm_ours_{name}'] = {'tflops': tf, 'ms': ms, 'frac_cublas': tf / dg}
+    if want('cfg4'):
+        out['cfg4'] = cfg4(2048 if a.quick else 8192, dg)
+    if want('em'):
+        out['em'] = em(1_000_000 if a.quick else 10_000_000)
+    if want('gmr'):
+        out['gmr'] = gmr(1 << (22 if a.quick else 26))
+    if want('quat'):
+        out['quat'] = quat(1 << (22 if a.quick else 26))
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()
