@@ -46,6 +46,8 @@ int kmpx_version(void);
 const char* kmpx_last_error(void);
 /* Number of kernels launched by this library in the calling process since load (bench.py's gpu_launches). */
 long long kmpx_launch_count(void);
+/* Profiling aid: cycle counters per phase of k_potrf_small / k_trtri_small accumulated by CTA 0 (16 host int64). */
+int kmpx_debug_phases(long long* out_host, int reset);
 
 /* ---- K1: kernel-matrix builder.  Replaces the N^2 Python loop of KMP.fit, KMP.py:146-156, with
  *      KMP.__kernel_matrix (KMP.py:93-128) evaluated in-kernel (plain RBF block or the finite-difference

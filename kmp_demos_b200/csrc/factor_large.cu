@@ -40,36 +40,71 @@ static int copy_block(const double* src, int ld_src, double* dst, int ld_dst, in
     return check_launch("k_copy_block");
 }
 
-// workspace layout (doubles): Dinv [LNB][LNB] | panel [n][LNB]
-static long long large_ws_doubles(int n) { return (long long)LNB * LNB + (long long)round_up(n, 2) * LNB; }
+// workspace layout (doubles): Dinv[2] [LNB][LNB] | panel [n][LNB]
+static long long large_ws_doubles(int n) { return 2LL * LNB * LNB + (long long)round_up(n, 2) * LNB; }
 
+struct SideStream {
+    cudaStream_t s = nullptr; cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    int ensure() {
+        if (s) return 0;
+        // highest priority: its single-CTA kernels must be dispatched as soon as any SM drains, ahead of the
+        // thousands of pending CTAs of the trailing update on the caller's stream
+        int least = 0, greatest = 0;
+        KMPX_TRY(check_cuda(cudaDeviceGetStreamPriorityRange(&least, &greatest), "cudaDeviceGetStreamPriorityRange"));
+        KMPX_TRY(check_cuda(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, greatest), "cudaStreamCreateWithPriority"));
+        KMPX_TRY(check_cuda(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming), "cudaEventCreate"));
+        KMPX_TRY(check_cuda(cudaEventCreateWithFlags(&ev_side, cudaEventDisableTiming), "cudaEventCreate"));
+        return 0;
+    }
+};
+static SideStream g_side;
+
+static int diag_factor(double* D, int lda, int nb, double* Dinv, int* info, int k, cudaStream_t st) {
+    KMPX_TRY(launch_potrf_small(D, lda, 0, nullptr, nb, 1, info, k, 1, st));
+    k_copy_lower<<<dim3(ceil_div(nb, 128), nb), 128, 0, st>>>(D, lda, Dinv, LNB, nb);
+    KMPX_TRY(check_launch("k_copy_lower"));
+    return launch_trtri_small(Dinv, LNB, 0, nullptr, nb, 1, st);
+}
+
+// Right-looking blocked Cholesky with one step of look-ahead: while the bulk of the trailing update of step s runs
+// on the caller's stream, the next diagonal block is factorised and inverted (single-CTA kernels) on a side stream.
 static int potrf_large(double* A, int lda, int n, int* info, double* ws, cudaStream_t st) {
-    double* Dinv = ws;
-    double* panel = ws + (size_t)LNB * LNB;
+    double* Dinv[2] = {ws, ws + (size_t)LNB * LNB};
+    double* panel = ws + 2 * (size_t)LNB * LNB;
+    KMPX_TRY(g_side.ensure());
     if (info) { k_set_int<<<1, 32, 0, st>>>(info, 0, 1); KMPX_TRY(check_launch("k_set_int")); }
-    for (int k = 0; k < n; k += LNB) {
+    KMPX_TRY(diag_factor(A, lda, n < LNB ? n : LNB, Dinv[0], info, 0, st));
+    int step = 0;
+    for (int k = 0; k < n; k += LNB, ++step) {
         const int nb = n - k < LNB ? n - k : LNB;
         const int m = n - k - nb;
-        double* D = A + (size_t)k * lda + k;
-        KMPX_TRY(launch_potrf_small(D, lda, 0, nullptr, nb, 1, info, k, 1, st));
         if (m <= 0) break;
-        k_copy_lower<<<dim3(ceil_div(nb, 128), nb), 128, 0, st>>>(D, lda, Dinv, LNB, nb);
-        KMPX_TRY(check_launch("k_copy_lower"));
-        KMPX_TRY(launch_trtri_small(Dinv, LNB, 0, nullptr, nb, 1, st));
         double* A21 = A + (size_t)(k + nb) * lda + k;
-        GemmArgs g1{m, nb, nb, 1.0, A21, lda, 0, Dinv, LNB, 0, 0.0, panel, LNB, 0, 0};
+        GemmArgs g1{m, nb, nb, 1.0, A21, lda, 0, Dinv[step & 1], LNB, 0, 0.0, panel, LNB, 0, 0};
         KMPX_TRY(launch_dgemm(0, 1, g1, 1, st));                               // panel = A21 * Dinv^T
         KMPX_TRY(copy_block(panel, LNB, A21, lda, m, nb, st));
         double* A22 = A + (size_t)(k + nb) * lda + k + nb;
-        GemmArgs g2{m, m, nb, -1.0, panel, LNB, 0, panel, LNB, 0, 1.0, A22, lda, 0, 1};
-        KMPX_TRY(launch_dgemm(0, 1, g2, 1, st));                               // A22 -= L21 L21^T (lower tiles)
+        const int nb2 = m < LNB ? m : LNB;
+        GemmArgs g2{m, nb2, nb, -1.0, panel, LNB, 0, panel, LNB, 0, 1.0, A22, lda, 0, 1};
+        KMPX_TRY(launch_dgemm(0, 1, g2, 1, st));                               // look-ahead: next block column
+        KMPX_TRY(check_cuda(cudaEventRecord(g_side.ev_main, st), "cudaEventRecord"));
+        KMPX_TRY(check_cuda(cudaStreamWaitEvent(g_side.s, g_side.ev_main, 0), "cudaStreamWaitEvent"));
+        KMPX_TRY(diag_factor(A22, lda, nb2, Dinv[(step + 1) & 1], info, k + nb, g_side.s));
+        KMPX_TRY(check_cuda(cudaEventRecord(g_side.ev_side, g_side.s), "cudaEventRecord"));
+        if (m > nb2) {
+            const int m2 = m - nb2;
+            double* P2 = panel + (size_t)nb2 * LNB;
+            GemmArgs g3{m2, m2, nb, -1.0, P2, LNB, 0, P2, LNB, 0, 1.0, A22 + (size_t)nb2 * lda + nb2, lda, 0, 1};
+            KMPX_TRY(launch_dgemm(0, 1, g3, 1, st));                           // rest of the trailing update (lower tiles)
+        }
+        KMPX_TRY(check_cuda(cudaStreamWaitEvent(st, g_side.ev_side, 0), "cudaStreamWaitEvent"));
     }
     return 0;
 }
 
 static int trtri_large(double* L, int lda, int n, double* ws, cudaStream_t st) {
     double* Dinv = ws;
-    double* T = ws + (size_t)LNB * LNB;
+    double* T = ws + 2 * (size_t)LNB * LNB;
     {
         dim3 blk(64, 4), grid(ceil_div(n, 64), ceil_div(n, 4));
         k_zero_upper<<<grid, blk, 0, st>>>(L, lda, n);

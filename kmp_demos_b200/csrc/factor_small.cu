@@ -21,9 +21,14 @@ constexpr int FBK = 8;       // k-step of the streamed operand
 constexpr int FLDT = 12;     // leading dimension of a stage tile [rows][8]   (12 = conflict-free, see dmma_tile.cuh)
 constexpr int FLDP = 36;     // leading dimension of the panel / diagonal blocks [rows][32]  (4 mod 16)
 constexpr int FLDB = 36;     // leading dimension of the k-major B stage tile [8][32]
-constexpr int FSTAGES = 3;
+constexpr int FSTAGES = 4;      // ring depth of k_potrf_small
+constexpr int TSTAGES = 3;      // ring depth of k_trtri_small (its stage also carries the B tile)
 constexpr int FTHREADS = 256;
 constexpr int FWARPS = FTHREADS / 32;
+
+// Cycle counters per phase, accumulated by thread 0 of CTA 0 (read with kmpx_debug_phases; profiling aid only).
+__device__ long long g_phase[16];
+#define PHASE_MARK(slot) do { if (blockIdx.x == 0 && tid == 0) { const long long _t = clock64(); g_phase[slot] += _t - t_phase; t_phase = _t; } } while (0)
 
 __host__ __device__ inline size_t potrf_small_smem(int n_max) {
     const size_t rows = (size_t)((n_max + 31) / 32) * 32;
@@ -33,7 +38,7 @@ __host__ __device__ inline size_t potrf_small_smem(int n_max) {
 }
 __host__ __device__ inline size_t trtri_small_smem(int n_max) {
     const size_t rows = (size_t)((n_max + 31) / 32) * 32;
-    return (size_t)FSTAGES * (rows * FLDT + FBK * FLDB) * sizeof(double) + 2 * 32 * FLDP * sizeof(double);
+    return (size_t)TSTAGES * (rows * FLDT + FBK * FLDB) * sizeof(double) + 2 * 32 * FLDP * sizeof(double);
 }
 
 // ---- 32 x 32 diagonal blocks, whole CTA, shared memory, small loops (a fully unrolled single-warp version
@@ -60,6 +65,146 @@ __device__ __forceinline__ void cta_potf2(double* P, double* Ld, int kb, int tid
             if (r > j && c > j && c <= r && r < kb) P[r * FLDP + c] -= (P[r * FLDP + j] * rinv) * P[c * FLDP + j];
         }
         __syncthreads();
+    }
+}
+
+// Reciprocal square root on the latency-critical pivot path: single-precision seed + two Newton steps in fp64
+// (relative error ~1e-16) instead of the much longer library sequence; out-of-range pivots take the library call.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    if (!(x > 1e-30 && x < 1e30)) return rsqrt(x);
+    double y = (double)rsqrtf((float)x);
+    const double hx = 0.5 * x;
+    y = y * (1.5 - hx * y * y);      // 22-bit seed -> ~44 bits
+    y = y * (1.5 - hx * y * y);      // -> fp64 accuracy (a third step would change the last bit at most)
+    return y;
+}
+
+// Single-warp variant without block barriers: lane = column.  Step j: every lane forms its own l_lane = P[lane][j] /
+// sqrt(p_jj); the trailing rows r > j are then updated one after the other, row r by the lanes j < c <= r with
+// l_r broadcast by a shuffle (conflict-free row accesses, iterations independent of each other).
+// Returns the 1-based index of the first non-positive pivot (0 if none); Ld gets L (identity-padded).
+__device__ __forceinline__ int warp_potf2_cols(double* P, double* Ld, int kb, int lane) {
+    for (int r = 0; r < 32; ++r) Ld[r * FLDP + lane] = (r == lane) ? 1.0 : 0.0;
+    __syncwarp();
+    int bad = 0;
+    double pjj = P[0];
+    double rs = fast_rsqrt(pjj);
+    for (int j = 0; j < kb; ++j) {
+        if (!(pjj > 0.0) && bad == 0) bad = j + 1;
+        double l = 0.0;
+        if (lane >= j && lane < kb) {
+            l = (lane == j) ? pjj * rs : P[lane * FLDP + j] * rs;
+            Ld[lane * FLDP + j] = l;
+        }
+        const bool mine = lane > j;
+        // look-ahead: the next pivot p_{j+1,j+1} - l_{j+1}^2 and its rsqrt are started before the bulk of the
+        // rank-1 update so that the long rsqrt latency overlaps with it (every lane computes them redundantly)
+        if (j + 1 < kb) {
+            const double l1 = __shfl_sync(0xffffffffu, l, j + 1);
+            pjj = P[(j + 1) * FLDP + j + 1] - l1 * l1;
+            rs = fast_rsqrt(pjj);
+            if (lane == j + 1) P[(j + 1) * FLDP + j + 1] = pjj;
+        }
+        // remaining rows in groups of 8: the eight loads are issued back to back so that their latencies overlap
+        for (int r0 = j + 2; r0 < kb; r0 += 8) {
+            double v[8], lr[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = r0 + q;
+                v[q] = (r < kb) ? P[r * FLDP + lane] : 0.0;
+                lr[q] = __shfl_sync(0xffffffffu, l, r & 31);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = r0 + q;
+                if (mine && r < kb && lane <= r) P[r * FLDP + lane] = v[q] - lr[q] * l;
+            }
+        }
+        __syncwarp();
+    }
+    return bad;
+}
+
+// Blocked variant: the 32 x 32 block is processed in four 8-column panels.  The 8 x 8 diagonal block (and its
+// inverse) is done by ONE thread entirely in registers (8 sequential pivots, no shared-memory round trips); the
+// panel solve and the rank-8 trailing update are spread over all threads.  Three barriers per panel, 12 in total,
+// instead of 32 latency-bound column steps.  S: >= 64 doubles of scratch (inverse of the 8 x 8 block).
+__device__ __forceinline__ void cta_potf2_b8(double* P, double* Ld, double* S, int kb, int tid, int* bad) {
+    if (tid == 0) *bad = 0;
+    for (int idx = tid; idx < 32 * 32; idx += FTHREADS) Ld[(idx >> 5) * FLDP + (idx & 31)] = ((idx >> 5) == (idx & 31)) ? 1.0 : 0.0;
+    __syncthreads();
+    for (int base = 0; base < kb; base += 8) {
+        const int w = min(8, kb - base);
+        if (tid == 0) {
+            double a[8][8], x[8][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    a[i][j] = (i < w && j <= i) ? P[(base + i) * FLDP + base + j] : ((i == j) ? 1.0 : 0.0);
+            int b = 0;
+            double rsv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double d = a[j][j];
+                if (!(d > 0.0) && b == 0 && j < w) b = base + j + 1;
+                const double rs = fast_rsqrt(d);
+                rsv[j] = rs;                 // = 1 / L_jj: the inverse below needs no division
+                a[j][j] = d * rs;
+#pragma unroll
+                for (int i = j + 1; i < 8; ++i) a[i][j] *= rs;
+#pragma unroll
+                for (int c = j + 1; c < 8; ++c)
+#pragma unroll
+                    for (int i = c; i < 8; ++i) a[i][c] -= a[i][j] * a[c][j];
+            }
+            if (b != 0 && *bad == 0) *bad = b;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i][c] = 0.0;
+                x[c][c] = rsv[c];
+#pragma unroll
+                for (int i = c + 1; i < 8; ++i) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int t = c; t < i; ++t) s += a[i][t] * x[t][c];
+                    x[i][c] = -s * rsv[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    S[i * 8 + j] = x[i][j];
+                    if (i < w && j <= i) Ld[(base + i) * FLDP + base + j] = a[i][j];
+                }
+        }
+        __syncthreads();
+        const int rb = kb - base - 8;        // rows below this 8 x 8 block
+        if (rb > 0) {
+            for (int idx = tid; idx < rb * 8; idx += FTHREADS) {
+                const int r = idx >> 3, c = idx & 7;
+                const double* arow = P + (base + 8 + r) * FLDP + base;
+                double sum = 0.0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) if (t <= c) sum += arow[t] * S[c * 8 + t];
+                Ld[(base + 8 + r) * FLDP + base + c] = sum;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < rb * rb; idx += FTHREADS) {
+                const int i = idx / rb, j = idx - i * rb;
+                if (j <= i) {
+                    const double* li = Ld + (base + 8 + i) * FLDP + base;
+                    const double* lj = Ld + (base + 8 + j) * FLDP + base;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) sum += li[t] * lj[t];
+                    P[(base + 8 + i) * FLDP + base + 8 + j] -= sum;
+                }
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -180,6 +325,7 @@ __global__ void __launch_bounds__(FTHREADS) k_potrf_small(FactorArgs p) {
         const int n = p.n_sys ? p.n_sys[b] : p.n_max;
         double* A = p.A + (size_t)b * p.strideA;
         int bad_total = 0;
+        long long t_phase = clock64();
         for (int k0 = 0; k0 < n; k0 += NB) {
             const int kb = min(NB, n - k0);
             const int m = n - k0;
@@ -191,31 +337,40 @@ __global__ void __launch_bounds__(FTHREADS) k_potrf_small(FactorArgs p) {
             const int nk = k0 / FBK;
             if (nk > 0) {
                 const double* gA = A + (size_t)k0 * p.lda;
+                // two k-tiles per barrier (nk is a multiple of 4): tiles kt, kt+1 are consumed while kt+2, kt+3 fly
+                auto issue2 = [&](int kt) {
 #pragma unroll
-                for (int s = 0; s < FSTAGES - 1; ++s) {
-                    if (s < nk) load_tile_async<FBK, FLDT, false>(stage0 + s * stage_elems, gA + s * FBK, p.lda, rows_t, m,
-                                                                  k0, s * FBK, k0, tid, FTHREADS);
+                    for (int u = 0; u < 2; ++u)
+                        if (kt + u < nk)
+                            load_tile_async<FBK, FLDT, false>(stage0 + ((kt + u) % FSTAGES) * stage_elems, gA + (kt + u) * FBK, p.lda,
+                                                              rows_t, m, k0, (kt + u) * FBK, k0, tid, FTHREADS);
                     cp_async_commit();
-                }
-                for (int kt = 0; kt < nk; ++kt) {
-                    cp_async_wait<FSTAGES - 2>();
+                };
+                issue2(0);
+                for (int kt = 0; kt < nk; kt += 2) {
+                    cp_async_wait<0>();
                     __syncthreads();
-                    const int nxt = kt + FSTAGES - 1;
-                    if (nxt < nk) load_tile_async<FBK, FLDT, false>(stage0 + (nxt % FSTAGES) * stage_elems, gA + nxt * FBK, p.lda,
-                                                                    rows_t, m, k0, nxt * FBK, k0, tid, FTHREADS);
-                    cp_async_commit();
-                    const double* tile = stage0 + (kt % FSTAGES) * stage_elems;
+                    issue2(kt + 2);
 #pragma unroll
-                    for (int kk = 0; kk < FBK; kk += 4) {
-                        if (warp < nch) warp_mma_k4<4, 4, false>(acc[0], tile + (warp * 32) * FLDT + kk, FLDT, tile + kk, FLDT, lane);
-                        if (warp + FWARPS < nch)
-                            warp_mma_k4<4, 4, false>(acc[1], tile + ((warp + FWARPS) * 32) * FLDT + kk, FLDT, tile + kk, FLDT, lane);
+                    for (int u = 0; u < 2; ++u) {
+                        const double* tile = stage0 + ((kt + u) % FSTAGES) * stage_elems;
+#pragma unroll
+                        for (int kk = 0; kk < FBK; kk += 4) {
+                            if (warp < nch) warp_mma_k4<4, 4, false>(acc[0], tile + (warp * 32) * FLDT + kk, FLDT, tile + kk, FLDT, lane);
+                            if (warp + FWARPS < nch)
+                                warp_mma_k4<4, 4, false>(acc[1], tile + ((warp + FWARPS) * 32) * FLDT + kk, FLDT, tile + kk, FLDT, lane);
+                        }
                     }
                 }
                 cp_async_wait<0>();
             }
             __syncthreads();   // the stage ring is dead from here on: the panel may overwrite it
-            // panel = A[k0:n, k0:k0+kb] - acc
+            PHASE_MARK(0);
+            // panel <- A[k0:n, k0:k0+kb] (coalesced 16-byte cp.async, all in flight at once), then panel -= acc
+            load_tile_async<NB, FLDP, false>(panel, A + (size_t)k0 * p.lda + k0, p.lda, m, m, k0, k0, k0 + kb, tid, FTHREADS);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const int ch = warp + c * FWARPS;
@@ -223,26 +378,28 @@ __global__ void __launch_bounds__(FTHREADS) k_potrf_small(FactorArgs p) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int r = ch * 32 + i * 8 + g;
+                        if (r < m) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int col = j * 8 + 2 * t4 + e;
-                                if (r < m && col < kb && (r >= NB || col <= r))
-                                    panel[r * FLDP + col] = A[(size_t)(k0 + r) * p.lda + k0 + col] - acc[c][i][j][e];
+                            for (int j = 0; j < 4; ++j) {
+                                double* dst = panel + r * FLDP + j * 8 + 2 * t4;
+                                dst[0] -= acc[c][i][j][0];
+                                dst[1] -= acc[c][i][j][1];
                             }
                         }
                     }
                 }
             }
             __syncthreads();
-            cta_potf2(panel, Ld, kb, tid, &sh_bad);
+            PHASE_MARK(1);
+            cta_potf2_b8(panel, Ld, scratch, kb, tid, &sh_bad);
+            PHASE_MARK(2);
             if (m > NB) cta_trtri32(Ld, Dinv, scratch, tid);
             for (int idx = tid; idx < NB * NB; idx += FTHREADS) {
                 const int r = idx >> 5, c = idx & 31;
                 if (r < kb && c <= r) panel[r * FLDP + c] = Ld[r * FLDP + c];
             }
             __syncthreads();
+            PHASE_MARK(3);
             if (sh_bad != 0 && bad_total == 0) bad_total = k0 + sh_bad;
             // panel rows below the diagonal block:  X = A21 * L_kk^{-T}   (only exists when kb == 32)
             if (m > NB) {
@@ -251,12 +408,14 @@ __global__ void __launch_bounds__(FTHREADS) k_potrf_small(FactorArgs p) {
                                            m - ch * 32, 1.0, lane);
             }
             __syncthreads();
+            PHASE_MARK(4);
             for (int idx = tid; idx < m * NB; idx += FTHREADS) {
                 const int r = idx >> 5, c = idx & 31;
                 if (c < kb && (r >= NB || c <= r)) A[(size_t)(k0 + r) * p.lda + k0 + c] = panel[r * FLDP + c];
             }
             __threadfence();   // the block column is read back through cp.async (L2) by later iterations
             __syncthreads();
+            PHASE_MARK(5);
         }
         if (tid == 0 && p.info) {
             if (!p.info_accumulate) p.info[b] = bad_total;
@@ -272,7 +431,7 @@ __global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
     const int rows_max = ((p.n_max + 31) / 32) * 32;
     const size_t stage_elems = (size_t)rows_max * FLDT + FBK * FLDB;
     double* stage0 = smem;
-    double* Dsm = smem + FSTAGES * stage_elems;
+    double* Dsm = smem + TSTAGES * stage_elems;
     double* Dinv = Dsm + 32 * FLDP;
     __shared__ double scratch[256];
 
@@ -312,7 +471,7 @@ __global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
                 zero_acc(acc[0]);
                 zero_acc(acc[1]);
                 auto issue = [&](int kt) {
-                    double* st = stage0 + (kt % FSTAGES) * stage_elems;
+                    double* st = stage0 + (kt % TSTAGES) * stage_elems;
                     load_tile_async<FBK, FLDT, true>(st, gA + kt * FBK, p.lda, rows_t, m, r_g0, r_g0 + kt * FBK, r_g0 + m,
                                                      tid, FTHREADS);
                     // B tile: rows kt*8 .. +8 of T, 32 columns -> [8][FLDB]
@@ -324,13 +483,13 @@ __global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
                     }
                 };
 #pragma unroll
-                for (int s = 0; s < FSTAGES - 1; ++s) { if (s < nk) issue(s); cp_async_commit(); }
+                for (int s = 0; s < TSTAGES - 1; ++s) { if (s < nk) issue(s); cp_async_commit(); }
                 for (int kt = 0; kt < nk; ++kt) {
-                    cp_async_wait<FSTAGES - 2>();
+                    cp_async_wait<TSTAGES - 2>();
                     __syncthreads();
-                    if (kt + FSTAGES - 1 < nk) issue(kt + FSTAGES - 1);
+                    if (kt + TSTAGES - 1 < nk) issue(kt + TSTAGES - 1);
                     cp_async_commit();
-                    const double* tile = stage0 + (kt % FSTAGES) * stage_elems;
+                    const double* tile = stage0 + (kt % TSTAGES) * stage_elems;
                     const double* bt = tile + (size_t)rows_max * FLDT;
 #pragma unroll
                     for (int kk = 0; kk < FBK; kk += 4) {
@@ -426,6 +585,12 @@ __global__ void __launch_bounds__(256) k_solve_alpha(AlphaArgs p) {
     }
 }
 
+int debug_phases(long long* out, int reset) {
+    KMPX_TRY(check_cuda(cudaMemcpyFromSymbol(out, g_phase, sizeof(long long) * 16), "cudaMemcpyFromSymbol"));
+    if (reset) { long long z[16] = {0}; KMPX_TRY(check_cuda(cudaMemcpyToSymbol(g_phase, z, sizeof(z)), "cudaMemcpyToSymbol")); }
+    return 0;
+}
+
 int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
                        int info_offset, int info_accumulate, cudaStream_t st) {
     const size_t smem = potrf_small_smem(n_max);
@@ -459,3 +624,5 @@ int launch_solve_alpha(const AlphaArgs& p, cudaStream_t st) {
 }
 
 }  // namespace kmpx
+
+extern "C" int kmpx_debug_phases(long long* out_host, int reset) { return kmpx::debug_phases(out_host, reset); }

@@ -73,6 +73,65 @@ __global__ void __launch_bounds__(256) k_kernel_build(BuildArgs p) {
     }
 }
 
+
+// Component-major fast path (what the factorisation consumes): a thread owns the point pair (i, j..j+1), evaluates
+// the kernel coefficients ONCE and writes them into every (a, b) block - n^2/O^2 exp instead of n^2/O, no integer
+// division.  Each store is 16 bytes; for fixed (i, a, b) a warp writes 512 contiguous bytes.
+template <bool TD>
+__global__ void __launch_bounds__(256) k_kernel_build_comp(BuildArgs p) {
+    const int bidx = blockIdx.z;
+    const int N = p.n_pts ? p.n_pts[bidx] : p.n_max;
+    const int Ns = comp_stride(N);
+    const int O = p.O, P = TD ? (O >> 1) : O;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j0 = blockIdx.x * kBuildCols + lane * 2;
+    const int ibase = blockIdx.y * kBuildRows;
+    if (ibase >= Ns || blockIdx.x * kBuildCols >= Ns) return;
+    const bool lower = p.uplo == KMPX_UPLO_LOWER;
+    if (lower && O == 1 && blockIdx.x * kBuildCols > ibase + kBuildRows - 1) return;
+    const double* s = p.s + (size_t)bidx * p.n_max * p.I;
+    const double* sig = p.sigma + (size_t)bidx * p.n_max * O * O;
+    double* A = p.A + (size_t)bidx * p.strideA;
+    if (j0 >= Ns) return;
+#pragma unroll 1
+    for (int ii = warp; ii < kBuildRows; ii += 8) {
+        const int i = ibase + ii;
+        if (i >= Ns) break;
+        double co[2][4];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            co[e][0] = co[e][1] = co[e][2] = co[e][3] = 0.0;
+            // plain kernel + lower-only: coefficients are only used in the diagonal (a == b) blocks, i.e. for j <= i
+            if (i < N && j0 + e < N && (TD || !lower || j0 + e <= i)) kernel_coeffs(s + (size_t)i * p.I, s + (size_t)(j0 + e) * p.I, p.I, p.sigma_f, TD, co[e]);
+        }
+        const bool diag0 = (i == j0), diag1 = (i == j0 + 1);
+        for (int a = 0; a < O; ++a) {
+            double* row = A + (size_t)(a * Ns + i) * p.lda;
+            for (int b = 0; b < O; ++b) {
+                if (lower && b > a) continue;
+                double v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const bool dg = e ? diag1 : diag0;
+                    double x;
+                    if (i >= N || j0 + e >= N) x = (a == b && dg) ? 1.0 : 0.0;           // identity padding
+                    else {
+                        x = TD ? (((a % P) == (b % P)) ? co[e][(a / P) * 2 + (b / P)] : 0.0) : ((a == b) ? co[e][0] : 0.0);
+                        if (dg) x += p.lambda * sig[((size_t)i * O + a) * O + b];
+                    }
+                    v[e] = x;
+                }
+                double* dst = row + b * Ns + j0;
+                if (lower && a == b) {
+                    if (j0 > i) continue;
+                    if (j0 + 1 > i) { dst[0] = v[0]; continue; }
+                }
+                *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // set_waypoint database update: one thread per problem (the search is over <= a few hundred points and
 // the via-point count is tiny); a warp-wide copy of the base trajectory precedes it.
@@ -162,6 +221,15 @@ extern "C" int kmpx_kernel_build(const double* s, const double* sigma, const int
     if (batch > 1 && strideA < (long long)lda * n) return fail_arg(10, "strideA too small");
     if (layout != KMPX_LAYOUT_POINT && layout != KMPX_LAYOUT_COMPONENT) return fail_arg(14, "unknown layout");
     BuildArgs p{s, sigma, n_pts, A, n_max, I, O, lda, strideA, sigma_f, lambda, time_driven, layout, uplo};
+    const bool vec_ok = ((lda & 1) == 0) && ((strideA & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    if (layout == KMPX_LAYOUT_COMPONENT && vec_ok) {
+        const int Ns = comp_stride(n_max);
+        dim3 grid(ceil_div(Ns, kBuildCols), ceil_div(Ns, kBuildRows), batch);
+        if (grid.y > 65535) return fail_arg(6, "n_max too large for one launch");
+        if (time_driven) k_kernel_build_comp<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        else k_kernel_build_comp<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        return check_launch("k_kernel_build_comp");
+    }
     dim3 grid(ceil_div(n, kBuildCols), ceil_div(n, kBuildRows), batch);
     if (grid.y > 65535) return fail_arg(6, "n_max*O too large for one launch");
     k_kernel_build<<<grid, 256, 0, (cudaStream_t)stream>>>(p);

@@ -5,7 +5,7 @@
 //   * a CTA owns 64 queries of one problem; kappa[m][j] (64 x N) is evaluated once and stays in shared memory;
 //   * each of the 8 warps owns a static list of 16-row chunks of Linv (the triangular costs grow with the row
 //     index, so the chunks are dealt from the bottom up in boustrophedon order) and streams them through a
-//     PRIVATE 3-stage cp.async ring - only __syncwarp inside the main loop;
+//     PRIVATE 2-stage cp.async ring (32 columns per stage) - only __syncwarp inside the main loop;
 //   * warp tile = 16 rows x 64 queries x both outputs: 16 independent DMMA.8x8x4 per k-step of 4 and output,
 //     10 LDS.64 per 16 DMMA;
 //   * the V tile is reduced straight from the accumulator registers (products, 3 xor-shuffles over the 8 row
@@ -19,9 +19,9 @@ namespace kmpx {
 
 constexpr int QT = 64;          // queries per CTA
 constexpr int RC = 16;          // rows of Linv per chunk
-constexpr int QK = 16;          // k per stage
-constexpr int QLD = 20;         // ring tile leading dimension (4 mod 16)
-constexpr int QST = 3;          // ring stages per warp
+constexpr int QK = 32;          // k per stage: 8 k-steps of 4 = 128 DMMA per warp between two ring hand-overs
+constexpr int QLD = 36;         // ring tile leading dimension (4 mod 16)
+constexpr int QST = 2;          // ring stages per warp (one tile in flight while one is consumed)
 constexpr int QWARPS = 8;
 constexpr int QTHREADS = QWARPS * 32;
 constexpr int QMAXCH = 80;      // chunks per problem: n_sys <= 1280
@@ -103,8 +103,19 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
     auto issue = [&](const Cursor& c, int slot) {
         const int cg0 = c.col0 + c.kb * QK;
         int rows_valid = n - c.r0; rows_valid = rows_valid > RC ? RC : rows_valid;
-        load_tile_async<QK, QLD, true>(ring + slot * RC * QLD, F + (size_t)c.r0 * p.lda + cg0, p.lda, RC, rows_valid,
-                                       c.r0, cg0, c.col0 + c.jmax, lane, 32);
+        double* dst = ring + slot * RC * QLD;
+        const double* src = F + (size_t)c.r0 * p.lda + cg0;
+        if (rows_valid == RC && cg0 + QK <= c.col0 + c.jmax && cg0 + QK <= c.r0 + 1) {
+            // interior tile (entirely below the diagonal, inside the block): 8 unconditional 16-byte copies per lane
+            const int q = lane & 15, rb = lane >> 4;
+#pragma unroll
+            for (int i = 0; i < RC / 2; ++i) {
+                const int r = rb + 2 * i;
+                cp_async16(dst + r * QLD + 2 * q, src + (size_t)r * p.lda + 2 * q, 16);
+            }
+        } else {
+            load_tile_async<QK, QLD, true>(dst, src, p.lda, RC, rows_valid, c.r0, cg0, c.col0 + c.jmax, lane, 32);
+        }
     };
 
     Cursor prod{0, 0, 0, 0, 0, 0, 0, false}, cons{0, 0, 0, 0, 0, 0, 0, false};
@@ -137,12 +148,23 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
         cp_async_commit();
         const double* tile = ring + (consumed % QST) * RC * QLD;
         const double* Bs = panel + cons.kb * QK;
-        if (O == 1 || cons.a == 0) {
+        const int kvalid = cons.jmax - cons.kb * QK;      // columns of this k-block that carry data
+        if (kvalid >= QK) {
+            if (O == 1 || cons.a == 0) {
 #pragma unroll
-            for (int kk = 0; kk < QK; kk += 4) warp_mma_k4<2, 8, false>(acc0, tile + kk, QLD, Bs + kk, ldp, lane);
-        } else {
+                for (int kk = 0; kk < QK; kk += 4) warp_mma_k4<2, 8, false>(acc0, tile + kk, QLD, Bs + kk, ldp, lane);
+            } else {
 #pragma unroll
-            for (int kk = 0; kk < QK; kk += 4) warp_mma_k4<2, 8, false>(acc1, tile + kk, QLD, Bs + kk, ldp, lane);
+                for (int kk = 0; kk < QK; kk += 4) warp_mma_k4<2, 8, false>(acc1, tile + kk, QLD, Bs + kk, ldp, lane);
+            }
+        } else {                                          // last k-block of a segment: skip the zero-filled tail
+            if (O == 1 || cons.a == 0) {
+#pragma unroll 1
+                for (int kk = 0; kk < kvalid; kk += 4) warp_mma_k4<2, 8, false>(acc0, tile + kk, QLD, Bs + kk, ldp, lane);
+            } else {
+#pragma unroll 1
+                for (int kk = 0; kk < kvalid; kk += 4) warp_mma_k4<2, 8, false>(acc1, tile + kk, QLD, Bs + kk, ldp, lane);
+            }
         }
         ++consumed;
         const int cur_ci = cons.ci, cur_r0 = cons.r0;
@@ -210,13 +232,13 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
 
 bool predict_fast_applicable(const PredictArgs& p) {
     if (p.time_driven || p.general || p.O > 2) return false;
-    const int ldp = (int)round_up(p.n_max, 16) + 4;
+    const int ldp = (int)round_up(p.n_max, QK) + 4;
     if ((long long)p.O * comp_stride(p.n_max) > (long long)QMAXCH * RC) return false;
     return fast_smem_bytes(p.O, p.I, p.n_max, ldp) <= 226 * 1024;
 }
 
 int launch_predict_fast(PredictArgs& p, cudaStream_t st) {
-    p.ldp = (int)round_up(p.n_max, 16) + 4;
+    p.ldp = (int)round_up(p.n_max, QK) + 4;      // 4 (mod 16) and long enough for the last k-block of a row
     p.resident = 1;
     const size_t smem = fast_smem_bytes(p.O, p.I, p.n_max, p.ldp);
     dim3 grid(ceil_div(p.M, QT), p.batch);
