@@ -35,6 +35,8 @@ struct PredictArgs {
 };
 bool predict_fast_applicable(const PredictArgs& p);
 int launch_predict_fast(PredictArgs& p, cudaStream_t st);
+bool predict_stream_applicable(const PredictArgs& p);
+int launch_predict_stream(PredictArgs& p, cudaStream_t st);
 
 int launch_dgemm(int transA, int transB, const GemmArgs& p, int batch, cudaStream_t st);
 int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
