@@ -178,46 +178,11 @@ def measure_dgemm_peak(torch, n=8192, seconds=1.5):
 
 
 def extras_single_gpu(torch, dgemm_tflops):
-    """Second headline of BASELINE.json (fp64 Cholesky TFLOP/s at N*O = 16384) and the HBM-bound kernel build,
-    on the cfg-4 system, timed with CUDA events (best of 3 after a warm-up)."""
-    from kmp_demos_b200 import _lib
-    lib = _lib.load()
-    N, O = 8192, 2
-    t, mu, sig = wl.cfg4_problem(N=N, seed=0)
-    n = int(lib.kmpx_sys_size(N, O, _lib.LAYOUT_COMPONENT))
-    lda = n
-    dev = torch.device('cuda')
-    s_d = torch.as_tensor(np.ascontiguousarray(t.T), device=dev)
-    g_d = torch.as_tensor(np.ascontiguousarray(np.transpose(sig, (2, 0, 1))), device=dev)
-    A = torch.empty((n, lda), dtype=torch.float64, device=dev)
-    nbytes = int(lib.kmpx_potrf_workspace_bytes(n, 1))
-    ws = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
-    info = torch.zeros(1, dtype=torch.int32, device=dev)
-    st = _lib.stream()
-    c = wl.CFG1
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    best_build, best_potrf = 1e30, 1e30
-    for rep in range(4):
-        e0, e1, e2 = ev(), ev(), ev()
-        e0.record()
-        _lib.call('kmpx_kernel_build', _lib.ptr(s_d), _lib.ptr(g_d), None, _lib.ptr(A), 1, N, 1, O, lda, n * lda,
-                  c['sigma_f'], c['lam'], 0, _lib.LAYOUT_COMPONENT, _lib.UPLO_FULL, st)
-        e1.record()
-        _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
-        e2.record(); e2.synchronize()
-        if rep > 0:
-            best_build = min(best_build, e0.elapsed_time(e1))
-            best_potrf = min(best_potrf, e1.elapsed_time(e2))
-    assert int(info.item()) == 0
-    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.isfile(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
-    hbm = peaks.get('hbm_gbs', 6650.0)
-    potrf_tf = n ** 3 / 3.0 / best_potrf * 1e-9
-    build_gbs = 8.0 * n * n / best_build * 1e-6
-    return {
-        'potrf_n16384': {'ms': best_potrf, 'tflops': potrf_tf, 'frac_of_dgemm': potrf_tf / dgemm_tflops},
-        'kernel_build_n16384': {'ms': best_build, 'gbs': build_gbs, 'frac_of_hbm': build_gbs / hbm,
-                                'hbm_peak_gbs': hbm, 'hbm_peak_source': 'measured' if peaks else 'fallback'},
-    }
+    """The other measured rows of SURVEY.md 8(d) on one GPU (kmp_demos_b200/perf.py): second headline of BASELINE.json
+    (fp64 Cholesky TFLOP/s at N*O = 16384), cfg-4 kernel build / triangular inverse / 100k-query predict rate,
+    fused EM pass at 10 M x 7, K = 64, GMR and quaternion maps on 2^26 elements."""
+    from kmp_demos_b200 import perf
+    return perf.run_all(quick=False, only=('dgemm', 'cfg4', 'em', 'gmr', 'quat'), dgemm_tflops=dgemm_tflops)
 
 
 def run_ours(args):
@@ -354,7 +319,7 @@ def run_ours(args):
         if world == 1:
             line['cpu_baseline'] = cpu_line
             if not args.no_extras:
-                log('extras: cfg-4 kernel build + Cholesky at n=16384')
+                log('extras: per-kernel figures (cfg 4, EM, GMR, quaternion maps)')
                 line['extras'] = extras_single_gpu(torch, dgemm_tf)
         print(json.dumps(line))
     if world > 1:

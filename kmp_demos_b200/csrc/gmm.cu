@@ -4,7 +4,7 @@
 //
 // One pass over the samples produces the sufficient statistics {sum r, sum r x', sum r x' x'^T} per
 // component and sum log p(x); responsibilities are never written to HBM.
-//   E-step : one (sample, half of the components) per thread; parameters broadcast from shared memory;
+//   E-step : one (sample, quarter of the components) per thread; parameters broadcast from shared memory;
 //            y = (x - mu_k) P_k with P_k upper-triangular, log-sum-exp over the components.
 //   M-step : stats[k][f] += sum_s R[s][k] * Phi[s][f] with Phi = [1, x', vech(x' x'^T)]  -- a
 //            (K x TS) x (TS x F) contraction per tile on DMMA, accumulators persistent in registers.
@@ -15,7 +15,8 @@
 
 namespace kmpx {
 
-constexpr int ETS = 128;          // samples per tile
+constexpr int ETS = 64;           // samples per tile
+constexpr int EPARTS = 4;         // threads per sample in the E-step: each owns a quarter of the components
 constexpr int ETHREADS = 256;
 constexpr double kLog2Pi = 1.8378770664093454835606594728112;
 
@@ -32,7 +33,7 @@ struct EmArgs {
 };
 
 template <int D, int KB>   // KB = 8-component blocks per warp (K_pad <= 64*KB)
-__global__ void __launch_bounds__(ETHREADS) k_gmm_em(EmArgs p) {
+__global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
     constexpr int F = 1 + D + D * (D + 1) / 2;
     constexpr int FP = (F + 7) & ~7;
     constexpr int NF = FP / 8;
@@ -47,8 +48,8 @@ __global__ void __launch_bounds__(ETHREADS) k_gmm_em(EmArgs p) {
     double* s_x = s_shift + D;                    // [ETS][D]
     double* s_R = s_x + (size_t)ETS * D;          // [ETS][ldr]
     double* s_Phi = s_R + (size_t)ETS * ldr;      // [ETS][ldf]
-    double* s_red = s_Phi + (size_t)ETS * ldf;    // [2][ETS] max / sum exchange
-    int* s_arg = reinterpret_cast<int*>(s_red + 2 * ETS);   // [2][ETS]
+    double* s_red = s_Phi + (size_t)ETS * ldf;    // [EPARTS][ETS] max / sum exchange
+    int* s_arg = reinterpret_cast<int*>(s_red + EPARTS * ETS);   // [EPARTS][ETS]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
@@ -73,9 +74,9 @@ __global__ void __launch_bounds__(ETHREADS) k_gmm_em(EmArgs p) {
         for (int j = 0; j < NF; ++j) { acc[q][j][0] = 0.0; acc[q][j][1] = 0.0; }
     double ll_acc = 0.0;
 
-    const int s_loc = tid & (ETS - 1), half = tid >> 7;       // sample in tile, component half
-    const int kh = (K + 1) >> 1;
-    const int kbeg = half ? kh : 0, kend = half ? K : kh;
+    const int s_loc = tid % ETS, half = tid / ETS;            // sample in tile, component quarter ("half" for short)
+    const int kper = (K + EPARTS - 1) / EPARTS;
+    const int kbeg = min(K, half * kper), kend = min(K, kbeg + kper);
     const long long ntiles = (p.n + ETS - 1) / ETS;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long base = tile * ETS;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(ETHREADS) k_gmm_em(EmArgs p) {
         if (hard) {
             const int lab = live ? p.hard_labels[base + s_loc] : -1;
             for (int k = kbeg; k < kend; ++k) Rrow[k] = (k == lab) ? 1.0 : 0.0;
-            if (half) for (int k = K; k < KP; ++k) Rrow[k] = 0.0;
+            if (half == EPARTS - 1) for (int k = K; k < KP; ++k) Rrow[k] = 0.0;
         } else {
             double mx = -INFINITY; int am = kbeg;
             for (int k = kbeg; k < kend; ++k) {
@@ -129,18 +130,24 @@ __global__ void __launch_bounds__(ETHREADS) k_gmm_em(EmArgs p) {
             }
             s_red[half * ETS + s_loc] = mx; s_arg[half * ETS + s_loc] = am;
             __syncthreads();
-            const double m0 = s_red[s_loc], m1 = s_red[ETS + s_loc];
-            const double m = m0 > m1 ? m0 : m1;                  // (K >= 2: both halves are non-empty)
-            const int amax = (m1 > m0) ? s_arg[ETS + s_loc] : s_arg[s_loc];   // first maximum wins
+            double m = s_red[s_loc];
+            int amax = s_arg[s_loc];
+#pragma unroll
+            for (int q = 1; q < EPARTS; ++q) {                   // first maximum wins (parts are in component order)
+                const double mq = s_red[q * ETS + s_loc];
+                if (mq > m) { m = mq; amax = s_arg[q * ETS + s_loc]; }
+            }
             __syncthreads();
             double se = 0.0;
             for (int k = kbeg; k < kend; ++k) { const double e = exp(Rrow[k] - m); Rrow[k] = e; se += e; }
             s_red[half * ETS + s_loc] = se;
             __syncthreads();
-            const double tot = s_red[s_loc] + s_red[ETS + s_loc];
+            double tot = 0.0;
+#pragma unroll
+            for (int q = 0; q < EPARTS; ++q) tot += s_red[q * ETS + s_loc];
             const double inv = live ? 1.0 / tot : 0.0;
             for (int k = kbeg; k < kend; ++k) Rrow[k] *= inv;
-            if (half) for (int k = K; k < KP; ++k) Rrow[k] = 0.0;
+            if (half == EPARTS - 1) for (int k = K; k < KP; ++k) Rrow[k] = 0.0;
             if (half == 0 && live) {
                 const double l = m + log(tot);
                 ll_acc += l;
@@ -179,8 +186,6 @@ __global__ void __launch_bounds__(ETHREADS) k_gmm_em(EmArgs p) {
             }
         }
     }
-    __syncthreads();
-    s_red[tid & 255] = 0.0;
     __syncthreads();
     if (half == 0) s_red[s_loc] = ll_acc;
     __syncthreads();
@@ -268,13 +273,13 @@ __global__ void k_gmm_finalize(FinArgs p) {
 
 static int em_grid(long long n) {
     const long long tiles = (n + ETS - 1) / ETS;
-    const long long g = tiles < kNumSMs ? tiles : kNumSMs;
+    const long long g = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;      // two CTAs per SM
     return (int)(g < 1 ? 1 : g);
 }
 static size_t em_smem(int d, int K) {
     const int F = gmm_F(d), FP = pad8(F), KP = pad8(K), TRI = d * (d + 1) / 2;
     size_t dbl = (size_t)K * d + (size_t)K * TRI + K + d + (size_t)ETS * d + (size_t)ETS * ld_conflict_free(KP) +
-                 (size_t)ETS * ld_conflict_free(FP) + 2 * ETS + 2 * ETS;
+                 (size_t)ETS * ld_conflict_free(FP) + 2 * EPARTS * ETS;
     return dbl * sizeof(double);
 }
 
@@ -327,7 +332,7 @@ using namespace kmpx;
 extern "C" long long kmpx_gmm_workspace_bytes(int n, int d, int K) {
     (void)n;
     const int F = gmm_F(d), FP = pad8(F), KP = pad8(K);
-    return (long long)kNumSMs * ((long long)KP * FP + 1) * (long long)sizeof(double);
+    return 2LL * kNumSMs * ((long long)KP * FP + 1) * (long long)sizeof(double);
 }
 
 extern "C" int kmpx_gmm_em_pass(const double* X, long long n, int d, int K, const double* shift,

@@ -1,8 +1,10 @@
 """Per-kernel throughput on the B200: DGEMM, large Cholesky / triangular inverse, kernel build,
 fused EM pass, GMR, quaternion maps, cfg-4 predict.  CUDA-event timing, best of `reps` after a warm-up.
-Prints one JSON object; `bench.py` reports the cfg-3 headline, this script the rest.
+`bench.py` reports the cfg-3 headline and embeds these figures under "extras";
 
-    python tools/perf_kernels.py [--quick] [--only dgemm,potrf,...]"""
+    python -m kmp_demos_b200.perf [--quick] [--only dgemm,cfg4,em,gmr,quat]
+
+prints them as one JSON object."""
 import argparse
 import json
 import os
@@ -12,8 +14,7 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-from kmp_demos_b200 import _lib, workloads as wl  # noqa: E402
+from . import _lib, workloads as wl
 
 f64 = torch.float64
 
@@ -136,30 +137,35 @@ def quat(M):
             'log_frac_hbm': 56.0 * M / ms_l * 1e-6 / peaks()}
 
 
+def run_all(quick=False, only=None, dgemm_tflops=None):
+    """All per-kernel figures as a dict (`only`: iterable of section names)."""
+    only = set(only) if only else None
+    want = lambda k: only is None or k in only  # noqa: E731
+    _lib.load()
+    out = {'gpu': torch.cuda.get_device_name(0), 'hbm_peak_gbs': peaks()}
+    dg = dgemm_tflops or dgemm_cublas(4096 if quick else 8192)
+    out['dgemm_cublas_tflops'] = dg
+    if want('dgemm'):
+        for name, (ta, tb, tri) in {'NT': (0, 1, 0), 'NN': (0, 0, 0), 'NT_lower': (0, 1, 1)}.items():
+            tf, ms = dgemm_ours(4096 if quick else 8192, ta, tb, tri)
+            out[f'dgemm_ours_{name}'] = {'tflops': tf, 'ms': ms, 'frac_cublas': tf / dg}
+    if want('cfg4'):
+        out['cfg4'] = cfg4(2048 if quick else 8192, dg)
+    if want('em'):
+        out['em'] = em(1_000_000 if quick else 10_000_000)
+    if want('gmr'):
+        out['gmr'] = gmr(1 << (22 if quick else 26))
+    if want('quat'):
+        out['quat'] = quat(1 << (22 if quick else 26))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--quick', action='store_true')
     ap.add_argument('--only', default='')
     a = ap.parse_args()
-    only = set(a.only.split(',')) if a.only else None
-    want = lambda k: only is None or k in only  # noqa: E731
-    _lib.load()
-    out = {'gpu': torch.cuda.get_device_name(0), 'hbm_peak_gbs': peaks()}
-    dg = dgemm_cublas(4096 if a.quick else 8192)
-    out['dgemm_cublas_tflops'] = dg
-    if want('dgemm'):
-        for name, (ta, tb, tri) in {'NT': (0, 1, 0), 'NN': (0, 0, 0), 'NT_lower': (0, 1, 1)}.items():
-            tf, ms = dgemm_ours(4096 if a.quick else 8192, ta, tb, tri)
-            out[f'dgemm_ours_{name}'] = {'tflops': tf, 'ms': ms, 'frac_cublas': tf / dg}
-    if want('cfg4'):
-        out['cfg4'] = cfg4(2048 if a.quick else 8192, dg)
-    if want('em'):
-        out['em'] = em(1_000_000 if a.quick else 10_000_000)
-    if want('gmr'):
-        out['gmr'] = gmr(1 << (22 if a.quick else 26))
-    if want('quat'):
-        out['quat'] = quat(1 << (22 if a.quick else 26))
-    print(json.dumps(out))
+    print(json.dumps(run_all(a.quick, a.only.split(',') if a.only else None)))
 
 
 if __name__ == '__main__':
