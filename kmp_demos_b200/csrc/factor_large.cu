@@ -102,32 +102,55 @@ static int potrf_large(double* A, int lda, int n, int* info, double* ws, cudaStr
     return 0;
 }
 
+// In-place inverse of the lower factor by recursive doubling over 256-blocks:
+//   [[A, 0], [B, C]]^{-1} = [[A^{-1}, 0], [-C^{-1} B A^{-1}, C^{-1}]]
+// level 0 inverts all diagonal 256-blocks in ONE batched launch of k_trtri_small; level S (S = 1, 2, 4, ... blocks)
+// merges neighbouring inverted spans with two GEMMs per pair, T = B * A^{-1} and B <- -C^{-1} * T, and all pairs of a
+// level run as one strided batch.  Every flop beyond level 0 is a large DMMA GEMM with thousands of CTAs (the
+// block-column sweep it replaces had only (n - k)/128 x 2 CTAs per step).  Workspace: (n/2)^2 doubles for T.
+static long long trtri_ws_doubles(int n) {
+    const long long half = round_up((long long)(n + 1) / 2, LNB);
+    return half * half + 2LL * LNB * LNB;
+}
+
 static int trtri_large(double* L, int lda, int n, double* ws, cudaStream_t st) {
-    double* Dinv = ws;
-    double* T = ws + 2 * (size_t)LNB * LNB;
+    double* T = ws;
     {
         dim3 blk(64, 4), grid(ceil_div(n, 64), ceil_div(n, 4));
         k_zero_upper<<<grid, blk, 0, st>>>(L, lda, n);
         KMPX_TRY(check_launch("k_zero_upper"));
     }
     const int nblk = (n + LNB - 1) / LNB;
-    for (int j = nblk - 1; j >= 0; --j) {
-        const int k0 = j * LNB;
-        const int nb = n - k0 < LNB ? n - k0 : LNB;
-        const int m = n - k0 - nb;
-        double* D = L + (size_t)k0 * lda + k0;
-        k_copy_lower<<<dim3(ceil_div(nb, 128), nb), 128, 0, st>>>(D, lda, Dinv, LNB, nb);
-        KMPX_TRY(check_launch("k_copy_lower"));
-        KMPX_TRY(launch_trtri_small(Dinv, LNB, 0, nullptr, nb, 1, st));
-        if (m > 0) {
-            double* L21 = L + (size_t)(k0 + nb) * lda + k0;
-            double* L22 = L + (size_t)(k0 + nb) * lda + k0 + nb;
-            GemmArgs g1{m, nb, nb, 1.0, L21, lda, 0, Dinv, LNB, 0, 0.0, T, LNB, 0, 0};
-            KMPX_TRY(launch_dgemm(0, 0, g1, 1, st));                           // T = L21 * Dinv
-            GemmArgs g2{m, nb, m, -1.0, L22, lda, 0, T, LNB, 0, 0.0, L21, lda, 0, 2};
-            KMPX_TRY(launch_dgemm(0, 0, g2, 1, st));                           // L21 <- -Linv22 * T
+    const long long dstride = (long long)LNB * lda + LNB;                // from one diagonal block to the next
+    const int nfull = n / LNB;
+    if (nfull > 0) KMPX_TRY(launch_trtri_small(L, lda, dstride, nullptr, LNB, nfull, st));
+    if (nblk > nfull) KMPX_TRY(launch_trtri_small(L + (size_t)nfull * dstride, lda, 0, nullptr, n - nfull * LNB, 1, st));
+    for (int S = 1; S < nblk; S *= 2) {
+        const int span = S * LNB;                                        // rows/cols of an inverted span
+        // groups [g, g + 2S): A = [g, g+S), C = [g+S, min(g+2S, nblk)); full groups have identical shapes
+        int nfullgrp = 0;
+        while ((long long)(nfullgrp + 1) * 2 * span <= n) ++nfullgrp;
+        const long long gstride = 2LL * span * lda + 2LL * span;
+        if (nfullgrp > 0) {
+            double* B0 = L + (size_t)span * lda;                         // B of group 0: rows [span, 2 span), cols [0, span)
+            double* A0 = L;
+            double* C0 = L + (size_t)span * lda + span;
+            GemmArgs g1{span, span, span, 1.0, B0, lda, gstride, A0, lda, gstride, 0.0, T, span, (long long)span * span, 3};
+            KMPX_TRY(launch_dgemm(0, 0, g1, nfullgrp, st));              // T = B * Ainv   (Ainv lower: k >= col)
+            GemmArgs g2{span, span, span, -1.0, C0, lda, gstride, T, span, (long long)span * span, 0.0, B0, lda, gstride, 2};
+            KMPX_TRY(launch_dgemm(0, 0, g2, nfullgrp, st));              // B <- -Cinv * T (Cinv lower: k <= row)
         }
-        KMPX_TRY(copy_block(Dinv, LNB, D, lda, nb, nb, st));
+        const long long g0 = (long long)nfullgrp * 2 * span;             // first row of the partial group, if any
+        const int mc = n - (int)g0 - span;                               // rows of its C part
+        if (mc > 0) {
+            double* A1 = L + (size_t)g0 * lda + g0;
+            double* B1 = L + (size_t)(g0 + span) * lda + g0;
+            double* C1 = L + (size_t)(g0 + span) * lda + g0 + span;
+            GemmArgs g1{mc, span, span, 1.0, B1, lda, 0, A1, lda, 0, 0.0, T, span, 0, 3};
+            KMPX_TRY(launch_dgemm(0, 0, g1, 1, st));
+            GemmArgs g2{mc, span, mc, -1.0, C1, lda, 0, T, span, 0, 0.0, B1, lda, 0, 2};
+            KMPX_TRY(launch_dgemm(0, 0, g2, 1, st));
+        }
     }
     return 0;
 }
@@ -189,7 +212,10 @@ extern "C" long long kmpx_potrf_workspace_bytes(int n_max, int batch) {
     (void)batch;
     return n_max <= KMPX_SMALL_MAX ? 0 : large_ws_doubles(n_max) * (long long)sizeof(double);
 }
-extern "C" long long kmpx_trtri_workspace_bytes(int n_max, int batch) { return kmpx_potrf_workspace_bytes(n_max, batch); }
+extern "C" long long kmpx_trtri_workspace_bytes(int n_max, int batch) {
+    (void)batch;
+    return n_max <= KMPX_SMALL_MAX ? 0 : trtri_ws_doubles(n_max) * (long long)sizeof(double);
+}
 
 static int check_factor_args(double* A, int lda, long long strideA, int n_max, int batch) {
     if (!A) return fail_arg(1, "matrix is NULL");

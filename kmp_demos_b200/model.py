@@ -70,7 +70,7 @@ def factorise(s, xi, sigma, lam, sigma_f, time_driven, layout=_lib.LAYOUT_COMPON
     w = torch.zeros(lda, dtype=torch.float64, device=dev)
     alpha = torch.empty((N, O), dtype=torch.float64, device=dev)
     if not general:
-        nbytes = int(lib.kmpx_potrf_workspace_bytes(n, 1))
+        nbytes = max(int(lib.kmpx_potrf_workspace_bytes(n, 1)), int(lib.kmpx_trtri_workspace_bytes(n, 1)))
         ws = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=dev)
         _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
         if int(info.item()) != 0:
@@ -262,7 +262,7 @@ def explicit_inverse(s, sigma, lam, sigma_f, time_driven):
     scale = float(np.max(np.abs(g_host)))
     asym = float(np.max(np.abs(g_host - np.transpose(g_host, (0, 2, 1)))))
     if asym <= 1e-12 * scale:
-        nbytes = int(lib.kmpx_potrf_workspace_bytes(n, 1))
+        nbytes = max(int(lib.kmpx_potrf_workspace_bytes(n, 1)), int(lib.kmpx_trtri_workspace_bytes(n, 1)))
         ws = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=dev)
         A0 = A.clone()
         _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)

@@ -59,7 +59,7 @@ def cfg4(N, dg):
     g_d = torch.as_tensor(np.ascontiguousarray(np.transpose(sig, (2, 0, 1))), device='cuda')
     y_d = torch.as_tensor(np.ascontiguousarray(mu.T), device='cuda')
     A = torch.empty((n, lda), dtype=f64, device='cuda')
-    nbytes = int(lib.kmpx_potrf_workspace_bytes(n, 1)); ws = torch.empty(max(nbytes, 8) // 8, dtype=f64, device='cuda')
+    nbytes = max(int(lib.kmpx_potrf_workspace_bytes(n, 1)), int(lib.kmpx_trtri_workspace_bytes(n, 1))); ws = torch.empty(max(nbytes, 8) // 8, dtype=f64, device='cuda')
     info = torch.zeros(1, dtype=torch.int32, device='cuda'); st = _lib.stream(); c = wl.CFG1
     build = lambda uplo: _lib.call('kmpx_kernel_build', _lib.ptr(s_d), _lib.ptr(g_d), None, _lib.ptr(A), 1, N, 1, O, lda, n * lda,  # noqa: E731
                                    c['sigma_f'], c['lam'], 0, _lib.LAYOUT_COMPONENT, uplo, st)

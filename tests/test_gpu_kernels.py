@@ -173,7 +173,7 @@ def test_potrf_trtri_large_blocked(T, n):
     lda = (n + 7) // 8 * 8
     A = T.zeros((n, lda), dtype=T.float64, device='cuda')
     A[:, :n] = dev(T, S)
-    nbytes = int(lib.kmpx_potrf_workspace_bytes(n, 1))
+    nbytes = max(int(lib.kmpx_potrf_workspace_bytes(n, 1)), int(lib.kmpx_trtri_workspace_bytes(n, 1)))
     ws = T.empty(nbytes // 8, dtype=T.float64, device='cuda')
     info = T.full((1,), -1, dtype=T.int32, device='cuda')
     _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, _lib.stream())
