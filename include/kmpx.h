@@ -48,6 +48,8 @@ const char* kmpx_last_error(void);
 long long kmpx_launch_count(void);
 /* Profiling aid: cycle counters per phase of k_potrf_small / k_trtri_small accumulated by CTA 0 (16 host int64). */
 int kmpx_debug_phases(long long* out_host, int reset);
+/* Profiling experiments on the small-system K-loops: bit 0 skips the MMAs, bit 1 the cp.async loads (results are then wrong). */
+int kmpx_debug_set(int flags);
 
 /* ---- K1: kernel-matrix builder.  Replaces the N^2 Python loop of KMP.fit, KMP.py:146-156, with
  *      KMP.__kernel_matrix (KMP.py:93-128) evaluated in-kernel (plain RBF block or the finite-difference

@@ -113,8 +113,9 @@ class KMPBatch:
                       strideA, self.sigma_f, self.l, td, _lib.LAYOUT_COMPONENT, _lib.UPLO_LOWER, st)
             self._launch('kmpx_potrf', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, _lib.ptr(info[c0:]), None, 0, st)
             self._launch('kmpx_trtri', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, None, 0, st)
+            # alpha = A^-1 mu is only needed by the mean-only predict; the fused mean+covariance kernel takes w
             self._launch('kmpx_solve_alpha', _lib.ptr(A), lda, strideA, _lib.ptr(npc), n_max_pts, O, bc,
-                      _lib.LAYOUT_COMPONENT, _lib.ptr(y), _lib.ptr(w), lda, _lib.ptr(al), st)
+                      _lib.LAYOUT_COMPONENT, _lib.ptr(y), _lib.ptr(w), lda, None if want_cov else _lib.ptr(al), st)
             if want_cov:
                 self._launch('kmpx_kmp_predict', _lib.ptr(A), lda, strideA, 0, _lib.ptr(w), lda, _lib.ptr(s), _lib.ptr(npc),
                           n_max_pts, I, O, bc, _lib.ptr(queries), 0, M, self.sigma_f, self.alpha, td,

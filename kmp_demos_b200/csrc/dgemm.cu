@@ -14,7 +14,7 @@
 
 namespace kmpx {
 
-constexpr int GBM = 128, GBN = 128, GBK = 16, GSTAGES = 3, GTHREADS = 256;
+constexpr int GBM = 128, GBN = 128, GBK = 32, GSTAGES = 3, GTHREADS = 256;
 constexpr int GLDK = GBK + 4;      // [rows][k] tiles
 constexpr int GLDM = GBM + 4;      // [k][rows] tiles
 constexpr int GTILE = (GBM * GLDK > GBK * GLDM) ? GBM * GLDK : GBK * GLDM;   // doubles per operand tile

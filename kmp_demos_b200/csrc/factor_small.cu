@@ -28,6 +28,7 @@ constexpr int FWARPS = FTHREADS / 32;
 
 // Cycle counters per phase, accumulated by thread 0 of CTA 0 (read with kmpx_debug_phases; profiling aid only).
 __device__ long long g_phase[16];
+__device__ int g_dbg;   // profiling experiments: bit 0 = skip the MMAs of the K-loops, bit 1 = skip their cp.async loads
 #define PHASE_MARK(slot) do { if (blockIdx.x == 0 && tid == 0) { const long long _t = clock64(); g_phase[slot] += _t - t_phase; t_phase = _t; } } while (0)
 
 __host__ __device__ inline size_t potrf_small_smem(int n_max) {
@@ -338,12 +339,25 @@ __global__ void __launch_bounds__(FTHREADS) k_potrf_small(FactorArgs p) {
             if (nk > 0) {
                 const double* gA = A + (size_t)k0 * p.lda;
                 // two k-tiles per barrier (nk is a multiple of 4): tiles kt, kt+1 are consumed while kt+2, kt+3 fly
+                // every thread copies the same (row, 16-byte chunk) slots in each k-tile: row = tid/4 + 64*i, chunk = tid%4;
+                // pointers are formed once per block column, the per-tile work is one add and one cp.async per slot
+                const int lr = tid >> 2, lq = tid & 3;
+                const double* lsrc = gA + (size_t)lr * p.lda + 2 * lq;
+                const int ldst = lr * FLDT + 2 * lq;
                 auto issue2 = [&](int kt) {
 #pragma unroll
-                    for (int u = 0; u < 2; ++u)
-                        if (kt + u < nk)
-                            load_tile_async<FBK, FLDT, false>(stage0 + ((kt + u) % FSTAGES) * stage_elems, gA + (kt + u) * FBK, p.lda,
-                                                              rows_t, m, k0, (kt + u) * FBK, k0, tid, FTHREADS);
+                    for (int u = 0; u < 2; ++u) {
+                        if (kt + u < nk && !(g_dbg & 2)) {
+                            double* st = stage0 + ((kt + u) % FSTAGES) * stage_elems + ldst;
+                            const double* src = lsrc + (kt + u) * FBK;
+                            for (int r = lr; r < rows_t; r += FTHREADS / 4) {
+                                const bool ok = r < m;
+                                cp_async16(st, ok ? src : gA, ok ? 16 : 0);
+                                st += (FTHREADS / 4) * FLDT;
+                                src += (size_t)(FTHREADS / 4) * p.lda;
+                            }
+                        }
+                    }
                     cp_async_commit();
                 };
                 issue2(0);
@@ -356,6 +370,7 @@ __global__ void __launch_bounds__(FTHREADS) k_potrf_small(FactorArgs p) {
                         const double* tile = stage0 + ((kt + u) % FSTAGES) * stage_elems;
 #pragma unroll
                         for (int kk = 0; kk < FBK; kk += 4) {
+                            if (g_dbg & 1) continue;
                             if (warp < nch) warp_mma_k4<4, 4, false>(acc[0], tile + (warp * 32) * FLDT + kk, FLDT, tile + kk, FLDT, lane);
                             if (warp + FWARPS < nch)
                                 warp_mma_k4<4, 4, false>(acc[1], tile + ((warp + FWARPS) * 32) * FLDT + kk, FLDT, tile + kk, FLDT, lane);
@@ -439,6 +454,7 @@ __global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
         const int n = p.n_sys ? p.n_sys[b] : p.n_max;
         double* L = p.A + (size_t)b * p.strideA;
         const int nblk = (n + NB - 1) / NB;
+        long long t_phase = clock64();
         for (int jb = nblk - 1; jb >= 0; --jb) {
             const int k0 = jb * NB;
             const int kb = min(NB, n - k0);
@@ -449,6 +465,7 @@ __global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
             }
             __syncthreads();
             cta_trtri32(Dsm, Dinv, scratch, tid);
+            PHASE_MARK(8);
             if (m > 0) {
                 // T = L21 * Dinv, in place in global memory, one 32-row chunk per warp (kb == 32 here)
                 {
@@ -460,6 +477,7 @@ __global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
                 }
                 __threadfence();
                 __syncthreads();
+                PHASE_MARK(9);
                 // X = -Linv22 * T   (Linv22 lower-triangular m x m, streamed; T streamed k-major)
                 const int nch = (m + 31) >> 5;
                 const int rows_t = nch * 32;
@@ -502,6 +520,7 @@ __global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
                 }
                 cp_async_wait<0>();
                 __syncthreads();   // every read of T is complete: X may overwrite it
+                PHASE_MARK(10);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int ch = warp + c * FWARPS;
@@ -526,6 +545,7 @@ __global__ void __launch_bounds__(FTHREADS) k_trtri_small(FactorArgs p) {
             }
             __threadfence();
             __syncthreads();
+            PHASE_MARK(11);
         }
     }
 }
@@ -564,10 +584,12 @@ __global__ void __launch_bounds__(256) k_solve_alpha(AlphaArgs p) {
         __syncthreads();
         if (!p.general) {
             if (p.w) for (int r = tid; r < n; r += blockDim.x) p.w[(size_t)b * p.ldw + r] = ws[r];
-            for (int c = tid; c < n; c += blockDim.x) {
-                double acc = 0.0;
-                for (int r = c; r < n; ++r) acc += F[(size_t)r * p.lda + c] * ws[r];
-                ys[c] = acc;       // each thread owns entry c
+            if (p.alpha) {         // second pass only when alpha itself is wanted (the fused predict needs w only)
+                for (int c = tid; c < n; c += blockDim.x) {
+                    double acc = 0.0;
+                    for (int r = c; r < n; ++r) acc += F[(size_t)r * p.lda + c] * ws[r];
+                    ys[c] = acc;       // each thread owns entry c
+                }
             }
             __syncthreads();
         }
@@ -584,6 +606,8 @@ __global__ void __launch_bounds__(256) k_solve_alpha(AlphaArgs p) {
         __syncthreads();
     }
 }
+
+int debug_set(int flags) { return check_cuda(cudaMemcpyToSymbol(g_dbg, &flags, sizeof(int)), "cudaMemcpyToSymbol"); }
 
 int debug_phases(long long* out, int reset) {
     KMPX_TRY(check_cuda(cudaMemcpyFromSymbol(out, g_phase, sizeof(long long) * 16), "cudaMemcpyFromSymbol"));
@@ -626,3 +650,4 @@ int launch_solve_alpha(const AlphaArgs& p, cudaStream_t st) {
 }  // namespace kmpx
 
 extern "C" int kmpx_debug_phases(long long* out_host, int reset) { return kmpx::debug_phases(out_host, reset); }
+extern "C" int kmpx_debug_set(int flags) { return kmpx::debug_set(flags); }
