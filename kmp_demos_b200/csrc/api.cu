@@ -4,6 +4,7 @@
 namespace kmpx {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+int g_host_dbg = 0;   // profiling experiments (kmpx_debug_set)
 }  // namespace kmpx
 
 extern "C" int kmpx_version(void) { return KMPX_VERSION; }

@@ -12,6 +12,7 @@ namespace kmpx {
 // ---------------------------------------------------------------- host side: errors, launch counting
 extern thread_local char g_err[512];
 extern std::atomic<long long> g_launches;
+extern int g_host_dbg;
 
 inline int fail_arg(int k, const char* what) {
     snprintf(g_err, sizeof(g_err), "kmpx: bad argument %d: %s", k, what);

@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(256) k_solve_alpha(AlphaArgs p) {
     }
 }
 
-int debug_set(int flags) { return check_cuda(cudaMemcpyToSymbol(g_dbg, &flags, sizeof(int)), "cudaMemcpyToSymbol"); }
+int debug_set(int flags) { g_host_dbg = flags; return check_cuda(cudaMemcpyToSymbol(g_dbg, &flags, sizeof(int)), "cudaMemcpyToSymbol"); }
 
 int debug_phases(long long* out, int reset) {
     KMPX_TRY(check_cuda(cudaMemcpyFromSymbol(out, g_phase, sizeof(long long) * 16), "cudaMemcpyFromSymbol"));

@@ -32,6 +32,7 @@ struct PredictArgs {
     double sigma_f, alpha_kmp; int time_driven;
     double* xi; double* sigma_out;
     int resident; int ldp;   // panel leading dimension (resident mode)
+    int dbg;                 // profiling experiments: bit 0 skip MMAs, bit 1 skip loads
 };
 bool predict_fast_applicable(const PredictArgs& p);
 int launch_predict_fast(PredictArgs& p, cudaStream_t st);

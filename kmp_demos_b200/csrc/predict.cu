@@ -351,7 +351,7 @@ extern "C" int kmpx_kmp_predict(const double* F, int lda, long long strideA, int
     if (!xi) return fail_arg(19, "xi is NULL");
     if ((reinterpret_cast<uintptr_t>(F) & 15) != 0) return fail_arg(1, "F must be 16-byte aligned");
     PredictArgs p{F, lda, strideA, factor_kind, w, ldw, s, n_pts, n_max, I, O, batch, sq, stride_sq, M,
-                  sigma_f, alpha_kmp, time_driven, xi, sigma_out, 0, 0};
+                  sigma_f, alpha_kmp, time_driven, xi, sigma_out, 0, 0, g_host_dbg};
     if (predict_fast_applicable(p)) return launch_predict_fast(p, (cudaStream_t)stream);
     if (predict_stream_applicable(p)) return launch_predict_stream(p, (cudaStream_t)stream);
     if (O <= 2) return launch_predict<64>(p, (cudaStream_t)stream);

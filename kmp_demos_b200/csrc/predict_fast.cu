@@ -8,8 +8,8 @@
 //     PRIVATE 2-stage cp.async ring (32 columns per stage) - only __syncwarp inside the main loop;
 //   * warp tile = 16 rows x 64 queries x both outputs: 16 independent DMMA.8x8x4 per k-step of 4 and output,
 //     10 LDS.64 per 16 DMMA;
-//   * the V tile is reduced straight from the accumulator registers (products, 3 xor-shuffles over the 8 row
-//     lanes) into a per-warp slice of shared memory; slices are summed in warp order at the end, so results are
+//   * the V tile is reduced straight from the accumulator registers (products, a 3-step reduce-scatter over the
+//     8 row lanes) into a per-warp slice of shared memory; slices are summed in warp order at the end, so results are
 //     bitwise reproducible and independent of the batch a problem sits in.
 // Algorithmic flops per problem: O^2 Ns^2 M (+ lower-order reductions); F is streamed from L2 once per CTA.
 #include "dmma_tile.cuh"
@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
         int rows_valid = n - c.r0; rows_valid = rows_valid > RC ? RC : rows_valid;
         double* dst = ring + slot * RC * QLD;
         const double* src = F + (size_t)c.r0 * p.lda + cg0;
+        if (p.dbg & 2) return;
         if (rows_valid == RC && cg0 + QK <= c.col0 + c.jmax && cg0 + QK <= c.r0 + 1) {
             // interior tile (entirely below the diagonal, inside the block): 8 unconditional 16-byte copies per lane
             const int q = lane & 15, rb = lane >> 4;
@@ -131,10 +132,15 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
     // queries, lane-strided over the stored points
     for (int m = warp; m < QT; m += QWARPS) {
         const bool live = m0 + m < p.M;
-        for (int j = lane; j < ldp; j += 32) {
-            double v = 0.0;
-            if (j < N && live) v = rbf(sqs + m * I, s + (size_t)j * I, I, p.sigma_f, 0.0, 0.0);
+        for (int j = lane; j < ldp; j += 64) {          // two independent exp chains per iteration
+            const int j2 = j + 32;
+            const bool c1 = j < N && live && !(p.dbg & 4), c2 = j2 < N && live && !(p.dbg & 4);
+            // branch-free (indices clamped, results selected) so that the two chains are interleaved by the scheduler
+            const double e1 = rbf(sqs + m * I, s + (size_t)min(j, N - 1) * I, I, p.sigma_f, 0.0, 0.0);
+            const double e2 = rbf(sqs + m * I, s + (size_t)min(j2, N - 1) * I, I, p.sigma_f, 0.0, 0.0);
+            const double v = c1 ? e1 : 0.0, v2 = c2 ? e2 : 0.0;
             panel[(size_t)m * ldp + j] = v;
+            if (j2 < ldp) panel[(size_t)m * ldp + j2] = v2;
         }
     }
     __syncthreads();
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
         cp_async_commit();
         const double* tile = ring + (consumed % QST) * RC * QLD;
         const double* Bs = panel + cons.kb * QK;
-        const int kvalid = cons.jmax - cons.kb * QK;      // columns of this k-block that carry data
+        const int kvalid = (p.dbg & 1) ? 0 : cons.jmax - cons.kb * QK;      // columns of this k-block that carry data
         if (kvalid >= QK) {
             if (O == 1 || cons.a == 0) {
 #pragma unroll
@@ -169,14 +175,15 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
         ++consumed;
         const int cur_ci = cons.ci, cur_r0 = cons.r0;
         advance(cons);
-        if (!cons.valid || cons.ci != cur_ci) {
+        if ((!cons.valid || cons.ci != cur_ci) && !(p.dbg & 8)) {
             // chunk complete: reduce the V tile over its 16 rows straight from the accumulators
             double wv[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) { const int r = cur_r0 + i * 8 + g; wv[i] = r < n ? wsh[r] : 0.0; }
+            // per-thread partial sums over its two row fragments: val[t][j][e] for column j*8 + 2*t4 + e
+            double val[NT][8][2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                double red[NT][2];
+            for (int j = 0; j < 8; ++j)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     double q00 = 0.0, q01 = 0.0, q11 = 0.0, mu0 = 0.0, mu1 = 0.0;
@@ -186,20 +193,34 @@ __global__ void __launch_bounds__(QTHREADS, 1) k_kmp_predict_fast(PredictArgs p)
                         q00 += v0 * v0; mu0 += v0 * wv[i];
                         if (O == 2) { const double v1 = acc1[i][j][e]; q01 += v0 * v1; q11 += v1 * v1; mu1 += v1 * wv[i]; }
                     }
-                    if (O == 1) { red[0][e] = q00; red[1][e] = mu0; }
-                    else { red[0][e] = q00; red[1][e] = q01; red[2][e] = q11; red[3][e] = mu0; red[NT - 1][e] = mu1; }
+                    if (O == 1) { val[0][j][e] = q00; val[1][j][e] = mu0; }
+                    else { val[0][j][e] = q00; val[1][j][e] = q01; val[2][j][e] = q11; val[3][j][e] = mu0; val[NT - 1][j][e] = mu1; }
                 }
+            // reduce-scatter over the 8 row lanes (lane bits 4,3,2 = g): each step halves the number of values a lane
+            // keeps, so 7 shuffles per (t, e) instead of 24; lane g ends up owning the column block j == g
+            const bool g2 = (lane & 16) != 0, g1 = (lane & 8) != 0, g0 = (lane & 4) != 0;
 #pragma unroll
-                for (int t = 0; t < NT; ++t)
+            for (int t = 0; t < NT; ++t)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        double v = red[t][e];
-                        v += __shfl_xor_sync(0xffffffffu, v, 4);
-                        v += __shfl_xor_sync(0xffffffffu, v, 8);
-                        v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        if (g == 0) my_racc[t * QT + j * 8 + 2 * t4 + e] += v;
+                for (int e = 0; e < 2; ++e) {
+                    double s4[4], s2[2];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const double keep = g2 ? val[t][jj + 4][e] : val[t][jj][e];
+                        const double send = g2 ? val[t][jj][e] : val[t][jj + 4][e];
+                        s4[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                     }
-            }
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const double keep = g1 ? s4[jj + 2] : s4[jj];
+                        const double send = g1 ? s4[jj] : s4[jj + 2];
+                        s2[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+                    const double keep = g0 ? s2[1] : s2[0];
+                    const double send = g0 ? s2[0] : s2[1];
+                    const double tot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    my_racc[t * QT + g * 8 + 2 * t4 + e] += tot;
+                }
             zero_acc(acc0);
             zero_acc(acc1);
         }
