@@ -42,31 +42,15 @@ __host__ __device__ inline size_t trtri_small_smem(int n_max) {
     return (size_t)TSTAGES * (rows * FLDT + FBK * FLDB) * sizeof(double) + 2 * 32 * FLDP * sizeof(double);
 }
 
-// ---- 32 x 32 diagonal blocks, whole CTA, shared memory, small loops (a fully unrolled single-warp version
-//      was measured to be instruction-cache bound) ------------------------------------------------------------
-// Right-looking Cholesky of the kb x kb block in P (leading dimension FLDP).  The factor goes to Ld (lower
-// triangle; rows/columns >= kb are set to the identity), P's trailing part is consumed.  One barrier per
-// column: column j of P stays unscaled while the trailing update of step j reads it.
-// *bad receives the 1-based index of the first non-positive pivot (0 if none).
-__device__ __forceinline__ void cta_potf2(double* P, double* Ld, int kb, int tid, int* bad) {
-    if (tid == 0) *bad = 0;
-    for (int idx = tid; idx < 32 * 32; idx += FTHREADS) {
-        const int r = idx >> 5, c = idx & 31;
-        if (r >= kb || c >= kb || c > r) Ld[r * FLDP + c] = (r == c) ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    for (int j = 0; j < kb; ++j) {
-        const double pjj = P[j * FLDP + j];
-        const double rs = rsqrt(pjj);
-        const double rinv = rs * rs;
-        if (tid == 0 && !(pjj > 0.0) && *bad == 0) *bad = j + 1;
-        if (tid >= j && tid < kb) Ld[tid * FLDP + j] = (tid == j) ? pjj * rs : P[tid * FLDP + j] * rs;
-        for (int idx = tid; idx < 32 * 32; idx += FTHREADS) {
-            const int r = idx >> 5, c = idx & 31;
-            if (r > j && c > j && c <= r && r < kb) P[r * FLDP + c] -= (P[r * FLDP + j] * rinv) * P[c * FLDP + j];
-        }
-        __syncthreads();
-    }
+// ---- 32 x 32 diagonal blocks, whole CTA, shared memory, small loops (fully unrolled single-warp versions were
+//      measured to be instruction-cache bound, barrier-per-column versions latency bound) --------------------
+
+// Barrier used inside the 32 x 32 block helpers: the whole CTA, or (NAMED) only the 256 threads of the MMA warps
+// of the TMA kernels, whose producer warp never joins.
+template <bool NAMED>
+__device__ __forceinline__ void block_sync() {
+    if (NAMED) asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    else __syncthreads();
 }
 
 // Reciprocal square root on the latency-critical pivot path: single-precision seed + two Newton steps in fp64
@@ -80,60 +64,15 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
     return y;
 }
 
-// Single-warp variant without block barriers: lane = column.  Step j: every lane forms its own l_lane = P[lane][j] /
-// sqrt(p_jj); the trailing rows r > j are then updated one after the other, row r by the lanes j < c <= r with
-// l_r broadcast by a shuffle (conflict-free row accesses, iterations independent of each other).
-// Returns the 1-based index of the first non-positive pivot (0 if none); Ld gets L (identity-padded).
-__device__ __forceinline__ int warp_potf2_cols(double* P, double* Ld, int kb, int lane) {
-    for (int r = 0; r < 32; ++r) Ld[r * FLDP + lane] = (r == lane) ? 1.0 : 0.0;
-    __syncwarp();
-    int bad = 0;
-    double pjj = P[0];
-    double rs = fast_rsqrt(pjj);
-    for (int j = 0; j < kb; ++j) {
-        if (!(pjj > 0.0) && bad == 0) bad = j + 1;
-        double l = 0.0;
-        if (lane >= j && lane < kb) {
-            l = (lane == j) ? pjj * rs : P[lane * FLDP + j] * rs;
-            Ld[lane * FLDP + j] = l;
-        }
-        const bool mine = lane > j;
-        // look-ahead: the next pivot p_{j+1,j+1} - l_{j+1}^2 and its rsqrt are started before the bulk of the
-        // rank-1 update so that the long rsqrt latency overlaps with it (every lane computes them redundantly)
-        if (j + 1 < kb) {
-            const double l1 = __shfl_sync(0xffffffffu, l, j + 1);
-            pjj = P[(j + 1) * FLDP + j + 1] - l1 * l1;
-            rs = fast_rsqrt(pjj);
-            if (lane == j + 1) P[(j + 1) * FLDP + j + 1] = pjj;
-        }
-        // remaining rows in groups of 8: the eight loads are issued back to back so that their latencies overlap
-        for (int r0 = j + 2; r0 < kb; r0 += 8) {
-            double v[8], lr[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int r = r0 + q;
-                v[q] = (r < kb) ? P[r * FLDP + lane] : 0.0;
-                lr[q] = __shfl_sync(0xffffffffu, l, r & 31);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int r = r0 + q;
-                if (mine && r < kb && lane <= r) P[r * FLDP + lane] = v[q] - lr[q] * l;
-            }
-        }
-        __syncwarp();
-    }
-    return bad;
-}
-
 // Blocked variant: the 32 x 32 block is processed in four 8-column panels.  The 8 x 8 diagonal block (and its
 // inverse) is done by ONE thread entirely in registers (8 sequential pivots, no shared-memory round trips); the
 // panel solve and the rank-8 trailing update are spread over all threads.  Three barriers per panel, 12 in total,
 // instead of 32 latency-bound column steps.  S: >= 64 doubles of scratch (inverse of the 8 x 8 block).
+template <bool NAMED = false>
 __device__ __forceinline__ void cta_potf2_b8(double* P, double* Ld, double* S, int kb, int tid, int* bad) {
     if (tid == 0) *bad = 0;
     for (int idx = tid; idx < 32 * 32; idx += FTHREADS) Ld[(idx >> 5) * FLDP + (idx & 31)] = ((idx >> 5) == (idx & 31)) ? 1.0 : 0.0;
-    __syncthreads();
+    block_sync<NAMED>();
     for (int base = 0; base < kb; base += 8) {
         const int w = min(8, kb - base);
         if (tid == 0) {
@@ -181,7 +120,7 @@ __device__ __forceinline__ void cta_potf2_b8(double* P, double* Ld, double* S, i
                     if (i < w && j <= i) Ld[(base + i) * FLDP + base + j] = a[i][j];
                 }
         }
-        __syncthreads();
+        block_sync<NAMED>();
         const int rb = kb - base - 8;        // rows below this 8 x 8 block
         if (rb > 0) {
             for (int idx = tid; idx < rb * 8; idx += FTHREADS) {
@@ -192,7 +131,7 @@ __device__ __forceinline__ void cta_potf2_b8(double* P, double* Ld, double* S, i
                 for (int t = 0; t < 8; ++t) if (t <= c) sum += arow[t] * S[c * 8 + t];
                 Ld[(base + 8 + r) * FLDP + base + c] = sum;
             }
-            __syncthreads();
+            block_sync<NAMED>();
             for (int idx = tid; idx < rb * rb; idx += FTHREADS) {
                 const int i = idx / rb, j = idx - i * rb;
                 if (j <= i) {
@@ -204,16 +143,17 @@ __device__ __forceinline__ void cta_potf2_b8(double* P, double* Ld, double* S, i
                     P[(base + 8 + i) * FLDP + base + 8 + j] -= sum;
                 }
             }
-            __syncthreads();
+            block_sync<NAMED>();
         }
     }
 }
 
 // X = L^{-1} for the 32 x 32 lower-triangular L (identity-padded), recursive 8 -> 16 -> 32 blocking:
 // [[L00,0],[L10,L11]]^{-1} = [[X00,0],[-X11 L10 X00, X11]].  S: 256 doubles of scratch.  Five barriers.
+template <bool NAMED = false>
 __device__ __forceinline__ void cta_trtri32(const double* L, double* X, double* S, int tid) {
     for (int idx = tid; idx < 32 * 32; idx += FTHREADS) X[(idx >> 5) * FLDP + (idx & 31)] = 0.0;
-    __syncthreads();
+    block_sync<NAMED>();
     if (tid < 32) {                                   // four 8x8 diagonal blocks, one thread per column
         const int base = (tid >> 3) * 8, c = tid & 7;
         double x[8];
@@ -231,7 +171,7 @@ __device__ __forceinline__ void cta_trtri32(const double* L, double* X, double* 
             X[(base + i) * FLDP + base + c] = v;
         }
     }
-    __syncthreads();
+    block_sync<NAMED>();
     if (tid < 128) {                                  // level 16: T = L10 X00 for both 16-blocks
         const int pb = (tid >> 6) * 16, r = (tid >> 3) & 7, c = tid & 7;
         double sum = 0.0;
@@ -239,7 +179,7 @@ __device__ __forceinline__ void cta_trtri32(const double* L, double* X, double* 
         for (int t = 0; t < 8; ++t) sum += L[(pb + 8 + r) * FLDP + pb + t] * X[(pb + t) * FLDP + pb + c];
         S[tid] = sum;
     }
-    __syncthreads();
+    block_sync<NAMED>();
     if (tid < 128) {                                  // X10 = -X11 T
         const int q = tid >> 6, pb = q * 16, r = (tid >> 3) & 7, c = tid & 7;
         double sum = 0.0;
@@ -247,7 +187,7 @@ __device__ __forceinline__ void cta_trtri32(const double* L, double* X, double* 
         for (int t = 0; t < 8; ++t) sum += X[(pb + 8 + r) * FLDP + pb + 8 + t] * S[q * 64 + t * 8 + c];
         X[(pb + 8 + r) * FLDP + pb + c] = -sum;
     }
-    __syncthreads();
+    block_sync<NAMED>();
     {                                                 // level 32: T = L10 X00 (16 x 16), one output per thread
         const int r = tid >> 4, c = tid & 15;
         double sum = 0.0;
@@ -255,7 +195,7 @@ __device__ __forceinline__ void cta_trtri32(const double* L, double* X, double* 
         for (int t = 0; t < 16; ++t) sum += L[(16 + r) * FLDP + t] * X[t * FLDP + c];
         S[tid] = sum;
     }
-    __syncthreads();
+    block_sync<NAMED>();
     {
         const int r = tid >> 4, c = tid & 15;
         double sum = 0.0;
@@ -263,7 +203,7 @@ __device__ __forceinline__ void cta_trtri32(const double* L, double* X, double* 
         for (int t = 0; t < 16; ++t) sum += X[(16 + r) * FLDP + 16 + t] * S[t * 16 + c];
         X[(16 + r) * FLDP + c] = -sum;
     }
-    __syncthreads();
+    block_sync<NAMED>();
 }
 
 // X(32 x 32) = A(32 x 32) * op(D) on DMMA for one warp.  A rows come from `src` (row-major, leading dimension
@@ -607,6 +547,10 @@ __global__ void __launch_bounds__(256) k_solve_alpha(AlphaArgs p) {
     }
 }
 
+}  // namespace kmpx
+#include "factor_tma.cuh"
+namespace kmpx {
+
 int debug_set(int flags) { g_host_dbg = flags; return check_cuda(cudaMemcpyToSymbol(g_dbg, &flags, sizeof(int)), "cudaMemcpyToSymbol"); }
 
 int debug_phases(long long* out, int reset) {
@@ -617,6 +561,16 @@ int debug_phases(long long* out, int reset) {
 
 int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
                        int info_offset, int info_accumulate, cudaStream_t st) {
+    if (tma_applicable(A, lda, strideA, n_max, batch, false)) {
+        CUtensorMap map;
+        KMPX_TRY(make_batch_map(&map, A, lda, strideA, n_max, batch));
+        const TmaSmem lay = tma_smem_layout(n_max, false, kMaxDynSmem);
+        static size_t tma_smem_set = 48 * 1024;
+        KMPX_TRY(ensure_dyn_smem(k_potrf_tma, lay.total, tma_smem_set, "k_potrf_tma"));
+        FactorArgs p{A, lda, strideA, n_sys, n_max, batch, info, info_offset, info_accumulate};
+        k_potrf_tma<<<batch < kNumSMs ? batch : kNumSMs, TTHREADS, lay.total, st>>>(map, p, lay);
+        return check_launch("k_potrf_tma");
+    }
     const size_t smem = potrf_small_smem(n_max);
     static size_t smem_set = 48 * 1024;
     KMPX_TRY(ensure_dyn_smem(k_potrf_small, smem, smem_set, "k_potrf_small"));
@@ -628,6 +582,16 @@ int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, 
 }
 
 int launch_trtri_small(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, cudaStream_t st) {
+    if (tma_applicable(L, lda, strideA, n_max, batch, true)) {
+        CUtensorMap map;
+        KMPX_TRY(make_batch_map(&map, L, lda, strideA, n_max, batch));
+        const TmaSmem lay = tma_smem_layout(n_max, true, kMaxDynSmem);
+        static size_t tma_smem_set = 48 * 1024;
+        KMPX_TRY(ensure_dyn_smem(k_trtri_tma, lay.total, tma_smem_set, "k_trtri_tma"));
+        FactorArgs p{L, lda, strideA, n_sys, n_max, batch, nullptr, 0, 0};
+        k_trtri_tma<<<batch < kNumSMs ? batch : kNumSMs, TTHREADS, lay.total, st>>>(map, p, lay);
+        return check_launch("k_trtri_tma");
+    }
     const size_t smem = trtri_small_smem(n_max);
     static size_t smem_set = 48 * 1024;
     KMPX_TRY(ensure_dyn_smem(k_trtri_small, smem, smem_set, "k_trtri_small"));
