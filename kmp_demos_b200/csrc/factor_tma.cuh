@@ -85,6 +85,8 @@ struct TileRing {
         return dst;
     }
 };
+// barrier among the 96 threads of the three auxiliary warps
+__device__ __forceinline__ void aux_warps_sync() { asm volatile("bar.sync 2, 96;\n" ::: "memory"); }
 // barrier among the 256 threads of the MMA warps (the producer warp never joins it)
 __device__ __forceinline__ void mma_warps_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 // progress counter in shared memory: written by one MMA thread after mma_warps_sync(), polled by the producer warp
@@ -148,12 +150,13 @@ __device__ __forceinline__ void chunk_mul_regs(double (&P)[4][4][2], const doubl
     }
 }
 
-// acc[c] += tile rows of chunk (warp + 8c) times the B fragments, for the two k-steps of one swizzled k-tile.
+// acc[c] += (32 tile rows starting at row offset ro_c) times the B fragments, for the two k-steps of one swizzled k-tile.
 //   B_FROM_TILE: B[k][n] = tile row n (the first 32 rows of the tile)         (potrf)
 //   else:        B[k][n] = Bk[(4*step + t4) * FLDB + n]  (k-major block in shared memory, rows already in k-step order)
+//   self (warp-uniform): acc[1] += R * R^T for the 32 tile rows R starting at ro1 (both operands are the same fragments)
 template <bool B_FROM_TILE>
 __device__ __forceinline__ void tile_mma(double (&acc)[2][4][4][2], const double* tile, const double* Bk, int o0, int o1,
-                                         bool live0, bool live1, int warp, int lane) {
+                                         bool live0, int ro0, bool live1, int ro1, bool self, int lane) {
     const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -164,20 +167,20 @@ __device__ __forceinline__ void tile_mma(double (&acc)[2][4][4][2], const double
         if (live0) {
             double a[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = tile[(warp * 32 + i * 8) * 8 + o];
+            for (int i = 0; i < 4; ++i) a[i] = tile[(ro0 + i * 8) * 8 + o];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma884(acc[0][i][j], a[i], bf[j]);
         }
-        if (live1) {
+        if (live1 || self) {
             double a[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = tile[((warp + FWARPS) * 32 + i * 8) * 8 + o];
+            for (int i = 0; i < 4; ++i) a[i] = tile[(ro1 + i * 8) * 8 + o];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[1][i][j], a[i], bf[j]);
+                for (int j = 0; j < 4; ++j) dmma884(acc[1][i][j], a[i], self ? a[j] : bf[j]);
         }
     }
 }
@@ -186,14 +189,14 @@ struct TmaSmem {   // carve-up of the dynamic shared memory of both kernels
     int S, ring_rows, t_rows;
     size_t ring_bytes, t_bytes, blocks_bytes, total;
 };
-__host__ __device__ inline TmaSmem tma_smem_layout(int n_max, bool with_t, size_t budget) {
+__host__ __device__ inline TmaSmem tma_smem_layout(int n_max, bool with_t, size_t budget) {   // with_t: trtri
     TmaSmem L;
     const int below = n_max > NB ? n_max - NB : 0;          // rows of the largest streamed tile
     L.ring_rows = (below + TBOX - 1) / TBOX * TBOX;
     L.t_rows = with_t ? (below + 7) / 8 * 8 : 0;
     L.t_bytes = (size_t)L.t_rows * FLDP * sizeof(double);
-    L.blocks_bytes = (size_t)3 * 32 * FLDP * sizeof(double);
-    const size_t fixed = L.t_bytes + L.blocks_bytes + 2 * TMAX_STAGES * 8 + 16 /* progress counter */ + 1024 /* alignment slack */;
+    L.blocks_bytes = (size_t)(with_t ? 3 : 5) * 32 * FLDP * sizeof(double);
+    const size_t fixed = L.t_bytes + L.blocks_bytes + 2 * TMAX_STAGES * 8 + 16 /* progress counters */ + 1024 /* alignment slack */;
     const size_t stage = (size_t)L.ring_rows * 64;
     int S = stage == 0 || budget < fixed ? 0 : (int)((budget - fixed) / stage);
     L.S = S > TMAX_STAGES ? TMAX_STAGES : S;
@@ -203,19 +206,26 @@ __host__ __device__ inline TmaSmem tma_smem_layout(int n_max, bool with_t, size_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-constexpr int TTHREADS = FTHREADS + 128;   // eight MMA warps + one producer warpgroup (one of its warps works)
+// Roles inside a CTA of 384 threads:
+//   warps 0-7   MMA warps: block-column contraction, panel solve, stores
+//   warp  8     producer: issues the TMA boxes
+//   warps 9-11  auxiliary warps: Cholesky factor and inverse of the 32 x 32 diagonal blocks, concurrently with the
+//               contraction (the diagonal block of the NEXT column is finished one step early, see k_potrf_tma)
+constexpr int TTHREADS = FTHREADS + 128;
+constexpr int AUXT = 96;
 // Register split between the roles (setmaxnreg works on warpgroups of four warps): each scheduler hosts two MMA
-// warps and one warp of the producer group, 2 * 232 + 40 registers per lane fit its 16K-entry file.
-__device__ __forceinline__ void producer_regs() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n"); }
-__device__ __forceinline__ void mma_regs() { asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n"); }
+// warps and one warp of the producer/auxiliary group, 2 * 208 + 88 registers per lane fit its 16K-entry file
+// (the auxiliary code needs 72; ptxas does not check a region against its setmaxnreg budget - see k_aux_regs_probe).
+__device__ __forceinline__ void producer_regs() { asm volatile("setmaxnreg.dec.sync.aligned.u32 88;\n"); }
+__device__ __forceinline__ void mma_regs() { asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n"); }
 
 struct TmaCta {   // what both kernels set up identically
-    TileRing ring; double* blocks; int* progress;
+    TileRing ring; double* blocks; int* progress;     // progress[0]: columns/steps done, [1], [2]: hand-overs with the aux warps
 };
 __device__ __forceinline__ TmaCta tma_cta_setup(unsigned char* smem_raw, const TmaSmem& lay, int tid) {
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     TmaCta c;
-    c.blocks = reinterpret_cast<double*>(base + lay.ring_bytes);        // [T rows (trtri)] + three 32 x FLDP blocks
+    c.blocks = reinterpret_cast<double*>(base + lay.ring_bytes);        // [T rows (trtri)] + the 32 x FLDP blocks
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + lay.ring_bytes + lay.t_bytes + lay.blocks_bytes);
     c.progress = reinterpret_cast<int*>(bars + 2 * TMAX_STAGES);
     c.ring.stage0 = reinterpret_cast<double*>(base); c.ring.S = lay.S; c.ring.stage_elems = lay.ring_rows * 8;
@@ -223,13 +233,191 @@ __device__ __forceinline__ TmaCta tma_cta_setup(unsigned char* smem_raw, const T
     c.ring.stage = 0; c.ring.par = 0; c.ring.wrapped = false;
     if (tid == 0) {
         for (int s = 0; s < lay.S; ++s) { mbar_init(c.ring.full0 + 8 * s, 1); mbar_init(c.ring.empty0 + 8 * s, FWARPS); }
-        *c.progress = 0;
+        c.progress[0] = 0; c.progress[1] = 0; c.progress[2] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
     return c;
 }
 
+// Reciprocal square root for the pivot chain of the 8 x 8 blocks, where every dependent FP64 operation costs its full
+// pipeline latency: hardware seed (rsqrt.approx.f64, ~2^-22) + ONE third-order step
+//   e = 1 - x y^2,   y' = y + y e (1/2 + 3/8 e)          (error O(e^3) < 2^-64)
+// = 5 dependent operations instead of the 9 of a single-precision seed with two Newton steps.
+__device__ __forceinline__ double rsqrt_chain(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double xy = x * y;
+    const double e = fma(-xy, y, 1.0);
+    const double pp = fma(0.375, e, 0.5);
+    const double ye = y * e;
+    return fma(ye, pp, y);
+}
+
+// One warp: Cholesky factor and inverse of the w x w (w <= 8, identity padded) diagonal block of P at (base, base).
+// Lane r (mod 8) owns row r of the factor and column r of the inverse; the diagonal is replicated in every lane so that
+// the pivot needs no broadcast; the dependent chain per pivot is rsqrt (5 ops), scale, diagonal update (7 FP64 ops).
+// The inverse x[i] = -(sum_{q<i} L[i][q] x[q]) / L_ii advances one row per pivot, off the critical path.
+// Outputs: Ld (lower triangle of the block), S[i*8+j] = Xblock[i][j], X diagonal block; *bad = first bad pivot (1-based).
+__device__ __forceinline__ void chol8_inverse(const double* P, double* Ld, double* X, double* S, int base, int w, int lane, int* bad) {
+    const int r = lane & 7;
+    double a[8], dd[8], x[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        a[c] = (r < w && c < r) ? P[(base + r) * FLDP + base + c] : 0.0;
+        dd[c] = c < w ? P[(base + c) * FLDP + base + c] : 1.0;
+    }
+    int bd = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        // column j, still unscaled, broadcast while the rsqrt of the pivot is in flight: no shuffle on the pivot chain
+        double ac[8];
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) ac[c] = __shfl_sync(0xffffffffu, a[j], c);
+        const double d = dd[j];
+        if (!(d > 0.0) && bd == 0 && j < w) bd = base + j + 1;
+        const double rs = rsqrt_chain(d);
+        const double l = r > j ? a[j] * rs : 0.0;
+        a[j] = (r == j) ? d * rs : l;
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) {
+            const double lc = ac[c] * rs;
+            dd[c] = fma(-lc, lc, dd[c]);
+            if (r > c) a[c] = fma(-l, lc, a[c]);
+        }
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < j; ++q) sum = fma(__shfl_sync(0xffffffffu, a[q], j), x[q], sum);
+        x[j] = (j < r) ? 0.0 : ((j == r) ? rs : -sum * rs);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (r < w && c <= r) Ld[(base + r) * FLDP + base + c] = a[c];
+            S[c * 8 + r] = x[c];
+            X[(base + c) * FLDP + base + r] = x[c];
+        }
+        if (lane == 0 && bd != 0 && *bad == 0) *bad = bd;
+    }
+}
+
+// ---- diagonal 32 x 32 blocks on the three auxiliary warps (t = 0..95, at most 64 registers) ----------------------
+// Cholesky factor of the kb x kb block in P -> Ld (identity padded) AND the inverses of its four 8 x 8 diagonal blocks
+// -> X (everything else of X zeroed).  8-column panels; the 8 x 8 block itself is factored and inverted by eight
+// lanes of one warp that hold one row / one column each and exchange entries by shuffles.
+__device__ __forceinline__ void aux_potf2(double* P, double* Ld, double* X, double* S, int kb, int t, int* bad) {
+    const int lane = t & 31;
+    for (int idx = t; idx < 32 * 32; idx += AUXT) {
+        const int r = idx >> 5, c = idx & 31;
+        Ld[r * FLDP + c] = (r == c) ? 1.0 : 0.0;
+        X[r * FLDP + c] = 0.0;
+    }
+    if (t == 0) *bad = 0;
+    aux_warps_sync();
+    for (int base = 0; base < 32; base += 8) {
+        const int w = min(8, kb - base);      // <= 0: identity block
+        long long t_in = clock64();
+        if (t < 32) chol8_inverse(P, Ld, X, S, base, w, lane, bad);
+        if (blockIdx.x == 0 && t == 0) { const long long t2 = clock64(); g_phase[6] += t2 - t_in; t_in = t2; }
+        aux_warps_sync();
+        const int rb = kb - base - 8;        // rows below this 8 x 8 block
+        if (rb > 0) {
+            // panel solve and rank-8 update on the tensor pipe, 8 x 8 tiles dealt to the three warps
+            const int aw = t >> 5, g = lane >> 2, t4 = lane & 3;
+            const int ntile = (rb + 7) >> 3;
+            for (int rt = aw; rt < ntile; rt += 3) {         // Ld[rows, panel] = P[rows, panel] * Xblock^T
+                const int row = base + 8 + 8 * rt + g;
+                double c[2] = {0.0, 0.0};
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) dmma884(c, P[row * FLDP + base + 4 * ks + t4], S[g * 8 + 4 * ks + t4]);
+                if (row < kb) { Ld[row * FLDP + base + 2 * t4] = c[0]; Ld[row * FLDP + base + 2 * t4 + 1] = c[1]; }
+            }
+            aux_warps_sync();
+            int tile = 0;
+            for (int ti = 0; ti < ntile; ++ti)
+                for (int tj = 0; tj <= ti; ++tj, ++tile) {   // P[ti, tj] -= Lp[ti] * Lp[tj]^T
+                    if (tile % 3 != aw) continue;
+                    const int row = base + 8 + 8 * ti + g;
+                    double* cp = P + row * FLDP + base + 8 + 8 * tj + 2 * t4;
+                    double c[2] = {cp[0], cp[1]};
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        dmma884(c, -Ld[row * FLDP + base + 4 * ks + t4], Ld[(base + 8 + 8 * tj + g) * FLDP + base + 4 * ks + t4]);
+                    cp[0] = c[0]; cp[1] = c[1];
+                }
+            aux_warps_sync();
+        }
+        if (blockIdx.x == 0 && t == 0) g_phase[7] += clock64() - t_in;
+    }
+}
+// Inverses of the four 8 x 8 diagonal blocks of the lower-triangular L -> X (rest of X zeroed), one thread per column.
+__device__ __forceinline__ void aux_diag8_inverse(const double* L, double* X, int t) {
+    for (int idx = t; idx < 32 * 32; idx += AUXT) X[(idx >> 5) * FLDP + (idx & 31)] = 0.0;
+    aux_warps_sync();
+    if (t < 32) {
+        const int base = (t >> 3) * 8, c = t & 7;
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double v = 0.0;
+            if (i == c) v = 1.0 / L[(base + i) * FLDP + base + i];
+            else if (i > c) {
+                double sum = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (q >= c && q < i) sum += L[(base + i) * FLDP + base + q] * x[q];
+                v = -sum / L[(base + i) * FLDP + base + i];
+            }
+            x[i] = v;
+            X[(base + i) * FLDP + base + c] = v;
+        }
+    }
+    aux_warps_sync();
+}
+// Completes X = L^{-1} (32 x 32) from the inverses of the 8 x 8 diagonal blocks: 8 -> 16 -> 32,
+// [[L00,0],[L10,L11]]^{-1} = [[X00,0],[-X11 L10 X00, X11]].  S: 256 doubles of scratch.
+__device__ __forceinline__ void aux_trtri32_finish(const double* L, double* X, double* S, int t) {
+    for (int idx = t; idx < 128; idx += AUXT) {            // level 16: T = L10 X00 for both 16-blocks
+        const int pb = (idx >> 6) * 16, r = (idx >> 3) & 7, c = idx & 7;
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sum += L[(pb + 8 + r) * FLDP + pb + q] * X[(pb + q) * FLDP + pb + c];
+        S[idx] = sum;
+    }
+    aux_warps_sync();
+    for (int idx = t; idx < 128; idx += AUXT) {            // X10 = -X11 T
+        const int qd = idx >> 6, pb = qd * 16, r = (idx >> 3) & 7, c = idx & 7;
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sum += X[(pb + 8 + r) * FLDP + pb + 8 + q] * S[qd * 64 + q * 8 + c];
+        X[(pb + 8 + r) * FLDP + pb + c] = -sum;
+    }
+    aux_warps_sync();
+    for (int idx = t; idx < 256; idx += AUXT) {            // level 32: T = L10 X00 (16 x 16)
+        const int r = idx >> 4, c = idx & 15;
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sum += L[(16 + r) * FLDP + q] * X[q * FLDP + c];
+        S[idx] = sum;
+    }
+    aux_warps_sync();
+    for (int idx = t; idx < 256; idx += AUXT) {
+        const int r = idx >> 4, c = idx & 15;
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sum += X[(16 + r) * FLDP + 16 + q] * S[q * 16 + c];
+        X[(16 + r) * FLDP + c] = -sum;
+    }
+    aux_warps_sync();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Left-looking blocked Cholesky.  Step j (block column k0 = 32 j, m = n - k0 rows):
+//   MMA warps   acc(unit u) = L[rows of unit u, 0:k0] * L[k0:k0+32, 0:k0]^T for the 32-row units below the diagonal
+//               block (unit u -> warp u % 8), and - warp 7, second accumulator - the self product of unit 0, i.e. the
+//               history of the NEXT diagonal block;   X(u) = (A - acc) * Dinv_j^T, stored from registers; warp 7 adds
+//               A_{j+1,j+1} and -X(0) X(0)^T (X(0) handed over in shared memory) and publishes the next diagonal block.
+//   aux warps   factor and invert the diagonal block j (published at the end of step j-1) while the MMA warps are in
+//               the contraction of step j; they also store L_jj.
 __global__ void __launch_bounds__(TTHREADS, 1) k_potrf_tma(const __grid_constant__ CUtensorMap tmap, FactorArgs p, TmaSmem lay) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -238,30 +426,63 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_potrf_tma(const __grid_constant
     __shared__ double scratch[256];
     TmaCta cta = tma_cta_setup(smem_raw, lay, tid);
     TileRing& ring = cta.ring;
-    double* Dblk = cta.blocks;            // updated diagonal block
+    double* Dblk = cta.blocks;            // updated diagonal block (warp 7 -> aux warps)
     double* Ld = Dblk + 32 * FLDP;
-    double* Dinv = Ld + 32 * FLDP;
+    double* Dinv2 = Ld + 32 * FLDP;       // aux warps -> MMA warps, two buffers alternating over the blocks of the CTA
+    double* Xs = Dinv2 + 2 * 32 * FLDP;   // X(0) of the current step (warp 0 -> warp 7)
+    int* diag_ready = cta.progress + 1;   // diagonal blocks published by warp 7
+    int* dinv_ready = cta.progress + 2;   // diagonal blocks factored + inverted by the aux warps
 
     if (warp >= FWARPS) {
         producer_regs();
-        if (warp > FWARPS) return;
-        // ---- producer warp: k-tile pkt (columns 8*pkt..) of the block column starting at pk0 needs the first
-        //      pkt/4 + 1 block columns of this problem to be final; `done` counts finished block columns of the CTA
-        int done_base = 0, seen = 0;
+        if (warp == FWARPS) {
+            // ---- producer warp: k-tile pkt (columns 8*pkt..) of the block column starting at pk0 needs the first
+            //      pkt/4 + 1 block columns of this problem to be final; progress[0] counts finished block columns
+            int done_base = 0, seen = 0;
+            for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+                const int n = p.n_sys ? p.n_sys[b] : p.n_max;
+                for (int pk0 = NB; pk0 + NB < n; pk0 += NB) {     // the last block column has no rows below its diagonal block
+                    const int nboxes = (n - pk0 + TBOX - 1) / TBOX;
+                    for (int pkt = 0; pkt < pk0 / 8; ++pkt) {
+                        seen = progress_wait(cta.progress, done_base + (pkt >> 2) + 1, seen);
+                        uint32_t bar;
+                        const uint32_t dst = ring.acquire_stage(bar, nboxes, lane);
+                        if (lane == 0 && !(g_dbg & 2))
+                            for (int q = 0; q < nboxes; ++q) tma_load_box(dst + q * TBOX_BYTES, &tmap, 8 * pkt, pk0 + q * TBOX, b, bar);
+                        __syncwarp();
+                    }
+                }
+                done_base += (n + NB - 1) / NB;
+            }
+            return;
+        }
+        // ---- auxiliary warps
+        const int t = tid - (FWARPS + 1) * 32;
+        int blocks = 0, seen = 0;
         for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
             const int n = p.n_sys ? p.n_sys[b] : p.n_max;
-            for (int pk0 = NB; pk0 < n; pk0 += NB) {
-                const int nboxes = (n - pk0 + TBOX - 1) / TBOX;
-                for (int pkt = 0; pkt < pk0 / 8; ++pkt) {
-                    seen = progress_wait(cta.progress, done_base + (pkt >> 2) + 1, seen);
-                    uint32_t bar;
-                    const uint32_t dst = ring.acquire_stage(bar, nboxes, lane);
-                    if (lane == 0 && !(g_dbg & 2))
-                        for (int q = 0; q < nboxes; ++q) tma_load_box(dst + q * TBOX_BYTES, &tmap, 8 * pkt, pk0 + q * TBOX, b, bar);
-                    __syncwarp();
+            double* A = p.A + (size_t)b * p.strideA;
+            for (int k0 = 0; k0 < n; k0 += NB) {
+                const int kb = min(NB, n - k0);
+                long long t_aux = clock64();
+#define AUX_MARK(slot) do { if (blockIdx.x == 0 && t == 0) { const long long _t = clock64(); g_phase[slot] += _t - t_aux; t_aux = _t; } } while (0)
+                double* Dinv = Dinv2 + (blocks & 1) * 32 * FLDP;
+                seen = progress_wait(diag_ready, blocks + 1, seen);
+                AUX_MARK(12);
+                aux_potf2(Dblk, Ld, Dinv, scratch, kb, t, &sh_bad);
+                AUX_MARK(13);
+                if (n - k0 > NB) aux_trtri32_finish(Ld, Dinv, scratch, t);
+                ++blocks;
+                if (t == 0) progress_publish(dinv_ready, blocks);      // (both helpers end with a barrier of the aux warps)
+                AUX_MARK(14);
+                // L_jj itself is off the critical path (no later step streams it)
+                for (int idx = t; idx < NB * NB; idx += AUXT) {
+                    const int r = idx >> 5, c = idx & 31;
+                    if (r < kb && c <= r) A[(size_t)(k0 + r) * p.lda + k0 + c] = Ld[r * FLDP + c];
                 }
+                aux_warps_sync();
+                AUX_MARK(15);
             }
-            done_base += (n + NB - 1) / NB;
         }
         return;
     }
@@ -269,108 +490,140 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_potrf_tma(const __grid_constant
     mma_regs();
     int o0, o1;
     swz_offsets(lane, o0, o1);
-    int done = 0;
+    int done = 0, seen_dinv = 0;
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
         const int n = p.n_sys ? p.n_sys[b] : p.n_max;
         double* A = p.A + (size_t)b * p.strideA;
         int bad_total = 0;
         long long t_phase = clock64();
+        double acc[2][4][4][2];
+        zero_acc(acc[1]);
         for (int k0 = 0; k0 < n; k0 += NB) {
             const int kb = min(NB, n - k0);
             const int m = n - k0;
-            const int nch = (m + 31) >> 5;
-            const bool live0 = warp < nch, live1 = warp + FWARPS < nch;
-            double acc[2][4][4][2];
+            const int nun = (m - 1) >> 5;                 // 32-row units below the diagonal block
+            const bool live0 = warp < nun, live1 = warp + FWARPS < nun;
+            const bool self = warp == FWARPS - 1 && nun > 0;          // warp 7's second accumulator: next diagonal block
+            // ---- first block column of a problem: warp 7 publishes A_00 (later diagonal blocks are published one step early)
+            if (warp == FWARPS - 1 && k0 == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int r = i * 8 + g, c = j * 8 + 2 * t4 + e;
+                            Dblk[r * FLDP + c] = (r < n && c < n) ? A[(size_t)r * p.lda + c] : 0.0;
+                        }
+                __syncwarp();
+                if (lane == 0) progress_publish(diag_ready, done + 1);
+            }
             zero_acc(acc[0]);
             zero_acc(acc[1]);
-            const int nk = k0 / 8;
+            const int nk = nun > 0 ? k0 / 8 : 0;
             for (int kt = 0; kt < nk; ++kt) {
                 const double* tile = ring.wait_tile();
-                if (!(g_dbg & 1)) tile_mma<true>(acc, tile, nullptr, o0, o1, live0, live1, warp, lane);
+                if (!(g_dbg & 1))
+                    tile_mma<true>(acc, tile, nullptr, o0, o1, live0, 32 + warp * 32, live1, self ? 32 : 32 + (warp + FWARPS) * 32, self, lane);
                 ring.release_tile(lane);
             }
             PHASE_MARK(0);
-            // P = A[k0:n, k0:k0+32] - acc, straight from global memory into the accumulator layout.  Full block
-            // columns: the sixteen 16-byte loads of a chunk are issued back to back (row index clamped, result
-            // masked) so that their latencies overlap; the ragged last block takes the guarded element-wise path.
+            // ---- P = A[rows, k0:k0+32] - acc straight from global memory into the accumulator layout (units exist only
+            //      below full block columns, kb == 32): sixteen 16-byte loads per unit in flight, row index clamped
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const int ch = warp + c * FWARPS;
-                if (ch < nch) {
-                    if (kb == NB) {
+                const int u = warp + c * FWARPS;
+                const bool nextdiag = c == 1 && self;
+                if (u < nun || nextdiag) {
+                    const int row0 = k0 + NB + (nextdiag ? 0 : u * 32);
+                    const int col0 = nextdiag ? k0 + NB : k0;
+                    if (!nextdiag || n - (k0 + NB) >= NB) {
                         double2 v[4][4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int gr = min(k0 + ch * 32 + i * 8 + g, n - 1);
+                            const int gr = min(row0 + i * 8 + g, n - 1);
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                v[i][j] = *reinterpret_cast<const double2*>(A + (size_t)gr * p.lda + k0 + j * 8 + 2 * t4);
+                                v[i][j] = *reinterpret_cast<const double2*>(A + (size_t)gr * p.lda + col0 + j * 8 + 2 * t4);
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const bool ok = k0 + ch * 32 + i * 8 + g < n;
+                            const bool ok = row0 + i * 8 + g < n;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 acc[c][i][j][0] = ok ? v[i][j].x - acc[c][i][j][0] : 0.0;
                                 acc[c][i][j][1] = ok ? v[i][j].y - acc[c][i][j][1] : 0.0;
                             }
                         }
-                    } else {
+                    } else {       // ragged last diagonal block: guarded element-wise loads
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int gr = k0 + ch * 32 + i * 8 + g;
+                        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int gc = k0 + j * 8 + 2 * t4;
-                                double v0 = 0.0, v1 = 0.0;
-                                if (gr < n && gc < n) v0 = A[(size_t)gr * p.lda + gc];
-                                if (gr < n && gc + 1 < n) v1 = A[(size_t)gr * p.lda + gc + 1];
-                                acc[c][i][j][0] = v0 - acc[c][i][j][0];
-                                acc[c][i][j][1] = v1 - acc[c][i][j][1];
-                            }
-                        }
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int gr = row0 + i * 8 + g, gc = col0 + j * 8 + 2 * t4 + e;
+                                    const double v = (gr < n && gc < n) ? A[(size_t)gr * p.lda + gc] : 0.0;
+                                    acc[c][i][j][e] = (gr < n && gc < n) ? v - acc[c][i][j][e] : 0.0;
+                                }
                     }
                 }
             }
-            if (warp == 0) {
+            PHASE_MARK(1);
+            // ---- wait for the factor / inverse of the diagonal block of this step
+            seen_dinv = progress_wait(dinv_ready, done + 1, seen_dinv);
+            PHASE_MARK(2);
+            if (sh_bad != 0 && bad_total == 0) bad_total = k0 + sh_bad;
+            const double* Dinv = Dinv2 + (done & 1) * 32 * FLDP;
+            // ---- next diagonal block first: warp 7 takes X(0) from warp 0 through shared memory, subtracts X(0) X(0)^T from
+            //      A_{j+1,j+1} - history (its second accumulator) and publishes the block, so that the aux warps factor
+            //      it while the MMA warps are still storing this block column and contracting the next one
+            if (self) {
+                asm volatile("bar.sync 3, 64;\n" ::: "memory");          // warp 0 arrives below once Xs is written
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    double xf[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) xf[i] = Xs[(i * 8 + g) * FLDP + 4 * q + t4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma884(acc[1][i][j], -xf[i], xf[j]);
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        Dblk[(i * 8 + g) * FLDP + j * 8 + 2 * t4] = acc[0][i][j][0];
-                        Dblk[(i * 8 + g) * FLDP + j * 8 + 2 * t4 + 1] = acc[0][i][j][1];
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<double2*>(Dblk + (i * 8 + g) * FLDP + j * 8 + 2 * t4) = make_double2(acc[1][i][j][0], acc[1][i][j][1]);
+                __syncwarp();
+                if (lane == 0) progress_publish(diag_ready, done + 2);
             }
-            mma_warps_sync();
-            PHASE_MARK(1);
-            cta_potf2_b8<true>(Dblk, Ld, scratch, kb, tid, &sh_bad);
-            PHASE_MARK(2);
-            if (m > NB) cta_trtri32<true>(Ld, Dinv, scratch, tid);
-            PHASE_MARK(3);
-            if (sh_bad != 0 && bad_total == 0) bad_total = k0 + sh_bad;
-            // rows below the diagonal block:  X = P * L_kk^{-T}, stored from registers   (only exists when kb == 32)
+            // ---- X = P * L_kk^{-T}, stored from registers
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const int ch = warp + c * FWARPS;
-                if (ch >= 1 && ch < nch) {
+                const int u = warp + c * FWARPS;
+                if (u < nun && !(c == 1 && self)) {
                     chunk_mul_regs<true>(acc[c], Dinv, 1.0, lane);
+                    if (u == 0) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int gr = k0 + ch * 32 + i * 8 + g;
-                        if (gr < n) {
+                        for (int i = 0; i < 4; ++i)
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                *reinterpret_cast<double2*>(A + (size_t)gr * p.lda + k0 + j * 8 + 2 * t4) =
-                                    make_double2(acc[c][i][j][0], acc[c][i][j][1]);
+                                *reinterpret_cast<double2*>(Xs + (i * 8 + g) * FLDP + j * 8 + 2 * t4) = make_double2(acc[c][i][j][0], acc[c][i][j][1]);
+                        asm volatile("bar.arrive 3, 64;\n" ::: "memory");
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int gr = k0 + NB + u * 32 + i * 8 + g;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const double2 v = make_double2(acc[c][i][j][0], acc[c][i][j][1]);
+                            if (gr < n) *reinterpret_cast<double2*>(A + (size_t)gr * p.lda + k0 + j * 8 + 2 * t4) = v;
                         }
                     }
                 }
             }
             PHASE_MARK(4);
-            for (int idx = tid; idx < NB * NB; idx += FTHREADS) {
-                const int r = idx >> 5, c = idx & 31;
-                if (r < kb && c <= r) A[(size_t)(k0 + r) * p.lda + k0 + c] = Ld[r * FLDP + c];
-            }
             fence_global_to_tma();   // the block column is read back by the TMA unit in later iterations
             mma_warps_sync();
             ++done;
@@ -388,7 +641,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_potrf_tma(const __grid_constant
 // In-place inverse of the lower factor, block columns right to left:  X[below, jb] = -Linv22 * (L21 * Dinv).
 // T = L21 * Dinv lives in shared memory (k-major B operand, rows stored in k-step order); Linv22 is streamed by TMA,
 // older block columns first so that they can be requested before the previous step has been written back.
-// Diagonal blocks are written back with an explicit zero upper triangle (the TMA tiles carry no triangular mask).
+// The aux warps invert the diagonal block of step jb-1 (double-buffered) while the MMA warps work on step jb, and write
+// it back with an explicit zero upper triangle (the TMA tiles carry no triangular mask).
 // tile order of a step with nk k-tiles: the tiles of older block columns (kt >= 4) first, then kt = 0..3
 __device__ __forceinline__ int trtri_tile_of(int pos, int nk) { return nk <= 4 ? pos : (pos < nk - 4 ? pos + 4 : pos - (nk - 4)); }
 
@@ -400,35 +654,67 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_trtri_tma(const __grid_constant
     TmaCta cta = tma_cta_setup(smem_raw, lay, tid);
     TileRing& ring = cta.ring;
     double* Tb = cta.blocks;                                  // [t_rows][FLDB]
-    double* Dsm = Tb + (size_t)lay.t_rows * FLDB;
-    double* Dinv = Dsm + 32 * FLDP;
+    double* Dsm = Tb + (size_t)lay.t_rows * FLDB;             // aux warps: diagonal block being inverted
+    double* Dinv2 = Dsm + 32 * FLDP;                          // two buffers, alternating over the steps of the CTA
+    int* dinv_ready = cta.progress + 1;                       // diagonal blocks inverted by the aux warps (count)
+    int* steps_done = cta.progress;                           // steps finished by the MMA warps (count)
 
     if (warp >= FWARPS) {
         producer_regs();
-        if (warp > FWARPS) return;
-        // ---- producer warp: k-tile kt of step pjb lies in block column pjb + 1 + kt/4, which is final once the steps
-        //      nblk-1 .. that column are done; `done` counts finished steps of the CTA
-        int done_base = 0, seen = 0;
+        if (warp == FWARPS) {
+            // ---- producer warp: k-tile kt of step pjb lies in block column pjb + 1 + kt/4, which is final once the steps
+            //      nblk-1 .. that column are done
+            int done_base = 0, seen = 0;
+            for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
+                const int n = p.n_sys ? p.n_sys[b] : p.n_max;
+                const int nblk = (n + NB - 1) / NB;
+                for (int pjb = nblk - 2; pjb >= 0; --pjb) {
+                    const int r0 = (pjb + 1) * NB;               // first trailing row / column of step pjb
+                    const int m = n - r0;
+                    const int nk = (m + 7) / 8;
+                    const int nboxes = (m + TBOX - 1) / TBOX;
+                    for (int pos = 0; pos < nk; ++pos) {
+                        const int kt = trtri_tile_of(pos, nk);
+                        seen = progress_wait(steps_done, done_base + nblk - (pjb + 1 + (kt >> 2)), seen);
+                        const int q0 = (kt >> 2) >> 1;           // rows above 32*(kt/4) never need this k-tile
+                        uint32_t bar;
+                        const uint32_t dst = ring.acquire_stage(bar, nboxes - q0, lane);
+                        if (lane == 0 && !(g_dbg & 2))
+                            for (int q = q0; q < nboxes; ++q) tma_load_box(dst + q * TBOX_BYTES, &tmap, r0 + 8 * kt, r0 + q * TBOX, b, bar);
+                        __syncwarp();
+                    }
+                }
+                done_base += nblk;
+            }
+            return;
+        }
+        // ---- auxiliary warps: a block may overwrite its buffer once the MMA warps have finished the step before the previous one
+        const int t = tid - (FWARPS + 1) * 32;
+        int blocks = 0, seen = 0;
         for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
             const int n = p.n_sys ? p.n_sys[b] : p.n_max;
+            double* L = p.A + (size_t)b * p.strideA;
             const int nblk = (n + NB - 1) / NB;
-            for (int pjb = nblk - 2; pjb >= 0; --pjb) {
-                const int r0 = (pjb + 1) * NB;               // first trailing row / column of step pjb
-                const int m = n - r0;
-                const int nk = (m + 7) / 8;
-                const int nboxes = (m + TBOX - 1) / TBOX;
-                for (int pos = 0; pos < nk; ++pos) {
-                    const int kt = trtri_tile_of(pos, nk);
-                    seen = progress_wait(cta.progress, done_base + nblk - (pjb + 1 + (kt >> 2)), seen);
-                    const int q0 = (kt >> 2) >> 1;           // rows above 32*(kt/4) never need this k-tile
-                    uint32_t bar;
-                    const uint32_t dst = ring.acquire_stage(bar, nboxes - q0, lane);
-                    if (lane == 0 && !(g_dbg & 2))
-                        for (int q = q0; q < nboxes; ++q) tma_load_box(dst + q * TBOX_BYTES, &tmap, r0 + 8 * kt, r0 + q * TBOX, b, bar);
-                    __syncwarp();
+            for (int jb = nblk - 1; jb >= 0; --jb) {
+                const int k0 = jb * NB, kb = min(NB, n - k0);
+                seen = progress_wait(steps_done, blocks - 1, seen);
+                double* Dinv = Dinv2 + (blocks & 1) * 32 * FLDP;
+                for (int idx = t; idx < NB * NB; idx += AUXT) {
+                    const int r = idx >> 5, c = idx & 31;
+                    Dsm[r * FLDP + c] = (r < kb && c <= r) ? L[(size_t)(k0 + r) * p.lda + k0 + c] : ((r == c) ? 1.0 : 0.0);
                 }
+                aux_warps_sync();
+                aux_diag8_inverse(Dsm, Dinv, t);
+                aux_trtri32_finish(Dsm, Dinv, scratch, t);
+                for (int idx = t; idx < NB * NB; idx += AUXT) {
+                    const int r = idx >> 5, c = idx & 31;
+                    if (r < kb && c < kb) L[(size_t)(k0 + r) * p.lda + k0 + c] = c <= r ? Dinv[r * FLDP + c] : 0.0;
+                }
+                fence_global_to_tma();
+                aux_warps_sync();
+                ++blocks;
+                if (t == 0) progress_publish(dinv_ready, blocks);
             }
-            done_base += nblk;
         }
         return;
     }
@@ -436,7 +722,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_trtri_tma(const __grid_constant
     mma_regs();
     int o0, o1;
     swz_offsets(lane, o0, o1);
-    int done = 0;
+    int done = 0, seen_dinv = 0;
     for (int b = blockIdx.x; b < p.batch; b += gridDim.x) {
         const int n = p.n_sys ? p.n_sys[b] : p.n_max;
         double* L = p.A + (size_t)b * p.strideA;
@@ -446,18 +732,13 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_trtri_tma(const __grid_constant
         if (n < p.n_max) {
             const int cw = min(p.n_max, (n + 7) / 8 * 8) - n;
             for (int idx = tid; idx < n * cw; idx += FTHREADS) L[(size_t)(idx / cw) * p.lda + n + idx % cw] = 0.0;
-            fence_global_to_tma();
         }
         for (int jb = nblk - 1; jb >= 0; --jb) {
             const int k0 = jb * NB;
             const int kb = min(NB, n - k0);
             const int m = n - k0 - kb;            // rows below the diagonal block
-            for (int idx = tid; idx < NB * NB; idx += FTHREADS) {
-                const int r = idx >> 5, c = idx & 31;
-                Dsm[r * FLDP + c] = (r < kb && c <= r) ? L[(size_t)(k0 + r) * p.lda + k0 + c] : ((r == c) ? 1.0 : 0.0);
-            }
-            mma_warps_sync();
-            cta_trtri32<true>(Dsm, Dinv, scratch, tid);
+            const double* Dinv = Dinv2 + (done & 1) * 32 * FLDP;
+            seen_dinv = progress_wait(dinv_ready, done + 1, seen_dinv);
             PHASE_MARK(8);
             if (m > 0) {
                 const int r_g0 = k0 + NB;
@@ -504,8 +785,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_trtri_tma(const __grid_constant
                     const double* tile = ring.wait_tile();
                     // a 32-row chunk ch only needs k < 32*(ch+1)
                     if (!(g_dbg & 1))
-                        tile_mma<false>(acc, tile, Tb + (size_t)kt * 8 * FLDB, o0, o1, live0 && kt < 4 * (warp + 1),
-                                        live1 && kt < 4 * (warp + FWARPS + 1), warp, lane);
+                        tile_mma<false>(acc, tile, Tb + (size_t)kt * 8 * FLDB, o0, o1, live0 && kt < 4 * (warp + 1), warp * 32,
+                                        live1 && kt < 4 * (warp + FWARPS + 1), (warp + FWARPS) * 32, false, lane);
                     ring.release_tile(lane);
                 }
                 PHASE_MARK(10);
@@ -526,17 +807,21 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_trtri_tma(const __grid_constant
                     }
                 }
             }
-            for (int idx = tid; idx < NB * NB; idx += FTHREADS) {
-                const int r = idx >> 5, c = idx & 31;
-                if (r < kb && c < kb) L[(size_t)(k0 + r) * p.lda + k0 + c] = c <= r ? Dinv[r * FLDP + c] : 0.0;
-            }
             fence_global_to_tma();
-            mma_warps_sync();   // also: every warp is done with T before the next step rewrites it
+            mma_warps_sync();   // also: every warp is done with T and this Dinv buffer
             ++done;
-            if (tid == 0) progress_publish(cta.progress, done);
+            if (tid == 0) progress_publish(steps_done, done);
             PHASE_MARK(11);
         }
     }
+}
+
+
+// register-budget probe for the code that runs on the auxiliary warps (never launched)
+__global__ void __launch_bounds__(AUXT) k_aux_regs_probe(double* P, double* Ld, double* X, double* S, int kb, int* bad) {
+    aux_potf2(P, Ld, X, S, kb, threadIdx.x, bad);
+    aux_diag8_inverse(Ld, X, threadIdx.x);
+    aux_trtri32_finish(Ld, X, S, threadIdx.x);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------

@@ -18,5 +18,5 @@ for flags in [0, 16] + extra:
     lib.kmpx_debug_phases(buf, 0)
     v = [x / 1e3 for x in buf]
     print(f'flags={flags}: potrf ' + ' '.join(f'p{i}={v[i]:.0f}k' for i in range(6)) + f' sum={sum(v[:6]):.0f}k | trtri ' +
-          ' '.join(f'p{i}={v[i]:.0f}k' for i in range(8, 12)) + f' sum={sum(v[8:12]):.0f}k')
+          ' '.join(f'p{i}={v[i]:.0f}k' for i in range(8, 12)) + f' sum={sum(v[8:12]):.0f}k | aux wait={v[12]:.0f}k potf2={v[13]:.0f}k trtri={v[14]:.0f}k store={v[15]:.0f}k (potf2: 8x8 part={v[6]:.0f}k panel part={v[7]:.0f}k)')
 lib.kmpx_debug_set(0)
