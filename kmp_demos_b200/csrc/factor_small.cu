@@ -563,7 +563,7 @@ int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, 
                        int info_offset, int info_accumulate, cudaStream_t st) {
     if (tma_applicable(A, lda, strideA, n_max, batch, false)) {
         CUtensorMap map;
-        KMPX_TRY(make_batch_map(&map, A, lda, strideA, n_max, batch));
+        KMPX_TRY(make_batch_map(&map, A, lda, strideA, n_max, batch, TBOX));
         const TmaSmem lay = tma_smem_layout(n_max, false, kMaxDynSmem);
         static size_t tma_smem_set = 48 * 1024;
         KMPX_TRY(ensure_dyn_smem(k_potrf_tma, lay.total, tma_smem_set, "k_potrf_tma"));
@@ -584,7 +584,7 @@ int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, 
 int launch_trtri_small(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, cudaStream_t st) {
     if (tma_applicable(L, lda, strideA, n_max, batch, true)) {
         CUtensorMap map;
-        KMPX_TRY(make_batch_map(&map, L, lda, strideA, n_max, batch));
+        KMPX_TRY(make_batch_map(&map, L, lda, strideA, n_max, batch, TBOX));
         const TmaSmem lay = tma_smem_layout(n_max, true, kMaxDynSmem);
         static size_t tma_smem_set = 48 * 1024;
         KMPX_TRY(ensure_dyn_smem(k_trtri_tma, lay.total, tma_smem_set, "k_trtri_tma"));

@@ -18,7 +18,7 @@
 // a half-warp (rows g = 0..3, four columns) hit sixteen distinct banks.  Both operands use the same column order,
 // so the contraction is unchanged.
 #pragma once
-#include <cuda.h>
+#include "tma_util.cuh"
 
 namespace kmpx {
 
@@ -26,39 +26,6 @@ constexpr int TBOX = 64;                  // rows per TMA box
 constexpr int TBOX_BYTES = TBOX * 64;     // 64 rows x 8 doubles
 constexpr int TMAX_STAGES = 8;
 constexpr size_t kMaxDynSmem = 227 * 1024 - 4096;   // 227 KB minus the static shared memory of the kernels
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MBAR_DONE;\n"
-        "bra MBAR_WAIT;\n"
-        "MBAR_DONE:\n"
-        "}\n" :: "r"(bar), "r"(parity) : "memory");
-}
-// box (8 columns x 64 rows) of problem `b` at (col, row) -> shared memory, completion on `bar`
-__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* map, int col, int row, int b, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
-        :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(col), "r"(row), "r"(b), "r"(bar) : "memory");
-}
-// makes global-memory writes of this thread visible to later TMA (async proxy) reads
-__device__ __forceinline__ void fence_global_to_tma() {
-    __threadfence();
-    asm volatile("fence.proxy.async;\n" ::: "memory");
-}
 
 // The ring of k-tiles shared by both kernels: tile t lives in stage t % S, its barriers are in phase (t / S) & 1.
 // Consumers (the eight MMA warps) and the producer warp each walk the ring with their own cursor.
@@ -223,7 +190,7 @@ struct TmaCta {   // what both kernels set up identically
     TileRing ring; double* blocks; int* progress;     // progress[0]: columns/steps done, [1], [2]: hand-overs with the aux warps
 };
 __device__ __forceinline__ TmaCta tma_cta_setup(unsigned char* smem_raw, const TmaSmem& lay, int tid) {
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* base = smem_align1k(smem_raw);
     TmaCta c;
     c.blocks = reinterpret_cast<double*>(base + lay.ring_bytes);        // [T rows (trtri)] + the 32 x FLDP blocks
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + lay.ring_bytes + lay.t_bytes + lay.blocks_bytes);
@@ -447,7 +414,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_potrf_tma(const __grid_constant
                         seen = progress_wait(cta.progress, done_base + (pkt >> 2) + 1, seen);
                         uint32_t bar;
                         const uint32_t dst = ring.acquire_stage(bar, nboxes, lane);
-                        if (lane == 0 && !(g_dbg & 2))
+                        if (lane == 0)
                             for (int q = 0; q < nboxes; ++q) tma_load_box(dst + q * TBOX_BYTES, &tmap, 8 * pkt, pk0 + q * TBOX, b, bar);
                         __syncwarp();
                     }
@@ -679,7 +646,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_trtri_tma(const __grid_constant
                         const int q0 = (kt >> 2) >> 1;           // rows above 32*(kt/4) never need this k-tile
                         uint32_t bar;
                         const uint32_t dst = ring.acquire_stage(bar, nboxes - q0, lane);
-                        if (lane == 0 && !(g_dbg & 2))
+                        if (lane == 0)
                             for (int q = q0; q < nboxes; ++q) tma_load_box(dst + q * TBOX_BYTES, &tmap, r0 + 8 * kt, r0 + q * TBOX, b, bar);
                         __syncwarp();
                     }
@@ -825,35 +792,6 @@ __global__ void __launch_bounds__(AUXT) k_aux_regs_probe(double* P, double* Ld, 
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
-typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-inline TensorMapEncodeFn tensor_map_encoder() {
-    static TensorMapEncodeFn fn = [] {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            ptr = nullptr;
-        return reinterpret_cast<TensorMapEncodeFn>(ptr);
-    }();
-    return fn;
-}
-
-// 3-D map over [problem][row][column] of a batch of row-major n_max x n_max matrices, boxes of 64 rows x 8 columns.
-inline int make_batch_map(CUtensorMap* map, const double* A, int lda, long long strideA, int n_max, int batch) {
-    TensorMapEncodeFn enc = tensor_map_encoder();
-    if (!enc) { snprintf(g_err, sizeof(g_err), "kmpx: cuTensorMapEncodeTiled is not available from the driver"); return (int)cudaErrorNotSupported; }
-    const cuuint64_t dims[3] = {(cuuint64_t)n_max, (cuuint64_t)n_max, (cuuint64_t)batch};
-    const cuuint64_t strides[2] = {(cuuint64_t)lda * 8, (cuuint64_t)(batch > 1 ? strideA : (long long)lda * n_max) * 8};
-    const cuuint32_t box[3] = {8, TBOX, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(A), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof(g_err), "kmpx: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return (int)cudaErrorInvalidValue; }
-    return 0;
-}
-
 // The TMA kernels need 16-byte aligned rows and problems, and at least three ring stages next to the fixed buffers.
 inline bool tma_applicable(const double* A, int lda, long long strideA, int n_max, int batch, bool with_t) {
     if (g_host_dbg & 16) return false;
