@@ -92,6 +92,50 @@ __device__ __forceinline__ double rbf(P1 s1, P2 s2, int I, double sigma_f, doubl
     return exp(-sigma_f * (r * r));
 }
 
+// exp(x) for x <= 0 without a single branch, so that several evaluations interleave in one instruction stream (the
+// library exp carries a rare-path branch that serialises them; a dependent FP64 operation costs 30-60 cycles here).
+// Cody-Waite reduction x = k ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation 4e-18), scaling through
+// the exponent field; results below the normal range (x < -708) flush to zero.  Error <= ~1 ulp.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double shift = 6755399441055744.0;                   // 1.5 * 2^52: the integer part lands in the low word
+    const double t = fma(x, 1.4426950408889634, shift);
+    const int k = __double2loint(t);
+    const double kd = t - shift;
+    double r = fma(kd, -6.93147180369123816490e-01, x);        // ln2 split: the high part has 33 significant bits
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double q = 1.6059043836821613e-10;                         // 1/13!
+    q = fma(q, r, 2.08767569878681e-09);                       // 1/12!
+    q = fma(q, r, 2.505210838544172e-08);
+    q = fma(q, r, 2.755731922398589e-07);
+    q = fma(q, r, 2.7557319223985893e-06);
+    q = fma(q, r, 2.48015873015873e-05);
+    q = fma(q, r, 1.984126984126984e-04);
+    q = fma(q, r, 1.388888888888889e-03);
+    q = fma(q, r, 8.333333333333333e-03);
+    q = fma(q, r, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = fma(q, r, 1.0);
+    const double res = __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
+    return x < -708.0 ? 0.0 : res;
+}
+// rbf() with the branch-free exponential (plain kernel, hot loops that evaluate many coefficients per thread)
+template <typename P1, typename P2>
+__device__ __forceinline__ double rbf_fast(P1 s1, P2 s2, int I, double sigma_f) {
+    double r2;
+    if (I == 1) {
+        const double r = fabs(s1[0] - s2[0]);
+        r2 = r * r;
+    } else {
+        double acc = 0.0;
+        for (int t = 0; t < I; ++t) { const double d = s1[t] - s2[t]; acc += d * d; }
+        const double r = sqrt(acc);                            // norm first, then squared, as the reference does
+        r2 = r * r;
+    }
+    return exp_nonpos(-sigma_f * r2);
+}
+
 // The coefficient block of one kernel evaluation: plain -> c[0]; time-driven -> c = {ktt, ktdt, kdtt, kdtdt}
 // by forward differences with dt = 1e-3 added to every input coordinate (KMP.py:113-123).
 template <typename P1, typename P2>

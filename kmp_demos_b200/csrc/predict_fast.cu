@@ -23,6 +23,7 @@
 #include "dmma_tile.cuh"
 #include "kmpx_internal.cuh"
 #include "tma_util.cuh"
+#include <type_traits>
 
 namespace kmpx {
 
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
 
+    const long long t_dbg0 = clock64();
     // ---------------------------------------------------------------- prologue (MMA warps; barrier 1 = these 256 threads)
     const double* s = p.s + (size_t)b * p.n_max * I;
     const double* sq = p.sq + (size_t)b * p.stride_sq;
@@ -153,26 +155,46 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
     for (int idx = tid; idx < n_sys_max; idx += QTHREADS) wsh[idx] = idx < n ? w[idx] : 0.0;
     for (int idx = tid; idx < QWARPS * NT * QT; idx += QTHREADS) racc[idx] = 0.0;
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    const long long t_dbg1 = clock64();
     // kappa panel (the B operand), evaluated while the first Linv tiles are in flight: warp-strided over the queries,
     // lane-strided over the stored points; column j goes to position (j & ~7) | swap_bits_1_2(j & 7)  (k-step order)
-    // (a dependent FP64 operation costs ~40 cycles here, so each lane keeps FILL_ILP independent exp chains in flight)
-    constexpr int FILL_ILP = 4;
-    for (int m = warp; m < QT; m += QWARPS) {
-        const bool live = m0 + m < p.M && !(p.dbg & 4);
-        for (int j0 = lane; j0 < ldp - 4; j0 += 32 * FILL_ILP) {     // ldp - 4 is a multiple of 32
-            double e[FILL_ILP];
+    // A dependent FP64 operation costs 40-60 cycles here and an exp is a chain of ~25 of them, so every lane keeps
+    // FILL_Q x FILL_J independent chains in flight (seven columns of one query; fourteen were measured slower); indices are clamped and the results selected, and the exponential
+    // itself is branch-free (exp_nonpos), so the chains really interleave.
+    constexpr int FILL_Q = 1, FILL_J = 7;
+    auto fill = [&](auto one_dim) {         // the I == 1 test is hoisted: a branch inside the chain body would serialise the chains
+        constexpr bool ONE = decltype(one_dim)::value;
+        for (int mb = warp; mb < QT && !(p.dbg & 4); mb += FILL_Q * QWARPS) {
+            for (int j0 = lane; j0 < ldp - 4; j0 += 32 * FILL_J) {       // ldp - 4 is a multiple of 32
+                double e[FILL_Q][FILL_J];
 #pragma unroll
-            for (int u = 0; u < FILL_ILP; ++u)      // indices clamped, results selected: branch-free, the chains interleave
-                e[u] = rbf(sqs + m * I, s + (size_t)min(j0 + 32 * u, N - 1) * I, I, p.sigma_f, 0.0, 0.0);
-            const int pj = (j0 & ~6) | ((j0 & 2) << 1) | ((j0 & 4) >> 1);       // the same permutation applies to j0 + 32 u
+                for (int u = 0; u < FILL_J; ++u) {
+                    const double* sp = s + (size_t)min(j0 + 32 * u, N - 1) * I;
 #pragma unroll
-            for (int u = 0; u < FILL_ILP; ++u) {
-                const int j = j0 + 32 * u;
-                if (j < ldp - 4) panel[(size_t)m * ldp + pj + 32 * u] = (j < N && live) ? e[u] : 0.0;
+                    for (int v = 0; v < FILL_Q; ++v) {
+                        const int m = mb + v * QWARPS;
+                        if (ONE) { const double d = fabs(sqs[m] - sp[0]); e[v][u] = exp_nonpos(-p.sigma_f * (d * d)); }
+                        else e[v][u] = rbf_fast(sqs + m * I, sp, I, p.sigma_f);
+                    }
+                }
+                const int pj = (j0 & ~6) | ((j0 & 2) << 1) | ((j0 & 4) >> 1);       // the same permutation applies to j0 + 32 u
+#pragma unroll
+                for (int v = 0; v < FILL_Q; ++v) {
+                    const int m = mb + v * QWARPS;
+                    const bool live = m0 + m < p.M;
+#pragma unroll
+                    for (int u = 0; u < FILL_J; ++u) {
+                        const int j = j0 + 32 * u;
+                        if (j < ldp - 4) panel[(size_t)m * ldp + pj + 32 * u] = (j < N && live) ? e[v][u] : 0.0;
+                    }
+                }
             }
         }
-    }
+    };
+    if (I == 1) fill(std::true_type{}); else fill(std::false_type{});
+    const long long t_dbg2 = clock64();
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    const long long t_dbg3 = clock64();
 
     // ---------------------------------------------------------------- per-warp streaming loop
     const double* ring = rings + (size_t)warp * QST * QSTAGE_ELEMS;
@@ -294,6 +316,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
     }
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
 
+    if ((p.dbg & 32) && blockIdx.x == 3 && blockIdx.y == 5 && (tid == 0 || tid == 224))
+        printf("tid %d: setup %lld  fill %lld  fill-barrier %lld  main+barrier %lld\n", tid, t_dbg1 - t_dbg0, t_dbg2 - t_dbg1, t_dbg3 - t_dbg2, clock64() - t_dbg3);
     // ---------------------------------------------------------------- outputs (reference layout, query last)
     double* xi = p.xi + (size_t)b * O * p.M;
     double* sg_out = p.sigma_out ? p.sigma_out + (size_t)b * O * O * p.M : nullptr;
