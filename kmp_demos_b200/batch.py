@@ -68,9 +68,12 @@ class KMPBatch:
         return self._bufs[key]
 
     # ------------------------------------------------------------------ device pipeline
-    def run_device(self, base_of, via_s, via_xi, via_sigma, queries, want_cov=True, out_xi=None, out_sigma=None):
+    def run_device(self, base_of, via_s, via_xi, via_sigma, queries, want_cov=True, out_xi=None, out_sigma=None,
+                   host_xi=None, host_sigma=None):
         """All arguments are device tensors: base_of int32 (B,), via_s (B,P,I), via_xi (B,P,O), via_sigma (B,P,O,O),
-        queries (M,I).  Returns (xi (B,O,M), sigma (B,O,O,M) or None, info (B,) int32, n_pts (B,) int32)."""
+        queries (M,I).  Returns (xi (B,O,M), sigma (B,O,O,M) or None, info (B,) int32, n_pts (B,) int32).
+        host_xi / host_sigma: optional pinned host tensors of the output shapes; the results of every chunk are copied
+        out on a side stream while the next chunk is computed, and the current stream waits for the last copy."""
         torch = _lib.require_cuda()
         lib = _lib.load()
         b = self._base
@@ -102,6 +105,12 @@ class KMPBatch:
         st = _lib.stream()
         td = int(self.time_driven_kernel)
         strideA = n_max * lda
+        copy_stream = None
+        if host_xi is not None or host_sigma is not None:
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream()
+            copy_stream = self._copy_stream
+            copy_stream.wait_stream(torch.cuda.current_stream())     # the previous contents of the host buffers are dead
         for c0 in range(0, B, Bc):
             bc = min(Bc, B - c0)
             npc = n_pts[c0:c0 + bc]
@@ -123,6 +132,17 @@ class KMPBatch:
             else:
                 self._launch('kmpx_kmp_predict_mean', _lib.ptr(al), _lib.ptr(s), _lib.ptr(npc), n_max_pts, I, O, bc,
                           _lib.ptr(queries), 0, M, self.sigma_f, td, _lib.ptr(xi[c0:]), st)
+            if copy_stream is not None:
+                done = torch.cuda.Event()
+                done.record()
+                copy_stream.wait_event(done)
+                with torch.cuda.stream(copy_stream):
+                    if host_xi is not None:
+                        host_xi[c0:c0 + bc].copy_(xi[c0:c0 + bc], non_blocking=True)
+                    if host_sigma is not None and sg is not None:
+                        host_sigma[c0:c0 + bc].copy_(sg[c0:c0 + bc], non_blocking=True)
+        if copy_stream is not None:
+            torch.cuda.current_stream().wait_stream(copy_stream)
         return xi, sg, info, n_pts
 
     # ------------------------------------------------------------------ host-facing call
@@ -140,11 +160,15 @@ class KMPBatch:
         d_vx = torch.as_tensor(np.ascontiguousarray(via_xi, dtype=np.float64), device=dev)
         d_vg = torch.as_tensor(np.ascontiguousarray(via_sigma, dtype=np.float64), device=dev)
         d_q = torch.as_tensor(np.ascontiguousarray(np.asarray(queries, dtype=np.float64).T), device=dev)
-        xi, sg, info, _ = self.run_device(d_base, d_vs, d_vx, d_vg, d_q, want_cov)
+        B, O, M = len(base_of), self._base['O'], d_q.shape[0]
+        h_xi = torch.empty((B, O, M), dtype=torch.float64).pin_memory()
+        h_sg = torch.empty((B, O, O, M), dtype=torch.float64).pin_memory() if want_cov else None
+        _, _, info, _ = self.run_device(d_base, d_vs, d_vx, d_vg, d_q, want_cov, host_xi=h_xi, host_sigma=h_sg)
+        torch.cuda.current_stream().synchronize()
         bad = int((info != 0).sum().item())
         if bad:
             raise np.linalg.LinAlgError(f'{bad} of {len(base_of)} systems are not positive definite')
-        return xi.cpu().numpy(), (sg.cpu().numpy() if sg is not None else None)
+        return h_xi.numpy(), (h_sg.numpy() if h_sg is not None else None)
 
 
 def shard_range(n_items, rank, world):

@@ -513,13 +513,24 @@ __global__ void __launch_bounds__(256) k_solve_alpha(AlphaArgs p) {
             ys[r] = y[idx];
         }
         __syncthreads();
-        for (int r = warp; r < n; r += 8) {
-            const double* row = F + (size_t)r * p.lda;
-            const int cend = p.general ? n : r + 1;
-            double acc = 0.0;
-            for (int c = lane; c < cend; c += 32) acc += row[c] * ys[c];
-            acc = warp_sum(acc);
-            if (lane == 0) ws[r] = acc;
+        // four rows per warp and pass: their loads are in flight together (one row at a time is latency bound)
+        for (int r0 = warp * 4; r0 < n; r0 += 32) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const int cmax = p.general ? n : min(n, r0 + 4);
+            for (int c = lane; c < cmax; c += 32) {
+                const double yv = ys[c];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = min(r0 + q, n - 1);
+                    const double v = F[(size_t)r * p.lda + c];
+                    if (p.general || c <= r0 + q) acc[q] += v * yv;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double tot = warp_sum(acc[q]);
+                if (lane == 0 && r0 + q < n) ws[r0 + q] = tot;
+            }
         }
         __syncthreads();
         if (!p.general) {
