@@ -152,6 +152,46 @@ def test_potrf_trtri_small_ragged_batch(T):
         assert rel_err(np.tril(Li[b, :n, :n]), ref) < 1e-12, n
 
 
+@pytest.mark.parametrize('nmax,lda,sizes', [(404, 408, [64, 65, 96, 100, 257, 333, 402, 404]), (202, 202, [200, 202, 128]),
+                                            (480, 480, [480, 449, 33])])
+def test_potrf_trtri_tma_variants_ragged(T, nmax, lda, sizes):
+    """Sizes at which BOTH small kernels take the TMA path (64 <= n_max, buffers fit): ragged batches, NaN everywhere
+    outside the lower triangles, leading dimension with and without padding columns."""
+    from kmp_demos_b200 import _lib
+    rng = np.random.default_rng(11)
+    A = T.full((len(sizes), nmax, lda), float('nan'), dtype=T.float64, device='cuda')
+    mats = []
+    for b, n in enumerate(sizes):
+        S = _spd(rng, n)
+        mats.append(S)
+        A[b, :n, :n] = dev(T, np.tril(S) + np.triu(np.full((n, n), np.nan), 1))
+    n_sys = dev(T, np.array(sizes, dtype=np.int32))
+    info = T.zeros(len(sizes), dtype=T.int32, device='cuda')
+    _lib.call('kmpx_potrf', _lib.ptr(A), lda, nmax * lda, _lib.ptr(n_sys), nmax, len(sizes), _lib.ptr(info), None, 0, _lib.stream())
+    Lh = A.cpu().numpy()
+    assert info.cpu().numpy().tolist() == [0] * len(sizes)
+    for b, n in enumerate(sizes):
+        assert rel_err(np.tril(Lh[b, :n, :n]), np.linalg.cholesky(mats[b])) < 1e-13, n
+    _lib.call('kmpx_trtri', _lib.ptr(A), lda, nmax * lda, _lib.ptr(n_sys), nmax, len(sizes), None, 0, _lib.stream())
+    Xh = A.cpu().numpy()
+    for b, n in enumerate(sizes):
+        assert rel_err(np.tril(Xh[b, :n, :n]), np.linalg.inv(np.linalg.cholesky(mats[b]))) < 1e-12, n
+        assert np.all(np.isnan(Xh[b, n:, :])), 'rows beyond the system must stay untouched'
+
+
+def test_potrf_tma_reports_first_bad_pivot(T):
+    from kmp_demos_b200 import _lib
+    rng = np.random.default_rng(12)
+    n = 160
+    good = _spd(rng, n)
+    bad = good.copy(); bad[100, 100] = -5.0
+    A = dev(T, np.stack([good, bad, good]))
+    info = T.zeros(3, dtype=T.int32, device='cuda')
+    _lib.call('kmpx_potrf', _lib.ptr(A), n, n * n, None, n, 3, _lib.ptr(info), None, 0, _lib.stream())
+    assert info.cpu().numpy().tolist() == [0, 101, 0]
+    assert rel_err(np.tril(A[2].cpu().numpy()), np.linalg.cholesky(good)) < 1e-13
+
+
 def test_potrf_reports_first_bad_pivot(T):
     from kmp_demos_b200 import _lib
     rng = np.random.default_rng(4)

@@ -141,6 +141,44 @@ def test_cfg3_batch_vs_reference_and_vs_single(golden):
     assert np.array_equal(x2, xi[lo:hi]) and np.array_equal(s2, sg[lo:hi])
 
 
+def test_cfg3_batch_ignores_poisoned_storage(golden):
+    """The strict upper triangle, the rows/columns beyond a system and the padding columns of the matrix buffer are
+    never part of a result: with the buffer pre-filled with NaN the batched path still reproduces the reference
+    (TMA tiles carry no mask; the kernels mask fragments in registers / rewrite what they stream)."""
+    import torch
+    from kmp_demos_b200.batch import KMPBatch
+    zl, z = golden('letters_ref.npz'), golden('cfg3_sample.npz')
+    c = wl.CFG1
+    kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=8)
+    kb.set_base(np.broadcast_to(wl.cfg1_kmp_grid(200), (26, 1, 200)), zl['gmr_mu'], zl['gmr_sigma'])
+    base_of, vs, vp, vv = [], [], [], []
+    for r in range(len(z['letter'])):
+        li, si = int(z['letter'][r]), int(z['set_idx'][r])
+        a, b, cc = wl.cfg3_via_sets(li, zl['gmr_mu'][li], si + 1)
+        base_of.append(li); vs.append(a[si]); vp.append(b[si]); vv.append(cc[si])
+    args = (np.array(base_of), np.array(vs), np.array(vp), np.array(vv), z['queries'])
+    xi0, sg0 = kb.fit_predict(*args)
+    for key, buf in kb._bufs.items():
+        if key[0] in ('A', 'w', 'alpha'):
+            buf.fill_(float('nan'))
+    xi1, sg1 = kb.fit_predict(*args)
+    assert np.array_equal(xi0, xi1) and np.array_equal(sg0, sg1)
+    for r in range(len(z['letter'])):
+        assert rel_err(xi1[r], z['xi'][r]) < MEAN_TOL and rel_err(sg1[r], z['sigma'][r]) < COV_TOL, r
+    # pinned-output form of the device call: same bits as the device tensors
+    dev = torch.device('cuda')
+    d = [torch.as_tensor(np.ascontiguousarray(x), device=dev) for x in
+         (np.array(base_of, dtype=np.int32), np.array(vs)[:, :, None], np.array(vp), np.array(vv), np.asarray(z['queries']).T)]
+    B, M = len(base_of), z['queries'].shape[1]
+    h_xi = torch.empty((B, 2, M), dtype=torch.float64).pin_memory()
+    h_sg = torch.empty((B, 2, 2, M), dtype=torch.float64).pin_memory()
+    xi_d, sg_d, info, _ = kb.run_device(*d, True, host_xi=h_xi, host_sigma=h_sg)
+    torch.cuda.synchronize()
+    assert int((info != 0).sum()) == 0
+    assert torch.equal(h_xi, xi_d.cpu()) and torch.equal(h_sg, sg_d.cpu())
+    assert np.array_equal(h_xi.numpy(), xi0)
+
+
 def test_demo2_pose_and_unlisted_sigma_quirk(golden):
     """cfg 2 (reference-faithful): O=3 KMPs on pose_data, un-listed covariance => non-symmetric system (H2)."""
     from kmp.model import KMP
