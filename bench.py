@@ -311,8 +311,16 @@ def run_ours(args):
         flops_step = float(np.sum(O * O * Ns * Ns * M_QUERIES + 2.0 * O * Ns * (O * (O + 1) / 2 + O) * M_QUERIES))
         avg_ms = sum(pred) / n_launch
         achieved = flops_step * args.steps / n_launch / avg_ms * 1e-9
+        # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/), scaled to the
+        # problems per launch of this run; None when the capture is absent
+        traffic = None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_ncu_traffic.json')
+        if os.path.isfile(tpath):
+            with open(tpath) as fh:
+                tk = json.load(fh)['k_kmp_predict_fast']
+            traffic = (tk['dram_bytes_read'] + tk['dram_bytes_write']) * (B * args.steps / n_launch) / tk['problems_per_launch']
         line['roofline'] = {'kernel': 'k_kmp_predict', 'bound': 'tensor', 'achieved': achieved, 'peak': dgemm_tf, 'unit': 'TFLOP/s',
-                            'frac': achieved / dgemm_tf, 'traffic': None, 'avg_launch_ms': avg_ms,
+                            'frac': achieved / dgemm_tf, 'traffic': traffic, 'avg_launch_ms': avg_ms,
                             'flops_per_launch': flops_step * args.steps / n_launch,
                             'peak_source': 'cuBLAS DGEMM 8192^3 sustained, measured in this run (FP64 tensor pipe)'}
         if world == 1:
