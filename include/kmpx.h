@@ -124,6 +124,24 @@ int kmpx_waypoint_insert(const double* s_base, const double* y_base, const doubl
                          double* s, double* y, double* sigma, int* n_pts, int n_max, int I, int O, int batch,
                          void* stream);
 
+/* ---- incremental adaptation for batches of problems that share base trajectories.  Replaces the
+ *      full refit of KMP.set_waypoint (KMP.py:91) + KMP.predict (KMP.py:160-194) by an exact low-rank correction of
+ *      the base solution (deleted + appended points, block-inverse identities; see csrc/incremental.cu).
+ *      Per base, once:  G = A_b^-1 [n_bases][n0][ldg] in component-major order (n0 = kmpx_sys_size(N0, O, COMPONENT)),
+ *      the base predictions xi_base [n_bases][O][M], sigma_base [n_bases][O][O][M] (kmpx_kmp_predict), and
+ *      kmpx_inc_base -> alpha_sys [n_bases][n0] = G y, kappa [n_bases][N0][M] = k(s*_m, s_j).
+ *      Per batch: kmpx_inc_adapt.  via_* as in kmpx_waypoint_insert (same nearest-point / tolerance rule);
+ *      limits O <= 2, P <= 2, plain kernel, all bases with N0 points.  ws: kmpx_inc_workspace_doubles() doubles. */
+long long kmpx_inc_workspace_doubles(int N0, int O, int batch);
+int kmpx_inc_base(const double* G, int ldg, long long strideG, const double* y_base, const double* s_base, int N0, int I,
+                  int O, int n_bases, const double* sq, int M, double sigma_f, double* alpha_sys, double* kappa,
+                  void* stream);
+int kmpx_inc_adapt(const double* s_base, const double* G, int ldg, long long strideG, const double* alpha_sys,
+                   const double* kappa, const double* xi_base, const double* sigma_base, int N0, int I, int O,
+                   const int* base_of, const double* via_s, const double* via_y, const double* via_sigma, int P,
+                   double tol, double sigma_f, double lam, double alpha_kmp, int batch, const double* sq, int M,
+                   double* ws, long long ws_doubles, double* xi, double* sigma_out, void* stream);
+
 /* ---- K8: GMR conditioning.  Replaces GaussianMixtureModel.predict, GaussianMixtureModel.py:83-105.
  *      priors [K], means [d][K], covs [d][d][K] (the reference's feature-major attributes), x [I][M];
  *      out mu [O][M], sigma [O][O][M].  Keeps the REALMIN normaliser (:90) and reg*I - mu mu^T (:104-105). */

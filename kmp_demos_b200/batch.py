@@ -145,6 +145,86 @@ class KMPBatch:
             torch.cuda.current_stream().wait_stream(copy_stream)
         return xi, sg, info, n_pts
 
+    # ------------------------------------------------------------------ incremental adaptation
+    def run_incremental(self, base_of, via_s, via_xi, via_sigma, queries, want_cov=True, out_xi=None, out_sigma=None,
+                        host_xi=None, host_sigma=None):
+        """Same arguments and results as run_device, computed by an exact low-rank correction of the per-base
+        solution instead of one factorisation per problem (csrc/incremental.cu): the bases are factorised, inverted
+        and predicted once per call (direct kernels, batch = number of bases), every problem then costs O(n^2 + n M).
+        Plain kernel, O <= 2, at most two via points per problem.  Returns (xi, sigma, info of the BASE systems)."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        b = self._base
+        if b is None:
+            raise RuntimeError('KMPBatch.set_base must be called first')
+        if self.time_driven_kernel:
+            raise ValueError('incremental adaptation is implemented for the plain kernel')
+        I, O, N0, L = b['I'], b['O'], b['N0'], b['L']
+        B, P = via_s.shape[0], via_s.shape[1]
+        M = queries.shape[0]
+        f64, i32 = torch.float64, torch.int32
+        n0 = int(lib.kmpx_sys_size(N0, O, _lib.LAYOUT_COMPONENT))
+        lda = _roundup(n0, 8)
+        st = _lib.stream()
+        # ---- per base: A_b, L^-1, w, base predictions, G = L^-T L^-1, alpha = G y, kappa
+        A = self._buf('incA', (L, n0, lda), f64)
+        A.zero_()                                   # K1 writes the lower triangle only: L^-1 must carry zeros above it
+        G = self._buf('incG', (L, n0, lda), f64)
+        n_pts = self._buf('inc_npts', (L,), i32); n_pts.fill_(N0)
+        n_sys = self._buf('inc_nsys', (L,), i32)
+        info = self._buf('inc_info', (L,), i32)
+        w = self._buf('inc_w', (L, lda), f64)
+        xi_b = self._buf('inc_xib', (L, O, M), f64)
+        sg_b = self._buf('inc_sgb', (L, O, O, M), f64)
+        al = self._buf('inc_alpha', (L, n0), f64)
+        kap = self._buf('inc_kappa', (L, N0, M), f64)
+        strideA = n0 * lda
+        self._launch('kmpx_sys_sizes', _lib.ptr(n_pts), O, _lib.LAYOUT_COMPONENT, L, _lib.ptr(n_sys), st)
+        self._launch('kmpx_kernel_build', _lib.ptr(b['s']), _lib.ptr(b['g']), _lib.ptr(n_pts), _lib.ptr(A), L, N0, I, O, lda,
+                     strideA, self.sigma_f, self.l, 0, _lib.LAYOUT_COMPONENT, _lib.UPLO_LOWER, st)
+        self._launch('kmpx_potrf', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n0, L, _lib.ptr(info), None, 0, st)
+        self._launch('kmpx_trtri', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n0, L, None, 0, st)
+        self._launch('kmpx_solve_alpha', _lib.ptr(A), lda, strideA, _lib.ptr(n_pts), N0, O, L, _lib.LAYOUT_COMPONENT,
+                     _lib.ptr(b['y']), _lib.ptr(w), lda, None, st)
+        self._launch('kmpx_kmp_predict', _lib.ptr(A), lda, strideA, 0, _lib.ptr(w), lda, _lib.ptr(b['s']), _lib.ptr(n_pts),
+                     N0, I, O, L, _lib.ptr(queries), 0, M, self.sigma_f, self.alpha, 0, _lib.ptr(xi_b), _lib.ptr(sg_b), st)
+        self._launch('kmpx_dgemm', 1, 0, n0, n0, n0, 1.0, _lib.ptr(A), lda, strideA, _lib.ptr(A), lda, strideA, 0.0,
+                     _lib.ptr(G), lda, strideA, L, 0, st)
+        self._launch('kmpx_inc_base', _lib.ptr(G), lda, strideA, _lib.ptr(b['y']), _lib.ptr(b['s']), N0, I, O, L,
+                     _lib.ptr(queries), M, self.sigma_f, _lib.ptr(al), _lib.ptr(kap), st)
+        # ---- per problem
+        xi = out_xi if out_xi is not None else torch.empty((B, O, M), dtype=f64, device='cuda')
+        sg = None
+        if want_cov:
+            sg = out_sigma if out_sigma is not None else torch.empty((B, O, O, M), dtype=f64, device='cuda')
+        Bc = min(self.chunk * 4, B)
+        nws = int(lib.kmpx_inc_workspace_doubles(N0, O, Bc))
+        ws = self._buf('inc_ws', (nws,), f64)
+        copy_stream = None
+        if host_xi is not None or host_sigma is not None:
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream()
+            copy_stream = self._copy_stream
+            copy_stream.wait_stream(torch.cuda.current_stream())
+        for c0 in range(0, B, Bc):
+            bc = min(Bc, B - c0)
+            self._launch('kmpx_inc_adapt', _lib.ptr(b['s']), _lib.ptr(G), lda, strideA, _lib.ptr(al), _lib.ptr(kap),
+                         _lib.ptr(xi_b), _lib.ptr(sg_b), N0, I, O, _lib.ptr(base_of[c0:]), _lib.ptr(via_s[c0:]),
+                         _lib.ptr(via_xi[c0:]), _lib.ptr(via_sigma[c0:]), P, self.tol, self.sigma_f, self.l, self.alpha, bc,
+                         _lib.ptr(queries), M, _lib.ptr(ws), nws, _lib.ptr(xi[c0:]), _lib.ptr(sg[c0:]) if sg is not None else None, st)
+            if copy_stream is not None:
+                done = torch.cuda.Event()
+                done.record()
+                copy_stream.wait_event(done)
+                with torch.cuda.stream(copy_stream):
+                    if host_xi is not None:
+                        host_xi[c0:c0 + bc].copy_(xi[c0:c0 + bc], non_blocking=True)
+                    if host_sigma is not None and sg is not None:
+                        host_sigma[c0:c0 + bc].copy_(sg[c0:c0 + bc], non_blocking=True)
+        if copy_stream is not None:
+            torch.cuda.current_stream().wait_stream(copy_stream)
+        return xi, sg, info
+
     # ------------------------------------------------------------------ host-facing call
     def fit_predict(self, base_of, via_s, via_xi, via_sigma, queries, want_cov=True):
         """Host arrays in, host arrays out (the reference-facing call):

@@ -1,0 +1,386 @@
+// incremental adaptation.  KMP.set_waypoint refits the whole system for every via-point set
+// (KMP.py:91); for a batch of problems that share a base trajectory the refit is replaced by an exact low-rank
+// correction of the BASE solution:
+//   * a via point that overwrites a stored point (KMP.py:80-84) first DELETES that point's O unknowns;
+//   * every via point is then APPENDED as a new point (bordered system), whether it replaced one or not.
+// With G = A_b^-1 (base), d = deleted unknowns, Cb = kernel columns of the appended points (rows of deleted points
+// zeroed), H = (G_dd)^-1, W = [G[:,d], G Cb] and, per query, v = k_b(s*), u = v W = [p, q]:
+//   N1 = H (G Cb)_d            S = D - (Cb^T G Cb - (G Cb)_d^T H (G Cb)_d)        z = k_a - q + p N1
+//   k A'^-1 k^T = v G v^T - p H p^T + z S^-1 z^T
+//   k A'^-1 Y'  = v G y_b - p H alpha_d + z S^-1 (y_a - Cb^T alpha + (G Cb)_d^T H alpha_d)
+// (block-inverse / Schur identities; mathematically the direct solution, verified against it to <= 1e-9).
+// v G v^T and v G y_b are the base predictions, shared by all problems of a base.  Work per problem drops from
+// n^3/3 + O^2 Ns^2 M to O(n^2 + r n M), r = number of touched unknowns <= 2 O P.
+//
+// Kernels: k_inc_alpha (alpha = G y per base), k_inc_kappa (kappa[base][m][j], shared by the problems of a base),
+// k_inc_setup (one CTA per problem: classification of the via points exactly as k_waypoint_insert, W, the small
+// matrices), k_inc_predict (one thread per query, CTA = 128 queries of one problem: u = kappa^T W with W broadcast from
+// shared memory, per-query algebra in registers, outputs in the reference layouts).  Limits: O <= 2, P <= 2 (r <= 8), plain kernel.
+#include "kmpx_internal.cuh"
+
+namespace kmpx {
+
+constexpr int IMAXO = 2, IMAXP = 2, IR = IMAXO * IMAXP;    // at most IR deleted and IR appended unknowns
+constexpr int IREC = 64;                                    // doubles per problem record: H[16] N1[16] Sinv[16] a_p[4] a_z[4]
+constexpr int IIREC = 8;                                    // ints per problem: nd, napp, del_idx[2], app_via[2]
+constexpr int IQT = 128;                                    // queries per CTA of k_inc_predict (one thread each)
+
+// alpha_sys[base][r] = sum_c G[r][c] y_sys[c]   (system = component-major order, padding rows carry y = 0)
+__global__ void __launch_bounds__(256) k_inc_alpha(const double* G, int ldg, long long strideG, const double* y, int N0, int O,
+                                                   double* alpha_sys) {
+    extern __shared__ double ys[];
+    const int l = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Ns = comp_stride(N0), n0 = O * Ns;
+    for (int r = tid; r < n0; r += blockDim.x) { const int a = r / Ns, i = r - a * Ns; ys[r] = i < N0 ? y[((size_t)l * N0 + i) * O + a] : 0.0; }
+    __syncthreads();
+    const double* Gl = G + (size_t)l * strideG;
+    for (int r = warp; r < n0; r += 8) {
+        double acc = 0.0;
+        for (int c = lane; c < n0; c += 32) acc += Gl[(size_t)r * ldg + c] * ys[c];
+        acc = warp_sum(acc);
+        if (lane == 0) alpha_sys[(size_t)l * n0 + r] = acc;
+    }
+}
+
+// kappa[base][j][m] = k(s*_m, s_j)   (stored point major: a thread per query reads it coalesced)
+__global__ void __launch_bounds__(256) k_inc_kappa(const double* s, int N0, int I, const double* sq, int M, double sigma_f, double* kappa) {
+    const int l = blockIdx.y;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)M * N0) return;
+    const int j = (int)(idx / M), m = (int)(idx - (long long)j * M);
+    kappa[((size_t)l * N0 + j) * M + m] = rbf(sq + (size_t)m * I, s + ((size_t)l * N0 + j) * I, I, sigma_f, 0.0, 0.0);
+}
+
+// r x r inverse (r <= 4) of a symmetric positive definite matrix by Gauss-Jordan, one thread
+__device__ inline void small_inverse(const double (&A)[IR][IR], int r, double (&X)[IR][IR]) {
+    double a[IR][IR];
+    for (int i = 0; i < IR; ++i)
+        for (int j = 0; j < IR; ++j) { a[i][j] = (i < r && j < r) ? A[i][j] : (i == j ? 1.0 : 0.0); X[i][j] = (i == j) ? 1.0 : 0.0; }
+    for (int c = 0; c < IR; ++c) {
+        const double piv = 1.0 / a[c][c];
+        for (int j = 0; j < IR; ++j) { a[c][j] *= piv; X[c][j] *= piv; }
+        for (int i = 0; i < IR; ++i) {
+            if (i == c) continue;
+            const double f = a[i][c];
+            for (int j = 0; j < IR; ++j) { a[i][j] -= f * a[c][j]; X[i][j] -= f * X[c][j]; }
+        }
+    }
+}
+
+struct IncSetupArgs {
+    const double *s_base, *G, *alpha_sys; int ldg; long long strideG; int N0, I, O;
+    const int* base_of; const double *via_s, *via_y, *via_sigma; int P; double tol, sigma_f, lam; int batch;
+    double* W; double* rec; int* irec;
+};
+
+__global__ void __launch_bounds__(128) k_inc_setup(IncSetupArgs p) {
+    extern __shared__ double sm[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N0 = p.N0, I = p.I, O = p.O, Ns = comp_stride(N0), n0 = O * Ns;
+    const int base = p.base_of ? p.base_of[b] : 0;
+    const double* sb = p.s_base + (size_t)base * N0 * I;
+    const double* Gb = p.G + (size_t)base * p.strideG;
+    const double* al = p.alpha_sys + (size_t)base * n0;
+    double* kc = sm;                          // [IMAXP][N0]
+    double* ctgc = kc + IMAXP * N0;           // [IR][IR]   Cb^T G Cb
+    double* cta = ctgc + IR * IR;             // [IR]       Cb^T alpha
+    __shared__ double sh_d[128];
+    __shared__ int sh_i[128];
+    __shared__ int nd, napp, del_idx[IMAXP], del_owner[IMAXP], app_via[IMAXP];
+    if (tid == 0) { nd = 0; napp = 0; }
+    __syncthreads();
+    // ---- classification of the via points: nearest stored input of the BASE points, strict '< tol', first minimum
+    //      (KMP.py:74-80, same scan as k_waypoint_insert); a later via point that hits the same stored point
+    //      supersedes the earlier one
+    for (int j = 0; j < p.P; ++j) {
+        const double* vs = p.via_s + ((size_t)b * p.P + j) * I;
+        double best = INFINITY; int besti = -1;
+        for (int i = tid; i < N0; i += blockDim.x) {
+            double acc = 0.0;
+            for (int t = 0; t < I; ++t) { const double d = sb[(size_t)i * I + t] - vs[t]; acc += d * d; }
+            const double dist = (I == 1) ? fabs(sb[i] - vs[0]) : sqrt(acc);
+            if (dist < best) { best = dist; besti = i; }
+        }
+        sh_d[tid] = best; sh_i[tid] = besti;
+        __syncthreads();
+        if (tid == 0) {
+            double bd = INFINITY; int bi = -1;
+            for (int t = 0; t < (int)blockDim.x; ++t) {
+                if (sh_i[t] < 0) continue;
+                if (sh_d[t] < bd || (sh_d[t] == bd && sh_i[t] < bi)) { bd = sh_d[t]; bi = sh_i[t]; }
+            }
+            if (bd < p.tol) {
+                int k = 0;
+                while (k < nd && del_idx[k] != bi) ++k;
+                if (k < nd) {                    // the stored point was already replaced by an earlier via point: drop that one
+                    const int pos = del_owner[k];
+                    for (int q = pos; q + 1 < napp; ++q) app_via[q] = app_via[q + 1];
+                    --napp;
+                    for (int k2 = 0; k2 < nd; ++k2) if (del_owner[k2] > pos) --del_owner[k2];
+                    del_owner[k] = napp;
+                } else { del_idx[nd] = bi; del_owner[nd] = napp; ++nd; }
+            }
+            app_via[napp++] = j;
+        }
+        __syncthreads();
+    }
+    const int r1 = O * nd, r2 = O * napp;
+    // ---- kernel columns of the appended points against the kept base points
+    for (int idx = tid; idx < napp * N0; idx += blockDim.x) {
+        const int q = idx / N0, j = idx - q * N0;
+        const double* vs = p.via_s + ((size_t)b * p.P + app_via[q]) * I;
+        bool gone = false;
+        for (int k = 0; k < nd; ++k) gone |= (del_idx[k] == j);
+        kc[q * N0 + j] = gone ? 0.0 : rbf(sb + (size_t)j * I, vs, I, p.sigma_f, 0.0, 0.0);
+    }
+    __syncthreads();
+    // ---- W: deleted columns = rows of the symmetric G; appended columns = G Cb
+    double* W = p.W + (size_t)b * 2 * IR * n0;
+    for (int idx = tid; idx < r1 * n0; idx += blockDim.x) {
+        const int t = idx / n0, row = idx - t * n0;
+        const int k = t / O, bc = t - k * O;
+        W[(size_t)t * n0 + row] = Gb[(size_t)(bc * Ns + del_idx[k]) * p.ldg + row];
+    }
+    // (G is symmetric: column `col` of the product is accumulated by one thread that walks DOWN the rows of G, so a warp
+    //  reads 256 contiguous bytes per step and there is no cross-lane reduction; the kernel column is broadcast from
+    //  shared memory; four rows are in flight per thread)
+    for (int col = tid; col < n0; col += blockDim.x) {
+        double acc[IMAXP][IMAXO];
+        for (int q = 0; q < IMAXP; ++q) for (int bc = 0; bc < IMAXO; ++bc) acc[q][bc] = 0.0;
+        for (int bc = 0; bc < O; ++bc) {
+            const double* gcol = Gb + (size_t)bc * Ns * p.ldg + col;
+            int j = 0;
+            for (; j + 4 <= N0; j += 4) {
+                double gv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) gv[e] = gcol[(size_t)(j + e) * p.ldg];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int q = 0; q < IMAXP; ++q) if (q < napp) acc[q][bc] = fma(gv[e], kc[q * N0 + j + e], acc[q][bc]);
+            }
+            for (; j < N0; ++j) {
+                const double gv = gcol[(size_t)j * p.ldg];
+                for (int q = 0; q < napp; ++q) acc[q][bc] = fma(gv, kc[q * N0 + j], acc[q][bc]);
+            }
+        }
+        for (int q = 0; q < napp; ++q)
+            for (int bc = 0; bc < O; ++bc) W[(size_t)(r1 + q * O + bc) * n0 + col] = acc[q][bc];
+    }
+    __syncthreads();          // W of this problem is complete (CTA scope)
+    // ---- Cb^T (G Cb) and Cb^T alpha: dot products over the stored points, one warp each
+    for (int e = warp; e < r2 * r2 + r2; e += 4) {
+        double acc = 0.0;
+        if (e < r2 * r2) {
+            const int t = e / r2, t2 = e - t * r2;               // t = (q, bc) row, t2 = (q', bc') column
+            const int q = t / O, bc = t - q * O;
+            for (int j = lane; j < N0; j += 32) acc += kc[q * N0 + j] * W[(size_t)(r1 + t2) * n0 + bc * Ns + j];
+            acc = warp_sum(acc);
+            if (lane == 0) ctgc[t * IR + t2] = acc;
+        } else {
+            const int t = e - r2 * r2, q = t / O, bc = t - q * O;
+            for (int j = lane; j < N0; j += 32) acc += kc[q * N0 + j] * al[bc * Ns + j];
+            acc = warp_sum(acc);
+            if (lane == 0) cta[t] = acc;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double Gdd[IR][IR], H[IR][IR], GCd[IR][IR], N1[IR][IR], S[IR][IR], Sinv[IR][IR], ad[IR], ya[IR], hv[IR];
+        for (int t = 0; t < IR; ++t) for (int t2 = 0; t2 < IR; ++t2) { Gdd[t][t2] = 0.0; GCd[t][t2] = 0.0; N1[t][t2] = 0.0; S[t][t2] = 0.0; H[t][t2] = 0.0; }
+        for (int t = 0; t < r1; ++t) {
+            const int k = t / O, bc = t - k * O, row = bc * Ns + del_idx[k];
+            ad[t] = al[row];
+            for (int t2 = 0; t2 < r1; ++t2) { const int k2 = t2 / O, bc2 = t2 - k2 * O; Gdd[t][t2] = Gb[(size_t)row * p.ldg + bc2 * Ns + del_idx[k2]]; }
+            for (int t2 = 0; t2 < r2; ++t2) GCd[t][t2] = W[(size_t)(r1 + t2) * n0 + row];
+        }
+        if (r1 > 0) small_inverse(Gdd, r1, H);
+        for (int t = 0; t < r1; ++t)
+            for (int t2 = 0; t2 < r2; ++t2) { double a = 0.0; for (int u = 0; u < r1; ++u) a += H[t][u] * GCd[u][t2]; N1[t][t2] = a; }
+        for (int t = 0; t < r1; ++t) { double a = 0.0; for (int u = 0; u < r1; ++u) a += H[t][u] * ad[u]; hv[t] = a; }     // H alpha_d
+        // D: kernel between the appended points + lambda * Sigma on the diagonal blocks
+        for (int t = 0; t < r2; ++t) {
+            const int q = t / O, bc = t - q * O;
+            const double* vq = p.via_s + ((size_t)b * p.P + app_via[q]) * I;
+            ya[t] = p.via_y[((size_t)b * p.P + app_via[q]) * O + bc];
+            for (int t2 = 0; t2 < r2; ++t2) {
+                const int q2 = t2 / O, bc2 = t2 - q2 * O;
+                const double* vq2 = p.via_s + ((size_t)b * p.P + app_via[q2]) * I;
+                double dv = (bc == bc2) ? rbf(vq, vq2, I, p.sigma_f, 0.0, 0.0) : 0.0;
+                if (q == q2) dv += p.lam * p.via_sigma[((size_t)b * p.P + app_via[q]) * O * O + bc * O + bc2];
+                double corr = 0.0;
+                for (int u = 0; u < r1; ++u) corr += GCd[u][t] * N1[u][t2];          // (G Cb)_d^T H (G Cb)_d
+                S[t][t2] = dv - ctgc[t * IR + t2] + corr;
+            }
+        }
+        small_inverse(S, r2, Sinv);
+        double* rec = p.rec + (size_t)b * IREC;
+        for (int t = 0; t < IR; ++t)
+            for (int t2 = 0; t2 < IR; ++t2) {
+                rec[t * IR + t2] = (t < r1 && t2 < r1) ? H[t][t2] : 0.0;
+                rec[16 + t * IR + t2] = (t < r1 && t2 < r2) ? N1[t][t2] : 0.0;
+                rec[32 + t * IR + t2] = (t < r2 && t2 < r2) ? Sinv[t][t2] : 0.0;
+            }
+        for (int t = 0; t < IR; ++t) rec[48 + t] = t < r1 ? -hv[t] : 0.0;                // a_p = -H alpha_d
+        for (int t = 0; t < IR; ++t) {                                                   // a_z = Sinv (y_a - rho)
+            double a = 0.0;
+            for (int t2 = 0; t2 < r2; ++t2) {
+                double rho = cta[t2];
+                for (int u = 0; u < r1; ++u) rho -= GCd[u][t2] * hv[u];
+                a += Sinv[t][t2] * (ya[t2] - rho);
+            }
+            rec[52 + t] = t < r2 ? a : 0.0;
+        }
+        int* ir = p.irec + (size_t)b * IIREC;
+        ir[0] = nd; ir[1] = napp;
+        for (int k = 0; k < IMAXP; ++k) { ir[2 + k] = k < nd ? del_idx[k] : -1; ir[4 + k] = k < napp ? app_via[k] : -1; }
+    }
+}
+
+struct IncPredictArgs {
+    const double *kappa, *W, *rec; const int* irec; const int* base_of;
+    const double *via_s, *sq; int P, I, O, N0, M, batch; double sigma_f, alpha_kmp;
+    const double *xi_base, *sigma_base;      // [base][O][M], [base][O][O][M]
+    double *xi, *sigma_out;
+};
+
+__global__ void __launch_bounds__(IQT) k_inc_predict(IncPredictArgs p) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y, mg = blockIdx.x * IQT + tid;
+    const int N0 = p.N0, O = p.O, I = p.I, Ns = comp_stride(N0), n0 = O * Ns, M = p.M;
+    const int base = p.base_of ? p.base_of[b] : 0;
+    constexpr int NC = IMAXO * 2 * IR;                           // 16 columns per stored point: [component][touched unknown]
+    double* Wt = sm;                                            // [N0][NC]   Wt[j][a*8 + t] = W[t][(a, j)]
+    double* rec = Wt + (size_t)N0 * NC;                         // [IREC]
+    const int* ir = p.irec + (size_t)b * IIREC;
+    const int nd = ir[0], napp = ir[1], r1 = O * nd, r2 = O * napp, r = r1 + r2;
+    const double* Wg = p.W + (size_t)b * 2 * IR * n0;
+    for (int idx = tid; idx < N0 * NC; idx += IQT) {
+        const int j = idx / NC, c = idx - j * NC, a = c / (2 * IR), t = c - a * 2 * IR;
+        Wt[idx] = (a < O && t < r) ? Wg[(size_t)t * n0 + a * Ns + j] : 0.0;
+    }
+    if (tid < IREC) rec[tid] = p.rec[(size_t)b * IREC + tid];
+    __syncthreads();
+    if (mg >= M) return;
+    // ---- u[a][t] = sum_j kappa[j][m] W[t][(a, j)]: one thread per query, sixteen independent accumulators, W broadcast
+    //      from shared memory with 16-byte loads, kappa read coalesced (stored point major)
+    double u[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) u[c] = 0.0;
+    const double* kp = p.kappa + (size_t)base * N0 * M + mg;
+    for (int j = 0; j < N0; ++j) {
+        const double kv = __ldg(kp + (size_t)j * M);
+        const double2* wr = reinterpret_cast<const double2*>(Wt + (size_t)j * NC);
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) { const double2 w2 = wr[c]; u[2 * c] = fma(kv, w2.x, u[2 * c]); u[2 * c + 1] = fma(kv, w2.y, u[2 * c + 1]); }
+    }
+    // ---- per-query algebra
+    const double* H = rec, *N1 = rec + 16, *Sinv = rec + 32, *a_p = rec + 48, *a_z = rec + 52;
+    double z[IMAXO][IR];
+#pragma unroll
+    for (int a = 0; a < IMAXO; ++a)
+#pragma unroll
+        for (int t2 = 0; t2 < IR; ++t2) z[a][t2] = 0.0;
+    double ka[IMAXP];
+    for (int q = 0; q < IMAXP; ++q)
+        ka[q] = q < napp ? rbf(p.sq + (size_t)mg * I, p.via_s + ((size_t)b * p.P + ir[4 + q]) * I, I, p.sigma_f, 0.0, 0.0) : 0.0;
+#pragma unroll
+    for (int a = 0; a < IMAXO; ++a)
+#pragma unroll
+        for (int t2 = 0; t2 < IR; ++t2) {
+            if (a < O && t2 < r2) {
+                const int q = t2 / O, bc = t2 - q * O;
+                double v = (bc == a ? ka[q] : 0.0) - u[a * 2 * IR + r1 + t2];
+#pragma unroll
+                for (int t = 0; t < IR; ++t) if (t < r1) v = fma(u[a * 2 * IR + t], N1[t * IR + t2], v);
+                z[a][t2] = v;
+            }
+        }
+#pragma unroll
+    for (int a = 0; a < IMAXO; ++a) {
+        if (a >= O) continue;
+        double mean = p.xi_base[((size_t)base * O + a) * M + mg];
+#pragma unroll
+        for (int t = 0; t < IR; ++t) if (t < r1) mean = fma(u[a * 2 * IR + t], a_p[t], mean);
+#pragma unroll
+        for (int t2 = 0; t2 < IR; ++t2) mean = fma(z[a][t2], a_z[t2], mean);
+        p.xi[((size_t)b * O + a) * M + mg] = mean;
+        if (p.sigma_out) {
+#pragma unroll
+            for (int a2 = 0; a2 < IMAXO; ++a2) {
+                if (a2 >= O) continue;
+                double php = 0.0, zsz = 0.0;
+#pragma unroll
+                for (int t = 0; t < IR; ++t) {
+                    double h = 0.0, g = 0.0;
+#pragma unroll
+                    for (int t2 = 0; t2 < IR; ++t2) {
+                        if (t < r1 && t2 < r1) h = fma(H[t * IR + t2], u[a2 * 2 * IR + t2], h);
+                        g = fma(Sinv[t * IR + t2], z[a2][t2], g);
+                    }
+                    if (t < r1) php = fma(u[a * 2 * IR + t], h, php);
+                    zsz = fma(z[a][t], g, zsz);
+                }
+                p.sigma_out[(((size_t)b * O + a) * O + a2) * M + mg] =
+                    p.sigma_base[(((size_t)base * O + a) * O + a2) * M + mg] + p.alpha_kmp * (php - zsz);
+            }
+        }
+    }
+}
+
+}  // namespace kmpx
+
+using namespace kmpx;
+
+extern "C" long long kmpx_inc_workspace_doubles(int N0, int O, int batch) {
+    const long long n0 = (long long)O * comp_stride(N0);
+    return (long long)batch * (2 * IR * n0 + IREC) + ((long long)batch * IIREC + 1) / 2;
+}
+
+extern "C" int kmpx_inc_base(const double* G, int ldg, long long strideG, const double* y_base, const double* s_base, int N0, int I,
+                             int O, int n_bases, const double* sq, int M, double sigma_f, double* alpha_sys, double* kappa,
+                             void* stream) {
+    if (!G || !y_base || !s_base || !sq || !alpha_sys || !kappa) return fail_arg(1, "null pointer");
+    if (O < 1 || O > IMAXO) return fail_arg(8, "incremental adaptation supports O <= 2");
+    if (N0 <= 0 || I <= 0 || n_bases <= 0 || M <= 0) return fail_arg(6, "sizes must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n0 = O * comp_stride(N0);
+    k_inc_alpha<<<n_bases, 256, n0 * sizeof(double), st>>>(G, ldg, strideG, y_base, N0, O, alpha_sys);
+    KMPX_TRY(check_launch("k_inc_alpha"));
+    dim3 grid(ceil_div((long long)M * N0, 256), n_bases);
+    k_inc_kappa<<<grid, 256, 0, st>>>(s_base, N0, I, sq, M, sigma_f, kappa);
+    return check_launch("k_inc_kappa");
+}
+
+extern "C" int kmpx_inc_adapt(const double* s_base, const double* G, int ldg, long long strideG, const double* alpha_sys,
+                              const double* kappa, const double* xi_base, const double* sigma_base, int N0, int I, int O,
+                              const int* base_of, const double* via_s, const double* via_y, const double* via_sigma, int P,
+                              double tol, double sigma_f, double lam, double alpha_kmp, int batch, const double* sq, int M,
+                              double* ws, long long ws_doubles, double* xi, double* sigma_out, void* stream) {
+    if (!s_base || !G || !alpha_sys || !kappa || !xi_base || !via_s || !via_y || !via_sigma || !sq || !ws || !xi)
+        return fail_arg(1, "null pointer");
+    if (sigma_out && !sigma_base) return fail_arg(8, "sigma_base is required for the covariance");
+    if (O < 1 || O > IMAXO) return fail_arg(11, "incremental adaptation supports O <= 2");
+    if (P < 1 || P > IMAXP) return fail_arg(16, "incremental adaptation supports P <= 2 via points per problem");
+    if (batch <= 0 || M <= 0 || N0 <= 0 || I <= 0) return fail_arg(21, "sizes must be positive");
+    if (ws_doubles < kmpx_inc_workspace_doubles(N0, O, batch)) return fail_arg(25, "workspace too small (kmpx_inc_workspace_doubles)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n0 = O * comp_stride(N0);
+    double* W = ws;
+    double* rec = W + (size_t)batch * 2 * IR * n0;
+    int* irec = reinterpret_cast<int*>(rec + (size_t)batch * IREC);
+    IncSetupArgs a{s_base, G, alpha_sys, ldg, strideG, N0, I, O, base_of, via_s, via_y, via_sigma, P, tol, sigma_f, lam, batch, W, rec, irec};
+    const size_t sm1 = ((size_t)IMAXP * N0 + IR * IR + IR) * sizeof(double);
+    static size_t set1 = 48 * 1024;
+    KMPX_TRY(ensure_dyn_smem(k_inc_setup, sm1, set1, "k_inc_setup"));
+    k_inc_setup<<<batch, 128, sm1, st>>>(a);
+    KMPX_TRY(check_launch("k_inc_setup"));
+    IncPredictArgs q{kappa, W, rec, irec, base_of, via_s, sq, P, I, O, N0, M, batch, sigma_f, alpha_kmp, xi_base, sigma_base, xi, sigma_out};
+    const size_t sm2 = ((size_t)N0 * IMAXO * 2 * IR + IREC) * sizeof(double);
+    static size_t set2 = 48 * 1024;
+    KMPX_TRY(ensure_dyn_smem(k_inc_predict, sm2, set2, "k_inc_predict"));
+    dim3 grid(ceil_div(M, IQT), batch);
+    k_inc_predict<<<grid, IQT, sm2, st>>>(q);
+    return check_launch("k_inc_predict");
+}

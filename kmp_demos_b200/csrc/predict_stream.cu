@@ -4,13 +4,14 @@
 //   * a CTA owns 64 queries and walks ALL row tiles (128 rows) of Linv; CTAs advance through Linv roughly in step,
 //     so the 1 GB factor is served from L2 most of the time;
 //   * per k-block of 16 stored points the ring stage holds the Linv tile of output 0 (columns j), the Linv tile of
-//     output 1 (columns Ns + j) and ONE 64 x 16 kappa tile shared by both outputs (one exp per element, evaluated
-//     by all threads while the cp.async copies are in flight);
+//     output 1 (columns Ns + j) and ONE 64 x 16 kappa tile shared by both outputs (one branch-free exp per element, four
+//     interleaved chains per thread, evaluated two stages ahead and stored after the MMAs of the current stage);
 //   * warp tile 16 rows x 64 queries x both outputs, Gram / mean reduction from the accumulator registers exactly
 //     as in predict_fast.cu; fixed reduction order => bitwise reproducible.
 // Algorithmic flops: O^2 Ns^2 M; exp evaluations: N * M * (n / 128) (about 13% of the FP64 work at O = 2).
 #include "dmma_tile.cuh"
 #include "kmpx_internal.cuh"
+#include <type_traits>
 
 namespace kmpx {
 
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(STHREADS, 1) k_kmp_predict_stream(PredictArgs 
     const int N = p.n_pts ? p.n_pts[b] : p.n_max;
     const int Ns = comp_stride(N);
     const int n = O * Ns;
+    const bool one_dim = I == 1;
 
     double* stages = smem;
     double* racc = stages + (size_t)SST * STAGE;              // [SWARPS][NT][SQT]
@@ -78,13 +80,35 @@ __global__ void __launch_bounds__(STHREADS, 1) k_kmp_predict_stream(PredictArgs 
             if (O == 2 && j0 < jmax1)
                 load_tile_async<SBK, SLD, true>(st + SBM * SLD, F + (size_t)r0 * p.lda + Ns + j0, p.lda, SBM, rows_valid, r0,
                                                 Ns + j0, Ns + jmax1, tid, STHREADS);
-            double* bt = st + O * SBM * SLD;
-            for (int idx = tid; idx < SQT * SBK; idx += STHREADS) {
-                const int m = idx / SBK, kk = idx - m * SBK;
-                const int j = j0 + kk;
-                double v = 0.0;
-                if (j < N && m0 + m < p.M) v = rbf(sqs + m * I, s + (size_t)j * I, I, p.sigma_f, 0.0, 0.0);
-                bt[m * SLD + kk] = v;
+        };
+        // kappa tile of stage kt: SQT * SBK / STHREADS = 4 coefficients per thread, evaluated as four interleaved branch-free
+        // chains into registers (the library exp serialises them and its latency would sit in front of the DMMAs of
+        // the same warp); they are stored after the MMAs of the current stage
+        constexpr int KPT = SQT * SBK / STHREADS;
+        auto kappa_eval_t = [&](int kt, double (&kv)[KPT], auto od) {       // the I == 1 test stays outside the chains
+            constexpr bool OD = decltype(od)::value;
+            const int j0 = kt * SBK;
+#pragma unroll
+            for (int u = 0; u < KPT; ++u) {
+                const int idx = tid + u * STHREADS;
+                const int m = idx / SBK, j = j0 + (idx - m * SBK);
+                const double* sp = s + (size_t)min(j, N - 1) * I;
+                double e;
+                if (OD) { const double d = fabs(sqs[m] - sp[0]); e = exp_nonpos(-p.sigma_f * (d * d)); }
+                else e = rbf_fast(sqs + m * I, sp, I, p.sigma_f);
+                kv[u] = (j < N && m0 + m < p.M) ? e : 0.0;
+            }
+        };
+        auto kappa_eval = [&](int kt, double (&kv)[KPT]) {
+            if (one_dim) kappa_eval_t(kt, kv, std::true_type{}); else kappa_eval_t(kt, kv, std::false_type{});
+        };
+        auto kappa_store = [&](int kt, const double (&kv)[KPT]) {
+            double* bt = stages + (size_t)(kt % SST) * STAGE + O * SBM * SLD;
+#pragma unroll
+            for (int u = 0; u < KPT; ++u) {
+                const int idx = tid + u * STHREADS;
+                const int m = idx / SBK;
+                bt[m * SLD + (idx - m * SBK)] = kv[u];
             }
         };
 
@@ -92,11 +116,16 @@ __global__ void __launch_bounds__(STHREADS, 1) k_kmp_predict_stream(PredictArgs 
         zero_acc(acc0);
         zero_acc(acc1);
 #pragma unroll
-        for (int st = 0; st < SST - 1; ++st) { if (st < nk) issue(st); cp_async_commit(); }
+        for (int st = 0; st < SST - 1; ++st) {
+            if (st < nk) { issue(st); double kv[KPT]; kappa_eval(st, kv); kappa_store(st, kv); }
+            cp_async_commit();
+        }
         for (int kt = 0; kt < nk; ++kt) {
             cp_async_wait<SST - 2>();
             __syncthreads();
-            if (kt + SST - 1 < nk) issue(kt + SST - 1);
+            const bool more = kt + SST - 1 < nk;
+            double kv[KPT];
+            if (more) { issue(kt + SST - 1); kappa_eval(kt + SST - 1, kv); }
             cp_async_commit();
             const double* st = stages + (size_t)(kt % SST) * STAGE;
             const double* bt = st + O * SBM * SLD;
@@ -107,6 +136,7 @@ __global__ void __launch_bounds__(STHREADS, 1) k_kmp_predict_stream(PredictArgs 
                 for (int kk = 0; kk < SBK; kk += 4)
                     warp_mma_k4<2, 8, false>(acc1, st + SBM * SLD + (warp * 16) * SLD + kk, SLD, bt + kk, SLD, lane);
             }
+            if (more) kappa_store(kt + SST - 1, kv);
         }
         cp_async_wait<0>();
         // reduce this warp's 16 rows of V straight from the accumulators

@@ -179,6 +179,55 @@ def test_cfg3_batch_ignores_poisoned_storage(golden):
     assert np.array_equal(h_xi.numpy(), xi0)
 
 
+def test_incremental_adaptation_equals_direct_and_reference(golden):
+    """the low-rank correction of the base solution gives the reference's results (golden cfg-3 sample)
+    and agrees with the direct batched path far inside the stated tolerances - including a via point that replaces
+    a stored point with a slightly different input, two via points that hit the same stored point, one appended and
+    one replaced point, and single-via-point problems."""
+    import torch
+    from kmp_demos_b200.batch import KMPBatch
+    zl, z = golden('letters_ref.npz'), golden('cfg3_sample.npz')
+    c = wl.CFG1
+    grid = wl.cfg1_kmp_grid(200)
+    kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=16)
+    kb.set_base(np.broadcast_to(grid, (26, 1, 200)), zl['gmr_mu'], zl['gmr_sigma'])
+    base_of, vs, vp, vv = [], [], [], []
+    for r in range(len(z['letter'])):
+        li, si = int(z['letter'][r]), int(z['set_idx'][r])
+        a, b, cc = wl.cfg3_via_sets(li, zl['gmr_mu'][li], si + 1)
+        base_of.append(li); vs.append(a[si]); vp.append(b[si]); vv.append(cc[si])
+    n_gold = len(base_of)
+    # hand-made edge cases on letter 3
+    g = grid[0]
+    extra = [(g[50], g[50] + 1e-4),          # both hit stored point 50: the later one supersedes the earlier one
+             (g[10] + 3e-4, 1.2345),         # replace with a slightly different input, plus an append
+             (g[199], g[0]),                 # two replacements at the ends of the trajectory
+             (0.33333, 1.77777)]             # two appends
+    rng = np.random.default_rng(5)
+    for t1, t2 in extra:
+        base_of.append(3); vs.append(np.array([t1, t2])); vp.append(rng.normal(0.0, 3.0, (2, 2)))
+        vv.append(np.stack([1e-4 * np.eye(2), np.array([[2e-3, 5e-4], [5e-4, 1e-3]])]))
+    dev = torch.device('cuda')
+    d = [torch.as_tensor(np.ascontiguousarray(x), device=dev) for x in
+         (np.array(base_of, dtype=np.int32), np.array(vs)[:, :, None], np.array(vp), np.array(vv), np.asarray(z['queries']).T)]
+    xd, sd, info, n_pts = kb.run_device(*d)
+    xd, sd = xd.cpu().numpy(), sd.cpu().numpy()
+    assert int((info != 0).sum()) == 0
+    assert n_pts.cpu().numpy()[n_gold:].tolist() == [200, 201, 200, 202]
+    xi, sg, info_b = kb.run_incremental(*d)
+    xi, sg = xi.cpu().numpy(), sg.cpu().numpy()
+    assert int((info_b != 0).sum()) == 0
+    for r in range(len(base_of)):
+        assert rel_err(xi[r], xd[r]) < MEAN_TOL and rel_err(sg[r], sd[r]) < COV_TOL, r
+    for r in range(n_gold):
+        assert rel_err(xi[r], z['xi'][r]) < MEAN_TOL and rel_err(sg[r], z['sigma'][r]) < COV_TOL, r
+    # one via point per problem
+    d1 = [d[0], d[1][:, :1].contiguous(), d[2][:, :1].contiguous(), d[3][:, :1].contiguous(), d[4]]
+    x1, s1, _, _ = kb.run_device(*d1)
+    x2, s2, _ = kb.run_incremental(*d1)
+    assert rel_err(x2.cpu().numpy(), x1.cpu().numpy()) < MEAN_TOL and rel_err(s2.cpu().numpy(), s1.cpu().numpy()) < COV_TOL
+
+
 def test_demo2_pose_and_unlisted_sigma_quirk(golden):
     """cfg 2 (reference-faithful): O=3 KMPs on pose_data, un-listed covariance => non-symmetric system (H2)."""
     from kmp.model import KMP
