@@ -276,6 +276,29 @@ def run_ours(args):
     # sanity on the copied-out results: finite, covariance diagonals non-negative up to rounding
     assert bool(torch.isfinite(h_xi[:64]).all()) and float(h_sg[:64, 0, 0].min()) > -1e-6
 
+    # ---- SURVEY 8(f1), reported NEXT TO the direct method (the metric, `value` and `roofline` stay the direct path):
+    #      the same problems through the incremental adaptation, device-resident and end to end, and its deviation
+    #      from the direct results of this very run
+    def step_inc_device():
+        return kb.run_incremental(d_base, d_vs, d_vp, d_vv, d_q, True, xi_inc, sg_inc)
+
+    def step_inc_e2e():
+        for dst, srcb in ((d_base, h_base), (d_vs, h_vs), (d_vp, h_vp), (d_vv, h_vv), (d_q, h_q)):
+            dst.copy_(srcb, non_blocking=True)
+        kb.run_incremental(d_base, d_vs, d_vp, d_vv, d_q, True, xi_inc, sg_inc, host_xi=h_xi, host_sigma=h_sg)
+
+    xi_inc, sg_inc = torch.empty_like(xi), torch.empty_like(sg)
+    step_device()
+    ms_inc, _, _, _ = timed(step_inc_device, False)
+    den_x = torch.linalg.norm(xi.reshape(B, -1), dim=1)
+    den_s = torch.linalg.norm(sg.reshape(B, -1), dim=1)
+    inc_err_mean = float((torch.linalg.norm((xi_inc - xi).reshape(B, -1), dim=1) / den_x).max())
+    inc_err_cov = float((torch.linalg.norm((sg_inc - sg).reshape(B, -1), dim=1) / den_s).max())
+    ms_inc_e2e, _, _, _ = timed(step_inc_e2e, False)
+    log(f'incremental adaptation: {ms_inc:.1f} ms/step device-resident, {ms_inc_e2e:.1f} ms/step end to end; '
+        f'max deviation from the direct path: mean {inc_err_mean:.1e}, covariance {inc_err_cov:.1e}')
+    assert inc_err_mean < 1e-9 and inc_err_cov < 1e-7, 'incremental adaptation deviates from the direct path'
+
     value = world * B / (ms_dev * 1e-3)
     e2e_value = world * B / (ms_e2e * 1e-3)
     h2d = sum(x.numel() * x.element_size() for x in (h_base, h_vs, h_vp, h_vv, h_q))
@@ -328,6 +351,13 @@ def run_ours(args):
             if not args.no_extras:
                 log('extras: per-kernel figures (cfg 4, EM, GMR, quaternion maps)')
                 line['extras'] = extras_single_gpu(torch, dgemm_tf)
+        line['incremental'] = {
+            'what': 'SURVEY 8(f1): same cfg-3 problems by exact low-rank correction of the per-base solution '
+                    '(KMPBatch.run_incremental) instead of one refit per via-point set; bases re-factorised inside every step',
+            'value': world * B / (ms_inc * 1e-3), 'unit': UNIT, 'ms_per_step': ms_inc,
+            'e2e': {'value': world * B / (ms_inc_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_inc_e2e,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'max_rel_dev_from_direct': {'mean': inc_err_mean, 'covariance': inc_err_cov}}
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()

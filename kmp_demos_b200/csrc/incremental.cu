@@ -143,19 +143,19 @@ __global__ void __launch_bounds__(128) k_inc_setup(IncSetupArgs p) {
     }
     // (G is symmetric: column `col` of the product is accumulated by one thread that walks DOWN the rows of G, so a warp
     //  reads 256 contiguous bytes per step and there is no cross-lane reduction; the kernel column is broadcast from
-    //  shared memory; four rows are in flight per thread)
+    //  shared memory)
     for (int col = tid; col < n0; col += blockDim.x) {
         double acc[IMAXP][IMAXO];
         for (int q = 0; q < IMAXP; ++q) for (int bc = 0; bc < IMAXO; ++bc) acc[q][bc] = 0.0;
         for (int bc = 0; bc < O; ++bc) {
             const double* gcol = Gb + (size_t)bc * Ns * p.ldg + col;
             int j = 0;
-            for (; j + 4 <= N0; j += 4) {
-                double gv[4];
+            for (; j + 16 <= N0; j += 16) {          // sixteen loads in flight per thread: the loop is L2-latency bound
+                double gv[16];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) gv[e] = gcol[(size_t)(j + e) * p.ldg];
+                for (int e = 0; e < 16; ++e) gv[e] = __ldg(gcol + (size_t)(j + e) * p.ldg);
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
+                for (int e = 0; e < 16; ++e)
 #pragma unroll
                     for (int q = 0; q < IMAXP; ++q) if (q < napp) acc[q][bc] = fma(gv[e], kc[q * N0 + j + e], acc[q][bc]);
             }
@@ -244,38 +244,10 @@ struct IncPredictArgs {
     double *xi, *sigma_out;
 };
 
-__global__ void __launch_bounds__(IQT) k_inc_predict(IncPredictArgs p) {
-    extern __shared__ __align__(16) double sm[];
-    const int tid = threadIdx.x;
-    const int b = blockIdx.y, mg = blockIdx.x * IQT + tid;
-    const int N0 = p.N0, O = p.O, I = p.I, Ns = comp_stride(N0), n0 = O * Ns, M = p.M;
-    const int base = p.base_of ? p.base_of[b] : 0;
-    constexpr int NC = IMAXO * 2 * IR;                           // 16 columns per stored point: [component][touched unknown]
-    double* Wt = sm;                                            // [N0][NC]   Wt[j][a*8 + t] = W[t][(a, j)]
-    double* rec = Wt + (size_t)N0 * NC;                         // [IREC]
-    const int* ir = p.irec + (size_t)b * IIREC;
-    const int nd = ir[0], napp = ir[1], r1 = O * nd, r2 = O * napp, r = r1 + r2;
-    const double* Wg = p.W + (size_t)b * 2 * IR * n0;
-    for (int idx = tid; idx < N0 * NC; idx += IQT) {
-        const int j = idx / NC, c = idx - j * NC, a = c / (2 * IR), t = c - a * 2 * IR;
-        Wt[idx] = (a < O && t < r) ? Wg[(size_t)t * n0 + a * Ns + j] : 0.0;
-    }
-    if (tid < IREC) rec[tid] = p.rec[(size_t)b * IREC + tid];
-    __syncthreads();
-    if (mg >= M) return;
-    // ---- u[a][t] = sum_j kappa[j][m] W[t][(a, j)]: one thread per query, sixteen independent accumulators, W broadcast
-    //      from shared memory with 16-byte loads, kappa read coalesced (stored point major)
-    double u[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) u[c] = 0.0;
-    const double* kp = p.kappa + (size_t)base * N0 * M + mg;
-    for (int j = 0; j < N0; ++j) {
-        const double kv = __ldg(kp + (size_t)j * M);
-        const double2* wr = reinterpret_cast<const double2*>(Wt + (size_t)j * NC);
-#pragma unroll
-        for (int c = 0; c < NC / 2; ++c) { const double2 w2 = wr[c]; u[2 * c] = fma(kv, w2.x, u[2 * c]); u[2 * c + 1] = fma(kv, w2.y, u[2 * c + 1]); }
-    }
-    // ---- per-query algebra
+// per-query algebra of k_inc_predict (u = v W for this query, in registers)
+__device__ __forceinline__ void inc_combine(const IncPredictArgs& p, const double (&u)[IMAXO * 2 * IR], const double* rec, const int* ir,
+                                            int b, int base, int mg, int r1, int r2, int napp) {
+    const int O = p.O, I = p.I, M = p.M;
     const double* H = rec, *N1 = rec + 16, *Sinv = rec + 32, *a_p = rec + 48, *a_z = rec + 52;
     double z[IMAXO][IR];
 #pragma unroll
@@ -283,15 +255,30 @@ __global__ void __launch_bounds__(IQT) k_inc_predict(IncPredictArgs p) {
 #pragma unroll
         for (int t2 = 0; t2 < IR; ++t2) z[a][t2] = 0.0;
     double ka[IMAXP];
+#pragma unroll
     for (int q = 0; q < IMAXP; ++q)
         ka[q] = q < napp ? rbf(p.sq + (size_t)mg * I, p.via_s + ((size_t)b * p.P + ir[4 + q]) * I, I, p.sigma_f, 0.0, 0.0) : 0.0;
+    // appended columns sit behind the r1 deleted ones: uq[a][t2] = u[a][r1 + t2] without dynamic register indexing
+    double uq[IMAXO][IR];
+#pragma unroll
+    for (int a = 0; a < IMAXO; ++a)
+#pragma unroll
+        for (int t2 = 0; t2 < IR; ++t2) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < 2 * IR; ++c) if (c == r1 + t2) v = u[a * 2 * IR + c];
+            uq[a][t2] = v;
+        }
 #pragma unroll
     for (int a = 0; a < IMAXO; ++a)
 #pragma unroll
         for (int t2 = 0; t2 < IR; ++t2) {
             if (a < O && t2 < r2) {
                 const int q = t2 / O, bc = t2 - q * O;
-                double v = (bc == a ? ka[q] : 0.0) - u[a * 2 * IR + r1 + t2];
+                double kav = 0.0;
+#pragma unroll
+                for (int qq = 0; qq < IMAXP; ++qq) if (qq == q && bc == a) kav = ka[qq];
+                double v = kav - uq[a][t2];
 #pragma unroll
                 for (int t = 0; t < IR; ++t) if (t < r1) v = fma(u[a * 2 * IR + t], N1[t * IR + t2], v);
                 z[a][t2] = v;
@@ -327,6 +314,47 @@ __global__ void __launch_bounds__(IQT) k_inc_predict(IncPredictArgs p) {
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(IQT) k_inc_predict(IncPredictArgs p) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y, mq0 = blockIdx.x * (2 * IQT) + tid, mq1 = mq0 + IQT;     // two queries per thread
+    const int N0 = p.N0, O = p.O, Ns = comp_stride(N0), n0 = O * Ns, M = p.M;
+    const int base = p.base_of ? p.base_of[b] : 0;
+    constexpr int NC = IMAXO * 2 * IR;                           // 16 columns per stored point: [component][touched unknown]
+    double* Wt = sm;                                            // [N0][NC]   Wt[j][a*8 + t] = W[t][(a, j)]
+    double* rec = Wt + (size_t)N0 * NC;                         // [IREC]
+    const int* ir = p.irec + (size_t)b * IIREC;
+    const int nd = ir[0], napp = ir[1], r1 = O * nd, r2 = O * napp, r = r1 + r2;
+    const double* Wg = p.W + (size_t)b * 2 * IR * n0;
+    for (int idx = tid; idx < N0 * NC; idx += IQT) {
+        const int j = idx / NC, c = idx - j * NC, a = c / (2 * IR), t = c - a * 2 * IR;
+        Wt[idx] = (a < O && t < r) ? Wg[(size_t)t * n0 + a * Ns + j] : 0.0;
+    }
+    if (tid < IREC) rec[tid] = p.rec[(size_t)b * IREC + tid];
+    __syncthreads();
+    if (mq0 >= M) return;
+    // ---- u[a][t] = sum_j kappa[j][m] W[t][(a, j)]: two queries per thread (every 16-byte broadcast load of W feeds four
+    //      FMAs), 2 x 16 independent accumulators, kappa read coalesced (stored point major)
+    const bool two = mq1 < M;
+    double u0[NC], u1[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { u0[c] = 0.0; u1[c] = 0.0; }
+    const double* kp0 = p.kappa + (size_t)base * N0 * M + mq0;
+    const double* kp1 = p.kappa + (size_t)base * N0 * M + (two ? mq1 : mq0);
+    for (int j = 0; j < N0; ++j) {
+        const double k0 = __ldg(kp0 + (size_t)j * M), k1 = __ldg(kp1 + (size_t)j * M);
+        const double2* wr = reinterpret_cast<const double2*>(Wt + (size_t)j * NC);
+#pragma unroll
+        for (int c = 0; c < NC / 2; ++c) {
+            const double2 w2 = wr[c];
+            u0[2 * c] = fma(k0, w2.x, u0[2 * c]); u0[2 * c + 1] = fma(k0, w2.y, u0[2 * c + 1]);
+            u1[2 * c] = fma(k1, w2.x, u1[2 * c]); u1[2 * c + 1] = fma(k1, w2.y, u1[2 * c + 1]);
+        }
+    }
+    inc_combine(p, u0, rec, ir, b, base, mq0, r1, r2, napp);
+    if (two) inc_combine(p, u1, rec, ir, b, base, mq1, r1, r2, napp);
 }
 
 }  // namespace kmpx
@@ -380,7 +408,7 @@ extern "C" int kmpx_inc_adapt(const double* s_base, const double* G, int ldg, lo
     const size_t sm2 = ((size_t)N0 * IMAXO * 2 * IR + IREC) * sizeof(double);
     static size_t set2 = 48 * 1024;
     KMPX_TRY(ensure_dyn_smem(k_inc_predict, sm2, set2, "k_inc_predict"));
-    dim3 grid(ceil_div(M, IQT), batch);
+    dim3 grid(ceil_div(M, 2 * IQT), batch);
     k_inc_predict<<<grid, IQT, sm2, st>>>(q);
     return check_launch("k_inc_predict");
 }
