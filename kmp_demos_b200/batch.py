@@ -197,7 +197,7 @@ class KMPBatch:
         sg = None
         if want_cov:
             sg = out_sigma if out_sigma is not None else torch.empty((B, O, O, M), dtype=f64, device='cuda')
-        Bc = min(self.chunk * 4, B)
+        Bc = min(self.chunk, B)
         nws = int(lib.kmpx_inc_workspace_doubles(N0, O, Bc))
         ws = self._buf('inc_ws', (nws,), f64)
         copy_stream = None
