@@ -110,6 +110,14 @@ int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kin
                      int batch, const double* sq, long long stride_sq, int M,
                      double sigma_f, double alpha_kmp, int time_driven,
                      double* xi, double* sigma_out, void* stream);
+/* The same prediction for ONE large system (n > KMPX_SMALL_MAX, plain kernel, O <= 2, symmetric factor) as DMMA GEMMs:
+ * kappa (N x Mc) once per chunk of queries, V_a = Linv[a Ns:, a Ns: a Ns + N] kappa with kmpx_dgemm's triangular mode,
+ * column reductions for xi / sigma.  F as left by kmpx_trtri for n > KMPX_SMALL_MAX (strict upper triangle zero).
+ * The workspace decides the chunk size Mc (a multiple of 128; 8192 queries of cfg 4 need 2.2 GB). */
+long long kmpx_kmp_predict_gemm_workspace_bytes(int N, int O, int Mc);
+int kmpx_kmp_predict_gemm(const double* F, int lda, const double* w, const double* s, int N, int I, int O,
+                          const double* sq, int M, double sigma_f, double alpha_kmp, double* ws, long long ws_bytes,
+                          double* xi, double* sigma_out, void* stream);
 /* mean-only predict from alpha (point-major [batch][n_max][O]): xi[a][m] = sum_i k(s*_m,s_i) alpha_i. */
 int kmpx_kmp_predict_mean(const double* alpha, const double* s, const int* n_pts, int n_max, int I, int O,
                           int batch, const double* sq, long long stride_sq, int M,

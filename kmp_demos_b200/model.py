@@ -167,9 +167,19 @@ class KMP:
         xi = torch.empty((f.O, M), dtype=torch.float64, device=dev)
         sg = torch.empty((f.O, f.O, M), dtype=torch.float64, device=dev)
         n = f.F.shape[0]
-        _lib.call('kmpx_kmp_predict', _lib.ptr(f.F), f.lda, n * f.lda, f.kind, _lib.ptr(f.w), f.lda,
-                  _lib.ptr(f.s_dev), None, f.N, f.I, f.O, 1, _lib.ptr(sq), 0, M, float(self.sigma_f),
-                  float(self.alpha), int(bool(self.time_driven_kernel)), _lib.ptr(xi), _lib.ptr(sg), _lib.stream())
+        if f.kind == 0 and not self.time_driven_kernel and f.O <= 2 and n > _lib.SMALL_MAX:
+            # one large system: kappa + DMMA GEMMs + column reductions (predict_gemm.cu), queries in chunks of <= 8192
+            lib = _lib.load()
+            mc = min((M + 127) // 128 * 128, 8192)
+            nbytes = int(lib.kmpx_kmp_predict_gemm_workspace_bytes(f.N, f.O, mc))
+            ws = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
+            _lib.call('kmpx_kmp_predict_gemm', _lib.ptr(f.F), f.lda, _lib.ptr(f.w), _lib.ptr(f.s_dev), f.N, f.I, f.O,
+                      _lib.ptr(sq), M, float(self.sigma_f), float(self.alpha), _lib.ptr(ws), nbytes, _lib.ptr(xi), _lib.ptr(sg),
+                      _lib.stream())
+        else:
+            _lib.call('kmpx_kmp_predict', _lib.ptr(f.F), f.lda, n * f.lda, f.kind, _lib.ptr(f.w), f.lda,
+                      _lib.ptr(f.s_dev), None, f.N, f.I, f.O, 1, _lib.ptr(sq), 0, M, float(self.sigma_f),
+                      float(self.alpha), int(bool(self.time_driven_kernel)), _lib.ptr(xi), _lib.ptr(sg), _lib.stream())
         self._logger.info("KMP predict done.")
         return xi.cpu().numpy(), sg.cpu().numpy()
 

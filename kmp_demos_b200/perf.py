@@ -93,6 +93,16 @@ def cfg4(N, dg):
                                   _lib.ptr(q), 0, M, c['sigma_f'], c['alpha'], 0, _lib.ptr(xi), _lib.ptr(sg), st), reps=1, warm=1)
     fl = float(O * O) * N * N * M
     out['predict_cov'] = {'M': M, 'ms': ms, 'tflops': fl / ms * 1e-9, 'frac_dgemm': fl / ms * 1e-9 / dg, 'ms_per_100k_queries': ms * 1e5 / M}
+    out['predict_cov_stream'] = out.pop('predict_cov')
+    xi2 = torch.empty_like(xi); sg2 = torch.empty_like(sg)
+    gbytes = int(lib.kmpx_kmp_predict_gemm_workspace_bytes(N, O, M)); gws = torch.empty(gbytes // 8, dtype=f64, device='cuda')
+    ms = timeit(lambda: _lib.call('kmpx_kmp_predict_gemm', _lib.ptr(A), lda, _lib.ptr(w), _lib.ptr(s_d), N, 1, O, _lib.ptr(q), M,
+                                  c['sigma_f'], c['alpha'], _lib.ptr(gws), gbytes, _lib.ptr(xi2), _lib.ptr(sg2), st), reps=2, warm=1)
+    dev_x = float((xi2 - xi).norm() / xi.norm()); dev_s = float((sg2 - sg).norm() / sg.norm())
+    out['predict_cov'] = {'M': M, 'route': 'kappa + k_dgemm + column reductions (predict_gemm.cu)', 'ms': ms, 'tflops': fl / ms * 1e-9,
+                          'frac_dgemm': fl / ms * 1e-9 / dg, 'ms_per_100k_queries': ms * 1e5 / M,
+                          'rel_dev_from_stream_kernel': {'mean': dev_x, 'covariance': dev_s}}
+    del gws
     ms = timeit(lambda: _lib.call('kmpx_kmp_predict_mean', _lib.ptr(al), _lib.ptr(s_d), None, N, 1, O, 1, _lib.ptr(q), 0, M, c['sigma_f'], 0,
                                   _lib.ptr(xi), st), reps=2, warm=1)
     out['predict_mean'] = {'M': M, 'ms': ms, 'gexp_per_s': N * M / ms * 1e-6}
