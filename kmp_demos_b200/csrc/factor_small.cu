@@ -1,16 +1,22 @@
 // K2/K3 for small systems (n <= KMPX_SMALL_MAX): one CTA per problem, persistent over the batch.
 //
+// This file holds the cp.async variants (taken for n < 64, unaligned operands or when the buffers of the TMA kernels
+// do not fit) and the 32 x 32 block helpers; the TMA-fed kernels with separate producer / auxiliary warps that serve
+// the benchmark sizes are in factor_tma.cuh, which is included at the end of this translation unit.
+//
 //   k_potrf_small   left-looking blocked Cholesky, block columns of 32.  The update of block column k0
 //                   (rows k0..n-1) by all previous columns is the only dense contraction:
 //                   C(m x 32) += L[k0:n, 0:k0] * L[k0:k0+32, 0:k0]^T  on DMMA, the operand streamed once
-//                   per block column through a 3-stage cp.async ring (the B operand is the first 32 rows
-//                   of the same tile).  Diagonal block: one warp, shared memory.  Panel solve: one thread
-//                   per row, registers.
+//                   per block column through a 4-stage cp.async ring, two k-tiles per barrier (the B operand is
+//                   the first 32 rows of the same tile).  Diagonal block: cta_potf2_b8 (8-column panels) and
+//                   cta_trtri32; panel solve = DMMA multiply by the inverse of the diagonal block.
 //   k_trtri_small   in-place inverse of the lower factor, right to left:
 //                   X = -Linv22 * (L21 * Dinv)   with the (m x m, lower) Linv22 streamed on DMMA.
-//   k_solve_alpha   w = Linv * y', alpha' = Linv^T * w   (two passes over Linv, bandwidth-bound).
+//   k_solve_alpha   w = Linv * y' (four rows in flight per warp), optionally alpha' = Linv^T * w.
 //
 // Algorithmic flops: n^3/3 each for potrf and trtri; bytes: the matrix is read and written once.
+// kmpx_debug_set / kmpx_debug_phases: profiling aids (skip the MMAs of the K-loops, force the cp.async variants,
+// per-phase cycle counters of CTA 0) used by tools/factor_phases.py; they do not change results when unset.
 #include "dmma_tile.cuh"
 #include "kmpx_internal.cuh"
 

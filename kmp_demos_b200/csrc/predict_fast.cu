@@ -143,7 +143,6 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
 
-    const long long t_dbg0 = clock64();
     // ---------------------------------------------------------------- prologue (MMA warps; barrier 1 = these 256 threads)
     const double* s = p.s + (size_t)b * p.n_max * I;
     const double* sq = p.sq + (size_t)b * p.stride_sq;
@@ -155,7 +154,6 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
     for (int idx = tid; idx < n_sys_max; idx += QTHREADS) wsh[idx] = idx < n ? w[idx] : 0.0;
     for (int idx = tid; idx < QWARPS * NT * QT; idx += QTHREADS) racc[idx] = 0.0;
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
-    const long long t_dbg1 = clock64();
     // kappa panel (the B operand), evaluated while the first Linv tiles are in flight: warp-strided over the queries,
     // lane-strided over the stored points; column j goes to position (j & ~7) | swap_bits_1_2(j & 7)  (k-step order)
     // A dependent FP64 operation costs 40-60 cycles here and an exp is a chain of ~25 of them, so every lane keeps
@@ -192,9 +190,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
         }
     };
     if (I == 1) fill(std::true_type{}); else fill(std::false_type{});
-    const long long t_dbg2 = clock64();
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
-    const long long t_dbg3 = clock64();
 
     // ---------------------------------------------------------------- per-warp streaming loop
     const double* ring = rings + (size_t)warp * QST * QSTAGE_ELEMS;
@@ -316,8 +312,6 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
     }
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
 
-    if ((p.dbg & 32) && blockIdx.x == 3 && blockIdx.y == 5 && (tid == 0 || tid == 224))
-        printf("tid %d: setup %lld  fill %lld  fill-barrier %lld  main+barrier %lld\n", tid, t_dbg1 - t_dbg0, t_dbg2 - t_dbg1, t_dbg3 - t_dbg2, clock64() - t_dbg3);
     // ---------------------------------------------------------------- outputs (reference layout, query last)
     double* xi = p.xi + (size_t)b * O * p.M;
     double* sg_out = p.sigma_out ? p.sigma_out + (size_t)b * O * O * p.M : nullptr;

@@ -13,7 +13,7 @@ for li in range(L):
 base_of = torch.as_tensor(np.repeat(np.arange(L, dtype=np.int32), 64), device='cuda')
 d_vs = torch.as_tensor(np.concatenate(ts)[:, :, None], device='cuda'); d_vp = torch.as_tensor(np.concatenate(ps), device='cuda'); d_vv = torch.as_tensor(np.concatenate(vs), device='cuda')
 q = torch.as_tensor(np.ascontiguousarray(wl.cfg1_query_grid(1000).T), device='cuda')
-for flags, name in ((32, 'timing printf'), (0, 'normal'), (4, 'no panel fill'), (1, 'no MMA'), (8, 'no reduce'), (13, 'none of them')):
+for flags, name in ((0, 'normal'), (4, 'no panel fill'), (1, 'no MMA'), (8, 'no reduce'), (13, 'none of them')):
     lib.kmpx_debug_set(flags)
     for rep in range(2):
         kb.events = []
