@@ -7,6 +7,7 @@
 // cfg 4 (n = 16384): potrf = n^3/3 = 1.47e12 flop, 64 block steps.
 #include "dmma_tile.cuh"
 #include "kmpx_internal.cuh"
+#include <vector>
 
 namespace kmpx {
 
@@ -74,6 +75,10 @@ static int potrf_large(double* A, int lda, int n, int* info, double* ws, cudaStr
     KMPX_TRY(g_side.ensure());
     if (info) { k_set_int<<<1, 32, 0, st>>>(info, 0, 1); KMPX_TRY(check_launch("k_set_int")); }
     KMPX_TRY(diag_factor(A, lda, n < LNB ? n : LNB, Dinv[0], info, 0, st));
+    // profiling aid (kmpx_debug_set bit 6): per-category device time on the caller's stream
+    const bool prof = (g_host_dbg & 64) != 0;
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() { if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evs.push_back(e); } };
     int step = 0;
     for (int k = 0; k < n; k += LNB, ++step) {
         const int nb = n - k < LNB ? n - k : LNB;
@@ -81,12 +86,16 @@ static int potrf_large(double* A, int lda, int n, int* info, double* ws, cudaStr
         if (m <= 0) break;
         double* A21 = A + (size_t)(k + nb) * lda + k;
         GemmArgs g1{m, nb, nb, 1.0, A21, lda, 0, Dinv[step & 1], LNB, 0, 0.0, panel, LNB, 0, 0};
+        mark();
         KMPX_TRY(launch_dgemm(0, 1, g1, 1, st));                               // panel = A21 * Dinv^T
+        mark();
         KMPX_TRY(copy_block(panel, LNB, A21, lda, m, nb, st));
+        mark();
         double* A22 = A + (size_t)(k + nb) * lda + k + nb;
         const int nb2 = m < LNB ? m : LNB;
         GemmArgs g2{m, nb2, nb, -1.0, panel, LNB, 0, panel, LNB, 0, 1.0, A22, lda, 0, 1};
         KMPX_TRY(launch_dgemm(0, 1, g2, 1, st));                               // look-ahead: next block column
+        mark();
         KMPX_TRY(check_cuda(cudaEventRecord(g_side.ev_main, st), "cudaEventRecord"));
         KMPX_TRY(check_cuda(cudaStreamWaitEvent(g_side.s, g_side.ev_main, 0), "cudaStreamWaitEvent"));
         KMPX_TRY(diag_factor(A22, lda, nb2, Dinv[(step + 1) & 1], info, k + nb, g_side.s));
@@ -97,7 +106,17 @@ static int potrf_large(double* A, int lda, int n, int* info, double* ws, cudaStr
             GemmArgs g3{m2, m2, nb, -1.0, P2, LNB, 0, P2, LNB, 0, 1.0, A22 + (size_t)nb2 * lda + nb2, lda, 0, 1};
             KMPX_TRY(launch_dgemm(0, 1, g3, 1, st));                           // rest of the trailing update (lower tiles)
         }
+        mark();
         KMPX_TRY(check_cuda(cudaStreamWaitEvent(st, g_side.ev_side, 0), "cudaStreamWaitEvent"));
+        mark();
+    }
+    if (prof && !evs.empty()) {
+        cudaStreamSynchronize(st);
+        double tot[6] = {0, 0, 0, 0, 0, 0};       // panel gemm, copy, look-ahead gemm, trailing gemm, wait for the side stream, (between steps)
+        for (size_t i = 0; i + 1 < evs.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); tot[i % 6] += ms; }
+        fprintf(stderr, "potrf_large n=%d: panel %.2f ms, copy %.2f, look-ahead %.2f, trailing %.2f, side wait %.2f, step gap %.2f\n", n,
+                tot[0], tot[1], tot[2], tot[3], tot[4], tot[5]);
+        for (cudaEvent_t e : evs) cudaEventDestroy(e);
     }
     return 0;
 }

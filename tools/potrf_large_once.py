@@ -11,6 +11,7 @@ del M
 nbytes = max(int(lib.kmpx_potrf_workspace_bytes(n, 1)), int(lib.kmpx_trtri_workspace_bytes(n, 1)))
 ws = torch.empty(nbytes // 8, dtype=torch.float64, device='cuda')
 info = torch.zeros(1, dtype=torch.int32, device='cuda')
+lib.kmpx_debug_set(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 for rep in range(3):
     A = A0.clone(); torch.cuda.synchronize()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
