@@ -1,7 +1,7 @@
 // Dense fp64 GEMM on DMMA: C = alpha * op(A) * op(B) + beta * C, row-major, strided batch.
 // The building block of the blocked large-n Cholesky / triangular inverse (factor_large.cu).
 //
-// CTA tile 128 x 128 x 16, 256 threads = 8 warps as 2 (rows) x 4 (cols), warp tile 64 x 32
+// CTA tile 128 x 128 x 32, 256 threads = 8 warps as 2 (rows) x 4 (cols), warp tile 64 x 32
 // (64 accumulators per thread), 3-stage cp.async ring.  Per k-step of 4 a warp issues 12 LDS.64 for 32
 // DMMA.8x8x4, so the FP64 tensor pipe (16 cycles per DMMA per SM sub-partition) is the limiter.
 //
@@ -88,6 +88,24 @@ __global__ void __launch_bounds__(GTHREADS) k_dgemm(GemmArgs p) {
     }
     cp_async_wait<0>();
     const bool vec_ok = ((p.ldc & 1) == 0) && ((p.strideC & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    // Interior tile with beta != 0: all thirty-two 16-byte reads of C are issued before the first use, so their (HBM)
+    // latency is paid once.  Left to the guarded loop below the reads are consumed one by one and the read-modify-write
+    // costs a quarter of a K = 256 tile (measured 20.9 vs 28.0 TFLOP/s for beta = 1 vs 0).
+    if (vec_ok && p.beta != 0.0 && m0 + GBM <= p.m && n0 + GBN <= p.n) {
+        double* cbase = C + (size_t)(m0 + wr * 64 + g) * p.ldc + n0 + wc * 32 + 2 * t4;
+        double2 o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[i][j] = *reinterpret_cast<const double2*>(cbase + (size_t)i * 8 * p.ldc + j * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<double2*>(cbase + (size_t)i * 8 * p.ldc + j * 8) =
+                    make_double2(fma(p.beta, o[i][j].x, p.alpha * acc[i][j][0]), fma(p.beta, o[i][j].y, p.alpha * acc[i][j][1]));
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int r = m0 + wr * 64 + i * 8 + g;
