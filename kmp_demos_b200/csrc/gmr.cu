@@ -82,6 +82,56 @@ __global__ void __launch_bounds__(128) k_gmr(GmrArgs p) {
             }
     }
     __syncthreads();
+    if (I == 1) {
+        // Scalar input (every demo of the reference): components in groups of four, their exponentials evaluated as four
+        // interleaved branch-free chains - the kernel is bound by FP64 instruction latency / issue, not by HBM
+        // (~400 FP64 operations per query at K = 8, O = 2 against 56 bytes).
+        for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < p.M; m += (long long)gridDim.x * blockDim.x) {
+            const double x0 = p.x[m];
+            double mean[O], sec[O][O];
+#pragma unroll
+            for (int a = 0; a < O; ++a) { mean[a] = 0.0;
+#pragma unroll
+                for (int b = 0; b < O; ++b) sec[a][b] = 0.0; }
+            double hsum = 0.0;
+            for (int k0 = 0; k0 < K; k0 += 4) {
+                double dev[4], h[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double* c = sh + (size_t)min(k0 + u, K - 1) * stride;        // [prior, logc, muI, Linv, muO (O), G (O), Sc (O*O)]
+                    dev[u] = x0 - c[2];
+                    const double z = c[3] * dev[u];
+                    h[u] = c[0] * exp_nonpos(fma(-0.5 * z, z, c[1]));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (k0 + u < K) {
+                        const double* c = sh + (size_t)(k0 + u) * stride;
+                        const double* muO = c + 4; const double* G = muO + O; const double* Sc = G + O;
+                        hsum += h[u] + kRealMin;
+                        double mk[O];
+#pragma unroll
+                        for (int a = 0; a < O; ++a) { mk[a] = fma(G[a], dev[u], muO[a]); mean[a] = fma(h[u], mk[a], mean[a]); }
+#pragma unroll
+                        for (int a = 0; a < O; ++a)
+#pragma unroll
+                            for (int b = 0; b < O; ++b) sec[a][b] = fma(h[u], fma(mk[a], mk[b], Sc[a * O + b]), sec[a][b]);
+                    }
+                }
+            }
+            const double inv = 1.0 / hsum;
+#pragma unroll
+            for (int a = 0; a < O; ++a) mean[a] *= inv;
+#pragma unroll
+            for (int a = 0; a < O; ++a) {
+                p.mu[(size_t)a * p.M + m] = mean[a];
+#pragma unroll
+                for (int b = 0; b < O; ++b)
+                    p.sigma[((size_t)a * O + b) * p.M + m] = sec[a][b] * inv + (a == b ? p.reg : 0.0) - mean[a] * mean[b];
+            }
+        }
+        return;
+    }
     for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < p.M; m += (long long)gridDim.x * blockDim.x) {
         double x[GMR_MAXI];
         for (int i = 0; i < I; ++i) x[i] = p.x[(size_t)i * p.M + m];
