@@ -139,7 +139,19 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
             }
             __syncthreads();
             double se = 0.0;
-            for (int k = kbeg; k < kend; ++k) { const double e = exp(Rrow[k] - m); Rrow[k] = e; se += e; }
+            // four interleaved branch-free exponentials (the arguments are <= 0); one at a time through the library exp
+            // the chains serialise and the E-step becomes FP64-latency bound
+            {
+                int k = kbeg;
+                for (; k + 4 <= kend; k += 4) {
+                    double e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) e[u] = exp_nonpos(Rrow[k + u] - m);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { Rrow[k + u] = e[u]; se += e[u]; }
+                }
+                for (; k < kend; ++k) { const double e = exp_nonpos(Rrow[k] - m); Rrow[k] = e; se += e; }
+            }
             s_red[half * ETS + s_loc] = se;
             __syncthreads();
             double tot = 0.0;
