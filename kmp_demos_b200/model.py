@@ -183,6 +183,65 @@ class KMP:
         self._logger.info("KMP predict done.")
         return xi.cpu().numpy(), sg.cpu().numpy()
 
+    # ------------------------------------------------------------------ one large system, queries sharded over the GPUs
+    def broadcast_fit(self, src: int = 0, group=None) -> None:
+        """Ships the fitted state (L^-1 or A^-1, w, alpha, inputs) of rank `src` to every rank of the process group
+        over NCCL, so that only one GPU pays for the factorisation (1.07 GB at n = 16384).  Every rank must have
+        called fit() on a problem of the same shape, or pass through here with an un-fitted model of rank != src
+        after set_shape_like(); the simplest use is: every rank builds the model, rank `src` fits, all call this."""
+        torch = _lib.require_cuda()
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        rank = dist.get_rank(group)
+        meta = [None]
+        if rank == src:
+            f = self._fact
+            meta = [dict(shape=tuple(f.F.shape), lda=f.lda, kind=f.kind, N=f.N, I=f.I, O=f.O, w=tuple(f.w.shape),
+                         alpha=tuple(f.alpha.shape), s=self.s, xi=self.xi, sigma=self.sigma)]
+        dist.broadcast_object_list(meta, src=src, group=group)
+        m = meta[0]
+        dev = torch.device('cuda', torch.cuda.current_device())
+        if rank != src:
+            e = lambda shp: torch.empty(shp, dtype=torch.float64, device=dev)  # noqa: E731
+            self.s, self.xi, self.sigma = m['s'], m['xi'], m['sigma']
+            self.O, self.N = self.xi.shape
+            self._fact = _Factorisation(e(m['shape']), m['lda'], m['kind'], e(m['w']), e(m['alpha']), e((m['N'], m['I'])),
+                                        m['N'], m['I'], m['O'])
+            self._estimator_cache = None
+        f = self._fact
+        for t in (f.F, f.w, f.alpha, f.s_dev):
+            dist.broadcast(t, src=src, group=group)
+
+    def predict_sharded(self, s: np.ndarray, group=None) -> Tuple[np.ndarray, np.ndarray]:
+        """predict() with the queries split contiguously over the ranks of the process group (each rank needs the
+        fitted state: fit() everywhere, or fit() on one rank + broadcast_fit()); the shards are all-gathered, so
+        every rank returns the full (O,M) mean and (O,O,M) covariance.  No collective touches the arithmetic."""
+        torch = _lib.require_cuda()
+        import torch.distributed as dist
+        from .dist import shard_range
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self.predict(s)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        s = np.asarray(s, dtype=np.float64)
+        M = s.shape[1]
+        lo, hi = shard_range(M, rank, world)
+        xi_l, sg_l = self.predict(s[:, lo:hi]) if hi > lo else (np.zeros((self.O, 0)), np.zeros((self.O, self.O, 0)))
+        per = max(shard_range(M, r, world)[1] - shard_range(M, r, world)[0] for r in range(world))
+        dev = torch.device('cuda', torch.cuda.current_device())
+        buf = torch.zeros((self.O + self.O * self.O, per), dtype=torch.float64, device=dev)
+        buf[:self.O, :hi - lo] = torch.as_tensor(xi_l, device=dev)
+        buf[self.O:, :hi - lo] = torch.as_tensor(sg_l.reshape(self.O * self.O, -1), device=dev)
+        out = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(out, buf, group=group)
+        xi = np.empty((self.O, M)); sg = np.empty((self.O, self.O, M))
+        for r in range(world):
+            a, b_ = shard_range(M, r, world)
+            h = out[r].cpu().numpy()
+            xi[:, a:b_] = h[:self.O, :b_ - a]
+            sg[:, :, a:b_] = h[self.O:, :b_ - a].reshape(self.O, self.O, -1)
+        return xi, sg
+
     def predict_mean(self, s: np.ndarray) -> np.ndarray:
         """Mean only, from alpha = (K + l*Sigma)^-1 mu: O(N*M) kernel evaluations instead of the GEMM."""
         torch = _lib.require_cuda()

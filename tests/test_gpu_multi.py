@@ -58,3 +58,43 @@ def test_partitioned_em_with_nccl_allreduce_equals_single_gpu(tmp_path):
     assert out['n_iter'] == out['n_iter_ref'] and out['allreduces'] == out['n_iter'] + 1
     assert abs(out['lower'] - out['lower_ref']) < 1e-12 * abs(out['lower_ref'])
     assert out['err_means'] < 1e-12 and out['err_covs'] < 1e-12 and out['err_weights'] < 1e-12
+
+
+_WORKER_F3 = r'''
+import os, sys, json
+sys.path.insert(0, os.environ["KMP_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from kmp_demos_b200 import dist as kd, workloads as wl
+from kmp.model import KMP
+rank, world, local = kd.init_process_group("nccl")
+t, mu, sig = wl.cfg4_problem(N=768, seed=0)                       # n = 1536: the large-system kernels
+q = np.linspace(0.0, 2.0, 1001).reshape(1, -1)
+c = wl.CFG1
+k = KMP(l=c["lam"], alpha=c["alpha"], sigma_f=c["sigma_f"], time_driven_kernel=False)
+if rank == 0:
+    k.fit(t, mu, sig)                                             # only one GPU factorises
+k.broadcast_fit(src=0)
+xi, sg = k.predict_sharded(q)
+if rank == 0:
+    x1, s1 = k.predict(q)
+    print("RESULT " + json.dumps(dict(same_mean=bool(np.array_equal(xi, x1)), same_cov=bool(np.array_equal(sg, s1)))))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_query_sharded_predict_of_one_large_system(tmp_path):
+    """SURVEY 8(f3): rank 0 factorises, the factor is broadcast over NCCL, every rank predicts its slice of the
+    queries; the gathered result equals the single-GPU prediction bit for bit."""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    script = tmp_path / 'worker_f3.py'
+    script.write_text(_WORKER_F3)
+    env = dict(os.environ, KMP_ROOT=ROOT, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', '29633', str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')][0][7:])
+    assert out['same_mean'] and out['same_cov']
