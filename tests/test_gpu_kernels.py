@@ -152,7 +152,7 @@ def test_potrf_trtri_small_ragged_batch(T):
         assert rel_err(np.tril(Li[b, :n, :n]), ref) < 1e-12, n
 
 
-@pytest.mark.parametrize('nmax,lda,sizes', [(404, 408, [64, 65, 96, 100, 257, 333, 402, 404]), (202, 202, [200, 202, 128]),
+@pytest.mark.parametrize('nmax,lda,sizes', [(404, 408, [64, 65, 96, 100, 257, 333, 402, 404, 1, 5, 31, 32, 33]), (202, 202, [200, 202, 128]),
                                             (480, 480, [480, 449, 33])])
 def test_potrf_trtri_tma_variants_ragged(T, nmax, lda, sizes):
     """Sizes at which BOTH small kernels take the TMA path (64 <= n_max, buffers fit): ragged batches, NaN everywhere

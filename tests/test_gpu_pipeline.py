@@ -228,6 +228,33 @@ def test_incremental_adaptation_equals_direct_and_reference(golden):
     assert rel_err(x2.cpu().numpy(), x1.cpu().numpy()) < MEAN_TOL and rel_err(s2.cpu().numpy(), s1.cpu().numpy()) < COV_TOL
 
 
+def test_incremental_adaptation_single_output():
+    """O = 1 (scalar trajectory), odd number of stored points (identity padding row in the component-major system):
+    incremental == direct."""
+    import torch
+    from kmp_demos_b200.batch import KMPBatch
+    rng = np.random.default_rng(9)
+    N0, L, B = 75, 3, 24
+    t = np.linspace(0.02, 1.5, N0)
+    mu = np.stack([np.sin(3.0 * t + l)[None] for l in range(L)])                        # (L,1,N0)
+    sig = (0.01 + 0.05 * rng.random((L, 1, 1, N0)))
+    kb = KMPBatch(l=0.7, alpha=10.0, sigma_f=150.0, chunk=8)
+    kb.set_base(np.broadcast_to(t[None, None, :], (L, 1, N0)), mu, sig)
+    base_of = rng.integers(0, L, B).astype(np.int32)
+    via_s = np.where(rng.random((B, 2)) < 0.5, t[rng.integers(0, N0, (B, 2))], rng.uniform(0.02, 1.5, (B, 2)))
+    via_s[:, 1] += 1e-3 * (np.abs(via_s[:, 1] - via_s[:, 0]) < 1e-3)
+    via_p = rng.normal(0.0, 1.0, (B, 2, 1))
+    via_v = np.full((B, 2, 1, 1), 1e-4)
+    q = np.linspace(0.0, 1.6, 333)[:, None]
+    d = [torch.as_tensor(np.ascontiguousarray(x), device='cuda') for x in (base_of, via_s[:, :, None], via_p, via_v, q)]
+    xd, sd, info, _ = kb.run_device(*d)
+    xd, sd = xd.cpu().numpy(), sd.cpu().numpy()
+    assert int((info != 0).sum()) == 0
+    xi, sg, _ = kb.run_incremental(*d)
+    for r in range(B):
+        assert rel_err(xi[r].cpu().numpy(), xd[r]) < MEAN_TOL and rel_err(sg[r].cpu().numpy(), sd[r]) < COV_TOL, r
+
+
 def test_demo2_pose_and_unlisted_sigma_quirk(golden):
     """cfg 2 (reference-faithful): O=3 KMPs on pose_data, un-listed covariance => non-symmetric system (H2)."""
     from kmp.model import KMP
