@@ -99,10 +99,23 @@ __global__ void __launch_bounds__(256) k_kernel_build_comp(BuildArgs p) {
         if (i >= Ns) break;
         double co[2][4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            co[e][0] = co[e][1] = co[e][2] = co[e][3] = 0.0;
-            // plain kernel + lower-only: coefficients are only used in the diagonal (a == b) blocks, i.e. for j <= i
-            if (i < N && j0 + e < N && (TD || !lower || j0 + e <= i)) kernel_coeffs(s + (size_t)i * p.I, s + (size_t)(j0 + e) * p.I, p.I, p.sigma_f, TD, co[e]);
+        for (int e = 0; e < 2; ++e) co[e][0] = co[e][1] = co[e][2] = co[e][3] = 0.0;
+        if (TD) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                if (i < N && j0 + e < N) kernel_coeffs(s + (size_t)i * p.I, s + (size_t)(j0 + e) * p.I, p.I, p.sigma_f, true, co[e]);
+        } else {
+            // plain kernel: both coefficients of the column pair as two interleaved branch-free chains (indices clamped,
+            // results selected; the library exp would serialise them and the kernel becomes latency bound on small
+            // systems).  Lower-only: coefficients are only used in the diagonal (a == b) blocks, i.e. for j <= i.
+            const bool any = i < N && j0 < N && (!lower || j0 <= i);
+            if (any) {
+                const double* si = s + (size_t)i * p.I;
+                const double e0 = rbf_fast(si, s + (size_t)j0 * p.I, p.I, p.sigma_f);
+                const double e1 = rbf_fast(si, s + (size_t)min(j0 + 1, N - 1) * p.I, p.I, p.sigma_f);
+                co[0][0] = e0;
+                co[1][0] = (j0 + 1 < N && (!lower || j0 + 1 <= i)) ? e1 : 0.0;
+            }
         }
         const bool diag0 = (i == j0), diag1 = (i == j0 + 1);
         for (int a = 0; a < O; ++a) {
