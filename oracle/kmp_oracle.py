@@ -554,3 +554,69 @@ def quat_from_rotation_vector(r):
         ang = np.linalg.norm(r)
         axis = r / ang
         return quat_normalize(np.concatenate(([np.abs(np.cos(ang / 2))], axis * np.sin(ang / 2))))
+
+
+# ----------------------------------------------------------------------------------------------
+# f1  Incremental adaptation: the same numbers as set_waypoint + fit + predict of a2-a4, obtained from
+#     the BASE solution by block-inverse identities.  This is the algebra the device kernels of csrc/incremental.cu
+#     implement; it is pinned against the direct restatement above (tests/test_oracle_golden.py).
+# ----------------------------------------------------------------------------------------------
+def kmp_incremental(s_b, xi_b, sigma_b, via_s, via_xi, via_sigma, s_query, lam, alpha, sigma_f, tol):
+    """Plain kernel, I = 1.  s_b (1,N0), xi_b (O,N0), sigma_b (O,O,N0): base trajectory; via_s list of P floats,
+    via_xi list of (1,O), via_sigma list of (O,O) as KMP.set_waypoint takes them (KMP.py:57); s_query (1,M).
+    A via point closer than ``tol`` to a stored input (first minimum, KMP.py:75-80) DELETES that stored point; every
+    via point is then APPENDED.  Point-major unknown order (KMP.py:151)."""
+    N0 = s_b.shape[1]
+    O = xi_b.shape[0]
+    M = s_query.shape[1]
+    A_b = kmp_matrix(s_b, sigma_b, lam, sigma_f, False)
+    G = np.linalg.inv(A_b)
+    kap = np.exp(-sigma_f * (s_b[0][:, None] - s_query[0][None, :]) ** 2)          # (N0, M)
+    alpha_b = G @ xi_b.T.reshape(-1)
+    eye = np.eye(O)
+    dele, app, owner = [], [], {}
+    for j in range(len(via_s)):
+        d = np.abs(s_b[0] - via_s[j])
+        idx = int(np.argmin(d))
+        if d[idx] < tol:
+            if idx in owner:
+                app.remove(owner[idx])          # a later via point on the same stored point supersedes the earlier one
+            else:
+                dele.append(idx)
+            owner[idx] = j
+        app.append(j)
+    r1, r2 = O * len(dele), O * len(app)
+    didx = np.array([i * O + a for i in dele for a in range(O)], dtype=int)
+    H = np.linalg.inv(G[np.ix_(didx, didx)]) if r1 else np.zeros((0, 0))
+    C = np.zeros((N0 * O, r2))
+    D = np.zeros((r2, r2))
+    ya = np.zeros(r2)
+    for k, j in enumerate(app):
+        kc = np.exp(-sigma_f * (s_b[0] - via_s[j]) ** 2)
+        kc[dele] = 0.0
+        C[:, k * O:(k + 1) * O] = np.kron(kc[:, None], eye)
+        ya[k * O:(k + 1) * O] = np.asarray(via_xi[j]).reshape(-1)
+        for k2, j2 in enumerate(app):
+            D[k * O:(k + 1) * O, k2 * O:(k2 + 1) * O] = np.exp(-sigma_f * (via_s[j] - via_s[j2]) ** 2) * eye
+        D[k * O:(k + 1) * O, k * O:(k + 1) * O] += lam * np.asarray(via_sigma[j])
+    GC = G @ C
+    GCd = GC[didx]
+    N1 = H @ GCd
+    Sinv = np.linalg.inv(D - (C.T @ GC - GCd.T @ H @ GCd))
+    a_p = -H @ alpha_b[didx]
+    a_z = Sinv @ (ya - (C.T @ alpha_b - GCd.T @ H @ alpha_b[didx]))
+    W = np.concatenate([G[:, didx], GC], axis=1)
+    xi = np.empty((O, M))
+    sg = np.empty((O, O, M))
+    for m in range(M):
+        v = np.kron(kap[:, m][None, :], eye)                                       # k_b(s*)  (O, n0)
+        u = v @ W
+        p, q = u[:, :r1], u[:, r1:]
+        ka = np.zeros((O, r2))
+        for k, j in enumerate(app):
+            ka[:, k * O:(k + 1) * O] = np.exp(-sigma_f * (s_query[0, m] - via_s[j]) ** 2) * eye
+        z = ka - q + p @ N1
+        quad = v @ G @ v.T - p @ H @ p.T + z @ Sinv @ z.T
+        sg[:, :, m] = alpha * (eye - quad)
+        xi[:, m] = v @ alpha_b + p @ a_p + z @ a_z
+    return xi, sg

@@ -168,3 +168,28 @@ def test_demo2_quirk_and_demo3(golden):
     est = orc.kmp_fit(s2, sig2, 1.0, 6.0, True)
     xi, sg = orc.kmp_predict(est, s2, xi2, tk, 40.0, 6.0, True)
     assert rel_err(xi, z3['adapt_xi']) < 1e-7 and rel_err(sg, z3['adapt_sigma']) < 1e-7   # H3: time-driven tolerance
+
+
+def test_incremental_algebra_equals_direct_restatement(golden):
+    """deleting / appending points on the base solution gives the reference's set_waypoint + fit + predict
+    numbers (golden cfg-3 sample, reference outputs) - the oracle of csrc/incremental.cu."""
+    zl, z = golden('letters_ref.npz'), golden('cfg3_sample.npz')
+    c = wl.CFG1
+    t = wl.cfg1_kmp_grid(200)
+    q = z['queries'][:, ::25]
+    for r in (0, 3, 11, 17):
+        li, si = int(z['letter'][r]), int(z['set_idx'][r])
+        a, b, cc = wl.cfg3_via_sets(li, zl['gmr_mu'][li], si + 1)
+        xi, sg = orc.kmp_incremental(t, zl['gmr_mu'][li], zl['gmr_sigma'][li], list(a[si]), [b[si][j].reshape(1, -1) for j in range(2)],
+                                     [cc[si][j] for j in range(2)], q, c['lam'], c['alpha'], c['sigma_f'], 0.0005)
+        assert rel_err(xi, z['xi'][r][:, ::25]) < 1e-9 and rel_err(sg, z['sigma'][r][:, :, ::25]) < 1e-7, r
+    # a via point that replaces a stored point with a slightly different input, and two via points on one stored point
+    li = 3
+    for vs in ([t[0, 10] + 3e-4, 1.2345], [t[0, 50], t[0, 50] + 1e-4]):
+        vp = [np.array([[1.0, -2.0]]), np.array([[0.5, 3.0]])]
+        vv = [1e-4 * np.eye(2), np.array([[2e-3, 5e-4], [5e-4, 1e-3]])]
+        s2, y2, g2 = orc.kmp_set_waypoint(t, zl['gmr_mu'][li], zl['gmr_sigma'][li], vs, vp, vv, 0.0005)
+        est = orc.kmp_fit(s2, g2, c['lam'], c['sigma_f'], False)
+        xr, sr = orc.kmp_predict(est, s2, y2, q, c['alpha'], c['sigma_f'], False)
+        xi, sg = orc.kmp_incremental(t, zl['gmr_mu'][li], zl['gmr_sigma'][li], vs, vp, vv, q, c['lam'], c['alpha'], c['sigma_f'], 0.0005)
+        assert rel_err(xi, xr) < 1e-9 and rel_err(sg, sr) < 1e-7
