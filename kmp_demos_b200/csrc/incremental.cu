@@ -96,9 +96,14 @@ __global__ void __launch_bounds__(128) k_inc_setup(IncSetupArgs p) {
         const double* vs = p.via_s + ((size_t)b * p.P + j) * I;
         double best = INFINITY; int besti = -1;
         for (int i = tid; i < N0; i += blockDim.x) {
+            // the scan sees the database as the earlier via points of this call left it (KMP.py:80-84 overwrites in
+            // place): a stored point that was replaced carries the input of the via point that replaced it
+            const double* si = sb + (size_t)i * I;
+            for (int k = 0; k < nd; ++k)
+                if (del_idx[k] == i) si = p.via_s + ((size_t)b * p.P + app_via[del_owner[k]]) * I;
             double acc = 0.0;
-            for (int t = 0; t < I; ++t) { const double d = sb[(size_t)i * I + t] - vs[t]; acc += d * d; }
-            const double dist = (I == 1) ? fabs(sb[i] - vs[0]) : sqrt(acc);
+            for (int t = 0; t < I; ++t) { const double d = si[t] - vs[t]; acc += d * d; }
+            const double dist = (I == 1) ? fabs(si[0] - vs[0]) : sqrt(acc);
             if (dist < best) { best = dist; besti = i; }
         }
         sh_d[tid] = best; sh_i[tid] = besti;

@@ -575,8 +575,9 @@ def kmp_incremental(s_b, xi_b, sigma_b, via_s, via_xi, via_sigma, s_query, lam, 
     alpha_b = G @ xi_b.T.reshape(-1)
     eye = np.eye(O)
     dele, app, owner = [], [], {}
+    s_work = s_b[0].copy()                      # the scan sees earlier in-place overwrites of the same call (KMP.py:80-84)
     for j in range(len(via_s)):
-        d = np.abs(s_b[0] - via_s[j])
+        d = np.abs(s_work - via_s[j])
         idx = int(np.argmin(d))
         if d[idx] < tol:
             if idx in owner:
@@ -584,6 +585,7 @@ def kmp_incremental(s_b, xi_b, sigma_b, via_s, via_xi, via_sigma, s_query, lam, 
             else:
                 dele.append(idx)
             owner[idx] = j
+            s_work[idx] = via_s[j]
         app.append(j)
     r1, r2 = O * len(dele), O * len(app)
     didx = np.array([i * O + a for i in dele for a in range(O)], dtype=int)

@@ -202,7 +202,8 @@ def test_incremental_adaptation_equals_direct_and_reference(golden):
     extra = [(g[50], g[50] + 1e-4),          # both hit stored point 50: the later one supersedes the earlier one
              (g[10] + 3e-4, 1.2345),         # replace with a slightly different input, plus an append
              (g[199], g[0]),                 # two replacements at the ends of the trajectory
-             (0.33333, 1.77777)]             # two appends
+             (0.33333, 1.77777),             # two appends
+             (1.1495463763276121, 1.1490554230079142)]   # the 2nd only matches point 114 after the 1st moved it (found by the 4-GPU bench)
     rng = np.random.default_rng(5)
     for t1, t2 in extra:
         base_of.append(3); vs.append(np.array([t1, t2])); vp.append(rng.normal(0.0, 3.0, (2, 2)))
@@ -213,7 +214,7 @@ def test_incremental_adaptation_equals_direct_and_reference(golden):
     xd, sd, info, n_pts = kb.run_device(*d)
     xd, sd = xd.cpu().numpy(), sd.cpu().numpy()
     assert int((info != 0).sum()) == 0
-    assert n_pts.cpu().numpy()[n_gold:].tolist() == [200, 201, 200, 202]
+    assert n_pts.cpu().numpy()[n_gold:].tolist() == [200, 201, 200, 202, 200]
     xi, sg, info_b = kb.run_incremental(*d)
     xi, sg = xi.cpu().numpy(), sg.cpu().numpy()
     assert int((info_b != 0).sum()) == 0

@@ -185,7 +185,8 @@ def test_incremental_algebra_equals_direct_restatement(golden):
         assert rel_err(xi, z['xi'][r][:, ::25]) < 1e-9 and rel_err(sg, z['sigma'][r][:, :, ::25]) < 1e-7, r
     # a via point that replaces a stored point with a slightly different input, and two via points on one stored point
     li = 3
-    for vs in ([t[0, 10] + 3e-4, 1.2345], [t[0, 50], t[0, 50] + 1e-4]):
+    # ... and a second via point that only matches the stored point AFTER the first one moved it (in-place overwrite)
+    for vs in ([t[0, 10] + 3e-4, 1.2345], [t[0, 50], t[0, 50] + 1e-4], [1.1495463763276121, 1.1490554230079142]):
         vp = [np.array([[1.0, -2.0]]), np.array([[0.5, 3.0]])]
         vv = [1e-4 * np.eye(2), np.array([[2e-3, 5e-4], [5e-4, 1e-3]])]
         s2, y2, g2 = orc.kmp_set_waypoint(t, zl['gmr_mu'][li], zl['gmr_sigma'][li], vs, vp, vv, 0.0005)
