@@ -177,12 +177,34 @@ def measure_dgemm_peak(torch, n=8192, seconds=1.5):
     return 2.0 * n ** 3 * reps / e0.elapsed_time(e1) * 1e-9
 
 
+def cfg1_cpu_port():
+    """cfg 1 on one host core through the oracle's literal restatement of the reference (GMM by the numpy EM port, GMR and
+    KMP with the reference's loop nests; predict on 100 of the 1000 steps, scaled - every query is an independent loop
+    iteration, KMP.py:178)."""
+    from oracle import kmp_oracle as orc
+    z = np.load(os.path.join(wl.GOLDEN_DIR, 'letters_ref.npz'))
+    gi = wl.LETTERS.index('G')
+    X = wl.cfg1_design_matrix(z['pos'][gi])
+    c = wl.CFG1
+    t = [time.perf_counter()]
+    r = orc.gmm_fit(X, 8, 1e-6); t.append(time.perf_counter())
+    pri, mea, cov = r['weights'], r['means'].T, np.transpose(r['covariances'], (1, 2, 0))
+    mu, sig = orc.gmr_literal(pri, mea, cov, wl.cfg1_gmr_grid(200), 1e-6); t.append(time.perf_counter())
+    s = wl.cfg1_kmp_grid(200)
+    est = orc.kmp_fit(s, sig, c['lam'], c['sigma_f'], False, literal=True); t.append(time.perf_counter())
+    q = wl.cfg1_query_grid(1000)[:, ::10]
+    orc.kmp_predict_literal(est, s, mu, q, c['alpha'], c['sigma_f'], False); t.append(time.perf_counter())
+    d = np.diff(t) * 1e3
+    return {'gmm_fit_ms': float(d[0]), 'gmr_ms': float(d[1]), 'kmp_fit_ms': float(d[2]), 'predict_ms': float(d[3] * 10.0),
+            'note': 'one core; refit after set_waypoint costs another kmp_fit; predict timed on 100 steps x 10'}
+
+
 def extras_single_gpu(torch, dgemm_tflops):
     """The other measured rows of SURVEY.md 8(d) on one GPU (kmp_demos_b200/perf.py): second headline of BASELINE.json
     (fp64 Cholesky TFLOP/s at N*O = 16384), cfg-4 kernel build / triangular inverse / 100k-query predict rate,
     fused EM pass at 10 M x 7, K = 64, GMR and quaternion maps on 2^26 elements."""
     from kmp_demos_b200 import perf
-    return perf.run_all(quick=False, only=('dgemm', 'cfg4', 'em', 'gmr', 'quat'), dgemm_tflops=dgemm_tflops)
+    return perf.run_all(quick=False, only=('dgemm', 'cfg1', 'cfg4', 'em', 'gmr', 'quat'), dgemm_tflops=dgemm_tflops)
 
 
 def run_ours(args):
@@ -351,6 +373,7 @@ def run_ours(args):
             if not args.no_extras:
                 log('extras: per-kernel figures (cfg 4, EM, GMR, quaternion maps)')
                 line['extras'] = extras_single_gpu(torch, dgemm_tf)
+                line['extras']['cfg1']['cpu_port'] = cfg1_cpu_port()
         line['incremental'] = {
             'what': 'SURVEY 8(f1): same cfg-3 problems by exact low-rank correction of the per-base solution '
                     '(KMPBatch.run_incremental) instead of one refit per via-point set; bases re-factorised inside every step',

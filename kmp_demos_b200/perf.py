@@ -147,6 +147,38 @@ def quat(M):
             'log_frac_hbm': 56.0 * M / ms_l * 1e-6 / peaks()}
 
 
+def cfg1():
+    """cfg 1 of BASELINE.json through the drop-in classes (the latency configuration: one trajectory, one model):
+    GMM(8) fit -> GMR on 200 points -> KMP fit -> two via points -> predict 1000 steps.  Wall-clock per stage,
+    host arrays in and out, best of three after one warm-up pass."""
+    import time
+    from .mixture import GaussianMixtureModel
+    from .model import KMP
+    z = np.load(os.path.join(wl.GOLDEN_DIR, 'letters_ref.npz'))          # the demonstrations of letter G travel with the fixture
+    gi = wl.LETTERS.index('G')
+    X = wl.cfg1_design_matrix(z['pos'][gi])
+    c = wl.CFG1
+    q = wl.cfg1_query_grid(1000)
+    via = ([0.5, 1.5], [np.array([[8.0, 4.0]]), np.array([[-3.0, -6.0]])], [1e-4 * np.eye(2)] * 2)
+    best = None
+    for rep in range(4):
+        t = [time.perf_counter()]
+        gmm = GaussianMixtureModel(n_components=8, diag_reg_factor=1e-6); gmm.fit(X); torch.cuda.synchronize(); t.append(time.perf_counter())
+        mu, sig = gmm.predict(wl.cfg1_gmr_grid(200)); t.append(time.perf_counter())
+        kmp = KMP(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False)
+        kmp.fit(wl.cfg1_kmp_grid(200), mu, sig); torch.cuda.synchronize(); t.append(time.perf_counter())
+        kmp.set_waypoint(*via); torch.cuda.synchronize(); t.append(time.perf_counter())
+        kmp.predict(q); t.append(time.perf_counter())
+        d = np.diff(t) * 1e3
+        if rep > 0 and (best is None or d.sum() < best.sum()):
+            best = d
+    names = ['gmm_fit_ms', 'gmr_ms', 'kmp_fit_ms', 'set_waypoint_refit_ms', 'predict_ms']
+    out = {k: float(v) for k, v in zip(names, best)}
+    out['total_ms'] = float(best.sum())
+    out['em_iterations'] = int(gmm.model.n_iter_)
+    return out
+
+
 def run_all(quick=False, only=None, dgemm_tflops=None):
     """All per-kernel figures as a dict (`only`: iterable of section names)."""
     only = set(only) if only else None
@@ -159,6 +191,8 @@ def run_all(quick=False, only=None, dgemm_tflops=None):
         for name, (ta, tb, tri) in {'NT': (0, 1, 0), 'NN': (0, 0, 0), 'NT_lower': (0, 1, 1)}.items():
             tf, ms = dgemm_ours(4096 if quick else 8192, ta, tb, tri)
             out[f'dgemm_ours_{name}'] = {'tflops': tf, 'ms': ms, 'frac_cublas': tf / dg}
+    if want('cfg1'):
+        out['cfg1'] = cfg1()
     if want('cfg4'):
         out['cfg4'] = cfg4(2048 if quick else 8192, dg)
     if want('em'):
