@@ -117,80 +117,83 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
     }
     __syncthreads();
 
-    if (warp >= QWARPS) {
-        // ---- producers: one lane per MMA warp runs that warp's tile cursor and issues its TMA boxes
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
-        if (lane >= 2) return;
-        const int cw = (warp - QWARPS) * 2 + lane;      // four producer warps, two streams each
-        Cursor prod{0, 0, 0, 0, 0, 0, 0, false};
-        fast_seek<O>(prod, cw, nchunks, N, Ns);
-        int stage = 0;
-        uint32_t par = 0;
-        bool wrapped = false;
-        while (prod.valid) {
-            const uint32_t bi = 8 * (cw * QST + stage);
-            if (wrapped && !mbar_test(empty0 + bi, par ^ 1)) { __nanosleep(100); continue; }   // polling must not eat the MMA warps' issue slots
-            const uint32_t bar = full0 + bi;
-            mbar_expect_tx(bar, QSTAGE_BYTES);
-            const uint32_t dst = smem_u32(rings + (size_t)(cw * QST + stage) * QSTAGE_ELEMS);
-            const int col = prod.col0 + prod.kb * QK;
-#pragma unroll
-            for (int q = 0; q < QK / 8; ++q) tma_load_box(dst + q * (RC * 64), &tmap, col + 8 * q, prod.r0, b, bar);
-            fast_advance<O>(prod, cw, nchunks, N, Ns);
-            if (++stage == QST) { stage = 0; par ^= 1; wrapped = true; }
-        }
-        return;
-    }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
-
-    // ---------------------------------------------------------------- prologue (MMA warps; barrier 1 = these 256 threads)
+    // ---------------------------------------------------------------- prologue: ALL twelve warps (the register split
+    //      between the roles is made afterwards, so the producer warps' lanes work on the kappa panel too)
     const double* s = p.s + (size_t)b * p.n_max * I;
     const double* sq = p.sq + (size_t)b * p.stride_sq;
     const double* w = p.w + (size_t)b * p.ldw;
-    for (int idx = tid; idx < QT * I; idx += QTHREADS) {
+    for (int idx = tid; idx < QT * I; idx += PTHREADS) {
         const int m = idx / I;
         sqs[idx] = (m0 + m < p.M) ? sq[(size_t)(m0 + m) * I + (idx - m * I)] : 0.0;
     }
-    for (int idx = tid; idx < n_sys_max; idx += QTHREADS) wsh[idx] = idx < n ? w[idx] : 0.0;
-    for (int idx = tid; idx < QWARPS * NT * QT; idx += QTHREADS) racc[idx] = 0.0;
-    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    for (int idx = tid; idx < n_sys_max; idx += PTHREADS) wsh[idx] = idx < n ? w[idx] : 0.0;
+    for (int idx = tid; idx < QWARPS * NT * QT; idx += PTHREADS) racc[idx] = 0.0;
+    // producer cursors (lanes 0, 1 of the four producer warps: two streams each); the first tiles are requested now
+    // so that they land while the panel is evaluated
+    const bool is_producer = warp >= QWARPS && lane < 2;
+    const int cw = is_producer ? (warp - QWARPS) * 2 + lane : 0;
+    Cursor prod{0, 0, 0, 0, 0, 0, 0, false};
+    int pstage = 0;
+    uint32_t ppar = 0;
+    bool pwrapped = false;
+    auto produce_one = [&]() {
+        const uint32_t bi = 8 * (cw * QST + pstage);
+        const uint32_t bar = full0 + bi;
+        mbar_expect_tx(bar, QSTAGE_BYTES);
+        const uint32_t dst = smem_u32(rings + (size_t)(cw * QST + pstage) * QSTAGE_ELEMS);
+        const int col = prod.col0 + prod.kb * QK;
+#pragma unroll
+        for (int q = 0; q < QK / 8; ++q) tma_load_box(dst + q * (RC * 64), &tmap, col + 8 * q, prod.r0, b, bar);
+        fast_advance<O>(prod, cw, nchunks, N, Ns);
+        if (++pstage == QST) { pstage = 0; ppar ^= 1; pwrapped = true; }
+    };
+    if (is_producer) {
+        fast_seek<O>(prod, cw, nchunks, N, Ns);
+        for (int t = 0; t < QST && prod.valid; ++t) produce_one();
+    }
+    __syncthreads();          // sqs is complete
     // kappa panel (the B operand), evaluated while the first Linv tiles are in flight: warp-strided over the queries,
-    // lane-strided over the stored points; column j goes to position (j & ~7) | swap_bits_1_2(j & 7)  (k-step order)
+    // lane-strided over the stored points; column j goes to position (j & ~7) | swap_bits_1_2(j & 7)  (k-step order).
     // A dependent FP64 operation costs 40-60 cycles here and an exp is a chain of ~25 of them, so every lane keeps
-    // FILL_Q x FILL_J independent chains in flight (seven columns of one query; fourteen were measured slower); indices are clamped and the results selected, and the exponential
-    // itself is branch-free (exp_nonpos), so the chains really interleave.
-    constexpr int FILL_Q = 1, FILL_J = 7;
+    // FILL_J independent chains in flight (seven columns of one query; fourteen were measured slower); indices are
+    // clamped and the results selected, and the exponential itself is branch-free (exp_nonpos), so the chains interleave.
+    constexpr int FILL_J = 7, FILL_WARPS = PTHREADS / 32;
     auto fill = [&](auto one_dim) {         // the I == 1 test is hoisted: a branch inside the chain body would serialise the chains
         constexpr bool ONE = decltype(one_dim)::value;
-        for (int mb = warp; mb < QT && !(p.dbg & 4); mb += FILL_Q * QWARPS) {
+        for (int m = warp; m < QT && !(p.dbg & 4); m += FILL_WARPS) {
+            const bool live = m0 + m < p.M;
             for (int j0 = lane; j0 < ldp - 4; j0 += 32 * FILL_J) {       // ldp - 4 is a multiple of 32
-                double e[FILL_Q][FILL_J];
+                double e[FILL_J];
 #pragma unroll
                 for (int u = 0; u < FILL_J; ++u) {
                     const double* sp = s + (size_t)min(j0 + 32 * u, N - 1) * I;
-#pragma unroll
-                    for (int v = 0; v < FILL_Q; ++v) {
-                        const int m = mb + v * QWARPS;
-                        if (ONE) { const double d = fabs(sqs[m] - sp[0]); e[v][u] = exp_nonpos(-p.sigma_f * (d * d)); }
-                        else e[v][u] = rbf_fast(sqs + m * I, sp, I, p.sigma_f);
-                    }
+                    if (ONE) { const double d = fabs(sqs[m] - sp[0]); e[u] = exp_nonpos(-p.sigma_f * (d * d)); }
+                    else e[u] = rbf_fast(sqs + m * I, sp, I, p.sigma_f);
                 }
                 const int pj = (j0 & ~6) | ((j0 & 2) << 1) | ((j0 & 4) >> 1);       // the same permutation applies to j0 + 32 u
 #pragma unroll
-                for (int v = 0; v < FILL_Q; ++v) {
-                    const int m = mb + v * QWARPS;
-                    const bool live = m0 + m < p.M;
-#pragma unroll
-                    for (int u = 0; u < FILL_J; ++u) {
-                        const int j = j0 + 32 * u;
-                        if (j < ldp - 4) panel[(size_t)m * ldp + pj + 32 * u] = (j < N && live) ? e[v][u] : 0.0;
-                    }
+                for (int u = 0; u < FILL_J; ++u) {
+                    const int j = j0 + 32 * u;
+                    if (j < ldp - 4) panel[(size_t)m * ldp + pj + 32 * u] = (j < N && live) ? e[u] : 0.0;
                 }
             }
         }
     };
     if (I == 1) fill(std::true_type{}); else fill(std::false_type{});
-    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    __syncthreads();          // panel, wsh, racc are complete
+
+    if (warp >= QWARPS) {
+        // ---- producers: one lane per MMA warp runs that warp's tile cursor and issues its TMA boxes
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (lane >= 2) return;
+        while (prod.valid) {
+            const uint32_t bi = 8 * (cw * QST + pstage);
+            if (pwrapped && !mbar_test(empty0 + bi, ppar ^ 1)) { __nanosleep(100); continue; }   // polling must not eat the MMA warps' issue slots
+            produce_one();
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
 
     // ---------------------------------------------------------------- per-warp streaming loop
     const double* ring = rings + (size_t)warp * QST * QSTAGE_ELEMS;
