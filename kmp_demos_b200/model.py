@@ -15,6 +15,7 @@ How the path maps to kernels (reference file:line -> entry point):
 from __future__ import annotations
 
 import copy
+import math
 import logging
 from typing import Tuple
 
@@ -291,7 +292,28 @@ class KMP:
                             self.time_driven_kernel, layout)
 
     def KL_divergence(self, xi, sigma, xi_ref, sigma_ref) -> float:
-        raise NotImplementedError("KL_divergence is unused by the reference (call commented out at KMP.py:192)")
+        """The reference's aggregate of point-wise "KL" terms (KMP.py:196-212; its only call site, KMP.py:192, is
+        commented out upstream): for each of the self.N stored points, with N(mu, S) the normal density,
+        kl_i = q_i log(q_i / p_i), p_i = N(xi_i; xi_i, sigma_i), q_i = N(xi_i; xi_ref_i, sigma_ref_i); the vector is
+        normalised by its 2-norm and averaged.  Host arithmetic (O x O blocks), densities as scipy's
+        multivariate_normal evaluates them (eigendecomposition, pseudo-determinant)."""
+        def pdf(x, mu, cov):
+            w, v = np.linalg.eigh(np.atleast_2d(cov))
+            eps = 1e6 * np.finfo(float).eps * np.max(np.abs(w))
+            if np.min(w) < -eps:
+                raise ValueError('the input matrix must be positive semidefinite')      # scipy's message
+            keep = w > eps
+            d = w[keep]
+            dev = np.atleast_1d(x) - np.atleast_1d(mu)
+            maha = np.sum(((dev @ v[:, keep]) / np.sqrt(d)) ** 2)
+            return math.exp(-0.5 * (int(keep.sum()) * math.log(2.0 * math.pi) + np.sum(np.log(d)) + maha))
+        kl = np.empty(self.N)
+        for i in range(self.N):
+            p_i = pdf(xi[:, i], xi[:, i], sigma[:, :, i])
+            q_i = pdf(xi[:, i], xi_ref[:, i], sigma_ref[:, :, i])
+            kl[i] = q_i * np.log(q_i / p_i)
+        kl /= np.linalg.norm(kl)
+        return float(np.mean(kl))
 
 
 def build_matrix(s, sigma, lam, sigma_f, time_driven, layout=_lib.LAYOUT_POINT):

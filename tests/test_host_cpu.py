@@ -131,3 +131,24 @@ def test_two_rank_gloo_allreduce_of_statistics(tmp_path):
                         '127.0.0.1', '--master-port', '29613', str(script)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count('ok') == 2
+
+
+def test_kl_divergence_follows_the_reference_formula():
+    """KMP.KL_divergence (KMP.py:196-212, unused upstream) is host arithmetic: checked against scipy's densities."""
+    from scipy.stats import multivariate_normal
+    from kmp.model import KMP
+    rng = np.random.default_rng(3)
+    N, O = 17, 2
+    k = KMP.__new__(KMP)
+    k.N = N
+    xi, xr = rng.normal(size=(O, N)), rng.normal(size=(O, N))
+    B1, B2 = rng.normal(size=(N, O, O)), rng.normal(size=(N, O, O))
+    sg = np.transpose(np.einsum('nab,ncb->nac', B1, B1) + 0.2 * np.eye(O), (1, 2, 0))
+    sr = np.transpose(np.einsum('nab,ncb->nac', B2, B2) + 0.2 * np.eye(O), (1, 2, 0))
+    ref = []
+    for i in range(N):
+        p = multivariate_normal(xi[:, i], sg[:, :, i]).pdf(xi[:, i])
+        q = multivariate_normal(xr[:, i], sr[:, :, i]).pdf(xi[:, i])
+        ref.append(q * np.log(q / p))
+    ref = np.array(ref); ref /= np.linalg.norm(ref)
+    assert abs(k.KL_divergence(xi, sg, xr, sr) - np.mean(ref)) < 1e-13
