@@ -150,6 +150,16 @@ int kmpx_inc_adapt(const double* s_base, const double* G, int ldg, long long str
                    double tol, double sigma_f, double lam, double alpha_kmp, int batch, const double* sq, int M,
                    double* ws, long long ws_doubles, double* xi, double* sigma_out, void* stream);
 
+/* The same with the problems sorted by base: group g = group_count[g] consecutive problems of base group_base[g]
+ * (HOST arrays).  The appended columns of a whole group come from one kmpx_dgemm-class GEMM per output component. */
+long long kmpx_inc_grouped_workspace_doubles(int N0, int O, int batch);
+int kmpx_inc_adapt_grouped(const double* s_base, const double* G, int ldg, long long strideG, const double* alpha_sys,
+                           const double* kappa, const double* xi_base, const double* sigma_base, int N0, int I, int O,
+                           const int* base_of, const int* group_base, const int* group_count, int n_groups,
+                           const double* via_s, const double* via_y, const double* via_sigma, int P,
+                           double tol, double sigma_f, double lam, double alpha_kmp, int batch, const double* sq, int M,
+                           double* ws, long long ws_doubles, double* xi, double* sigma_out, void* stream);
+
 /* ---- K8: GMR conditioning.  Replaces GaussianMixtureModel.predict, GaussianMixtureModel.py:83-105.
  *      priors [K], means [d][K], covs [d][d][K] (the reference's feature-major attributes), x [I][M];
  *      out mu [O][M], sigma [O][O][M].  Keeps the REALMIN normaliser (:90) and reg*I - mu mu^T (:104-105). */

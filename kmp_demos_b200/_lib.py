@@ -42,6 +42,9 @@ _SIGNATURES = {
     'kmpx_inc_base': [_p, _i, _ll, _p, _p, _i, _i, _i, _i, _p, _i, _d, _p, _p, _p],
     'kmpx_inc_adapt': [_p, _p, _i, _ll, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _d, _d, _d, _d, _i, _p, _i,
                        _p, _ll, _p, _p, _p],
+    'kmpx_inc_grouped_workspace_doubles': [_i, _i, _i],
+    'kmpx_inc_adapt_grouped': [_p, _p, _i, _ll, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _p, _p, _p, _i, _d, _d, _d, _d, _i, _p, _i,
+                               _p, _ll, _p, _p, _p],
     'kmpx_kmp_predict_gemm_workspace_bytes': [_i, _i, _i],
     'kmpx_kmp_predict_gemm': [_p, _i, _p, _p, _i, _i, _i, _p, _i, _d, _d, _p, _ll, _p, _p, _p],
     'kmpx_kmp_predict_mean': [_p, _p, _p, _i, _i, _i, _i, _p, _ll, _i, _d, _i, _p, _p],
@@ -71,6 +74,7 @@ _RESTYPES = {
     'kmpx_inverse_workspace_bytes': _ll,
     'kmpx_gmm_workspace_bytes': _ll,
     'kmpx_inc_workspace_doubles': _ll,
+    'kmpx_inc_grouped_workspace_doubles': _ll,
     'kmpx_kmp_predict_gemm_workspace_bytes': _ll,
 }
 EXPORTED = tuple(_SIGNATURES)

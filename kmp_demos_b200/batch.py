@@ -198,7 +198,10 @@ class KMPBatch:
         if want_cov:
             sg = out_sigma if out_sigma is not None else torch.empty((B, O, O, M), dtype=f64, device='cuda')
         Bc = min(self.chunk, B)
-        nws = int(lib.kmpx_inc_workspace_doubles(N0, O, Bc))
+        # problems sorted by base (the usual case): the appended columns of all problems of a base come from one GEMM
+        base_host = base_of.cpu().numpy()
+        grouped = bool(np.all(base_host[1:] >= base_host[:-1]))
+        nws = int((lib.kmpx_inc_grouped_workspace_doubles if grouped else lib.kmpx_inc_workspace_doubles)(N0, O, Bc))
         ws = self._buf('inc_ws', (nws,), f64)
         copy_stream = None
         if host_xi is not None or host_sigma is not None:
@@ -208,10 +211,20 @@ class KMPBatch:
             copy_stream.wait_stream(torch.cuda.current_stream())
         for c0 in range(0, B, Bc):
             bc = min(Bc, B - c0)
-            self._launch('kmpx_inc_adapt', _lib.ptr(b['s']), _lib.ptr(G), lda, strideA, _lib.ptr(al), _lib.ptr(kap),
-                         _lib.ptr(xi_b), _lib.ptr(sg_b), N0, I, O, _lib.ptr(base_of[c0:]), _lib.ptr(via_s[c0:]),
-                         _lib.ptr(via_xi[c0:]), _lib.ptr(via_sigma[c0:]), P, self.tol, self.sigma_f, self.l, self.alpha, bc,
-                         _lib.ptr(queries), M, _lib.ptr(ws), nws, _lib.ptr(xi[c0:]), _lib.ptr(sg[c0:]) if sg is not None else None, st)
+            if grouped:
+                ids, counts = np.unique(base_host[c0:c0 + bc], return_counts=True)
+                ids = np.ascontiguousarray(ids, dtype=np.int32)
+                counts = np.ascontiguousarray(counts, dtype=np.int32)
+                self._launch('kmpx_inc_adapt_grouped', _lib.ptr(b['s']), _lib.ptr(G), lda, strideA, _lib.ptr(al), _lib.ptr(kap),
+                             _lib.ptr(xi_b), _lib.ptr(sg_b), N0, I, O, _lib.ptr(base_of[c0:]), ids.ctypes.data, counts.ctypes.data,
+                             len(ids), _lib.ptr(via_s[c0:]), _lib.ptr(via_xi[c0:]), _lib.ptr(via_sigma[c0:]), P, self.tol,
+                             self.sigma_f, self.l, self.alpha, bc, _lib.ptr(queries), M, _lib.ptr(ws), nws, _lib.ptr(xi[c0:]),
+                             _lib.ptr(sg[c0:]) if sg is not None else None, st)
+            else:
+                self._launch('kmpx_inc_adapt', _lib.ptr(b['s']), _lib.ptr(G), lda, strideA, _lib.ptr(al), _lib.ptr(kap),
+                             _lib.ptr(xi_b), _lib.ptr(sg_b), N0, I, O, _lib.ptr(base_of[c0:]), _lib.ptr(via_s[c0:]),
+                             _lib.ptr(via_xi[c0:]), _lib.ptr(via_sigma[c0:]), P, self.tol, self.sigma_f, self.l, self.alpha, bc,
+                             _lib.ptr(queries), M, _lib.ptr(ws), nws, _lib.ptr(xi[c0:]), _lib.ptr(sg[c0:]) if sg is not None else None, st)
             if copy_stream is not None:
                 done = torch.cuda.Event()
                 done.record()

@@ -14,7 +14,7 @@
 //
 // Kernels: k_inc_alpha (alpha = G y per base), k_inc_kappa (kappa[base][m][j], shared by the problems of a base),
 // k_inc_setup (one CTA per problem: classification of the via points exactly as k_waypoint_insert, W, the small
-// matrices), k_inc_predict (one thread per query, CTA = 128 queries of one problem: u = kappa^T W with W broadcast from
+// matrices; in the grouped form the appended columns of W come from one GEMM per base and component instead), k_inc_predict (one thread per query, CTA = 128 queries of one problem: u = kappa^T W with W broadcast from
 // shared memory, per-query algebra in registers, outputs in the reference layouts).  Limits: O <= 2, P <= 2 (r <= 8), plain kernel.
 #include "kmpx_internal.cuh"
 
@@ -23,6 +23,10 @@ namespace kmpx {
 constexpr int IMAXO = 2, IMAXP = 2, IR = IMAXO * IMAXP;    // at most IR deleted and IR appended unknowns
 constexpr int IREC = 64;                                    // doubles per problem record: H[16] N1[16] Sinv[16] a_p[4] a_z[4]
 constexpr int IIREC = 8;                                    // ints per problem: nd, napp, del_idx[2], app_via[2]
+// W keeps eight FIXED column slots per problem so that the appended columns of all problems of a base can be produced
+// by one GEMM with a uniform row stride:  deleted (k, bc) -> slot 4k + bc,  appended (q, bc) -> slot 4q + 2 + bc.
+__host__ __device__ inline int slot_del(int k, int bc) { return 4 * k + bc; }
+__host__ __device__ inline int slot_app(int q, int bc) { return 4 * q + 2 + bc; }
 constexpr int IQT = 128;                                    // queries per CTA of k_inc_predict (one thread each)
 
 // alpha_sys[base][r] = sum_c G[r][c] y_sys[c]   (system = component-major order, padding rows carry y = 0)
@@ -71,6 +75,7 @@ struct IncSetupArgs {
     const double *s_base, *G, *alpha_sys; int ldg; long long strideG; int N0, I, O;
     const int* base_of; const double *via_s, *via_y, *via_sigma; int P; double tol, sigma_f, lam; int batch;
     double* W; double* rec; int* irec;
+    double* kcg; int mode;      // mode 0: everything; 1: classification + kernel columns -> kcg [b][IMAXP][Ns]; 2: the rest (W appended columns given)
 };
 
 __global__ void __launch_bounds__(128) k_inc_setup(IncSetupArgs p) {
@@ -89,10 +94,19 @@ __global__ void __launch_bounds__(128) k_inc_setup(IncSetupArgs p) {
     __shared__ int nd, napp, del_idx[IMAXP], del_owner[IMAXP], app_via[IMAXP];
     if (tid == 0) { nd = 0; napp = 0; }
     __syncthreads();
+    if (p.mode == 2) {           // classification and kernel columns were produced by the mode-1 pass
+        if (tid == 0) {
+            const int* ir = p.irec + (size_t)b * IIREC;
+            nd = ir[0]; napp = ir[1];
+            for (int k = 0; k < IMAXP; ++k) { del_idx[k] = ir[2 + k]; app_via[k] = ir[4 + k]; }
+        }
+        for (int idx = tid; idx < IMAXP * N0; idx += blockDim.x) kc[idx] = p.kcg[((size_t)b * IMAXP + idx / N0) * Ns + idx % N0];
+        __syncthreads();
+    }
     // ---- classification of the via points: nearest stored input of the BASE points, strict '< tol', first minimum
     //      (KMP.py:74-80, same scan as k_waypoint_insert); a later via point that hits the same stored point
     //      supersedes the earlier one
-    for (int j = 0; j < p.P; ++j) {
+    for (int j = 0; j < (p.mode == 2 ? 0 : p.P); ++j) {
         const double* vs = p.via_s + ((size_t)b * p.P + j) * I;
         double best = INFINITY; int besti = -1;
         for (int i = tid; i < N0; i += blockDim.x) {
@@ -131,25 +145,39 @@ __global__ void __launch_bounds__(128) k_inc_setup(IncSetupArgs p) {
     }
     const int r1 = O * nd, r2 = O * napp;
     // ---- kernel columns of the appended points against the kept base points
-    for (int idx = tid; idx < napp * N0; idx += blockDim.x) {
-        const int q = idx / N0, j = idx - q * N0;
-        const double* vs = p.via_s + ((size_t)b * p.P + app_via[q]) * I;
-        bool gone = false;
-        for (int k = 0; k < nd; ++k) gone |= (del_idx[k] == j);
-        kc[q * N0 + j] = gone ? 0.0 : rbf(sb + (size_t)j * I, vs, I, p.sigma_f, 0.0, 0.0);
+    if (p.mode != 2) {
+        for (int idx = tid; idx < napp * N0; idx += blockDim.x) {
+            const int q = idx / N0, j = idx - q * N0;
+            const double* vs = p.via_s + ((size_t)b * p.P + app_via[q]) * I;
+            bool gone = false;
+            for (int k = 0; k < nd; ++k) gone |= (del_idx[k] == j);
+            kc[q * N0 + j] = gone ? 0.0 : rbf(sb + (size_t)j * I, vs, I, p.sigma_f, 0.0, 0.0);
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    if (p.mode == 1) {           // hand the kernel columns (zero rows for absent via points) and the classification over
+        for (int idx = tid; idx < IMAXP * Ns; idx += blockDim.x) {
+            const int q = idx / Ns, j = idx - q * Ns;
+            p.kcg[((size_t)b * IMAXP + q) * Ns + j] = (q < napp && j < N0) ? kc[q * N0 + j] : 0.0;
+        }
+        if (tid == 0) {
+            int* ir = p.irec + (size_t)b * IIREC;
+            ir[0] = nd; ir[1] = napp;
+            for (int k = 0; k < IMAXP; ++k) { ir[2 + k] = k < nd ? del_idx[k] : -1; ir[4 + k] = k < napp ? app_via[k] : -1; }
+        }
+        return;
+    }
     // ---- W: deleted columns = rows of the symmetric G; appended columns = G Cb
     double* W = p.W + (size_t)b * 2 * IR * n0;
     for (int idx = tid; idx < r1 * n0; idx += blockDim.x) {
         const int t = idx / n0, row = idx - t * n0;
         const int k = t / O, bc = t - k * O;
-        W[(size_t)t * n0 + row] = Gb[(size_t)(bc * Ns + del_idx[k]) * p.ldg + row];
+        W[(size_t)slot_del(k, bc) * n0 + row] = Gb[(size_t)(bc * Ns + del_idx[k]) * p.ldg + row];
     }
     // (G is symmetric: column `col` of the product is accumulated by one thread that walks DOWN the rows of G, so a warp
     //  reads 256 contiguous bytes per step and there is no cross-lane reduction; the kernel column is broadcast from
     //  shared memory)
-    for (int col = tid; col < n0; col += blockDim.x) {
+    for (int col = tid; col < (p.mode == 2 ? 0 : n0); col += blockDim.x) {
         double acc[IMAXP][IMAXO];
         for (int q = 0; q < IMAXP; ++q) for (int bc = 0; bc < IMAXO; ++bc) acc[q][bc] = 0.0;
         for (int bc = 0; bc < O; ++bc) {
@@ -170,7 +198,7 @@ __global__ void __launch_bounds__(128) k_inc_setup(IncSetupArgs p) {
             }
         }
         for (int q = 0; q < napp; ++q)
-            for (int bc = 0; bc < O; ++bc) W[(size_t)(r1 + q * O + bc) * n0 + col] = acc[q][bc];
+            for (int bc = 0; bc < O; ++bc) W[(size_t)slot_app(q, bc) * n0 + col] = acc[q][bc];
     }
     __syncthreads();          // W of this problem is complete (CTA scope)
     // ---- Cb^T (G Cb) and Cb^T alpha: dot products over the stored points, one warp each
@@ -179,7 +207,7 @@ __global__ void __launch_bounds__(128) k_inc_setup(IncSetupArgs p) {
         if (e < r2 * r2) {
             const int t = e / r2, t2 = e - t * r2;               // t = (q, bc) row, t2 = (q', bc') column
             const int q = t / O, bc = t - q * O;
-            for (int j = lane; j < N0; j += 32) acc += kc[q * N0 + j] * W[(size_t)(r1 + t2) * n0 + bc * Ns + j];
+            for (int j = lane; j < N0; j += 32) acc += kc[q * N0 + j] * W[(size_t)slot_app(t2 / O, t2 % O) * n0 + bc * Ns + j];
             acc = warp_sum(acc);
             if (lane == 0) ctgc[t * IR + t2] = acc;
         } else {
@@ -197,7 +225,7 @@ __global__ void __launch_bounds__(128) k_inc_setup(IncSetupArgs p) {
             const int k = t / O, bc = t - k * O, row = bc * Ns + del_idx[k];
             ad[t] = al[row];
             for (int t2 = 0; t2 < r1; ++t2) { const int k2 = t2 / O, bc2 = t2 - k2 * O; Gdd[t][t2] = Gb[(size_t)row * p.ldg + bc2 * Ns + del_idx[k2]]; }
-            for (int t2 = 0; t2 < r2; ++t2) GCd[t][t2] = W[(size_t)(r1 + t2) * n0 + row];
+            for (int t2 = 0; t2 < r2; ++t2) GCd[t][t2] = W[(size_t)slot_app(t2 / O, t2 % O) * n0 + row];
         }
         if (r1 > 0) small_inverse(Gdd, r1, H);
         for (int t = 0; t < r1; ++t)
@@ -263,16 +291,18 @@ __device__ __forceinline__ void inc_combine(const IncPredictArgs& p, const doubl
 #pragma unroll
     for (int q = 0; q < IMAXP; ++q)
         ka[q] = q < napp ? rbf(p.sq + (size_t)mg * I, p.via_s + ((size_t)b * p.P + ir[4 + q]) * I, I, p.sigma_f, 0.0, 0.0) : 0.0;
-    // appended columns sit behind the r1 deleted ones: uq[a][t2] = u[a][r1 + t2] without dynamic register indexing
-    double uq[IMAXO][IR];
+    // compact views of the fixed column slots (no dynamic register indexing): up[a][t] deleted unknown t = k*O + bc,
+    // uq[a][t2] appended unknown t2 = q*O + bc
+    double up[IMAXO][IR], uq[IMAXO][IR];
 #pragma unroll
     for (int a = 0; a < IMAXO; ++a)
 #pragma unroll
-        for (int t2 = 0; t2 < IR; ++t2) {
-            double v = 0.0;
+        for (int t = 0; t < IR; ++t) {
+            const int sd = slot_del(t / O, t % O), sa = slot_app(t / O, t % O);
+            double vd = 0.0, va = 0.0;
 #pragma unroll
-            for (int c = 0; c < 2 * IR; ++c) if (c == r1 + t2) v = u[a * 2 * IR + c];
-            uq[a][t2] = v;
+            for (int c = 0; c < 2 * IR; ++c) { if (c == sd) vd = u[a * 2 * IR + c]; if (c == sa) va = u[a * 2 * IR + c]; }
+            up[a][t] = vd; uq[a][t] = va;
         }
 #pragma unroll
     for (int a = 0; a < IMAXO; ++a)
@@ -285,7 +315,7 @@ __device__ __forceinline__ void inc_combine(const IncPredictArgs& p, const doubl
                 for (int qq = 0; qq < IMAXP; ++qq) if (qq == q && bc == a) kav = ka[qq];
                 double v = kav - uq[a][t2];
 #pragma unroll
-                for (int t = 0; t < IR; ++t) if (t < r1) v = fma(u[a * 2 * IR + t], N1[t * IR + t2], v);
+                for (int t = 0; t < IR; ++t) if (t < r1) v = fma(up[a][t], N1[t * IR + t2], v);
                 z[a][t2] = v;
             }
         }
@@ -294,7 +324,7 @@ __device__ __forceinline__ void inc_combine(const IncPredictArgs& p, const doubl
         if (a >= O) continue;
         double mean = p.xi_base[((size_t)base * O + a) * M + mg];
 #pragma unroll
-        for (int t = 0; t < IR; ++t) if (t < r1) mean = fma(u[a * 2 * IR + t], a_p[t], mean);
+        for (int t = 0; t < IR; ++t) if (t < r1) mean = fma(up[a][t], a_p[t], mean);
 #pragma unroll
         for (int t2 = 0; t2 < IR; ++t2) mean = fma(z[a][t2], a_z[t2], mean);
         p.xi[((size_t)b * O + a) * M + mg] = mean;
@@ -308,10 +338,10 @@ __device__ __forceinline__ void inc_combine(const IncPredictArgs& p, const doubl
                     double h = 0.0, g = 0.0;
 #pragma unroll
                     for (int t2 = 0; t2 < IR; ++t2) {
-                        if (t < r1 && t2 < r1) h = fma(H[t * IR + t2], u[a2 * 2 * IR + t2], h);
+                        if (t < r1 && t2 < r1) h = fma(H[t * IR + t2], up[a2][t2], h);
                         g = fma(Sinv[t * IR + t2], z[a2][t2], g);
                     }
-                    if (t < r1) php = fma(u[a * 2 * IR + t], h, php);
+                    if (t < r1) php = fma(up[a][t], h, php);
                     zsz = fma(z[a][t], g, zsz);
                 }
                 p.sigma_out[(((size_t)b * O + a) * O + a2) * M + mg] =
@@ -331,11 +361,12 @@ __global__ void __launch_bounds__(IQT) k_inc_predict(IncPredictArgs p) {
     double* Wt = sm;                                            // [N0][NC]   Wt[j][a*8 + t] = W[t][(a, j)]
     double* rec = Wt + (size_t)N0 * NC;                         // [IREC]
     const int* ir = p.irec + (size_t)b * IIREC;
-    const int nd = ir[0], napp = ir[1], r1 = O * nd, r2 = O * napp, r = r1 + r2;
+    const int nd = ir[0], napp = ir[1], r1 = O * nd, r2 = O * napp;
     const double* Wg = p.W + (size_t)b * 2 * IR * n0;
     for (int idx = tid; idx < N0 * NC; idx += IQT) {
         const int j = idx / NC, c = idx - j * NC, a = c / (2 * IR), t = c - a * 2 * IR;
-        Wt[idx] = (a < O && t < r) ? Wg[(size_t)t * n0 + a * Ns + j] : 0.0;
+        const bool used = a < O && (t & 1) < O && ((t & 2) ? (t >> 2) < napp : (t >> 2) < nd);
+        Wt[idx] = used ? Wg[(size_t)t * n0 + a * Ns + j] : 0.0;
     }
     if (tid < IREC) rec[tid] = p.rec[(size_t)b * IREC + tid];
     __syncthreads();
@@ -368,7 +399,8 @@ using namespace kmpx;
 
 extern "C" long long kmpx_inc_workspace_doubles(int N0, int O, int batch) {
     const long long n0 = (long long)O * comp_stride(N0);
-    return (long long)batch * (2 * IR * n0 + IREC) + ((long long)batch * IIREC + 1) / 2;
+    const long long d = (long long)batch * (2 * IR * n0 + IREC) + ((long long)batch * IIREC + 1) / 2;
+    return (d + 1) & ~1LL;       // even: what follows the record block stays 16-byte aligned
 }
 
 extern "C" int kmpx_inc_base(const double* G, int ldg, long long strideG, const double* y_base, const double* s_base, int N0, int I,
@@ -384,6 +416,68 @@ extern "C" int kmpx_inc_base(const double* G, int ldg, long long strideG, const 
     dim3 grid(ceil_div((long long)M * N0, 256), n_bases);
     k_inc_kappa<<<grid, 256, 0, st>>>(s_base, N0, I, sq, M, sigma_f, kappa);
     return check_launch("k_inc_kappa");
+}
+
+// Grouped form: the problems [0, batch) are sorted by base; group g holds group_count[g] consecutive problems of base
+// group_base[g] (host arrays).  The appended columns G Cb of a whole group come from one DMMA GEMM per component
+// (rows = (problem, via point), K = stored points) instead of one pass over G per problem.
+extern "C" long long kmpx_inc_grouped_workspace_doubles(int N0, int O, int batch) {
+    return kmpx_inc_workspace_doubles(N0, O, batch) + (long long)batch * IMAXP * comp_stride(N0);
+}
+
+extern "C" int kmpx_inc_adapt_grouped(const double* s_base, const double* G, int ldg, long long strideG, const double* alpha_sys,
+                                      const double* kappa, const double* xi_base, const double* sigma_base, int N0, int I, int O,
+                                      const int* base_of, const int* group_base, const int* group_count, int n_groups,
+                                      const double* via_s, const double* via_y, const double* via_sigma, int P,
+                                      double tol, double sigma_f, double lam, double alpha_kmp, int batch, const double* sq, int M,
+                                      double* ws, long long ws_doubles, double* xi, double* sigma_out, void* stream) {
+    if (!s_base || !G || !alpha_sys || !kappa || !xi_base || !via_s || !via_y || !via_sigma || !sq || !ws || !xi || !base_of)
+        return fail_arg(1, "null pointer");
+    if (!group_base || !group_count || n_groups <= 0) return fail_arg(13, "group description missing");
+    if (sigma_out && !sigma_base) return fail_arg(8, "sigma_base is required for the covariance");
+    if (O < 1 || O > IMAXO) return fail_arg(11, "incremental adaptation supports O <= 2");
+    if (P < 1 || P > IMAXP) return fail_arg(19, "incremental adaptation supports P <= 2 via points per problem");
+    if (batch <= 0 || M <= 0 || N0 <= 0 || I <= 0) return fail_arg(24, "sizes must be positive");
+    if ((ldg & 1) || (strideG & 1) || (reinterpret_cast<uintptr_t>(G) & 15)) return fail_arg(2, "G must be 16-byte aligned with even strides");
+    if (ws_doubles < kmpx_inc_grouped_workspace_doubles(N0, O, batch)) return fail_arg(28, "workspace too small (kmpx_inc_grouped_workspace_doubles)");
+    long long total = 0;
+    for (int g = 0; g < n_groups; ++g) total += group_count[g];
+    if (total != batch) return fail_arg(15, "group counts do not add up to the batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Ns = comp_stride(N0), n0 = O * Ns;
+    double* W = ws;
+    double* rec = W + (size_t)batch * 2 * IR * n0;
+    int* irec = reinterpret_cast<int*>(rec + (size_t)batch * IREC);
+    double* kcg = ws + kmpx_inc_workspace_doubles(N0, O, batch);
+    IncSetupArgs a{s_base, G, alpha_sys, ldg, strideG, N0, I, O, base_of, via_s, via_y, via_sigma, P, tol, sigma_f, lam, batch, W, rec, irec, kcg, 1};
+    const size_t sm1 = ((size_t)IMAXP * N0 + IR * IR + IR) * sizeof(double);
+    static size_t set1 = 48 * 1024;
+    KMPX_TRY(ensure_dyn_smem(k_inc_setup, sm1, set1, "k_inc_setup"));
+    k_inc_setup<<<batch, 128, sm1, st>>>(a);                                   // classification + kernel columns
+    KMPX_TRY(check_launch("k_inc_setup"));
+    long long off = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const int cnt = group_count[g];
+        if (cnt <= 0) continue;
+        const double* Gb = G + (size_t)group_base[g] * strideG;
+        for (int bc = 0; bc < O; ++bc) {
+            // rows (problem, via point) x columns (system index):  W[.., slot_app(q, bc), :] = kc(problem, q) * G[(bc, :), :]
+            GemmArgs ga{IMAXP * cnt, n0, N0, 1.0, kcg + (size_t)off * IMAXP * Ns, Ns, 0, Gb + (size_t)bc * Ns * ldg, ldg, 0, 0.0,
+                        W + (size_t)off * 2 * IR * n0 + (size_t)slot_app(0, bc) * n0, 4 * n0, 0, 0};
+            KMPX_TRY(launch_dgemm(0, 0, ga, 1, st));
+        }
+        off += cnt;
+    }
+    a.mode = 2;
+    k_inc_setup<<<batch, 128, sm1, st>>>(a);                                   // deleted columns, small matrices
+    KMPX_TRY(check_launch("k_inc_setup"));
+    IncPredictArgs q{kappa, W, rec, irec, base_of, via_s, sq, P, I, O, N0, M, batch, sigma_f, alpha_kmp, xi_base, sigma_base, xi, sigma_out};
+    const size_t sm2 = ((size_t)N0 * IMAXO * 2 * IR + IREC) * sizeof(double);
+    static size_t set2 = 48 * 1024;
+    KMPX_TRY(ensure_dyn_smem(k_inc_predict, sm2, set2, "k_inc_predict"));
+    dim3 grid(ceil_div(M, 2 * IQT), batch);
+    k_inc_predict<<<grid, IQT, sm2, st>>>(q);
+    return check_launch("k_inc_predict");
 }
 
 extern "C" int kmpx_inc_adapt(const double* s_base, const double* G, int ldg, long long strideG, const double* alpha_sys,
