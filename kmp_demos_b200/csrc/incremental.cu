@@ -27,7 +27,8 @@ constexpr int IIREC = 8;                                    // ints per problem:
 // by one GEMM with a uniform row stride:  deleted (k, bc) -> slot 4k + bc,  appended (q, bc) -> slot 4q + 2 + bc.
 __host__ __device__ inline int slot_del(int k, int bc) { return 4 * k + bc; }
 __host__ __device__ inline int slot_app(int q, int bc) { return 4 * q + 2 + bc; }
-constexpr int IQT = 128;                                    // queries per CTA of k_inc_predict (one thread each)
+constexpr int IQT = 128;                                    // threads per CTA of k_inc_predict
+constexpr int IQPT = 2;                                     // queries per thread (four were measured slower: 208 registers, half the CTAs)
 
 // alpha_sys[base][r] = sum_c G[r][c] y_sys[c]   (system = component-major order, padding rows carry y = 0)
 __global__ void __launch_bounds__(256) k_inc_alpha(const double* G, int ldg, long long strideG, const double* y, int N0, int O,
@@ -354,7 +355,7 @@ __device__ __forceinline__ void inc_combine(const IncPredictArgs& p, const doubl
 __global__ void __launch_bounds__(IQT) k_inc_predict(IncPredictArgs p) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x;
-    const int b = blockIdx.y, mq0 = blockIdx.x * (2 * IQT) + tid, mq1 = mq0 + IQT;     // two queries per thread
+    const int b = blockIdx.y, mq0 = blockIdx.x * (IQPT * IQT) + tid;                   // IQPT queries per thread: mq0 + q * IQT
     const int N0 = p.N0, O = p.O, Ns = comp_stride(N0), n0 = O * Ns, M = p.M;
     const int base = p.base_of ? p.base_of[b] : 0;
     constexpr int NC = IMAXO * 2 * IR;                           // 16 columns per stored point: [component][touched unknown]
@@ -371,26 +372,32 @@ __global__ void __launch_bounds__(IQT) k_inc_predict(IncPredictArgs p) {
     if (tid < IREC) rec[tid] = p.rec[(size_t)b * IREC + tid];
     __syncthreads();
     if (mq0 >= M) return;
-    // ---- u[a][t] = sum_j kappa[j][m] W[t][(a, j)]: two queries per thread (every 16-byte broadcast load of W feeds four
-    //      FMAs), 2 x 16 independent accumulators, kappa read coalesced (stored point major)
-    const bool two = mq1 < M;
-    double u0[NC], u1[NC];
+    // ---- u[a][t] = sum_j kappa[j][m] W[t][(a, j)]: IQPT queries per thread, so that every 16-byte broadcast load of W
+    //      feeds 2 * IQPT FMAs, IQPT x 16
+    //      independent accumulators, kappa read coalesced (stored point major)
+    double u[IQPT][NC];
+    const double* kp[IQPT];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) { u0[c] = 0.0; u1[c] = 0.0; }
-    const double* kp0 = p.kappa + (size_t)base * N0 * M + mq0;
-    const double* kp1 = p.kappa + (size_t)base * N0 * M + (two ? mq1 : mq0);
+    for (int q = 0; q < IQPT; ++q) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) u[q][c] = 0.0;
+        kp[q] = p.kappa + (size_t)base * N0 * M + min(mq0 + q * IQT, M - 1);
+    }
     for (int j = 0; j < N0; ++j) {
-        const double k0 = __ldg(kp0 + (size_t)j * M), k1 = __ldg(kp1 + (size_t)j * M);
+        double kv[IQPT];
+#pragma unroll
+        for (int q = 0; q < IQPT; ++q) kv[q] = __ldg(kp[q] + (size_t)j * M);
         const double2* wr = reinterpret_cast<const double2*>(Wt + (size_t)j * NC);
 #pragma unroll
         for (int c = 0; c < NC / 2; ++c) {
             const double2 w2 = wr[c];
-            u0[2 * c] = fma(k0, w2.x, u0[2 * c]); u0[2 * c + 1] = fma(k0, w2.y, u0[2 * c + 1]);
-            u1[2 * c] = fma(k1, w2.x, u1[2 * c]); u1[2 * c + 1] = fma(k1, w2.y, u1[2 * c + 1]);
+#pragma unroll
+            for (int q = 0; q < IQPT; ++q) { u[q][2 * c] = fma(kv[q], w2.x, u[q][2 * c]); u[q][2 * c + 1] = fma(kv[q], w2.y, u[q][2 * c + 1]); }
         }
     }
-    inc_combine(p, u0, rec, ir, b, base, mq0, r1, r2, napp);
-    if (two) inc_combine(p, u1, rec, ir, b, base, mq1, r1, r2, napp);
+#pragma unroll
+    for (int q = 0; q < IQPT; ++q)
+        if (mq0 + q * IQT < M) inc_combine(p, u[q], rec, ir, b, base, mq0 + q * IQT, r1, r2, napp);
 }
 
 }  // namespace kmpx
@@ -475,7 +482,7 @@ extern "C" int kmpx_inc_adapt_grouped(const double* s_base, const double* G, int
     const size_t sm2 = ((size_t)N0 * IMAXO * 2 * IR + IREC) * sizeof(double);
     static size_t set2 = 48 * 1024;
     KMPX_TRY(ensure_dyn_smem(k_inc_predict, sm2, set2, "k_inc_predict"));
-    dim3 grid(ceil_div(M, 2 * IQT), batch);
+    dim3 grid(ceil_div(M, IQPT * IQT), batch);
     k_inc_predict<<<grid, IQT, sm2, st>>>(q);
     return check_launch("k_inc_predict");
 }
@@ -507,7 +514,7 @@ extern "C" int kmpx_inc_adapt(const double* s_base, const double* G, int ldg, lo
     const size_t sm2 = ((size_t)N0 * IMAXO * 2 * IR + IREC) * sizeof(double);
     static size_t set2 = 48 * 1024;
     KMPX_TRY(ensure_dyn_smem(k_inc_predict, sm2, set2, "k_inc_predict"));
-    dim3 grid(ceil_div(M, 2 * IQT), batch);
+    dim3 grid(ceil_div(M, IQPT * IQT), batch);
     k_inc_predict<<<grid, IQT, sm2, st>>>(q);
     return check_launch("k_inc_predict");
 }
