@@ -67,7 +67,11 @@ long long kmpx_potrf_workspace_bytes(int n_max, int batch);
 int kmpx_potrf(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch,
                int* info, void* ws, long long ws_bytes, void* stream);
 
-/* ---- K3: in-place inverse of the lower-triangular factor, L <- L^{-1} (same dispatch as potrf). */
+/* ---- K3: in-place inverse of the lower-triangular factor, L <- L^{-1} (same dispatch as potrf).
+ *      Only the lower triangle of the result is defined.  What the call may write besides it: the strict upper
+ *      triangle (zeros; all of it for n > KMPX_SMALL_MAX, the 32 x 32 diagonal blocks otherwise) and, in a ragged
+ *      batch, the columns n_sys[b] .. n_max-1 of the rows of problem b (zeros; scratch inside the problem's own
+ *      n_max x lda slot).  Rows >= n_sys[b] are never touched. */
 long long kmpx_trtri_workspace_bytes(int n_max, int batch);
 int kmpx_trtri(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch,
                void* ws, long long ws_bytes, void* stream);
