@@ -368,3 +368,40 @@ def test_cfg4_shape_reduced_and_properties():
     assert rel_err(xi, mu[:, ::16]) < 5e-3                      # interpolation property for small lambda
     d0, d1 = sg[0, 0], sg[1, 1]
     assert np.all(d0 > -1e-6) and np.all(d1 > -1e-6) and np.all(d0 < 1.0 + 1e-6)
+
+
+@pytest.mark.parametrize('O', [1, 2])
+def test_large_system_gemm_route_equals_streaming_kernel(O):
+    """kmpx_kmp_predict_gemm (kappa + GEMMs + column reductions) against the fused streaming kernel on one n > 512
+    system: several query chunks forced by a small workspace, M not a multiple of the chunk, odd N (padding row)."""
+    import torch
+    from kmp.model import KMP
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    N = 601
+    t = np.linspace(0.0, 2.0, N).reshape(1, -1)
+    mu = np.stack([np.sin(2.0 * t[0] + a) for a in range(O)])
+    B = rng.normal(size=(N, O, O))
+    sig = np.transpose(np.einsum('nab,ncb->nac', B, B) * 0.05 + 0.05 * np.eye(O), (1, 2, 0))
+    k = KMP(l=0.5, alpha=3.0, sigma_f=150.0, time_driven_kernel=False)
+    k.fit(t, mu, sig)
+    f = k._fact
+    n = f.F.shape[0]
+    assert n > _lib.SMALL_MAX and f.kind == 0
+    M = 300
+    q = torch.as_tensor(np.linspace(-0.1, 2.1, M).reshape(-1, 1), device='cuda')
+    xs = torch.empty((O, M), dtype=torch.float64, device='cuda'); ss = torch.empty((O, O, M), dtype=torch.float64, device='cuda')
+    _lib.call('kmpx_kmp_predict', _lib.ptr(f.F), f.lda, n * f.lda, 0, _lib.ptr(f.w), f.lda, _lib.ptr(f.s_dev), None, N, 1, O, 1,
+              _lib.ptr(q), 0, M, 150.0, 3.0, 0, _lib.ptr(xs), _lib.ptr(ss), _lib.stream())
+    nbytes = int(lib.kmpx_kmp_predict_gemm_workspace_bytes(N, O, 128))            # room for chunks of 128 queries only
+    ws = torch.empty(nbytes // 8, dtype=torch.float64, device='cuda')
+    xg = torch.empty_like(xs); sg = torch.empty_like(ss)
+    _lib.call('kmpx_kmp_predict_gemm', _lib.ptr(f.F), f.lda, _lib.ptr(f.w), _lib.ptr(f.s_dev), N, 1, O, _lib.ptr(q), M, 150.0, 3.0,
+              _lib.ptr(ws), nbytes, _lib.ptr(xg), _lib.ptr(sg), _lib.stream())
+    assert rel_err(xg.cpu().numpy(), xs.cpu().numpy()) < 1e-12 and rel_err(sg.cpu().numpy(), ss.cpu().numpy()) < 1e-11
+    x1, s1 = k.predict(np.linspace(-0.1, 2.1, M).reshape(1, -1))                  # the class takes the GEMM route for n > 512
+    assert rel_err(x1, xs.cpu().numpy()) < 1e-12 and rel_err(s1, ss.cpu().numpy()) < 1e-11
+    with pytest.raises(_lib.KmpxError):
+        _lib.call('kmpx_kmp_predict_gemm', _lib.ptr(f.F), f.lda, _lib.ptr(f.w), _lib.ptr(f.s_dev), N, 1, O, _lib.ptr(q), M, 150.0, 3.0,
+                  _lib.ptr(ws), 1024, _lib.ptr(xg), _lib.ptr(sg), _lib.stream())
