@@ -394,7 +394,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--sets', type=int, default=N_SETS, help='via-point sets per letter (1024 = the named config)')
-    ap.add_argument('--chunk', type=int, default=2048)
+    ap.add_argument('--chunk', type=int, default=4440, help='systems resident at once (a multiple of the 148 SMs: the factor kernels run one CTA per SM)')
     ap.add_argument('--no-extras', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -24,7 +24,7 @@ class KMPBatch:
     Parameters mirror ``KMP`` (l, alpha, sigma_f, adaptation_tol, time_driven_kernel).  ``chunk`` bounds the
     number of systems resident at once (each is n^2 doubles)."""
 
-    def __init__(self, l=0.5, alpha=40.0, sigma_f=1.0, adaptation_tol=0.0005, time_driven_kernel=False, chunk=2048):
+    def __init__(self, l=0.5, alpha=40.0, sigma_f=1.0, adaptation_tol=0.0005, time_driven_kernel=False, chunk=4440):
         self.l, self.alpha, self.sigma_f = float(l), float(alpha), float(sigma_f)
         self.tol, self.time_driven_kernel, self.chunk = float(adaptation_tol), bool(time_driven_kernel), int(chunk)
         self._bufs = {}
