@@ -93,6 +93,18 @@ __global__ void __launch_bounds__(256) k_kernel_build_comp(BuildArgs p) {
     const double* sig = p.sigma + (size_t)bidx * p.n_max * O * O;
     double* A = p.A + (size_t)bidx * p.strideA;
     if (j0 >= Ns) return;
+    if (!TD && lower && blockIdx.x * kBuildCols > ibase + kBuildRows - 1) {
+        // plain kernel, lower-only, tile strictly above the point diagonal: nothing to evaluate - the only entries of the
+        // lower triangle in these columns are the zeros of the off-diagonal component blocks (a > b)
+        for (int ii = warp; ii < kBuildRows; ii += 8) {
+            const int i = ibase + ii;
+            if (i >= Ns) break;
+            for (int a = 1; a < O; ++a)
+                for (int b = 0; b < a; ++b)
+                    *reinterpret_cast<double2*>(A + (size_t)(a * Ns + i) * p.lda + b * Ns + j0) = make_double2(0.0, 0.0);
+        }
+        return;
+    }
 #pragma unroll 1
     for (int ii = warp; ii < kBuildRows; ii += 8) {
         const int i = ibase + ii;
