@@ -310,6 +310,62 @@ __global__ void __launch_bounds__(128) k_kmp_predict_mean(MeanArgs p) {
     if (m < p.M) for (int a = 0; a < O; ++a) p.xi[((size_t)b * O + a) * p.M + m] = acc[a];
 }
 
+// Plain kernel: CTA = 32 queries (lane = query), eight warps split the stored points of every staged chunk; the
+// coefficients are four interleaved branch-free exponentials per lane (the loop above evaluates one library exp at a
+// time with one thread per query: 19.6 G exp/s at cfg 4); the eight partial sums are added in warp order (deterministic).
+constexpr int MEANP_WARPS = 8;
+__global__ void __launch_bounds__(MEANP_WARPS * 32) k_kmp_predict_mean_plain(MeanArgs p) {
+    __shared__ double s_sh[MEAN_CHUNK * 4];
+    __shared__ double a_sh[MEAN_CHUNK * 8];
+    __shared__ double red[MEANP_WARPS][8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, m = blockIdx.x * 32 + lane;
+    const int O = p.O, I = p.I;
+    const int N = p.n_pts ? p.n_pts[b] : p.n_max;
+    const double* s = p.s + (size_t)b * p.n_max * I;
+    const double* al = p.alpha + (size_t)b * p.n_max * O;
+    const double* sq = p.sq + (size_t)b * p.stride_sq;
+    double q[4];
+    for (int t = 0; t < I; ++t) q[t] = sq[(size_t)min(m, p.M - 1) * I + t];
+    double acc[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) acc[a] = 0.0;
+    constexpr int PER = MEAN_CHUNK / MEANP_WARPS;       // 32 points per warp and chunk
+    for (int i0 = 0; i0 < N; i0 += MEAN_CHUNK) {
+        const int cnt = min(MEAN_CHUNK, N - i0);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < MEAN_CHUNK * I; idx += blockDim.x) s_sh[idx] = idx < cnt * I ? s[(size_t)i0 * I + idx] : 0.0;
+        for (int idx = threadIdx.x; idx < MEAN_CHUNK * O; idx += blockDim.x) a_sh[idx] = idx < cnt * O ? al[(size_t)i0 * O + idx] : 0.0;   // alpha = 0 beyond N
+        __syncthreads();
+        if (warp * PER >= cnt) continue;
+        for (int i = warp * PER; i < (warp + 1) * PER; i += 4) {
+            double e[4];
+            if (I == 1) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { const double d = fabs(q[0] - s_sh[i + u]); e[u] = exp_nonpos(-p.sigma_f * (d * d)); }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e[u] = rbf_fast(q, s_sh + (i + u) * I, I, p.sigma_f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int a = 0; a < 8; ++a) if (a < O) acc[a] = fma(e[u], a_sh[(i + u) * O + a], acc[a]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) if (a < O) red[warp][a][lane] = acc[a];
+    __syncthreads();
+    if (warp == 0 && m < p.M) {
+        for (int a = 0; a < O; ++a) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < MEANP_WARPS; ++w) v += red[w][a][lane];
+            p.xi[((size_t)b * O + a) * p.M + m] = v;
+        }
+    }
+}
+
 template <int MT>
 static int launch_predict(PredictArgs& p, cudaStream_t st) {
     // resident coefficient panel only for the plain kernel and when it fits
@@ -370,6 +426,11 @@ extern "C" int kmpx_kmp_predict_mean(const double* alpha, const double* s, const
     if (M <= 0) return fail_arg(10, "M must be > 0");
     if (!xi) return fail_arg(13, "xi is NULL");
     MeanArgs p{alpha, s, n_pts, n_max, I, O, batch, sq, stride_sq, M, sigma_f, time_driven, xi};
+    if (!time_driven) {
+        dim3 gridp(ceil_div(M, 32), batch);
+        k_kmp_predict_mean_plain<<<gridp, MEANP_WARPS * 32, 0, (cudaStream_t)stream>>>(p);
+        return check_launch("k_kmp_predict_mean_plain");
+    }
     dim3 grid(ceil_div(M, 128), batch);
     k_kmp_predict_mean<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
     return check_launch("k_kmp_predict_mean");
