@@ -38,14 +38,14 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
     constexpr int FP = (F + 7) & ~7;
     constexpr int NF = FP / 8;
     constexpr int TRI = D * (D + 1) / 2;
+    constexpr int POFF = (D + 2) & ~1;                 // offset of the packed precision factor inside a parameter record (even)
+    constexpr int PREC = (POFF + TRI + 1) & ~1;        // doubles per record (even)
     extern __shared__ __align__(16) double smem[];
     const int K = p.K, KP = pad8(K);
     const int ldr = ld_conflict_free(KP), ldf = ld_conflict_free(FP);
-    double* s_mu = smem;                          // [K][D]
-    double* s_pc = s_mu + (size_t)K * D;          // [K][TRI] packed upper triangle, row order
-    double* s_c = s_pc + (size_t)K * TRI;         // [K] log_det + log_weight - D/2 log(2 pi)
-    double* s_shift = s_c + K;                    // [D]
-    double* s_x = s_shift + D;                    // [ETS][D]
+    double* s_par = smem;                         // [K][PREC]: mu (D), c = log_det + log_weight - D/2 log(2 pi), pad, packed upper triangle (row order)
+    double* s_shift = s_par + (size_t)K * PREC;   // [D] (+1 pad: what follows stays 16-byte aligned)
+    double* s_x = s_shift + ((D + 1) & ~1);       // [ETS][D]
     double* s_R = s_x + (size_t)ETS * D;          // [ETS][ldr]
     double* s_Phi = s_R + (size_t)ETS * ldr;      // [ETS][ldf]
     double* s_red = s_Phi + (size_t)ETS * ldf;    // [EPARTS][ETS] max / sum exchange
@@ -56,13 +56,14 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
     const bool hard = p.hard_labels != nullptr;
 
     if (!hard) {
-        for (int idx = tid; idx < K * D; idx += ETHREADS) s_mu[idx] = p.means[idx];
+        for (int idx = tid; idx < K * D; idx += ETHREADS) s_par[(size_t)(idx / D) * PREC + idx % D] = p.means[idx];
         for (int idx = tid; idx < K * TRI; idx += ETHREADS) {
             const int k = idx / TRI; int t = idx - k * TRI, i = 0;
+            const int t0 = t;
             while (t >= D - i) { t -= D - i; ++i; }
-            s_pc[idx] = p.prec_chol[((size_t)k * D + i) * D + i + t];
+            s_par[(size_t)k * PREC + POFF + t0] = p.prec_chol[((size_t)k * D + i) * D + i + t];
         }
-        for (int k = tid; k < K; k += ETHREADS) s_c[k] = p.log_det[k] + p.log_weights[k] - 0.5 * D * kLog2Pi;
+        for (int k = tid; k < K; k += ETHREADS) s_par[(size_t)k * PREC + D] = p.log_det[k] + p.log_weights[k] - 0.5 * D * kLog2Pi;
     }
     for (int i = tid; i < D; i += ETHREADS) s_shift[i] = p.shift ? p.shift[i] : 0.0;
     __syncthreads();
@@ -111,20 +112,24 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
         } else {
             double mx = -INFINITY; int am = kbeg;
             for (int k = kbeg; k < kend; ++k) {
-                const double* mu = s_mu + (size_t)k * D;
-                const double* pc = s_pc + (size_t)k * TRI;
+                // the parameters of a component are one 16-byte aligned record [mu (D), c, pad, pc (TRI)] read with 16-byte
+                // broadcast loads: with 8-byte loads the shared-memory pipe, not the FP64 pipe, limits this loop
+                double par[PREC];
+                const double2* pr = reinterpret_cast<const double2*>(s_par + (size_t)k * PREC);
+#pragma unroll
+                for (int t = 0; t < PREC / 2; ++t) { const double2 v = pr[t]; par[2 * t] = v.x; par[2 * t + 1] = v.y; }
                 double df[D], y[D];
 #pragma unroll
-                for (int i = 0; i < D; ++i) { df[i] = x[i] - mu[i]; y[i] = 0.0; }
+                for (int i = 0; i < D; ++i) { df[i] = x[i] - par[i]; y[i] = 0.0; }
                 int t = 0;
 #pragma unroll
                 for (int i = 0; i < D; ++i)
 #pragma unroll
-                    for (int j = i; j < D; ++j) y[j] += df[i] * pc[t++];
+                    for (int j = i; j < D; ++j) y[j] += df[i] * par[POFF + t++];
                 double q = 0.0;
 #pragma unroll
                 for (int j = 0; j < D; ++j) q += y[j] * y[j];
-                const double wlp = s_c[k] - 0.5 * q;
+                const double wlp = par[D] - 0.5 * q;
                 Rrow[k] = wlp;
                 if (wlp > mx) { mx = wlp; am = k; }
             }
@@ -290,7 +295,8 @@ static int em_grid(long long n) {
 }
 static size_t em_smem(int d, int K) {
     const int F = gmm_F(d), FP = pad8(F), KP = pad8(K), TRI = d * (d + 1) / 2;
-    size_t dbl = (size_t)K * d + (size_t)K * TRI + K + d + (size_t)ETS * d + (size_t)ETS * ld_conflict_free(KP) +
+    const int poff = (d + 2) & ~1, prec = (poff + TRI + 1) & ~1;       // parameter record of k_gmm_em
+    size_t dbl = (size_t)K * prec + ((d + 1) & ~1) + (size_t)ETS * d + (size_t)ETS * ld_conflict_free(KP) +
                  (size_t)ETS * ld_conflict_free(FP) + 2 * EPARTS * ETS;
     return dbl * sizeof(double);
 }
