@@ -405,3 +405,28 @@ def test_large_system_gemm_route_equals_streaming_kernel(O):
     with pytest.raises(_lib.KmpxError):
         _lib.call('kmpx_kmp_predict_gemm', _lib.ptr(f.F), f.lda, _lib.ptr(f.w), _lib.ptr(f.s_dev), N, 1, O, _lib.ptr(q), M, 150.0, 3.0,
                   _lib.ptr(ws), 1024, _lib.ptr(xg), _lib.ptr(sg), _lib.stream())
+
+
+def test_batched_mean_only_path_equals_fused_path(golden):
+    """KMPBatch with want_cov=False (alpha = A^-1 mu, then the mean-only predict kernel) against the fused
+    mean+covariance path and the golden cfg-3 means."""
+    import torch
+    from kmp_demos_b200.batch import KMPBatch
+    zl, z = golden('letters_ref.npz'), golden('cfg3_sample.npz')
+    c = wl.CFG1
+    kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=8)
+    kb.set_base(np.broadcast_to(wl.cfg1_kmp_grid(200), (26, 1, 200)), zl['gmr_mu'], zl['gmr_sigma'])
+    base_of, vs, vp, vv = [], [], [], []
+    for r in range(len(z['letter'])):
+        li, si = int(z['letter'][r]), int(z['set_idx'][r])
+        a, b, cc = wl.cfg3_via_sets(li, zl['gmr_mu'][li], si + 1)
+        base_of.append(li); vs.append(a[si]); vp.append(b[si]); vv.append(cc[si])
+    d = [torch.as_tensor(np.ascontiguousarray(x), device='cuda') for x in
+         (np.array(base_of, dtype=np.int32), np.array(vs)[:, :, None], np.array(vp), np.array(vv), np.asarray(z['queries']).T)]
+    x_full, _, info, _ = kb.run_device(*d, True)
+    x_full = x_full.cpu().numpy()
+    x_mean, sg_none, _, _ = kb.run_device(*d, False)
+    assert sg_none is None and int((info != 0).sum()) == 0
+    x_mean = x_mean.cpu().numpy()
+    for r in range(len(base_of)):
+        assert rel_err(x_mean[r], x_full[r]) < MEAN_TOL and rel_err(x_mean[r], z['xi'][r]) < MEAN_TOL, r
