@@ -125,22 +125,27 @@ class KMPBatch:
             # alpha = A^-1 mu is only needed by the mean-only predict; the fused mean+covariance kernel takes w
             self._launch('kmpx_solve_alpha', _lib.ptr(A), lda, strideA, _lib.ptr(npc), n_max_pts, O, bc,
                       _lib.LAYOUT_COMPONENT, _lib.ptr(y), _lib.ptr(w), lda, None if want_cov else _lib.ptr(al), st)
-            if want_cov:
-                self._launch('kmpx_kmp_predict', _lib.ptr(A), lda, strideA, 0, _lib.ptr(w), lda, _lib.ptr(s), _lib.ptr(npc),
-                          n_max_pts, I, O, bc, _lib.ptr(queries), 0, M, self.sigma_f, self.alpha, td,
-                          _lib.ptr(xi[c0:]), _lib.ptr(sg[c0:]), st)
-            else:
-                self._launch('kmpx_kmp_predict_mean', _lib.ptr(al), _lib.ptr(s), _lib.ptr(npc), n_max_pts, I, O, bc,
-                          _lib.ptr(queries), 0, M, self.sigma_f, td, _lib.ptr(xi[c0:]), st)
-            if copy_stream is not None:
-                done = torch.cuda.Event()
-                done.record()
-                copy_stream.wait_event(done)
-                with torch.cuda.stream(copy_stream):
-                    if host_xi is not None:
-                        host_xi[c0:c0 + bc].copy_(xi[c0:c0 + bc], non_blocking=True)
-                    if host_sigma is not None and sg is not None:
-                        host_sigma[c0:c0 + bc].copy_(sg[c0:c0 + bc], non_blocking=True)
+            # with host outputs the predict of the LAST chunk is launched in four parts, so that only the copy of the last
+            # quarter is left when the compute stream is done (the copies of earlier chunks overlap with the next chunk)
+            parts = 4 if (copy_stream is not None and c0 + bc >= B and bc >= 64) else 1
+            for q0, q1 in ((bc * i // parts, bc * (i + 1) // parts) for i in range(parts)):
+                nb = q1 - q0
+                if want_cov:
+                    self._launch('kmpx_kmp_predict', _lib.ptr(A[q0:]), lda, strideA, 0, _lib.ptr(w[q0:]), lda, _lib.ptr(s[q0:]),
+                              _lib.ptr(npc[q0:]), n_max_pts, I, O, nb, _lib.ptr(queries), 0, M, self.sigma_f, self.alpha, td,
+                              _lib.ptr(xi[c0 + q0:]), _lib.ptr(sg[c0 + q0:]), st)
+                else:
+                    self._launch('kmpx_kmp_predict_mean', _lib.ptr(al[q0:]), _lib.ptr(s[q0:]), _lib.ptr(npc[q0:]), n_max_pts, I, O, nb,
+                              _lib.ptr(queries), 0, M, self.sigma_f, td, _lib.ptr(xi[c0 + q0:]), st)
+                if copy_stream is not None:
+                    done = torch.cuda.Event()
+                    done.record()
+                    copy_stream.wait_event(done)
+                    with torch.cuda.stream(copy_stream):
+                        if host_xi is not None:
+                            host_xi[c0 + q0:c0 + q1].copy_(xi[c0 + q0:c0 + q1], non_blocking=True)
+                        if host_sigma is not None and sg is not None:
+                            host_sigma[c0 + q0:c0 + q1].copy_(sg[c0 + q0:c0 + q1], non_blocking=True)
         if copy_stream is not None:
             torch.cuda.current_stream().wait_stream(copy_stream)
         return xi, sg, info, n_pts
