@@ -202,7 +202,9 @@ class KMPBatch:
         sg = None
         if want_cov:
             sg = out_sigma if out_sigma is not None else torch.empty((B, O, O, M), dtype=f64, device='cuda')
-        Bc = min(self.chunk, B)
+        # small chunks when the results stream out to the host: the step is bound by that copy, and only the first chunk's
+        # compute and the last chunk's copy are not overlapped
+        Bc = min(self.chunk if (host_xi is None and host_sigma is None) else min(self.chunk, 1184), B)
         # problems sorted by base (the usual case): the appended columns of all problems of a base come from one GEMM
         base_host = base_of.cpu().numpy()
         grouped = bool(np.all(base_host[1:] >= base_host[:-1]))
