@@ -370,6 +370,58 @@ def test_cfg4_shape_reduced_and_properties():
     assert np.all(d0 > -1e-6) and np.all(d1 > -1e-6) and np.all(d0 < 1.0 + 1e-6)
 
 
+def test_cfg4_full_size_against_independent_lu_solve():
+    """cfg 4 at BASELINE.json's full size (N = 8192, O = 2, n = 16384) through the class API.  The numpy oracle would
+    need minutes for inv(A) here, so the checker is an independent fp64 LU route on the device (torch.linalg.solve on
+    an A assembled in torch from the definition, KMP.py:146-156) - the same algebra the reference runs
+    (k inv(A) Y, alpha (k** - k inv(A) k^T), KMP.py:187-190) - plus the size-independent identity
+    L^-1 A L^-T = I on the stored factor."""
+    import torch
+    from kmp.model import KMP
+    c = wl.CFG1
+    N, O = 8192, 2
+    t, mu, sig = wl.cfg4_problem(N=N, seed=3)
+    k = KMP(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False)
+    k.fit(t, mu, sig)
+    M = 96
+    q = np.linspace(-0.05, 2.05, M).reshape(1, -1)
+    xi, sg = k.predict(q)
+    dev = torch.device('cuda')
+    td = torch.as_tensor(t[0], device=dev)
+    n = N * O
+    A = torch.zeros((n, n), dtype=torch.float64, device=dev)             # component-major: row = a*N + i
+    Kd = torch.exp(-c['sigma_f'] * (td[:, None] - td[None, :]) ** 2)
+    sd = torch.as_tensor(sig, device=dev)
+    for a in range(O):
+        A[a * N:(a + 1) * N, a * N:(a + 1) * N] = Kd
+        for b in range(O):
+            A[a * N:(a + 1) * N, b * N:(b + 1) * N] += torch.diag(c['lam'] * sd[a, b])
+    del Kd
+    f = k._fact
+    assert f.kind == 0 and f.F.shape[0] == n
+    Li = torch.tril(f.F[:, :n])
+    R = Li @ A @ Li.T
+    R.diagonal().sub_(1.0)
+    ident = float(R.abs().max())
+    del R, Li
+    qd = torch.as_tensor(q[0], device=dev)
+    ks = torch.exp(-c['sigma_f'] * (qd[:, None] - td[None, :]) ** 2)     # (M, N)
+    rhs = torch.zeros((n, 1 + O * M), dtype=torch.float64, device=dev)
+    rhs[:, 0] = torch.as_tensor(mu, device=dev).reshape(-1)              # Y in the component-major order
+    for a in range(O):
+        rhs[a * N:(a + 1) * N, 1 + a * M:1 + (a + 1) * M] = ks.T         # columns of k*^T for output a
+    sol = torch.linalg.solve(A, rhs)
+    xr = np.empty((O, M)); sr = np.empty((O, O, M))
+    for a in range(O):
+        xr[a] = (ks @ sol[a * N:(a + 1) * N, 0]).cpu().numpy()
+        for b in range(O):
+            quad = (ks * sol[a * N:(a + 1) * N, 1 + b * M:1 + (b + 1) * M].T).sum(1)
+            sr[a, b] = (c['alpha'] * ((1.0 if a == b else 0.0) - quad)).cpu().numpy()
+    assert ident < 1e-9, ident
+    assert rel_err(xi, xr) < MEAN_TOL, rel_err(xi, xr)
+    assert rel_err(sg, sr) < COV_TOL, rel_err(sg, sr)
+
+
 @pytest.mark.parametrize('O', [1, 2])
 def test_large_system_gemm_route_equals_streaming_kernel(O):
     """kmpx_kmp_predict_gemm (kappa + GEMMs + column reductions) against the fused streaming kernel on one n > 512
