@@ -377,10 +377,22 @@ __device__ __forceinline__ void aux_trtri32_finish(const double* L, double* X, d
     aux_warps_sync();
 }
 
+// L2 prefetch of rows [c0, n) x columns [c0, c0 + NB) of A by the 256 threads of the MMA warps (a row segment of
+// 256 bytes touches two or three 128-byte lines depending on its alignment).
+__device__ __forceinline__ void prefetch_block_column(const double* A, int lda, int c0, int n, int tid) {
+    const int w = min(NB, n - c0) * (int)sizeof(double);
+    for (int r = c0 + tid; r < n; r += FTHREADS) {
+        const char* q = reinterpret_cast<const char*>(A + (size_t)r * lda + c0);
+        asm volatile("prefetch.global.L2 [%0];\n" :: "l"(q));
+        if (w > 128) asm volatile("prefetch.global.L2 [%0];\n" :: "l"(q + 128));
+        asm volatile("prefetch.global.L2 [%0];\n" :: "l"(q + w - 8));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Left-looking blocked Cholesky.  Step j (block column k0 = 32 j, m = n - k0 rows):
 //   MMA warps   acc(unit u) = L[rows of unit u, 0:k0] * L[k0:k0+32, 0:k0]^T for the 32-row units below the diagonal
-//               block (unit u -> warp u % 8), and - warp 7, second accumulator - the self product of unit 0, i.e. the
+//               block (unit u -> warp u % 7), and - warp 7, second accumulator - the self product of unit 0, i.e. the
 //               history of the NEXT diagonal block;   X(u) = (A - acc) * Dinv_j^T, stored from registers; warp 7 adds
 //               A_{j+1,j+1} and -X(0) X(0)^T (X(0) handed over in shared memory) and publishes the next diagonal block.
 //   aux warps   factor and invert the diagonal block j (published at the end of step j-1) while the MMA warps are in
@@ -469,7 +481,11 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_potrf_tma(const __grid_constant
             const int kb = min(NB, n - k0);
             const int m = n - k0;
             const int nun = (m - 1) >> 5;                 // 32-row units below the diagonal block
-            const bool live0 = warp < nun, live1 = warp + FWARPS < nun;
+            // unit u -> (warp u % 7, accumulator u / 7) for u < 14, unit 14 (n > 480 only) -> (warp 7, accumulator 0):
+            // warp 7 normally carries nothing but the self product, whose tail (wait for X(0), rank-32 update, publish)
+            // is then as long as the two panel products of the other warps instead of coming on top of one
+            const int u0 = warp < FWARPS - 1 ? warp : 14, u1 = warp + (FWARPS - 1);
+            const bool live0 = u0 < nun, live1 = warp < FWARPS - 1 && u1 < nun;
             const bool self = warp == FWARPS - 1 && nun > 0;          // warp 7's second accumulator: next diagonal block
             // ---- first block column of a problem: warp 7 publishes A_00 (later diagonal blocks are published one step early)
             if (warp == FWARPS - 1 && k0 == 0) {
@@ -487,11 +503,23 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_potrf_tma(const __grid_constant
             }
             zero_acc(acc[0]);
             zero_acc(acc[1]);
+            // ---- L2 prefetch of what the NEXT step reads straight from global memory (its block column of A, diagonal
+            //      block included), and in the last two steps the first two block columns of the CTA's next problem:
+            //      the per-SM share of the HBM bandwidth (~27 B/clk) would otherwise be paid as a burst in front of the
+            //      panel solve (128 KB per step) while the memory system idles during the contraction
+            if (!(g_dbg & 32)) {
+                const int last = (n - 1) / NB * NB;                 // k0 of the last step
+                const int bn = b + gridDim.x;
+                const int nn = (k0 + 2 * NB > last && bn < p.batch) ? (p.n_sys ? p.n_sys[bn] : p.n_max) : 0;
+                if (k0 + NB <= last) prefetch_block_column(A, p.lda, k0 + NB, n, tid);
+                else if (nn > NB) prefetch_block_column(p.A + (size_t)bn * p.strideA, p.lda, NB, nn, tid);
+                if (k0 + NB <= last && nn > 0) prefetch_block_column(p.A + (size_t)bn * p.strideA, p.lda, 0, nn, tid);
+            }
             const int nk = nun > 0 ? k0 / 8 : 0;
             for (int kt = 0; kt < nk; ++kt) {
                 const double* tile = ring.wait_tile();
                 if (!(g_dbg & 1))
-                    tile_mma<true>(acc, tile, nullptr, o0, o1, live0, 32 + warp * 32, live1, self ? 32 : 32 + (warp + FWARPS) * 32, self, lane);
+                    tile_mma<true>(acc, tile, nullptr, o0, o1, live0, 32 + u0 * 32, live1, self ? 32 : 32 + u1 * 32, self, lane);
                 ring.release_tile(lane);
             }
             PHASE_MARK(0);
@@ -499,9 +527,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_potrf_tma(const __grid_constant
             //      below full block columns, kb == 32): sixteen 16-byte loads per unit in flight, row index clamped
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const int u = warp + c * FWARPS;
+                const int u = c ? u1 : u0;
                 const bool nextdiag = c == 1 && self;
-                if (u < nun || nextdiag) {
+                if ((c ? live1 : live0) || nextdiag) {
                     const int row0 = k0 + NB + (nextdiag ? 0 : u * 32);
                     const int col0 = nextdiag ? k0 + NB : k0;
                     if (!nextdiag || n - (k0 + NB) >= NB) {
@@ -568,8 +596,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_potrf_tma(const __grid_constant
             // ---- X = P * L_kk^{-T}, stored from registers
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                const int u = warp + c * FWARPS;
-                if (u < nun && !(c == 1 && self)) {
+                const int u = c ? u1 : u0;
+                if (c ? live1 : live0) {
                     chunk_mul_regs<true>(acc[c], Dinv, 1.0, lane);
                     if (u == 0) {
 #pragma unroll

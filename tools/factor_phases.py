@@ -3,7 +3,7 @@ import ctypes, sys, os, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from kmp_demos_b200 import _lib
 lib = _lib.load()
-n, batch, lda = 404, 148, 408
+n, batch, lda = 404, int(os.environ.get('BATCH', 148)), 408
 rng = np.random.default_rng(0)
 M = rng.normal(size=(n, n)); S = M @ M.T / n + np.eye(n)
 A0 = torch.zeros((batch, n, lda), dtype=torch.float64, device='cuda'); A0[:, :, :n] = torch.as_tensor(S, device='cuda')

@@ -5,7 +5,7 @@ from kmp_demos_b200 import _lib
 lib = _lib.load()
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 t0 = time.time(); worst = 0.0; rounds = 0
-while time.time() - t0 < float(sys.argv[2]) if len(sys.argv) > 2 else 60:
+while time.time() - t0 < (float(sys.argv[2]) if len(sys.argv) > 2 else 60):
     nmax = int(rng.choice([96, 130, 202, 300, 404, 448, 512]))
     batch = int(rng.integers(1, 700))
     lda = nmax + int(rng.choice([0, 2, 4, 8]))
