@@ -317,22 +317,35 @@ __device__ __forceinline__ void aux_potf2(double* P, double* Ld, double* X, doub
         if (blockIdx.x == 0 && t == 0) g_phase[7] += clock64() - t_in;
     }
 }
+// Branch-free reciprocal (hardware seed + two Newton steps, ~1 ulp).
+__device__ __forceinline__ double rcp_chain(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
 // Inverses of the four 8 x 8 diagonal blocks of the lower-triangular L -> X (rest of X zeroed), one thread per column.
+// The reciprocals of the diagonal are formed up front (lane (block, c) holds entry c, shuffled to the block's lanes),
+// so that a row costs two dependent operations (last product of the sum, scaling) instead of a division.
 __device__ __forceinline__ void aux_diag8_inverse(const double* L, double* X, int t) {
     for (int idx = t; idx < 32 * 32; idx += AUXT) X[(idx >> 5) * FLDP + (idx & 31)] = 0.0;
     aux_warps_sync();
     if (t < 32) {
         const int base = (t >> 3) * 8, c = t & 7;
         double x[8];
+        const double rc = rcp_chain(L[(base + c) * FLDP + base + c]);      // lane (block, c): reciprocal of diagonal entry c
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+            const double ri = __shfl_sync(0xffffffffu, rc, (t & 24) | i);
             double v = 0.0;
-            if (i == c) v = 1.0 / L[(base + i) * FLDP + base + i];
+            if (i == c) v = ri;
             else if (i > c) {
                 double sum = 0.0;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) if (q >= c && q < i) sum += L[(base + i) * FLDP + base + q] * x[q];
-                v = -sum / L[(base + i) * FLDP + base + i];
+                v = -sum * ri;
             }
             x[i] = v;
             X[(base + i) * FLDP + base + c] = v;
@@ -524,7 +537,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_potrf_tma(const __grid_constant
             }
             PHASE_MARK(0);
             // ---- P = A[rows, k0:k0+32] - acc straight from global memory into the accumulator layout (units exist only
-            //      below full block columns, kb == 32): sixteen 16-byte loads per unit in flight, row index clamped
+            //      below full block columns, kb == 32): sixteen 16-byte loads per unit in flight, row index clamped.
+            //      (Loading -A into the accumulators BEFORE the contraction instead was measured 2 % slower: the same
+            //      transfer time then stalls the first DMMAs of every warp.)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const int u = c ? u1 : u0;
@@ -733,8 +748,19 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_trtri_tma(const __grid_constant
             const int kb = min(NB, n - k0);
             const int m = n - k0 - kb;            // rows below the diagonal block
             const double* Dinv = Dinv2 + (done & 1) * 32 * FLDP;
-            seen_dinv = progress_wait(dinv_ready, done + 1, seen_dinv);
-            PHASE_MARK(8);
+            bool waited = false;      // the inverse of the diagonal block is awaited with the loads of L21 already in flight
+            // L2 prefetch of the block column the NEXT step (and the aux warps) read from global memory; in the last step
+            // the last two block columns of the CTA's next problem (see k_potrf_tma)
+            if (!(g_dbg & 32)) {
+                if (jb > 0) prefetch_block_column(L, p.lda, k0 - NB, n, tid);
+                else if (b + (int)gridDim.x < p.batch) {
+                    const int bn = b + gridDim.x;
+                    const int nn = p.n_sys ? p.n_sys[bn] : p.n_max;
+                    const int cl = (nn - 1) / NB * NB;
+                    if (nn > 0) prefetch_block_column(p.A + (size_t)bn * p.strideA, p.lda, cl, nn, tid);
+                    if (cl >= NB) prefetch_block_column(p.A + (size_t)bn * p.strideA, p.lda, cl - NB, nn, tid);
+                }
+            }
             if (m > 0) {
                 const int r_g0 = k0 + NB;
                 const int nch = (m + 31) >> 5;
@@ -756,6 +782,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_trtri_tma(const __grid_constant
                                 acc[0][i][j][0] = r < m ? v.x : 0.0; acc[0][i][j][1] = r < m ? v.y : 0.0;
                             }
                         }
+                        if (!waited) { seen_dinv = progress_wait(dinv_ready, done + 1, seen_dinv); waited = true; PHASE_MARK(8); }
                         chunk_mul_regs<false>(acc[0], Dinv, 1.0, lane);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -771,6 +798,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_trtri_tma(const __grid_constant
                         }
                     }
                 }
+                if (!waited) { seen_dinv = progress_wait(dinv_ready, done + 1, seen_dinv); waited = true; }
                 mma_warps_sync();
                 PHASE_MARK(9);
                 zero_acc(acc[0]);
@@ -802,6 +830,9 @@ __global__ void __launch_bounds__(TTHREADS, 1) k_trtri_tma(const __grid_constant
                     }
                 }
             }
+            // (the aux warps' write-back of the inverted diagonal block precedes dinv_ready: it must be awaited before
+            //  steps_done lets the producer stream that block)
+            if (!waited) seen_dinv = progress_wait(dinv_ready, done + 1, seen_dinv);
             fence_global_to_tma();
             mma_warps_sync();   // also: every warp is done with T and this Dinv buffer
             ++done;
