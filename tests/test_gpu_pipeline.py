@@ -3,6 +3,8 @@ golden outputs of the reference itself (tests/golden/*.npz) and the CPU oracle.
 
 Tolerances (BASELINE.json north star): means <= 1e-9, covariances <= 1e-7 (norm-wise relative);
 time-driven kernel <= 1e-7 on both."""
+import os
+
 import numpy as np
 import pytest
 
@@ -482,3 +484,72 @@ def test_batched_mean_only_path_equals_fused_path(golden):
     x_mean = x_mean.cpu().numpy()
     for r in range(len(base_of)):
         assert rel_err(x_mean[r], x_full[r]) < MEAN_TOL and rel_err(x_mean[r], z['xi'][r]) < MEAN_TOL, r
+
+
+def _demo_data_root(tmp_path, golden):
+    """Rebuilds the reference's data files (absent on the GPU box) from the committed fixtures: 2Dletters/G.mat as a
+    1 x 5 cell array of structs (pos from letters_ref.npz, vel from the demo-3 design matrix) and
+    quaternion_trajectories/pose_data.npy as pickled Point records."""
+    import scipy.io as sio
+    from kmp.types.point import Point
+    from kmp.types.quaternion import quaternion
+    pos = golden('letters_ref.npz')['pos'][6]                     # letter G: (5, 2, 200)
+    X3 = golden('demo3_vel.npz')['X']                             # (1000, 5) = [t, pos, vel]
+    cells = np.empty((1, 5), dtype=object)
+    for h in range(5):
+        blk = X3[h * 200:(h + 1) * 200]
+        assert np.array_equal(blk[:, 1:3].T, pos[h])
+        cells[0, h] = {'pos': pos[h], 'vel': blk[:, 3:5].T.copy(), 'acc': np.zeros((2, 200))}
+    os.makedirs(tmp_path / '2Dletters')
+    sio.savemat(str(tmp_path / '2Dletters' / 'G.mat'), {'demos': cells})
+    z = golden('demo2_pose.npz')
+    pts = []
+    for i in range(z['time'].shape[1]):
+        pose = np.zeros(6); pose[:3] = z['pos'][:, i]
+        pts.append(Point(time=float(z['time'][0, i]), pose=pose, quat=quaternion.from_array(z['quat'][i]), quat_eucl=z['quat_eucl'][:, i].copy()))
+    os.makedirs(tmp_path / 'quaternion_trajectories')
+    arr = np.empty(len(pts), dtype=object)
+    arr[:] = pts
+    np.save(str(tmp_path / 'quaternion_trajectories' / 'pose_data.npy'), arr, allow_pickle=True)
+    return str(tmp_path)
+
+
+def test_headless_demos_reproduce_the_reference_pipelines(tmp_path, golden):
+    """`from kmp import demo1, demo2, demo3` (main.py:12) without a display - every stage of the three demo
+    pipelines against the outputs of the reference's own classes on the same files."""
+    from kmp import demo1, demo2, demo3
+    root = _demo_data_root(tmp_path, golden)
+    z = golden('cfg1_G.npz')
+    d = demo1(root=root)                                           # letter G, C = 8, every fourth sample
+    assert d.gmm.model.n_iter_ == int(z['d1_n_iter'])
+    assert rel_err(d.mu, z['d1_gmr_mu']) < MEAN_TOL and rel_err(d.sigma, z['d1_gmr_sigma']) < COV_TOL
+    assert rel_err(d.mu_kmp, z['d1_pred_xi']) < MEAN_TOL and rel_err(d.sigma_kmp, z['d1_pred_sigma']) < COV_TOL
+    t = d.add_waypoint(2.0, -1.0)                                  # ctrl-click: time of the closest GMR point
+    dist = np.linalg.norm(d.mu[:2].T - np.array([2.0, -1.0]), axis=1)
+    assert t == 0.01 * (int(np.argmin(dist)) + 1) and d.kmp.N == 50 + (0 if np.any(np.abs(d.time - t) < 5e-4) else 1)
+    assert d.waypoints.shape == (1, 2) and set(d.results()) == set(demo1._fields)
+    d.update()                                                     # "Update" resets the adaptation
+    d.kmp.set_waypoint([0.25], [np.array([[2.0, -1.0]])], [1e-4 * np.eye(2)])
+    xi, sg = d.kmp.predict(d.time)
+    assert rel_err(xi, z['d1_adapt_xi']) < MEAN_TOL and rel_err(sg, z['d1_adapt_sigma']) < COV_TOL
+
+    z = golden('demo3_vel.npz')
+    d3 = demo3(root=root)
+    assert d3.gmm.model.n_iter_ == int(z['n_iter'])
+    assert rel_err(d3.mu, z['gmr_mu']) < MEAN_TOL and rel_err(d3.sigma, z['gmr_sigma']) < COV_TOL
+    assert d3.kmp.N == int(z['adapt_N'])
+    assert rel_err(d3.mu_kmp, z['adapt_xi']) < 1e-7 and rel_err(d3.sigma_kmp, z['adapt_sigma']) < 1e-7    # H3 tolerance
+    out = d3.save(str(tmp_path / 'demo3.npz'))
+    assert np.array_equal(np.load(out)['mu_kmp'], d3.mu_kmp)
+
+    z = golden('demo2_pose.npz')
+    d2 = demo2(root=root)
+    assert d2.gmm.model.n_iter_ == int(z['pos_n_iter']) and d2.gmm_quat.model.n_iter_ == int(z['quat_n_iter'])
+    assert rel_err(d2.mu_pos, z['pos_gmr_mu']) < MEAN_TOL and rel_err(d2.sigma_pos, z['pos_gmr_sigma']) < COV_TOL
+    assert rel_err(d2.mu_pos_kmp, z['pos_pred_xi']) < MEAN_TOL and rel_err(d2.sigma_pos_kmp, z['pos_pred_sigma']) < COV_TOL
+    assert rel_err(d2.mu_pos_kmp_ad, z['pos_adapt_xi']) < MEAN_TOL and rel_err(d2.sigma_pos_kmp_ad, z['pos_adapt_sigma']) < COV_TOL
+    assert rel_err(d2.mu_quat_kmp, z['quat_pred_xi']) < MEAN_TOL and rel_err(d2.sigma_quat_kmp, z['quat_pred_sigma']) < COV_TOL
+    assert np.allclose(d2.waypoint_quat, z['quat_wp'], atol=1e-13)
+    assert rel_err(d2.mu_quat_kmp_ad, z['quat_adapt_xi']) < MEAN_TOL and rel_err(d2.sigma_quat_kmp_ad, z['quat_adapt_sigma']) < COV_TOL
+    assert rel_err(d2.kmp_quats_ad, z['quat_adapt_back']) < 1e-9
+    assert np.allclose(np.linalg.norm(d2.kmp_quats, axis=0), 1.0, atol=1e-12)

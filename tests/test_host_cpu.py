@@ -152,3 +152,13 @@ def test_kl_divergence_follows_the_reference_formula():
         ref.append(q * np.log(q / p))
     ref = np.array(ref); ref /= np.linalg.norm(ref)
     assert abs(k.KL_divergence(xi, sg, xr, sr) - np.mean(ref)) < 1e-13
+
+
+def test_headless_demos_import_like_main_py():
+    """main.py:12 `from kmp import demo1, demo2, demo3` resolves without a display or a device; unknown names still fail."""
+    import kmp
+    from kmp import demo1, demo2, demo3
+    from kmp.demos import demo1 as d1
+    assert d1 is demo1 and {c.__name__ for c in (demo1, demo2, demo3)} == {'demo1', 'demo2', 'demo3'}
+    with pytest.raises(AttributeError):
+        kmp.demo4
