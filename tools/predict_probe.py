@@ -13,9 +13,11 @@ for li in range(L):
 base_of = torch.as_tensor(np.repeat(np.arange(L, dtype=np.int32), 64), device='cuda')
 d_vs = torch.as_tensor(np.concatenate(ts)[:, :, None], device='cuda'); d_vp = torch.as_tensor(np.concatenate(ps), device='cuda'); d_vv = torch.as_tensor(np.concatenate(vs), device='cuda')
 q = torch.as_tensor(np.ascontiguousarray(wl.cfg1_query_grid(1000).T), device='cuda')
-for flags, name in ((0, 'normal'), (4, 'no panel fill'), (1, 'no MMA'), (8, 'no reduce'), (13, 'none of them')):
+sets = ((0, 'normal'), (4, 'no panel fill'), (1, 'no MMA'), (8, 'no reduce'), (13, 'none of them'))
+if len(sys.argv) > 1: sets = tuple((int(a), f'flags {a}') for a in sys.argv[1:])
+for flags, name in sets:
     lib.kmpx_debug_set(flags)
-    for rep in range(2):
+    for rep in range(3):
         kb.events = []
         kb.run_device(base_of, d_vs, d_vp, d_vv, q); torch.cuda.synchronize()
     ms = sum(a.elapsed_time(b) for n, a, b in kb.events if n == 'kmpx_kmp_predict')
