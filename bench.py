@@ -114,7 +114,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    _RESULT.append(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -381,10 +381,13 @@ def run_ours(args):
             'e2e': {'value': world * B / (ms_inc_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_inc_e2e,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
             'max_rel_dev_from_direct': {'mean': inc_err_mean, 'covariance': inc_err_cov}, 'within_tolerance': bool(inc_ok)}
-        print(json.dumps(line))
+        _RESULT.append(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+
+
+_RESULT = []      # the JSON line(s) of this process, printed by main() once stdout is restored
 
 
 def main():
@@ -397,10 +400,23 @@ def main():
     ap.add_argument('--chunk', type=int, default=4440, help='systems resident at once (a multiple of the 148 SMs: the factor kernels run one CTA per SM)')
     ap.add_argument('--no-extras', action='store_true')
     args = ap.parse_args()
-    if args.impl == 'reference':
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly one JSON line: whatever libraries write to file descriptor 1 while the run is on (NCCL's
+    # version banner under NCCL_DEBUG=VERSION, for one) is sent to stderr, and the descriptor is restored for the result
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _RESULT.clear()
+    try:
+        if args.impl == 'reference':
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for text in _RESULT:
+        print(text, flush=True)
 
 
 if __name__ == '__main__':
