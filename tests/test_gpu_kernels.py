@@ -153,7 +153,8 @@ def test_potrf_trtri_small_ragged_batch(T):
 
 
 @pytest.mark.parametrize('nmax,lda,sizes', [(404, 408, [64, 65, 96, 100, 257, 333, 402, 404, 1, 5, 31, 32, 33]), (202, 202, [200, 202, 128]),
-                                            (480, 480, [480, 449, 33])])
+                                            (480, 480, [480, 449, 33]),
+                                            (512, 512, [512, 511, 497, 481, 480, 300])])      # n > 480: the fifteenth 32-row unit (warp 7)
 def test_potrf_trtri_tma_variants_ragged(T, nmax, lda, sizes):
     """Sizes at which BOTH small kernels take the TMA path (64 <= n_max, buffers fit): ragged batches, NaN everywhere
     outside the lower triangles, leading dimension with and without padding columns."""
