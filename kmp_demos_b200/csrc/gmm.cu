@@ -110,8 +110,14 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
             for (int k = kbeg; k < kend; ++k) Rrow[k] = (k == lab) ? 1.0 : 0.0;
             if (half == EPARTS - 1) for (int k = K; k < KP; ++k) Rrow[k] = 0.0;
         } else {
+            // Weighted log-probabilities of this thread's components.  For K <= 64 (KB == 1: at most 16 components per
+            // thread) they stay in registers through the max / exp / normalise passes and R is written once: with the
+            // rows of s_R as scratch the kernel was bound by the shared-memory pipe (85 % of its wavefronts, a third of
+            // them bank conflicts of the 8-byte accesses with stride ldr), not by FP64.
+            constexpr int KREG = KB == 1 ? 16 : 1;
+            double wl[KREG];
             double mx = -INFINITY; int am = kbeg;
-            for (int k = kbeg; k < kend; ++k) {
+            auto weighted_logp = [&](int k) {
                 // the parameters of a component are one 16-byte aligned record [mu (D), c, pad, pc (TRI)] read with 16-byte
                 // broadcast loads: with 8-byte loads the shared-memory pipe, not the FP64 pipe, limits this loop
                 double par[PREC];
@@ -129,9 +135,25 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
                 double q = 0.0;
 #pragma unroll
                 for (int j = 0; j < D; ++j) q += y[j] * y[j];
-                const double wlp = par[D] - 0.5 * q;
-                Rrow[k] = wlp;
-                if (wlp > mx) { mx = wlp; am = k; }
+                return par[D] - 0.5 * q;
+            };
+            if (KB == 1) {
+#pragma unroll
+                for (int kk = 0; kk < KREG; ++kk) {
+                    const int k = kbeg + kk;
+                    double wlp = -INFINITY;
+                    if (k < kend) {
+                        wlp = weighted_logp(k);
+                        if (wlp > mx) { mx = wlp; am = k; }
+                    }
+                    wl[kk] = wlp;
+                }
+            } else {
+                for (int k = kbeg; k < kend; ++k) {
+                    const double wlp = weighted_logp(k);
+                    Rrow[k] = wlp;
+                    if (wlp > mx) { mx = wlp; am = k; }
+                }
             }
             s_red[half * ETS + s_loc] = mx; s_arg[half * ETS + s_loc] = am;
             __syncthreads();
@@ -146,7 +168,18 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
             double se = 0.0;
             // four interleaved branch-free exponentials (the arguments are <= 0); one at a time through the library exp
             // the chains serialise and the E-step becomes FP64-latency bound
-            {
+            if (KB == 1) {
+#pragma unroll
+                for (int kk = 0; kk < KREG; kk += 4) {
+                    if (kbeg + kk < kend) {
+                        double e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) e[u] = exp_nonpos(wl[kk + u] - m);          // -inf beyond kend -> 0
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { wl[kk + u] = e[u]; se += e[u]; }
+                    }
+                }
+            } else {
                 int k = kbeg;
                 for (; k + 4 <= kend; k += 4) {
                     double e[4];
@@ -163,7 +196,12 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
 #pragma unroll
             for (int q = 0; q < EPARTS; ++q) tot += s_red[q * ETS + s_loc];
             const double inv = live ? 1.0 / tot : 0.0;
-            for (int k = kbeg; k < kend; ++k) Rrow[k] *= inv;
+            if (KB == 1) {
+#pragma unroll
+                for (int kk = 0; kk < KREG; ++kk) if (kbeg + kk < kend) Rrow[kbeg + kk] = wl[kk] * inv;
+            } else {
+                for (int k = kbeg; k < kend; ++k) Rrow[k] *= inv;
+            }
             if (half == EPARTS - 1) for (int k = K; k < KP; ++k) Rrow[k] = 0.0;
             if (half == 0 && live) {
                 const double l = m + log(tot);
