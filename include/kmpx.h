@@ -48,7 +48,12 @@ const char* kmpx_last_error(void);
 long long kmpx_launch_count(void);
 /* Profiling aid: cycle counters per phase of k_potrf_small / k_trtri_small accumulated by CTA 0 (16 host int64). */
 int kmpx_debug_phases(long long* out_host, int reset);
-/* Profiling experiments on the small-system K-loops: bit 0 skips the MMAs, bit 1 the cp.async loads (results are then wrong). */
+/* Profiling experiments (tools/ only; 0 = normal operation).  Results are WRONG with bits 0-3 set.
+ *   bit 0 (1)  skip the DMMAs of the contractions (factor kernels, fused predict)
+ *   bit 1 (2)  skip the cp.async loads of k_potrf_small / k_trtri_small
+ *   bit 2 (4)  skip the kappa panel fill of the fused predict;  bit 3 (8) skip its per-chunk reductions
+ *   bit 4 (16) force the cp.async factor kernels instead of the TMA ones;  bit 5 (32) no L2 prefetch in the TMA factor kernels
+ *   bit 6 (64) per-category timing printout of the blocked large-n Cholesky (host side) */
 int kmpx_debug_set(int flags);
 
 /* ---- K1: kernel-matrix builder.  Replaces the N^2 Python loop of KMP.fit, KMP.py:146-156, with
