@@ -92,8 +92,9 @@ class KMPBatch:
         sg = None
         if want_cov:
             sg = out_sigma if out_sigma is not None else torch.empty((B, O, O, M), dtype=f64, device='cuda')
-        info = self._buf('info', (B,), i32)
-        n_pts = self._buf('n_pts', (B,), i32)
+        # results handed to the caller are allocated per call (never a cached buffer a later call would overwrite)
+        info = torch.empty((B,), dtype=i32, device='cuda')
+        n_pts = torch.empty((B,), dtype=i32, device='cuda')
         Bc = min(self.chunk, B)
         A = self._buf('A', (Bc, n_max, lda), f64)
         s = self._buf('s', (Bc, n_max_pts, I), f64)
@@ -156,7 +157,8 @@ class KMPBatch:
         """Same arguments and results as run_device, computed by an exact low-rank correction of the per-base
         solution instead of one factorisation per problem (csrc/incremental.cu): the bases are factorised, inverted
         and predicted once per call (direct kernels, batch = number of bases), every problem then costs O(n^2 + n M).
-        Plain kernel, O <= 2, at most two via points per problem.  Returns (xi, sigma, info of the BASE systems)."""
+        Plain kernel, O <= 2, at most two via points per problem.  Returns (xi, sigma, info of the BASE systems);
+        the caller checks `info` (check_base_info) - the call itself never synchronises with the host."""
         torch = _lib.require_cuda()
         lib = _lib.load()
         b = self._base
@@ -205,8 +207,13 @@ class KMPBatch:
         # small chunks when the results stream out to the host: the step is bound by that copy, and only the first chunk's
         # compute and the last chunk's copy are not overlapped
         Bc = min(self.chunk if (host_xi is None and host_sigma is None) else min(self.chunk, 1184), B)
-        # problems sorted by base (the usual case): the appended columns of all problems of a base come from one GEMM
-        base_host = base_of.cpu().numpy()
+        # problems sorted by base (the usual case): the appended columns of all problems of a base come from one GEMM.
+        # The grouping is a launch-structure parameter (HOST arrays in the C ABI); it is read back once per distinct
+        # base_of tensor, not once per call
+        gkey = (base_of.data_ptr(), base_of._version, B)
+        if getattr(self, '_group_key', None) != gkey:
+            self._group_key, self._group_host = gkey, base_of.cpu().numpy()
+        base_host = self._group_host
         grouped = bool(np.all(base_host[1:] >= base_host[:-1]))
         nws = int((lib.kmpx_inc_grouped_workspace_doubles if grouped else lib.kmpx_inc_workspace_doubles)(N0, O, Bc))
         ws = self._buf('inc_ws', (nws,), f64)
@@ -243,7 +250,14 @@ class KMPBatch:
                         host_sigma[c0:c0 + bc].copy_(sg[c0:c0 + bc], non_blocking=True)
         if copy_stream is not None:
             torch.cuda.current_stream().wait_stream(copy_stream)
-        return xi, sg, info
+        return xi, sg, info.clone()
+
+    def check_base_info(self, info):
+        """Raises numpy.linalg.LinAlgError when a BASE system of run_incremental was not positive definite (every
+        problem of that base would be garbage).  One host read - call it outside timed regions."""
+        bad = int((info != 0).sum().item())
+        if bad:
+            raise np.linalg.LinAlgError(f'{bad} of {info.numel()} base systems are not positive definite')
 
     # ------------------------------------------------------------------ host-facing call
     def fit_predict(self, base_of, via_s, via_xi, via_sigma, queries, want_cov=True):
@@ -271,8 +285,4 @@ class KMPBatch:
         return h_xi.numpy(), (h_sg.numpy() if h_sg is not None else None)
 
 
-def shard_range(n_items, rank, world):
-    """Contiguous static split of n_items units over `world` ranks: [lo, hi) of `rank`."""
-    per, rem = divmod(n_items, world)
-    lo = rank * per + min(rank, rem)
-    return lo, lo + per + (1 if rank < rem else 0)
+from .dist import shard_range  # noqa: E402,F401  (re-export: one definition, dist.py)

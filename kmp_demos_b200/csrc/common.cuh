@@ -34,10 +34,18 @@ inline int check_cuda(cudaError_t e, const char* what) {
     }
     return 0;
 }
-// Opt-in to more than 48 KB of dynamic shared memory; `cur` caches the largest size requested so far for this
-// kernel (the limit is 227 KB minus the kernel's static shared memory).
+// Opt-in to more than 48 KB of dynamic shared memory; `cache` holds, per device, the largest size requested so far for
+// this kernel (the attribute is per device and only ever raised; the limit is 227 KB minus the kernel's static shared
+// memory).  One cache object per kernel: entry points that launch the same kernel share it.
+constexpr int kMaxDevices = 64;
+struct SmemCache {
+    size_t v[kMaxDevices];
+    SmemCache() { for (int i = 0; i < kMaxDevices; ++i) v[i] = 48 * 1024; }
+};
+inline int current_device() { int d = 0; (void)cudaGetDevice(&d); return (d >= 0 && d < kMaxDevices) ? d : 0; }
 template <typename Kern>
-inline int ensure_dyn_smem(Kern kernel, size_t bytes, size_t& cur, const char* name) {
+inline int ensure_dyn_smem(Kern kernel, size_t bytes, SmemCache& cache, const char* name) {
+    size_t& cur = cache.v[current_device()];
     if (bytes <= cur) return 0;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
@@ -50,7 +58,18 @@ inline int ensure_dyn_smem(Kern kernel, size_t bytes, size_t& cur, const char* n
 }
 #define KMPX_TRY(expr) do { int _rc = (expr); if (_rc != 0) return _rc; } while (0)
 
-constexpr int kNumSMs = 148;   // B200
+constexpr int kNumSMsB200 = 148;   // upper bound used for workspace sizing (the only target is the B200)
+// SM count of the current device (queried once per device); grids of the persistent kernels are sized from it
+inline int num_sms() {
+    static int cache[kMaxDevices] = {};
+    const int dev = current_device();
+    if (cache[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { (void)cudaGetLastError(); v = kNumSMsB200; }
+        cache[dev] = v;
+    }
+    return cache[dev];
+}
 __host__ __device__ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 __host__ __device__ inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }
 
@@ -118,7 +137,7 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     q = fma(q, r, 1.0);
     q = fma(q, r, 1.0);
     const double res = __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
-    return x < -708.0 ? 0.0 : res;
+    return x < -708.0 ? 0.0 : (x != x ? x : res);            // NaN propagates (select, still branch-free)
 }
 // rbf() with the branch-free exponential (plain kernel, hot loops that evaluate many coefficients per thread)
 template <typename P1, typename P2>

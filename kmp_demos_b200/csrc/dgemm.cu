@@ -131,13 +131,14 @@ __global__ void __launch_bounds__(GTHREADS) k_dgemm(GemmArgs p) {
 int launch_dgemm(int transA, int transB, const GemmArgs& p, int batch, cudaStream_t st) {
     if (p.m <= 0 || p.n <= 0) return 0;
     constexpr size_t smem = (size_t)GSTAGES * 2 * GTILE * sizeof(double);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[kMaxDevices] = {};          // the attribute is per device
+    const int dev = current_device();
+    if (!attr_done[dev]) {
         KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_dgemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr dgemm NN"));
         KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_dgemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr dgemm NT"));
         KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_dgemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr dgemm TN"));
         KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_dgemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr dgemm TT"));
-        attr_done = true;
+        attr_done[dev] = true;
     }
     dim3 grid(ceil_div(p.n, GBN), ceil_div(p.m, GBM), batch);
     if (!transA && !transB) k_dgemm<false, false><<<grid, GTHREADS, smem, st>>>(p);

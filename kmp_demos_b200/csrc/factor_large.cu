@@ -58,7 +58,8 @@ struct SideStream {
         return 0;
     }
 };
-static SideStream g_side;
+static SideStream g_side_dev[kMaxDevices];       // streams and events belong to a device
+#define g_side (g_side_dev[current_device()])
 
 static int diag_factor(double* D, int lda, int nb, double* Dinv, int* info, int k, cudaStream_t st) {
     KMPX_TRY(launch_potrf_small(D, lda, 0, nullptr, nb, 1, info, k, 1, st));

@@ -582,18 +582,18 @@ int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, 
         CUtensorMap map;
         KMPX_TRY(make_batch_map(&map, A, lda, strideA, n_max, batch, TBOX));
         const TmaSmem lay = tma_smem_layout(n_max, false, kMaxDynSmem);
-        static size_t tma_smem_set = 48 * 1024;
+        static SmemCache tma_smem_set;
         KMPX_TRY(ensure_dyn_smem(k_potrf_tma, lay.total, tma_smem_set, "k_potrf_tma"));
         FactorArgs p{A, lda, strideA, n_sys, n_max, batch, info, info_offset, info_accumulate};
-        k_potrf_tma<<<batch < kNumSMs ? batch : kNumSMs, TTHREADS, lay.total, st>>>(map, p, lay);
+        k_potrf_tma<<<batch < num_sms() ? batch : num_sms(), TTHREADS, lay.total, st>>>(map, p, lay);
         return check_launch("k_potrf_tma");
     }
     const size_t smem = potrf_small_smem(n_max);
-    static size_t smem_set = 48 * 1024;
+    static SmemCache smem_set;
     KMPX_TRY(ensure_dyn_smem(k_potrf_small, smem, smem_set, "k_potrf_small"));
     FactorArgs p{A, lda, strideA, n_sys, n_max, batch, info, info_offset, info_accumulate};
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;
-    const int grid = batch < kNumSMs * per_sm ? batch : kNumSMs * per_sm;
+    const int grid = batch < num_sms() * per_sm ? batch : num_sms() * per_sm;
     k_potrf_small<<<grid, FTHREADS, smem, st>>>(p);
     return check_launch("k_potrf_small");
 }
@@ -603,27 +603,27 @@ int launch_trtri_small(double* L, int lda, long long strideA, const int* n_sys, 
         CUtensorMap map;
         KMPX_TRY(make_batch_map(&map, L, lda, strideA, n_max, batch, TBOX));
         const TmaSmem lay = tma_smem_layout(n_max, true, kMaxDynSmem);
-        static size_t tma_smem_set = 48 * 1024;
+        static SmemCache tma_smem_set;
         KMPX_TRY(ensure_dyn_smem(k_trtri_tma, lay.total, tma_smem_set, "k_trtri_tma"));
         FactorArgs p{L, lda, strideA, n_sys, n_max, batch, nullptr, 0, 0};
-        k_trtri_tma<<<batch < kNumSMs ? batch : kNumSMs, TTHREADS, lay.total, st>>>(map, p, lay);
+        k_trtri_tma<<<batch < num_sms() ? batch : num_sms(), TTHREADS, lay.total, st>>>(map, p, lay);
         return check_launch("k_trtri_tma");
     }
     const size_t smem = trtri_small_smem(n_max);
-    static size_t smem_set = 48 * 1024;
+    static SmemCache smem_set;
     KMPX_TRY(ensure_dyn_smem(k_trtri_small, smem, smem_set, "k_trtri_small"));
     FactorArgs p{L, lda, strideA, n_sys, n_max, batch, nullptr, 0, 0};
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;
-    const int grid = batch < kNumSMs * per_sm ? batch : kNumSMs * per_sm;
+    const int grid = batch < num_sms() * per_sm ? batch : num_sms() * per_sm;
     k_trtri_small<<<grid, FTHREADS, smem, st>>>(p);
     return check_launch("k_trtri_small");
 }
 
 int launch_solve_alpha(const AlphaArgs& p, cudaStream_t st) {
     const size_t smem = (size_t)2 * sys_size(p.n_max, p.O, p.layout) * sizeof(double);
-    static size_t smem_set = 48 * 1024;
+    static SmemCache smem_set;
     KMPX_TRY(ensure_dyn_smem(k_solve_alpha, smem, smem_set, "k_solve_alpha"));
-    const int grid = p.batch < kNumSMs * 4 ? p.batch : kNumSMs * 4;
+    const int grid = p.batch < num_sms() * 4 ? p.batch : num_sms() * 4;
     k_solve_alpha<<<grid, 256, smem, st>>>(p);
     return check_launch("k_solve_alpha");
 }

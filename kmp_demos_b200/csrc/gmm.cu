@@ -328,7 +328,7 @@ __global__ void k_gmm_finalize(FinArgs p) {
 
 static int em_grid(long long n) {
     const long long tiles = (n + ETS - 1) / ETS;
-    const long long g = tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;      // two CTAs per SM
+    const long long g = tiles < 2 * num_sms() ? tiles : 2 * num_sms();      // two CTAs per SM
     return (int)(g < 1 ? 1 : g);
 }
 static size_t em_smem(int d, int K) {
@@ -388,7 +388,8 @@ using namespace kmpx;
 extern "C" long long kmpx_gmm_workspace_bytes(int n, int d, int K) {
     (void)n;
     const int F = gmm_F(d), FP = pad8(F), KP = pad8(K);
-    return 2LL * kNumSMs * ((long long)KP * FP + 1) * (long long)sizeof(double);
+    const int sms = num_sms() > kNumSMsB200 ? num_sms() : kNumSMsB200;
+    return 2LL * sms * ((long long)KP * FP + 1) * (long long)sizeof(double);
 }
 
 extern "C" int kmpx_gmm_em_pass(const double* X, long long n, int d, int K, const double* shift,
@@ -396,7 +397,6 @@ extern "C" int kmpx_gmm_em_pass(const double* X, long long n, int d, int K, cons
                                 const double* log_det, double* stats, int* labels, double* lse,
                                 void* ws, long long ws_bytes, void* stream) {
     if (!log_weights || !means || !prec_chol || !log_det) return fail_arg(6, "mixture parameters are NULL");
-    if (K < 2) return fail_arg(4, "K must be >= 2");
     EmArgs p{X, n, d, K, shift, log_weights, means, prec_chol, log_det, nullptr, nullptr, labels, lse};
     return run_em(p, stats, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -177,7 +177,7 @@ static int launch_gmr(const GmrArgs& p, cudaStream_t st) {
     if (smem > 200 * 1024) { snprintf(g_err, sizeof(g_err), "kmpx: too many mixture components for k_gmr"); return -4; }
     KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_gmr<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr k_gmr"));
     const long long blocks = (p.M + 127) / 128;
-    const int grid = (int)(blocks < kNumSMs * 16 ? blocks : kNumSMs * 16);
+    const int grid = (int)(blocks < num_sms() * 16 ? blocks : num_sms() * 16);
     k_gmr<O><<<grid, 128, smem, st>>>(p);
     return check_launch("k_gmr");
 }

@@ -404,6 +404,8 @@ __global__ void __launch_bounds__(IQT) k_inc_predict(IncPredictArgs p) {
 
 using namespace kmpx;
 
+static SmemCache g_inc_setup_smem, g_inc_predict_smem;    // one per kernel: both entry points launch the same two kernels
+
 extern "C" long long kmpx_inc_workspace_doubles(int N0, int O, int batch) {
     const long long n0 = (long long)O * comp_stride(N0);
     const long long d = (long long)batch * (2 * IR * n0 + IREC) + ((long long)batch * IIREC + 1) / 2;
@@ -458,8 +460,7 @@ extern "C" int kmpx_inc_adapt_grouped(const double* s_base, const double* G, int
     double* kcg = ws + kmpx_inc_workspace_doubles(N0, O, batch);
     IncSetupArgs a{s_base, G, alpha_sys, ldg, strideG, N0, I, O, base_of, via_s, via_y, via_sigma, P, tol, sigma_f, lam, batch, W, rec, irec, kcg, 1};
     const size_t sm1 = ((size_t)IMAXP * N0 + IR * IR + IR) * sizeof(double);
-    static size_t set1 = 48 * 1024;
-    KMPX_TRY(ensure_dyn_smem(k_inc_setup, sm1, set1, "k_inc_setup"));
+    KMPX_TRY(ensure_dyn_smem(k_inc_setup, sm1, g_inc_setup_smem, "k_inc_setup"));
     k_inc_setup<<<batch, 128, sm1, st>>>(a);                                   // classification + kernel columns
     KMPX_TRY(check_launch("k_inc_setup"));
     long long off = 0;
@@ -480,8 +481,7 @@ extern "C" int kmpx_inc_adapt_grouped(const double* s_base, const double* G, int
     KMPX_TRY(check_launch("k_inc_setup"));
     IncPredictArgs q{kappa, W, rec, irec, base_of, via_s, sq, P, I, O, N0, M, batch, sigma_f, alpha_kmp, xi_base, sigma_base, xi, sigma_out};
     const size_t sm2 = ((size_t)N0 * IMAXO * 2 * IR + IREC) * sizeof(double);
-    static size_t set2 = 48 * 1024;
-    KMPX_TRY(ensure_dyn_smem(k_inc_predict, sm2, set2, "k_inc_predict"));
+    KMPX_TRY(ensure_dyn_smem(k_inc_predict, sm2, g_inc_predict_smem, "k_inc_predict"));
     dim3 grid(ceil_div(M, IQPT * IQT), batch);
     k_inc_predict<<<grid, IQT, sm2, st>>>(q);
     return check_launch("k_inc_predict");
@@ -506,14 +506,12 @@ extern "C" int kmpx_inc_adapt(const double* s_base, const double* G, int ldg, lo
     int* irec = reinterpret_cast<int*>(rec + (size_t)batch * IREC);
     IncSetupArgs a{s_base, G, alpha_sys, ldg, strideG, N0, I, O, base_of, via_s, via_y, via_sigma, P, tol, sigma_f, lam, batch, W, rec, irec};
     const size_t sm1 = ((size_t)IMAXP * N0 + IR * IR + IR) * sizeof(double);
-    static size_t set1 = 48 * 1024;
-    KMPX_TRY(ensure_dyn_smem(k_inc_setup, sm1, set1, "k_inc_setup"));
+    KMPX_TRY(ensure_dyn_smem(k_inc_setup, sm1, g_inc_setup_smem, "k_inc_setup"));
     k_inc_setup<<<batch, 128, sm1, st>>>(a);
     KMPX_TRY(check_launch("k_inc_setup"));
     IncPredictArgs q{kappa, W, rec, irec, base_of, via_s, sq, P, I, O, N0, M, batch, sigma_f, alpha_kmp, xi_base, sigma_base, xi, sigma_out};
     const size_t sm2 = ((size_t)N0 * IMAXO * 2 * IR + IREC) * sizeof(double);
-    static size_t set2 = 48 * 1024;
-    KMPX_TRY(ensure_dyn_smem(k_inc_predict, sm2, set2, "k_inc_predict"));
+    KMPX_TRY(ensure_dyn_smem(k_inc_predict, sm2, g_inc_predict_smem, "k_inc_predict"));
     dim3 grid(ceil_div(M, IQPT * IQT), batch);
     k_inc_predict<<<grid, IQT, sm2, st>>>(q);
     return check_launch("k_inc_predict");

@@ -101,7 +101,7 @@ extern "C" int kmpx_inverse(double* A, int lda, long long strideA, const int* n_
     if (!ws || ws_bytes < kmpx_inverse_workspace_bytes(n_max, batch)) return fail_arg(8, "workspace too small");
     GjArgs p{A, lda, strideA, n_sys, n_max, batch, info, (int*)ws};
     const size_t smem = (size_t)2 * n_max * sizeof(double);
-    const int grid = batch < kNumSMs ? batch : kNumSMs;
+    const int grid = batch < num_sms() ? batch : num_sms();
     k_inverse_gj<<<grid, GJ_THREADS, smem, (cudaStream_t)stream>>>(p);
     return check_launch("k_inverse_gj");
 }

@@ -154,7 +154,7 @@ extern "C" int kmpx_kpp_candidates(const double* X, const double* x_sq, long lon
     if (!cand) return fail_arg(5, "cand is NULL");
     if (T < 1 || T > KPP_MAXT) return fail_arg(6, "T must be in 1..8");
     if (!dist || !pot) return fail_arg(8, "dist / pot is NULL");
-    const int grid = (int)((n + KPP_THREADS - 1) / KPP_THREADS < kNumSMs * 4 ? (n + KPP_THREADS - 1) / KPP_THREADS : kNumSMs * 4);
+    const int grid = (int)((n + KPP_THREADS - 1) / KPP_THREADS < num_sms() * 4 ? (n + KPP_THREADS - 1) / KPP_THREADS : num_sms() * 4);
     if (!ws || ws_bytes < (long long)grid * KPP_MAXT * (long long)sizeof(double)) return fail_arg(10, "workspace too small (148*4*8 doubles)");
     k_kpp_candidates<<<grid, KPP_THREADS, 0, (cudaStream_t)stream>>>(X, x_sq, n, d, cand, T, closest, dist, (double*)ws);
     KMPX_TRY(check_launch("k_kpp_candidates"));
@@ -171,7 +171,7 @@ extern "C" int kmpx_kmeans_assign(const double* X, long long n, int d, int K, co
     if (!centers) return fail_arg(5, "centers is NULL");
     if (!labels) return fail_arg(7, "labels is NULL");
     const long long blocks = (n + 255) / 256;
-    const int grid = (int)(blocks < kNumSMs * 8 ? blocks : kNumSMs * 8);
+    const int grid = (int)(blocks < num_sms() * 8 ? blocks : num_sms() * 8);
     const size_t smem = ((size_t)K * d + K) * sizeof(double);
     k_kmeans_assign<<<grid, 256, smem, (cudaStream_t)stream>>>(X, n, d, K, centers, labels_prev, labels, n_changed);
     return check_launch("k_kmeans_assign");

@@ -375,7 +375,7 @@ static int launch_predict(PredictArgs& p, cudaStream_t st) {
     p.ldp = ldp;
     const size_t smem = PredictSmem<MT>::total(p.O, p.I, p.resident, ldp);
     if (smem > 226 * 1024) { snprintf(g_err, sizeof(g_err), "kmpx: predict tile does not fit shared memory (O=%d)", p.O); return -11; }
-    static size_t smem_set = 48 * 1024;
+    static SmemCache smem_set;
     KMPX_TRY(ensure_dyn_smem(k_kmp_predict<MT>, smem, smem_set, "k_kmp_predict"));
     dim3 grid(ceil_div(p.M, MT), p.batch);
     k_kmp_predict<MT><<<grid, PTHREADS, smem, st>>>(p);

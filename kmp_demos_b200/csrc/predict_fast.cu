@@ -355,11 +355,11 @@ int launch_predict_fast(PredictArgs& p, cudaStream_t st) {
     KMPX_TRY(make_batch_map(&map, p.F, p.lda, p.strideA, n_sys_max, p.batch, RC));
     dim3 grid(ceil_div(p.M, QT), p.batch);
     if (p.O == 1) {
-        static size_t set1 = 48 * 1024;
+        static SmemCache set1;
         KMPX_TRY(ensure_dyn_smem(k_kmp_predict_fast<1>, lay.total, set1, "k_kmp_predict_fast<1>"));
         k_kmp_predict_fast<1><<<grid, PTHREADS, lay.total, st>>>(map, p, lay);
     } else {
-        static size_t set2 = 48 * 1024;
+        static SmemCache set2;
         KMPX_TRY(ensure_dyn_smem(k_kmp_predict_fast<2>, lay.total, set2, "k_kmp_predict_fast<2>"));
         k_kmp_predict_fast<2><<<grid, PTHREADS, lay.total, st>>>(map, p, lay);
     }

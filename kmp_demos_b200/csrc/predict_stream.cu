@@ -201,12 +201,12 @@ int launch_predict_stream(PredictArgs& p, cudaStream_t st) {
     dim3 grid(ceil_div(p.M, SQT), p.batch);
     if (p.O == 1) {
         const size_t smem = stream_smem_bytes<1>(p.I);
-        static size_t set1 = 48 * 1024;
+        static SmemCache set1;
         KMPX_TRY(ensure_dyn_smem(k_kmp_predict_stream<1>, smem, set1, "k_kmp_predict_stream<1>"));
         k_kmp_predict_stream<1><<<grid, STHREADS, smem, st>>>(p);
     } else {
         const size_t smem = stream_smem_bytes<2>(p.I);
-        static size_t set2 = 48 * 1024;
+        static SmemCache set2;
         KMPX_TRY(ensure_dyn_smem(k_kmp_predict_stream<2>, smem, set2, "k_kmp_predict_stream<2>"));
         k_kmp_predict_stream<2><<<grid, STHREADS, smem, st>>>(p);
     }

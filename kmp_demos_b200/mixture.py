@@ -323,6 +323,9 @@ class GaussianMixtureModel:
         K = self.n_components
         if n < K:
             raise ValueError(f"Expected n_samples >= n_components but got n_components = {K}, n_samples = {n}")
+        if not 1 <= d <= 8 or not 1 <= K <= 128:
+            raise ValueError(f"the device EM kernels cover 1 <= n_features <= 8 and 1 <= n_components <= 128 "
+                             f"(got n_features = {d}, n_components = {K})")
         self.n_features = d
         X = torch.as_tensor(data, device='cuda')
         rs = np.random.RandomState(420)

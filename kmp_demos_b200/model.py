@@ -160,29 +160,39 @@ class KMP:
         torch = _lib.require_cuda()
         if self._fact is None:
             raise AttributeError("KMP.predict called before fit")
-        f = self._fact
         s = np.asarray(s, dtype=np.float64)
-        M = s.shape[1]
-        dev = torch.device('cuda')
-        sq = torch.as_tensor(np.ascontiguousarray(s.T), dtype=torch.float64, device=dev)
-        xi = torch.empty((f.O, M), dtype=torch.float64, device=dev)
-        sg = torch.empty((f.O, f.O, M), dtype=torch.float64, device=dev)
+        sq = torch.as_tensor(np.ascontiguousarray(s.T), dtype=torch.float64, device=torch.device('cuda'))
+        xi, sg = self.predict_device(sq)
+        self._logger.info("KMP predict done.")
+        return xi.cpu().numpy(), sg.cpu().numpy()
+
+    def predict_device(self, sq, xi=None, sg=None):
+        """predict() on device tensors: sq (M,I) float64 CUDA -> xi (O,M), sg (O,O,M) CUDA tensors (optionally
+        caller-provided).  No host synchronisation."""
+        torch = _lib.require_cuda()
+        f = self._fact
+        M = sq.shape[0]
+        dev = sq.device
+        if xi is None:
+            xi = torch.empty((f.O, M), dtype=torch.float64, device=dev)
+        if sg is None:
+            sg = torch.empty((f.O, f.O, M), dtype=torch.float64, device=dev)
         n = f.F.shape[0]
         if f.kind == 0 and not self.time_driven_kernel and f.O <= 2 and n > _lib.SMALL_MAX:
             # one large system: kappa + DMMA GEMMs + column reductions (predict_gemm.cu), queries in chunks of <= 8192
             lib = _lib.load()
             mc = min((M + 127) // 128 * 128, 8192)
             nbytes = int(lib.kmpx_kmp_predict_gemm_workspace_bytes(f.N, f.O, mc))
-            ws = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
+            if getattr(self, '_gemm_ws', None) is None or self._gemm_ws.numel() * 8 < nbytes or self._gemm_ws.device != dev:
+                self._gemm_ws = torch.empty(nbytes // 8, dtype=torch.float64, device=dev)
             _lib.call('kmpx_kmp_predict_gemm', _lib.ptr(f.F), f.lda, _lib.ptr(f.w), _lib.ptr(f.s_dev), f.N, f.I, f.O,
-                      _lib.ptr(sq), M, float(self.sigma_f), float(self.alpha), _lib.ptr(ws), nbytes, _lib.ptr(xi), _lib.ptr(sg),
-                      _lib.stream())
+                      _lib.ptr(sq), M, float(self.sigma_f), float(self.alpha), _lib.ptr(self._gemm_ws), nbytes, _lib.ptr(xi),
+                      _lib.ptr(sg), _lib.stream())
         else:
             _lib.call('kmpx_kmp_predict', _lib.ptr(f.F), f.lda, n * f.lda, f.kind, _lib.ptr(f.w), f.lda,
                       _lib.ptr(f.s_dev), None, f.N, f.I, f.O, 1, _lib.ptr(sq), 0, M, float(self.sigma_f),
                       float(self.alpha), int(bool(self.time_driven_kernel)), _lib.ptr(xi), _lib.ptr(sg), _lib.stream())
-        self._logger.info("KMP predict done.")
-        return xi.cpu().numpy(), sg.cpu().numpy()
+        return xi, sg
 
     # ------------------------------------------------------------------ SURVEY 8(f3): one large system, queries sharded over the GPUs
     def broadcast_fit(self, src: int = 0, group=None) -> None:
@@ -216,32 +226,47 @@ class KMP:
 
     def predict_sharded(self, s: np.ndarray, group=None) -> Tuple[np.ndarray, np.ndarray]:
         """predict() with the queries split contiguously over the ranks of the process group (each rank needs the
-        fitted state: fit() everywhere, or fit() on one rank + broadcast_fit()); the shards are all-gathered, so
-        every rank returns the full (O,M) mean and (O,O,M) covariance.  No collective touches the arithmetic."""
+        fitted state: fit() everywhere, or fit() on one rank + broadcast_fit()); the shards are all-gathered on the
+        device (NCCL), so every rank returns the full (O,M) mean and (O,O,M) covariance after ONE device-to-host copy.
+        No collective touches the arithmetic."""
+        torch = _lib.require_cuda()
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self.predict(s)
+        s = np.asarray(s, dtype=np.float64)
+        dev = torch.device('cuda', torch.cuda.current_device())
+        sq = torch.as_tensor(np.ascontiguousarray(s.T), dtype=torch.float64, device=dev)
+        out = self.predict_sharded_device(sq, group)
+        O = self.O
+        h = out.cpu().numpy()
+        return h[:O].copy(), h[O:].reshape(O, O, -1).copy()
+
+    def predict_sharded_device(self, sq, group=None):
+        """Device form of predict_sharded: sq (M,I) CUDA tensor (the same on every rank) -> (O + O*O, M) CUDA tensor
+        [means; covariances] holding all queries on every rank."""
         torch = _lib.require_cuda()
         import torch.distributed as dist
         from .dist import shard_range
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-            return self.predict(s)
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        s = np.asarray(s, dtype=np.float64)
-        M = s.shape[1]
+        M, O = sq.shape[0], self.O
         lo, hi = shard_range(M, rank, world)
-        xi_l, sg_l = self.predict(s[:, lo:hi]) if hi > lo else (np.zeros((self.O, 0)), np.zeros((self.O, self.O, 0)))
-        per = max(shard_range(M, r, world)[1] - shard_range(M, r, world)[0] for r in range(world))
-        dev = torch.device('cuda', torch.cuda.current_device())
-        buf = torch.zeros((self.O + self.O * self.O, per), dtype=torch.float64, device=dev)
-        buf[:self.O, :hi - lo] = torch.as_tensor(xi_l, device=dev)
-        buf[self.O:, :hi - lo] = torch.as_tensor(sg_l.reshape(self.O * self.O, -1), device=dev)
-        out = [torch.empty_like(buf) for _ in range(world)]
-        dist.all_gather(out, buf, group=group)
-        xi = np.empty((self.O, M)); sg = np.empty((self.O, self.O, M))
+        per = shard_range(M, 0, world)[1]                       # rank 0 holds the longest shard
+        dev = sq.device
+        gath = torch.empty((world, O + O * O, per), dtype=torch.float64, device=dev)
+        mine = gath[rank]
+        if hi > lo:
+            # the kernels write straight into this rank's slot of the gather buffer (rows of `per` columns)
+            xi_l, sg_l = self.predict_device(sq[lo:hi].contiguous())
+            mine[:O, :hi - lo] = xi_l
+            mine[O:, :hi - lo] = sg_l.reshape(O * O, -1)
+        dist.all_gather_into_tensor(gath.view(-1), mine.reshape(-1).clone(), group=group)
+        if M == per * world:
+            return gath.permute(1, 0, 2).reshape(O + O * O, M)
+        out = torch.empty((O + O * O, M), dtype=torch.float64, device=dev)
         for r in range(world):
             a, b_ = shard_range(M, r, world)
-            h = out[r].cpu().numpy()
-            xi[:, a:b_] = h[:self.O, :b_ - a]
-            sg[:, :, a:b_] = h[self.O:, :b_ - a].reshape(self.O, self.O, -1)
-        return xi, sg
+            out[:, a:b_] = gath[r, :, :b_ - a]
+        return out
 
     def predict_mean(self, s: np.ndarray) -> np.ndarray:
         """Mean only, from alpha = (K + l*Sigma)^-1 mu: O(N*M) kernel evaluations instead of the GEMM."""
@@ -265,6 +290,7 @@ class KMP:
         for j in range(len(s)):
             d = np.linalg.norm(self.s[:, :self.N] - np.asarray(s[j], dtype=float).reshape(-1, 1), axis=0) \
                 if self.s.shape[0] > 1 else np.abs(self.s[0, :self.N] - s[j])
+            d = np.where(np.isnan(d), np.inf, d)          # the reference's `dist < min_dist` scan skips NaN (KMP.py:75-79)
             idx = int(np.argmin(d)) if self.N > 0 else -1
             if idx >= 0 and d[idx] < self.tol:
                 self.s[:, idx] = s[j]

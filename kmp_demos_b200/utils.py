@@ -27,6 +27,7 @@ def find_closest_index(list, val):
     """Index of the column of ``list`` closest to ``val`` (first minimum), kmp/utils.py:31-38."""
     cols = np.asarray(list).T
     dists = np.array([np.linalg.norm(val - c) for c in cols])
+    dists = np.where(np.isnan(dists), np.inf, dists)      # `dist < smallest_dist` never accepts a NaN (utils.py:34)
     return int(np.argmin(dists))
 
 

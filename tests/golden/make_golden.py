@@ -316,8 +316,24 @@ def sklearn_gmm_synth():
          labels=g.model.predict(X), bic=np.array(g.bic(X)))
 
 
+def sklearn_gmm_cfg5():
+    """cfg 5 at its own K: the reference wrapper (sklearn GaussianMixture, random_state=420) on a 200 k-row draw of the
+    cfg-5 generator, K=64, reg 1e-6 - the shape whose E-step sits on the 16-components-per-thread register boundary
+    of the CUDA kernel.  Labels are stored as uint8 (K <= 256)."""
+    import time
+    X, _, _ = wl.cfg5_samples(200000, K=64, d=7, seed=0)
+    g = GaussianMixtureModel(n_components=64, diag_reg_factor=1e-6)
+    t0 = time.perf_counter()
+    g.fit(X)
+    sec = time.perf_counter() - t0
+    save('gmm_cfg5_k64.npz', seed=np.array(0), n=np.array(200000), K=np.array(64), priors=g.priors, means=g.means,
+         covs=g.covariances, n_iter=np.array(g.model.n_iter_), lower_bound=np.array(g.model.lower_bound_),
+         converged=np.array(g.model.converged_), labels=g.model.predict(X).astype(np.uint8), bic=np.array(g.bic(X)),
+         fit_seconds=np.array(sec), cores=np.array(len(os.sched_getaffinity(0))))
+
+
 if __name__ == '__main__':
-    parts = sys.argv[1:] or ['letters', 'cfg1', 'cfg3', 'demo2', 'demo3', 'small', 'gmm_synth']
+    parts = sys.argv[1:] or ['letters', 'cfg1', 'cfg3', 'demo2', 'demo3', 'small', 'gmm_synth', 'gmm_cfg5']
     if 'letters' in parts:
         pos_all, gmu, gsig = letters()
     else:
@@ -335,3 +351,5 @@ if __name__ == '__main__':
         small_random()
     if 'gmm_synth' in parts:
         sklearn_gmm_synth()
+    if 'gmm_cfg5' in parts:
+        sklearn_gmm_cfg5()

