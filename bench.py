@@ -14,8 +14,13 @@ problems (different via-point seeds), no data-path collective.
            every step, inside the timed region.
 `roofline`: the dominant kernel (k_kmp_predict, FP64 tensor pipe) timed per launch with CUDA events inside the
            timed region; peak = cuBLAS DGEMM 8192^3 measured in the same run (MEASURED_PEAKS.json has no FP64 figure).
-`--impl reference`: the reference's own algorithm (literal loop nest of kmp/model/KMP.py, oracle port) on all host
-           cores, a bounded sample of the same problems per step.
+`strong` : the SAME 26 624 problems (rank 0's set) split over the N ranks by dist.shard_range - strong scaling of the
+           named batch, results asserted bit-identical to the unsharded run.
+`em`     : cfg 5 (10 M x 7, K = 64) row-partitioned over the N ranks, one NCCL all-reduce per iteration, at every N.
+`extras` : per-kernel figures of SURVEY.md 8(d), the 100 k-query predict of the n = 16384 system sharded over the N
+           ranks (8 f3), and (N = 1) the CPU lines of BASELINE.md section 4.
+`--impl reference`: the reference's own classes (unmodified kmp/model/KMP.py from baseline/_ref; the oracle port when
+           that copy is absent) on all host cores, a bounded sample of the same problems per step.
 """
 import argparse
 import json
@@ -46,6 +51,7 @@ METRIC = 'KMP fit+predict problems/sec (batched)'
 UNIT = 'problems/s'
 N_SETS = 1024
 M_QUERIES = 1000
+WORKLOAD = 'cfg3: 26 letters x 1024 via-point sets, N=200..202, O=2, M=1000 queries, mean+covariance'
 
 
 def build_problem_set(mu, sig, n_sets, seed_offset):
@@ -60,23 +66,23 @@ def build_problem_set(mu, sig, n_sets, seed_offset):
 
 # ------------------------------------------------------------------------------------------ CPU arm
 def _cpu_one_problem(args):
-    """One cfg-3 problem the way the reference computes it (literal loops), oracle port."""
-    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
-    from oracle import kmp_oracle as orc
-    t, mu, sig, vt, vp, vv, q = args
-    c = wl.CFG1
-    s2, y2, g2 = orc.kmp_set_waypoint(t, mu, sig, list(vt), [vp[j].reshape(1, -1) for j in range(len(vt))],
-                                      [vv[j] for j in range(len(vt))], 5e-4)
-    est = orc.kmp_fit(s2, g2, c['lam'], c['sigma_f'], False, literal=True)
-    xi, sg = orc.kmp_predict_literal(est, s2, y2, q, c['alpha'], c['sigma_f'], False)
-    return float(xi[0, 0])
+    """One cfg-3 problem through the reference's own classes (oracle/cpu_lines.py: unmodified KMP.set_waypoint -> fit ->
+    predict when baseline/_ref is present, the oracle's literal port otherwise)."""
+    from oracle import cpu_lines
+    return cpu_lines.cfg3_one_problem(args)
+
+
+def _cpu_kind():
+    from oracle import ref_loader
+    return 'reference' if ref_loader.available() else 'port'
 
 
 def cpu_sample_args(mu, sig, base_of, via_s, via_p, via_v, count):
     t = wl.cfg1_kmp_grid(mu.shape[2])
     q = wl.cfg1_query_grid(M_QUERIES)
     idx = np.linspace(0, len(base_of) - 1, count).astype(int)       # stratified over the letters
-    return [(t, mu[base_of[i]], sig[base_of[i]], via_s[i, :, 0], via_p[i], via_v[i], q) for i in idx]
+    use_ref = _cpu_kind() == 'reference'
+    return [(t, mu[base_of[i]], sig[base_of[i]], via_s[i, :, 0], via_p[i], via_v[i], q, use_ref) for i in idx]
 
 
 def time_cpu(pool, sample):
@@ -102,15 +108,17 @@ def run_reference(args):
         t = [time_cpu(pool, sample) for _ in range(args.steps)]
     sec = float(np.mean(t))
     value = per_step / sec
+    kind = _cpu_kind()
+    how = ("the reference's own KMP class (baseline/_ref/kmp/model/KMP.py, unmodified: set_waypoint -> fit -> predict)"
+           if kind == 'reference' else "oracle port of KMP.set_waypoint/fit/predict (literal loops)")
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': src,
-        'config': {'workload': 'cfg3: 26 letters x via-point sets, N=200..202, O=2, M=1000 queries, mean+covariance',
-                   'step': f'{per_step} problems (one per host core) through the literal KMP.py loop nest'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': f'{per_step} cfg-3 problems per step x {args.steps} steps, oracle port of KMP.fit/predict '
-                                   f'(literal loops), one process per core'},
+        'config': {'workload': WORKLOAD,
+                   'step': f'bounded sample of the workload: {per_step} of its problems (one per host core) through {how}'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                         'sample': f'{per_step} cfg-3 problems per step x {args.steps} steps, {how}, one process per core'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -177,34 +185,12 @@ def measure_dgemm_peak(torch, n=8192, seconds=1.5):
     return 2.0 * n ** 3 * reps / e0.elapsed_time(e1) * 1e-9
 
 
-def cfg1_cpu_port():
-    """cfg 1 on one host core through the oracle's literal restatement of the reference (GMM by the numpy EM port, GMR and
-    KMP with the reference's loop nests; predict on 100 of the 1000 steps, scaled - every query is an independent loop
-    iteration, KMP.py:178)."""
-    from oracle import kmp_oracle as orc
-    z = np.load(os.path.join(wl.GOLDEN_DIR, 'letters_ref.npz'))
-    gi = wl.LETTERS.index('G')
-    X = wl.cfg1_design_matrix(z['pos'][gi])
-    c = wl.CFG1
-    t = [time.perf_counter()]
-    r = orc.gmm_fit(X, 8, 1e-6); t.append(time.perf_counter())
-    pri, mea, cov = r['weights'], r['means'].T, np.transpose(r['covariances'], (1, 2, 0))
-    mu, sig = orc.gmr_literal(pri, mea, cov, wl.cfg1_gmr_grid(200), 1e-6); t.append(time.perf_counter())
-    s = wl.cfg1_kmp_grid(200)
-    est = orc.kmp_fit(s, sig, c['lam'], c['sigma_f'], False, literal=True); t.append(time.perf_counter())
-    q = wl.cfg1_query_grid(1000)[:, ::10]
-    orc.kmp_predict_literal(est, s, mu, q, c['alpha'], c['sigma_f'], False); t.append(time.perf_counter())
-    d = np.diff(t) * 1e3
-    return {'gmm_fit_ms': float(d[0]), 'gmr_ms': float(d[1]), 'kmp_fit_ms': float(d[2]), 'predict_ms': float(d[3] * 10.0),
-            'note': 'one core; refit after set_waypoint costs another kmp_fit; predict timed on 100 steps x 10'}
-
-
 def extras_single_gpu(torch, dgemm_tflops):
     """The other measured rows of SURVEY.md 8(d) on one GPU (kmp_demos_b200/perf.py): second headline of BASELINE.json
     (fp64 Cholesky TFLOP/s at N*O = 16384), cfg-4 kernel build / triangular inverse / 100k-query predict rate,
     fused EM pass at 10 M x 7, K = 64, GMR and quaternion maps on 2^26 elements."""
     from kmp_demos_b200 import perf
-    return perf.run_all(quick=False, only=('dgemm', 'cfg1', 'cfg4', 'em', 'gmr', 'quat'), dgemm_tflops=dgemm_tflops)
+    return perf.run_all(quick=False, only=('dgemm', 'cfg1', 'cfg2', 'cfg4', 'gmr', 'quat'), dgemm_tflops=dgemm_tflops)
 
 
 def run_ours(args):
@@ -222,7 +208,7 @@ def run_ours(args):
     log(f'rank {rank}/{world}: building {L} x {args.sets} via-point sets')
     base_of, via_s, via_p, via_v = build_problem_set(mu, sig, args.sets, seed_offset=rank)
     B = len(base_of)
-    cpu_line = None
+    cpu_line = cpu_other = None
     if rank == 0 and world == 1:
         # CPU baseline first (before the CUDA context exists in this process): oracle port on all host cores
         import multiprocessing as mp
@@ -234,9 +220,16 @@ def run_ours(args):
             pool.map(_cpu_one_problem, sample[:cores], chunksize=1)          # warm-up: imports, page-in
             sec = time_cpu(pool, sample)
         os.environ.pop('OPENBLAS_NUM_THREADS', None)
-        cpu_line = {'value': len(sample) / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                    'sample': f'{len(sample)} cfg-3 problems, oracle port of KMP.set_waypoint/fit/predict with the '
-                              f"reference's literal loop nest, one process per core, {sec:.1f} s wall"}
+        kind = _cpu_kind()
+        cpu_line = {'value': len(sample) / sec, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                    'sample': f'{len(sample)} cfg-3 problems, '
+                              + ("the reference's own KMP class (baseline/_ref, unmodified) set_waypoint -> fit -> predict"
+                                 if kind == 'reference' else "oracle port of KMP.set_waypoint/fit/predict (literal loop nest)")
+                              + f', one process per core, {sec:.1f} s wall'}
+        if not args.no_extras:
+            from oracle import cpu_lines
+            log('cpu lines of the other configurations (BASELINE.md section 4)')
+            cpu_other = cpu_lines.all_lines(cores)
         log(f'cpu_baseline done: {cpu_line["value"]:.2f} problems/s')
     c = wl.CFG1
     kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=args.chunk)
@@ -321,16 +314,74 @@ def run_ours(args):
         f'max deviation from the direct path: mean {inc_err_mean:.1e}, covariance {inc_err_cov:.1e}')
     inc_ok = inc_err_mean < 1e-9 and inc_err_cov < 1e-7      # reported, never fatal: the metric is the direct method
 
+    # ---- strong scaling of the NAMED batch (north star: "all 26 letters x 1024 via-point sets ... sharded across
+    #      1/2/4/8 GPUs"): rank 0's 26 624 problems split contiguously by dist.shard_range, no collective in the data
+    #      path.  Every rank also runs the unsharded batch once and asserts that its shard's results are the same bits.
+    strong = None
+    if world > 1:
+        b0, s0, p0, v0 = build_problem_set(mu, sig, args.sets, seed_offset=0) if rank != 0 else (base_of, via_s, via_p, via_v)
+        f_base, f_vs, f_vp, f_vv = (torch.as_tensor(np.ascontiguousarray(x), device=dev) for x in (b0, s0, p0, v0))
+        kb.run_device(f_base, f_vs, f_vp, f_vv, d_q, True, xi, sg)              # unsharded results (xi, sg)
+        lo, hi = kd.shard_range(B, rank, world)
+        Bl = hi - lo
+        l_base, l_vs, l_vp, l_vv = (x[lo:hi].contiguous() for x in (f_base, f_vs, f_vp, f_vv))
+        hl_base, hl_vs, hl_vp, hl_vv = (pin(x.cpu().numpy()) for x in (l_base, l_vs, l_vp, l_vv))
+        xi_l, sg_l = xi_inc[:Bl], sg_inc[:Bl]                                    # scratch of the right shape
+        kb.chunk = strong_chunk(Bl, args.chunk)
+
+        def step_strong_device():
+            return kb.run_device(l_base, l_vs, l_vp, l_vv, d_q, True, xi_l, sg_l)
+
+        def step_strong_e2e():
+            for dst, srcb in ((l_base, hl_base), (l_vs, hl_vs), (l_vp, hl_vp), (l_vv, hl_vv), (d_q, h_q)):
+                dst.copy_(srcb, non_blocking=True)
+            kb.run_device(l_base, l_vs, l_vp, l_vv, d_q, True, xi_l, sg_l, host_xi=h_xi[:Bl], host_sigma=h_sg[:Bl])
+
+        ms_s, _, _, _ = timed(step_strong_device, False)
+        same = bool(torch.equal(xi_l, xi[lo:hi]) and torch.equal(sg_l, sg[lo:hi]))
+        ms_se, _, _, _ = timed(step_strong_e2e, False)
+        same_all = kd.max_over_ranks(0.0 if same else 1.0, dev) == 0.0
+        kb.chunk = args.chunk
+        log(f'strong scaling: {ms_s:.1f} ms/step device-resident, {ms_se:.1f} ms/step end to end, bit-identical: {same_all}')
+        assert same_all, 'a sharded result differs from the unsharded run'
+        strong = {'what': 'the same 26 624 problems (rank 0 set) split over the ranks by shard_range; no collective',
+                  'problems_total': B, 'problems_per_gpu': Bl, 'chunk': strong_chunk(Bl, args.chunk),
+                  'value': B / (ms_s * 1e-3), 'unit': UNIT, 'ms_per_step': ms_s,
+                  'e2e': {'value': B / (ms_se * 1e-3), 'unit': UNIT, 'ms_per_step': ms_se},
+                  'one_gpu_ms_per_step_same_run': ms_dev, 'speedup_vs_one_gpu': ms_dev / ms_s,
+                  'efficiency': ms_dev / ms_s / world, 'e2e_efficiency': ms_e2e / ms_se / world,
+                  'bit_identical_to_unsharded': same_all}
+    else:
+        strong = {'what': 'one GPU: the sharded batch is the whole batch', 'problems_total': B, 'problems_per_gpu': B,
+                  'value': B / (ms_dev * 1e-3), 'unit': UNIT, 'ms_per_step': ms_dev,
+                  'e2e': {'value': B / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e}, 'efficiency': 1.0}
+    del xi_inc, sg_inc
+
     value = world * B / (ms_dev * 1e-3)
     e2e_value = world * B / (ms_e2e * 1e-3)
     h2d = sum(x.numel() * x.element_size() for x in (h_base, h_vs, h_vp, h_vv, h_q))
     d2h = h_xi.numel() * 8 + h_sg.numel() * 8
+    del xi, sg, h_xi, h_sg
+    torch.cuda.empty_cache()
+
+    dgemm_tf = measure_dgemm_peak(torch)
+    log(f'cuBLAS DGEMM peak {dgemm_tf:.2f} TFLOP/s')
+    # ---- cfg 5: EM on row-partitioned samples with the NCCL all-reduce, at every N (all ranks take part)
+    from kmp_demos_b200 import perf
+    em_block = f3_block = None
+    if not args.no_extras:
+        log('cfg 5: partitioned EM')
+        em_block = perf.em_partitioned(rank, world, dev, dgemm_tf)
+        log(f'em: {em_block["ms_per_iter"]:.3f} ms/iter on {world} rank(s)')
+        log('cfg 4: query-sharded predict of the n = 16384 system')
+        f3_block = perf.cfg4_sharded_predict(rank, world, dev, dgemm_tf)
+        torch.cuda.empty_cache()
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': src + '; via-point sets seeded per (letter, rank, set)',
-        'config': {'workload': 'cfg3: 26 letters x 1024 via-point sets, N=200..202, O=2, M=1000 queries, mean+covariance',
+        'config': {'workload': WORKLOAD,
                    'problems_per_gpu': B, 'chunk': args.chunk,
                    'l2': 'inputs larger than L2: each step streams ~35 GB of system matrices per GPU (126 MB L2)'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
@@ -347,8 +398,6 @@ def run_ours(args):
         for v in kern.values():
             v['share'] = v['ms_per_step'] / tot
         line['kernels'] = kern
-        dgemm_tf = measure_dgemm_peak(torch)
-        log(f'cuBLAS DGEMM peak {dgemm_tf:.2f} TFLOP/s')
         pred = per['kmpx_kmp_predict']
         n_launch = len(pred)
         # algorithmic flops of the fused predict: triangular V = Linv k*^T (O^2 Ns^2 M) + Gram/mean reduction
@@ -356,24 +405,36 @@ def run_ours(args):
         flops_step = float(np.sum(O * O * Ns * Ns * M_QUERIES + 2.0 * O * Ns * (O * (O + 1) / 2 + O) * M_QUERIES))
         avg_ms = sum(pred) / n_launch
         achieved = flops_step * args.steps / n_launch / avg_ms * 1e-9
-        # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (profiles/), scaled to the
-        # problems per launch of this run; None when the capture is absent
-        traffic = None
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r01_ncu_traffic.json')
-        if os.path.isfile(tpath):
-            with open(tpath) as fh:
-                tk = json.load(fh)['k_kmp_predict_fast']
-            traffic = (tk['dram_bytes_read'] + tk['dram_bytes_write']) * (B * args.steps / n_launch) / tk['problems_per_launch']
+        # DRAM bytes per launch of the same kernel: STATIC figure from the committed ncu --set full capture under
+        # profiles/ (not measured in this run), scaled to the problems per launch of this run; None when absent
+        traffic, traffic_src = None, None
+        for cand in ('r02_ncu_traffic.json', 'r01_ncu_traffic.json'):
+            tpath = os.path.join(ROOT, 'profiles', cand)
+            if os.path.isfile(tpath):
+                with open(tpath) as fh:
+                    tk = json.load(fh)['k_kmp_predict_fast']
+                traffic = (tk['dram_bytes_read'] + tk['dram_bytes_write']) * (B * args.steps / n_launch) / tk['problems_per_launch']
+                traffic_src = f'static: profiles/{cand} (ncu --set full of this kernel), scaled to the problems per launch'
+                break
         line['roofline'] = {'kernel': 'k_kmp_predict', 'bound': 'tensor', 'achieved': achieved, 'peak': dgemm_tf, 'unit': 'TFLOP/s',
-                            'frac': achieved / dgemm_tf, 'traffic': traffic, 'avg_launch_ms': avg_ms,
+                            'frac': achieved / dgemm_tf, 'traffic': traffic, 'traffic_source': traffic_src, 'avg_launch_ms': avg_ms,
                             'flops_per_launch': flops_step * args.steps / n_launch,
                             'peak_source': 'cuBLAS DGEMM 8192^3 sustained, measured in this run (FP64 tensor pipe)'}
+        line['strong'] = strong
+        line['em'] = em_block
         if world == 1:
             line['cpu_baseline'] = cpu_line
-            if not args.no_extras:
-                log('extras: per-kernel figures (cfg 4, EM, GMR, quaternion maps)')
-                line['extras'] = extras_single_gpu(torch, dgemm_tf)
-                line['extras']['cfg1']['cpu_port'] = cfg1_cpu_port()
+        if not args.no_extras:
+            log('extras: per-kernel figures (cfg 1, cfg 2, cfg 4, GMR, quaternion maps)')
+            line['extras'] = extras_single_gpu(torch, dgemm_tf)
+            line['extras']['cfg4']['predict_100k_sharded'] = f3_block
+            # second headline of BASELINE.json, promoted to a top-level key
+            po = line['extras']['cfg4']['potrf']
+            line['cholesky_n16384'] = {'metric': 'fp64 Cholesky TFLOP/s at N*O=16384', 'value': po['tflops'], 'unit': 'TFLOP/s',
+                                       'ms': po['ms'], 'frac_dgemm': po['frac_dgemm'], 'cusolver_ms_same_run': po.get('cusolver_ms'),
+                                       'cusolver_tflops_same_run': po.get('cusolver_tflops')}
+            if cpu_other is not None:
+                line['extras']['cpu_lines'] = cpu_other
         line['incremental'] = {
             'what': 'SURVEY 8(f1): same cfg-3 problems by exact low-rank correction of the per-base solution '
                     '(KMPBatch.run_incremental) instead of one refit per via-point set; bases re-factorised inside every step',
@@ -385,6 +446,17 @@ def run_ours(args):
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+
+
+def strong_chunk(b_local, chunk):
+    """Systems resident at once for a shard of b_local problems: the factor kernels run one CTA per SM (148), so a
+    shard is cut into near-equal chunks whose sizes are multiples of 148 where the shard allows it (3 328 problems at
+    N = 8 -> one chunk, 22.5 waves: the partial wave costs < 1 % of a step)."""
+    if b_local <= chunk:
+        return b_local
+    n_chunks = -(-b_local // chunk)
+    per = -(-b_local // n_chunks)
+    return -(-per // 148) * 148
 
 
 _RESULT = []      # the JSON line(s) of this process, printed by main() once stdout is restored

@@ -64,11 +64,19 @@ class EMEngine:
         self.log_det = torch.empty(K, dtype=f64, device=dev)
         self.info = torch.zeros(K, dtype=torch.int32, device=dev)
         self.allreduce_count = 0
+        self.allreduce_events = None      # set to a list to collect (start, end) CUDA events around every all-reduce
 
     def _allreduce(self):
         if self.group is not None:
             import torch.distributed as dist
-            dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
+            if self.allreduce_events is not None:
+                e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+                e0.record()
+                dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
+                e1.record()
+                self.allreduce_events.append((e0, e1))
+            else:
+                dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)
             self.allreduce_count += 1
 
     def _finalize(self, first):

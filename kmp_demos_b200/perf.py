@@ -77,6 +77,19 @@ def cfg4(N, dg):
         e1.record(); e1.synchronize(); best = min(best, e0.elapsed_time(e1))
     assert int(info.item()) == 0
     out['potrf'] = {'n': n, 'ms': best, 'tflops': n ** 3 / 3 / best * 1e-9, 'frac_dgemm': n ** 3 / 3 / best * 1e-9 / dg}
+    # the vendor library on the same matrix in the same run (torch.linalg.cholesky_ex -> cuSOLVER potrf; a measurement
+    # aid, never on the product path): the figure kmpx_potrf has to match
+    cus = 1e30
+    for _ in range(3):
+        build(_lib.UPLO_LOWER)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        Lc, _ = torch.linalg.cholesky_ex(A[:, :n], check_errors=False)
+        e1.record(); e1.synchronize(); cus = min(cus, e0.elapsed_time(e1))
+    del Lc
+    out['potrf'].update(cusolver_ms=cus, cusolver_tflops=n ** 3 / 3 / cus * 1e-9, vs_cusolver=cus / best)
+    build(_lib.UPLO_LOWER)
+    _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     _lib.call('kmpx_trtri', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(ws), nbytes, st)
@@ -109,21 +122,186 @@ def cfg4(N, dg):
     return out
 
 
-def em(n, K=64, d=7):
-    from kmp_demos_b200.mixture import EMEngine
-    X, means, _ = wl.cfg5_samples(min(n, 2_000_000), K=K, d=d, seed=0)
-    Xd = torch.as_tensor(X, device='cuda')
-    if n > Xd.shape[0]:
-        Xd = Xd.repeat((n + Xd.shape[0] - 1) // Xd.shape[0], 1)[:n].contiguous()
-    lab = torch.as_tensor(np.argmin(((X[:200000, None, :] - means[None]) ** 2).sum(-1), axis=1).astype(np.int32), device='cuda')
-    lab = lab.repeat((n + lab.shape[0] - 1) // lab.shape[0])[:n].contiguous()
-    eng = EMEngine(Xd, K, 1e-6, shift=Xd[:100000].mean(dim=0))
-    eng.init_from_labels(lab)
-    ms = timeit(lambda: eng.em_pass(), reps=3, warm=1)
-    F = 1 + d + d * (d + 1) // 2
-    flops = float(n) * K * ((d * (d + 1) / 2 + 2 * d) * 2 + 60 + 2 * F)
-    return {'n': n, 'K': K, 'd': d, 'ms_per_iter': ms, 'gbs': 8.0 * n * d / ms * 1e-6, 'frac_hbm': 8.0 * n * d / ms * 1e-6 / peaks(),
-            'tflops_est': flops / ms * 1e-9}
+def em(n, K=64, d=7, dgemm_tflops=None):
+    """Single-GPU fused EM pass on cfg-5 data (rows with their own nearest-mean initial labels)."""
+    return em_partitioned(0, 1, torch.device('cuda', torch.cuda.current_device()), dgemm_tflops, n=n, K=K, d=d)
+
+
+def cfg5_on_device(n, K, d, seed, dev):
+    """cfg-5 samples drawn on the device: the mixture is wl.cfg5_mixture (numpy, seeded), the component ids and normal
+    deviates come from torch's CUDA generator.  Returns X (n,d) and, as the initial hard assignment, the label of the
+    nearest true mean OF EACH ROW (int32)."""
+    means, A, _ = wl.cfg5_mixture(K, d, seed)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + seed)
+    md, Ad = torch.as_tensor(means, device=dev), torch.as_tensor(A, device=dev)
+    X = torch.empty((n, d), dtype=f64, device=dev)
+    lab = torch.empty(n, dtype=torch.int32, device=dev)
+    step = 1 << 20
+    for c0 in range(0, n, step):
+        c1 = min(n, c0 + step)
+        comp = torch.randint(0, K, (c1 - c0,), generator=g, device=dev)
+        z = torch.randn((c1 - c0, d), generator=g, dtype=f64, device=dev)
+        X[c0:c1] = md[comp] + torch.einsum('nij,nj->ni', Ad[comp], z)
+        lab[c0:c1] = torch.cdist(X[c0:c1], md).argmin(dim=1).to(torch.int32)
+    return X, lab
+
+
+def em_partitioned(rank, world, dev, dgemm_tflops, n=10_000_000, K=64, d=7, iters=20, warm=3):
+    """cfg 5: EM over n rows split contiguously over `world` ranks (dist.shard_range), one NCCL all-reduce of the packed
+    sufficient statistics per iteration.  Rank 0 draws the data and broadcasts it, so every rank slices the same rows.
+    Timed: `iters` passes (E+M kernel, all-reduce, finalize) after `warm` passes, CUDA events, max over ranks; the
+    all-reduce alone from events around torch.distributed.all_reduce.  At world > 1 rank 0 then repeats the same
+    init + warm + iters passes on ALL rows alone: the one-GPU time of the same run (efficiency) and the parameters
+    the partitioned run must reproduce (max deviation)."""
+    import torch.distributed as dist
+    from .mixture import EMEngine
+    from . import dist as kd
+    if rank == 0:
+        X, lab = cfg5_on_device(n, K, d, 0, dev)
+        shift = X[:1_000_000].mean(dim=0)
+    else:
+        X = torch.empty((n, d), dtype=f64, device=dev)
+        lab = torch.empty(n, dtype=torch.int32, device=dev)
+        shift = torch.empty(d, dtype=f64, device=dev)
+    if world > 1:
+        for t in (X, lab, shift):
+            dist.broadcast(t, src=0)
+    lo, hi = kd.shard_range(n, rank, world)
+
+    def run(Xp, labp, group):
+        eng = EMEngine(Xp, K, 1e-6, shift=shift, group=group, n_total=n)
+        eng.init_from_labels(labp)
+        for _ in range(warm):
+            eng.em_pass()
+        torch.cuda.synchronize()
+        if group is not None:
+            dist.barrier()
+            eng.allreduce_events = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            eng.em_pass()
+        e1.record()
+        e1.synchronize()
+        return eng, e0.elapsed_time(e1) / iters
+
+    eng, ms = run(X[lo:hi], lab[lo:hi], dist.group.WORLD if world > 1 else None)
+    ms = kd.max_over_ranks(ms, dev)
+    flops = 180.0 * n * K                                   # SURVEY 8(d): ~180 n K per iteration
+    out = {'n': n, 'K': K, 'd': d, 'iters': iters, 'ranks': world, 'rows_per_rank': hi - lo, 'ms_per_iter': ms,
+           'tflops_8d': flops / ms * 1e-9, 'frac_fp64': flops / ms * 1e-9 / (dgemm_tflops * world) if dgemm_tflops else None,
+           'frac_hbm': 8.0 * n * d / ms * 1e-6 / (peaks() * world),
+           'loglik_per_row': float(eng.stats[-1].item()) / n, 'info_max': int(eng.info.abs().max().item())}
+    if world > 1:
+        us = sorted(a.elapsed_time(b) * 1e3 for a, b in eng.allreduce_events)
+        out['allreduce_us_median'] = us[len(us) // 2]
+        out['allreduce_us_min'] = us[0]
+        out['allreduce_bytes'] = eng.stats.numel() * 8
+        if rank == 0:
+            ref, ms1 = run(X, lab, None)
+            rel = lambda a, b: float((a - b).abs().max() / b.abs().max())  # noqa: E731
+            out['one_gpu_ms_per_iter_same_run'] = ms1
+            out['efficiency_vs_one_gpu'] = ms1 / (world * ms)
+            out['max_rel_dev_from_one_rank'] = {'weights': rel(eng.weights, ref.weights), 'means': rel(eng.means, ref.means),
+                                                'covariances': rel(eng.covs, ref.covs)}
+        dist.barrier()
+    return out
+
+
+def cfg4_sharded_predict(rank, world, dev, dgemm_tflops, N=8192, M=100_000):
+    """KMP.predict of the n = 16384 system at M queries.  Rank 0 fits; with world > 1 the factor is
+    broadcast over NCCL (KMP.broadcast_fit) and every rank predicts a contiguous slice of the queries, the slices are
+    all-gathered on the device (KMP.predict_sharded_device).  Device times by CUDA events, max over ranks."""
+    import torch.distributed as dist
+    from .model import KMP
+    from . import dist as kd
+    c = wl.CFG1
+    t, mu, sig = wl.cfg4_problem(N=N, seed=0)
+    k = KMP(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False)
+    k._logger.disabled = True
+    out = {'n': 2 * N, 'M': M, 'ranks': world}
+    if rank == 0:
+        k.fit(t, mu, sig)
+    sq = torch.as_tensor(np.linspace(0.0, 2.0, M).reshape(-1, 1), device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    if world > 1:
+        dist.barrier()
+        e0, e1 = ev(), ev()
+        e0.record(); k.broadcast_fit(src=0); e1.record(); e1.synchronize()
+        out['broadcast_fit_ms'] = kd.max_over_ranks(e0.elapsed_time(e1), dev)
+        out['broadcast_bytes'] = int(k._fact.F.numel() * 8)
+        k.predict_sharded_device(sq[:4096].contiguous())                  # warm-up: kernels loaded, workspace allocated
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = ev(), ev()
+        e0.record(); res = k.predict_sharded_device(sq); e1.record(); e1.synchronize()
+        out['predict_ms'] = kd.max_over_ranks(e0.elapsed_time(e1), dev)
+    if rank == 0:
+        k.predict_device(sq[:4096].contiguous())
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record(); xi, sg = k.predict_device(sq); e1.record(); e1.synchronize()
+        out['one_gpu_predict_ms'] = e0.elapsed_time(e1)
+        fl = 4.0 * N * N * M
+        out['one_gpu_tflops'] = fl / out['one_gpu_predict_ms'] * 1e-9
+        if world > 1:
+            out['bit_identical_to_one_gpu'] = bool(torch.equal(res[:2], xi) and torch.equal(res[2:], sg.reshape(4, -1)))
+            out['speedup'] = out['one_gpu_predict_ms'] / out['predict_ms']
+            out['tflops_aggregate'] = fl / out['predict_ms'] * 1e-9
+        else:
+            out['predict_ms'] = out['one_gpu_predict_ms']
+    if world > 1:
+        dist.barrier()
+    return out
+
+
+def cfg2():
+    """cfg 2 through the drop-in classes: (a) reference-faithful demo2 (two O = 3 KMPs, N = 150, K = 10) and (b) the
+    variant BASELINE.json names (joint 7-D GMM, GMR on 400 points, one O = 6 KMP: n = 2400, via point, predict 400).
+    Wall-clock per stage, host arrays in and out, best of three after a warm-up pass."""
+    import time
+    from .mixture import GaussianMixtureModel
+    from .model import KMP
+    z = np.load(os.path.join(wl.GOLDEN_DIR, 'demo2_pose.npz'))
+    tm, ts = z['time'], z['time'][:, :150]
+    names = ['gmm_fit_ms', 'gmr_ms', 'kmp_fit_ms', 'set_waypoint_refit_ms', 'predict_ms']
+
+    def faithful():
+        tot = np.zeros(5)
+        for Y, wp in ((z['pos'], np.array([0.0, 0.85, 0.3])), (z['quat_eucl'], z['quat_wp'])):
+            X = np.vstack((tm, Y)).T
+            t = [time.perf_counter()]
+            g = GaussianMixtureModel(n_demos=6); g.fit(X); torch.cuda.synchronize(); t.append(time.perf_counter())
+            mu, sig = g.predict(ts); t.append(time.perf_counter())
+            k = KMP(l=0.5, alpha=60, sigma_f=4, time_driven_kernel=False)
+            k.fit(ts, mu, sig); torch.cuda.synchronize(); t.append(time.perf_counter())
+            k.set_waypoint([1], wp.reshape(1, -1), np.eye(3) * 1e-6); torch.cuda.synchronize(); t.append(time.perf_counter())
+            k.predict(ts); t.append(time.perf_counter())
+            tot += np.diff(t) * 1e3
+        return tot
+
+    def named():
+        X = np.vstack((tm, z['pos'], z['quat_eucl'])).T
+        tq = np.linspace(0.01, 1.5, 400).reshape(1, -1)
+        t = [time.perf_counter()]
+        g = GaussianMixtureModel(n_demos=6); g.fit(X); torch.cuda.synchronize(); t.append(time.perf_counter())
+        mu, sig = g.predict(tq); t.append(time.perf_counter())
+        k = KMP(l=0.5, alpha=60, sigma_f=4, time_driven_kernel=False)
+        k.fit(tq, mu, sig); torch.cuda.synchronize(); t.append(time.perf_counter())
+        k.set_waypoint([1.0], [mu[:, 266:267].T + 0.05], [np.eye(6) * 1e-6]); torch.cuda.synchronize(); t.append(time.perf_counter())
+        k.predict(tq); t.append(time.perf_counter())
+        return np.diff(t) * 1e3
+
+    out = {}
+    for key, fn in (('reference_faithful_2xO3_N150', faithful), ('named_O6_N400', named)):
+        best = None
+        for rep in range(4):
+            d = fn()
+            if rep > 0 and (best is None or d.sum() < best.sum()):
+                best = d
+        out[key] = {k_: float(v) for k_, v in zip(names, best)}
+        out[key]['total_ms'] = float(best.sum())
+    return out
 
 
 def gmr(M, K=8, O=2):
@@ -193,10 +371,12 @@ def run_all(quick=False, only=None, dgemm_tflops=None):
             out[f'dgemm_ours_{name}'] = {'tflops': tf, 'ms': ms, 'frac_cublas': tf / dg}
     if want('cfg1'):
         out['cfg1'] = cfg1()
+    if want('cfg2'):
+        out['cfg2'] = cfg2()
     if want('cfg4'):
         out['cfg4'] = cfg4(2048 if quick else 8192, dg)
     if want('em'):
-        out['em'] = em(1_000_000 if quick else 10_000_000)
+        out['em'] = em(1_000_000 if quick else 10_000_000, dgemm_tflops=dg)
     if want('gmr'):
         out['gmr'] = gmr(1 << (22 if quick else 26))
     if want('quat'):

@@ -78,9 +78,9 @@ def cfg4_problem(N=8192, seed=0):
     return t, mu, sig
 
 
-def cfg5_samples(n, K=64, d=7, seed=0):
-    """Synthetic GMM EM data (SURVEY.md 8d cfg 5): samples of a K-component mixture whose means follow
-    a smooth random curve in d dims and whose covariances are random SPD with eigenvalues in [1e-3,1e-1]."""
+def cfg5_mixture(K=64, d=7, seed=0):
+    """The ground-truth mixture of cfg 5: means (K,d) along a smooth random curve, factors A (K,d,d) of random SPD
+    covariances with eigenvalues in [1e-3,1e-1]; also returns the generator positioned after these draws."""
     rng = np.random.default_rng(seed)
     knots = np.linspace(0.0, 1.0, K)
     freq = rng.uniform(0.5, 2.0, size=d)
@@ -92,6 +92,13 @@ def cfg5_samples(n, K=64, d=7, seed=0):
         Q, _ = np.linalg.qr(rng.normal(size=(d, d)))
         ev = 10.0 ** rng.uniform(-3, -1, size=d)
         A[k] = Q * np.sqrt(ev)
+    return means, A, rng
+
+
+def cfg5_samples(n, K=64, d=7, seed=0):
+    """Synthetic GMM EM data (SURVEY.md 8d cfg 5): samples of a K-component mixture whose means follow
+    a smooth random curve in d dims and whose covariances are random SPD with eigenvalues in [1e-3,1e-1]."""
+    means, A, rng = cfg5_mixture(K, d, seed)
     comp = rng.integers(0, K, size=n)
     z = rng.normal(size=(n, d))
     X = means[comp] + np.einsum('nij,nj->ni', A[comp], z)

@@ -98,6 +98,18 @@ def test_gmm_fit_synthetic_7d(golden):
     assert abs(orc.gmm_bic(X, r['weights'], r['means'], r['covariances']) - float(z['bic'])) < 1e-6 * abs(float(z['bic']))
 
 
+def test_gmm_fit_cfg5_shape_k64(golden):
+    """The oracle at cfg 5's own K (64 components, 200 k rows; ~75 s on 8 cores): same iteration count and lower bound
+    as sklearn through the reference wrapper, parameters to 1e-10."""
+    z = golden('gmm_cfg5_k64.npz')
+    X, _, _ = wl.cfg5_samples(int(z['n']), K=int(z['K']), d=7, seed=int(z['seed']))
+    r = orc.gmm_fit(X, int(z['K']), 1e-6)
+    assert r['n_iter'] == int(z['n_iter'])
+    assert abs(r['lower_bound'] - float(z['lower_bound'])) < 1e-11
+    assert rel_err(r['means'].T, z['means']) < 1e-10 and rel_err(r['weights'], z['priors']) < 1e-10
+    assert rel_err(np.transpose(r['covariances'], (1, 2, 0)), z['covs']) < 1e-9
+
+
 def test_cfg1_kmp_pipeline(golden):
     zl = golden('letters_ref.npz')
     z = golden('cfg1_G.npz')
