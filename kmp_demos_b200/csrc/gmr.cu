@@ -83,51 +83,100 @@ __global__ void __launch_bounds__(128) k_gmr(GmrArgs p) {
     }
     __syncthreads();
     if (I == 1) {
-        // Scalar input (every demo of the reference): components in groups of four, their exponentials evaluated as four
-        // interleaved branch-free chains - the kernel is bound by FP64 instruction latency / issue, not by HBM
-        // (~400 FP64 operations per query at K = 8, O = 2 against 56 bytes).
-        for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < p.M; m += (long long)gridDim.x * blockDim.x) {
-            const double x0 = p.x[m];
-            double mean[O], sec[O][O];
+        // Scalar input (every demo of the reference).  The kernel is bound by FP64 issue, not by HBM, unless the work per
+        // query shrinks (56 bytes against ~40 FP64 operations per component), so:
+        //   * pass 1 evaluates only the exponents  e_k = log(pi_k) + logc_k - z_k^2/2  (2 FMA + 1 max per component) and
+        //     their maximum; pass 2 recomputes them and evaluates exp / gain / second moments only for components within
+        //     60 ln 2 of that maximum: anything smaller contributes less than 2^-60 of the leading activation - far below
+        //     half an ulp of every output - and is accounted as exactly 0 (+ REALMIN in the normaliser, like every
+        //     component, GaussianMixtureModel.py:90).  On a time grid neighbouring queries activate the same 2-3 components,
+        //     so the branch is warp-uniform; the per-lane select keeps a query's result independent of its neighbours;
+        //   * two queries per thread (m, m + half a CTA-stride apart: both accesses stay coalesced) run as independent
+        //     dependency chains, and the covariance accumulates its upper triangle only.
+        // Per-component record for this path (overlay on the generic one, rebuilt here):
+        //   [a = Linv/sqrt2, b = -a muI, e0 = logc + log prior, aO (O) = muO - G muI, G (O), Sc upper (O(O+1)/2)]
+        constexpr int NP = O * (O + 1) / 2;
+        constexpr int RS = 3 + 2 * O + NP;
+        double* rec = sh + (size_t)K * stride;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const double* c = sh + (size_t)k * stride;
+            const double* muO = c + 4; const double* G = muO + O; const double* Sc = G + O;
+            double* r = rec + (size_t)k * RS;
+            const double a = c[3] * 0.70710678118654752440;
+            r[0] = a; r[1] = -a * c[2]; r[2] = c[1] + log(c[0]);
+            for (int o = 0; o < O; ++o) { r[3 + o] = muO[o] - G[o] * c[2]; r[3 + O + o] = G[o]; }
+            int t = 0;
+            for (int o = 0; o < O; ++o) for (int q = o; q < O; ++q) r[3 + 2 * O + t++] = Sc[o * O + q];
+        }
+        __syncthreads();
+        constexpr double kSkip = 41.58883083359672;      // 60 ln 2
+        const long long span = (long long)gridDim.x * blockDim.x;
+        for (long long m0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; m0 < p.M; m0 += 2 * span) {
+            const long long m1 = m0 + span;
+            const bool two = m1 < p.M;
+            double x[2] = {p.x[m0], two ? p.x[m1] : 0.0};
+            double mx[2] = {-INFINITY, -INFINITY};
+            for (int k = 0; k < K; ++k) {
+                const double* r = rec + (size_t)k * RS;
 #pragma unroll
-            for (int a = 0; a < O; ++a) { mean[a] = 0.0;
-#pragma unroll
-                for (int b = 0; b < O; ++b) sec[a][b] = 0.0; }
-            double hsum = 0.0;
-            for (int k0 = 0; k0 < K; k0 += 4) {
-                double dev[4], h[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double* c = sh + (size_t)min(k0 + u, K - 1) * stride;        // [prior, logc, muI, Linv, muO (O), G (O), Sc (O*O)]
-                    dev[u] = x0 - c[2];
-                    const double z = c[3] * dev[u];
-                    h[u] = c[0] * exp_nonpos(fma(-0.5 * z, z, c[1]));
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (k0 + u < K) {
-                        const double* c = sh + (size_t)(k0 + u) * stride;
-                        const double* muO = c + 4; const double* G = muO + O; const double* Sc = G + O;
-                        hsum += h[u] + kRealMin;
-                        double mk[O];
-#pragma unroll
-                        for (int a = 0; a < O; ++a) { mk[a] = fma(G[a], dev[u], muO[a]); mean[a] = fma(h[u], mk[a], mean[a]); }
-#pragma unroll
-                        for (int a = 0; a < O; ++a)
-#pragma unroll
-                            for (int b = 0; b < O; ++b) sec[a][b] = fma(h[u], fma(mk[a], mk[b], Sc[a * O + b]), sec[a][b]);
-                    }
+                for (int u = 0; u < 2; ++u) {
+                    const double z = fma(r[0], x[u], r[1]);
+                    mx[u] = fmax(mx[u], fma(-z, z, r[2]));
                 }
             }
-            const double inv = 1.0 / hsum;
+            double mean[2][O], sec[2][NP], hsum[2] = {0.0, 0.0};
 #pragma unroll
-            for (int a = 0; a < O; ++a) mean[a] *= inv;
+            for (int u = 0; u < 2; ++u) {
 #pragma unroll
-            for (int a = 0; a < O; ++a) {
-                p.mu[(size_t)a * p.M + m] = mean[a];
+                for (int o = 0; o < O; ++o) mean[u][o] = 0.0;
 #pragma unroll
-                for (int b = 0; b < O; ++b)
-                    p.sigma[((size_t)a * O + b) * p.M + m] = sec[a][b] * inv + (a == b ? p.reg : 0.0) - mean[a] * mean[b];
+                for (int t = 0; t < NP; ++t) sec[u][t] = 0.0;
+            }
+            for (int k = 0; k < K; ++k) {
+                const double* r = rec + (size_t)k * RS;
+                double e[2]; bool act[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const double z = fma(r[0], x[u], r[1]);
+                    e[u] = fma(-z, z, r[2]);
+                    act[u] = !(e[u] < mx[u] - kSkip);               // a NaN query stays active and propagates, as in the reference
+                }
+                if (__any_sync(0xffffffffu, act[0] || act[1])) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const double h = act[u] ? exp_nonpos(e[u]) : 0.0;
+                        hsum[u] += h + kRealMin;
+                        double mk[O];
+#pragma unroll
+                        for (int o = 0; o < O; ++o) { mk[o] = fma(r[3 + O + o], x[u], r[3 + o]); mean[u][o] = fma(h, mk[o], mean[u][o]); }
+                        int t = 0;
+#pragma unroll
+                        for (int o = 0; o < O; ++o)
+#pragma unroll
+                            for (int q = o; q < O; ++q) { sec[u][t] = fma(h, fma(mk[o], mk[q], r[3 + 2 * O + t]), sec[u][t]); ++t; }
+                    }
+                } else {
+                    hsum[0] += kRealMin; hsum[1] += kRealMin;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                const long long m = u ? m1 : m0;
+                const double inv = 1.0 / hsum[u];
+#pragma unroll
+                for (int o = 0; o < O; ++o) mean[u][o] *= inv;
+                int t = 0;
+#pragma unroll
+                for (int o = 0; o < O; ++o) {
+                    p.mu[(size_t)o * p.M + m] = mean[u][o];
+#pragma unroll
+                    for (int q = o; q < O; ++q) {
+                        const double v = sec[u][t++] * inv + (o == q ? p.reg : 0.0) - mean[u][o] * mean[u][q];
+                        p.sigma[((size_t)o * O + q) * p.M + m] = v;
+                        if (q != o) p.sigma[((size_t)q * O + o) * p.M + m] = v;
+                    }
+                }
             }
         }
         return;
@@ -173,10 +222,10 @@ __global__ void __launch_bounds__(128) k_gmr(GmrArgs p) {
 
 template <int O>
 static int launch_gmr(const GmrArgs& p, cudaStream_t st) {
-    const size_t smem = (size_t)p.K * gmr_stride(p.I, O) * sizeof(double);
+    const size_t smem = (size_t)p.K * (gmr_stride(p.I, O) + 3 + 2 * O + O * (O + 1) / 2) * sizeof(double);
     if (smem > 200 * 1024) { snprintf(g_err, sizeof(g_err), "kmpx: too many mixture components for k_gmr"); return -4; }
     KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_gmr<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr k_gmr"));
-    const long long blocks = (p.M + 127) / 128;
+    const long long blocks = (p.M + 255) / 256;             // two queries per thread on the scalar-input path
     const int grid = (int)(blocks < num_sms() * 16 ? blocks : num_sms() * 16);
     k_gmr<O><<<grid, 128, smem, st>>>(p);
     return check_launch("k_gmr");

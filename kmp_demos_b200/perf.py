@@ -305,16 +305,30 @@ def cfg2():
 
 
 def gmr(M, K=8, O=2):
+    """GMR on M queries (K = 8, O = 2, scalar input: cfg 1's shape).  Two workloads: (a) the case SURVEY 8(d) names - a time
+    GRID (linspace over the demonstrations' time span) through the reference's own cfg-1 mixture of letter G
+    (tests/golden/letters_ref.npz): neighbouring queries activate the same 2-3 components; (b) worst case - unordered
+    random queries through a random mixture whose components all overlap (nothing to skip, divergent warps)."""
+    by = 8.0 * M * (1 + O + O * O)
+    mu = torch.empty((O, M), dtype=f64, device='cuda'); sg = torch.empty((O, O, M), dtype=f64, device='cuda')
+
+    def run(pri, mea, cov, x, reg):
+        ms = timeit(lambda: _lib.call('kmpx_gmr', _lib.ptr(pri), _lib.ptr(mea), _lib.ptr(cov), K, 1, O, _lib.ptr(x), M, reg, _lib.ptr(mu),
+                                      _lib.ptr(sg), _lib.stream()))
+        return {'ms': ms, 'gbs': by / ms * 1e-6, 'frac_hbm': by / ms * 1e-6 / peaks()}
+
+    z = np.load(os.path.join(wl.GOLDEN_DIR, 'letters_ref.npz'))
+    gi = wl.LETTERS.index('G')
+    dv = lambda a: torch.as_tensor(np.ascontiguousarray(a), device='cuda')  # noqa: E731
+    grid = torch.linspace(0.0, 2.0, M, dtype=f64, device='cuda').reshape(1, M)
+    out = {'M': M, 'K': K, 'O': O, 'grid_cfg1': run(dv(z['priors'][gi]), dv(z['means'][gi]), dv(z['covariances'][gi]), grid, 1e-6)}
     rng = np.random.default_rng(0)
     d = 1 + O
-    pri = torch.as_tensor(np.full(K, 1.0 / K), device='cuda')
-    mea = torch.as_tensor(rng.normal(size=(d, K)), device='cuda')
     Bm = rng.normal(size=(K, d, d))
-    cov = torch.as_tensor(np.ascontiguousarray(np.transpose(np.einsum('kab,kcb->kac', Bm, Bm) + 0.1 * np.eye(d), (1, 2, 0))), device='cuda')
-    x = torch.randn(1, M, dtype=f64, device='cuda'); mu = torch.empty((O, M), dtype=f64, device='cuda'); sg = torch.empty((O, O, M), dtype=f64, device='cuda')
-    ms = timeit(lambda: _lib.call('kmpx_gmr', _lib.ptr(pri), _lib.ptr(mea), _lib.ptr(cov), K, 1, O, _lib.ptr(x), M, 1e-6, _lib.ptr(mu), _lib.ptr(sg), _lib.stream()))
-    by = 8.0 * M * (1 + O + O * O)
-    return {'M': M, 'K': K, 'O': O, 'ms': ms, 'gbs': by / ms * 1e-6, 'frac_hbm': by / ms * 1e-6 / peaks()}
+    cov = dv(np.transpose(np.einsum('kab,kcb->kac', Bm, Bm) + 0.1 * np.eye(d), (1, 2, 0)))
+    out['random_overlapping'] = run(dv(np.full(K, 1.0 / K)), dv(rng.normal(size=(d, K))), cov, torch.randn(1, M, dtype=f64, device='cuda'), 1e-6)
+    out.update(ms=out['grid_cfg1']['ms'], gbs=out['grid_cfg1']['gbs'], frac_hbm=out['grid_cfg1']['frac_hbm'])
+    return out
 
 
 def quat(M):

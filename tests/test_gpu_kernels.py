@@ -268,6 +268,28 @@ def test_gmr_matches_reference(T, golden):
         assert np.all(mu[:, -1] == 0) and rel_err(sg[:, :, -1], float(reg) * np.eye(int(O))) < 1e-15   # all-underflow query
 
 
+def test_gmr_time_grid_with_component_skipping_vs_oracle(T, golden):
+    """The scalar-input GMR path skips components more than 60 ln 2 below the leading exponent (k_gmr): on a dense time
+    grid through the reference's own cfg-1 mixtures - where most components are skipped - the result must equal the
+    oracle's full sum to 1e-12, far-away and NaN queries included."""
+    from kmp_demos_b200.mixture import GaussianMixtureModel
+    from oracle import kmp_oracle as orc
+    z = golden('letters_ref.npz')
+    x = np.concatenate([np.linspace(-0.5, 2.5, 20001), [50.0, -1e3]]).reshape(1, -1)
+    for li in (0, 6, 18, 25):
+        g = GaussianMixtureModel(n_components=8, diag_reg_factor=1e-6)
+        g.n_features = 3
+        g.priors, g.means, g.covariances = z['priors'][li], z['means'][li], z['covariances'][li]
+        mu, sg = g.predict(x)
+        mr, sr = orc.gmr(g.priors, g.means, g.covariances, x, 1e-6)
+        assert np.max(np.abs(mu - mr)) < 1e-12 * max(1.0, np.max(np.abs(mr))), li
+        assert np.max(np.abs(sg - sr)) < 1e-12 * max(1.0, np.max(np.abs(sr))), li
+        assert np.array_equal(sg[0, 1], sg[1, 0])
+    xn = np.array([[0.5, np.nan, 1.0]])
+    mu, sg = g.predict(xn)
+    assert np.isnan(mu[:, 1]).all() and np.isfinite(mu[:, [0, 2]]).all()
+
+
 def test_reference_kmeans_labels_bit_exact(T, golden):
     from kmp_demos_b200.cluster import KMeans, Uniform
     z = golden('small_cases.npz')
