@@ -55,6 +55,9 @@ int kmpx_debug_phases(long long* out_host, int reset);
  *   bit 4 (16) force the cp.async factor kernels instead of the TMA ones;  bit 5 (32) no L2 prefetch in the TMA factor kernels
  *   bit 6 (64) per-category timing printout of the blocked large-n Cholesky (host side) */
 int kmpx_debug_set(int flags);
+/* y[i] = exp(x[i]) through the branch-free exponentials of the hot kernels (mode 0: exp_nonpos, 1: table-driven exp_tab);
+ * accuracy probe for the tests, x and y are device arrays. */
+int kmpx_debug_exp(const double* x, double* y, long long n, int mode, void* stream);
 
 /* ---- K1: kernel-matrix builder.  Replaces the N^2 Python loop of KMP.fit, KMP.py:146-156, with
  *      KMP.__kernel_matrix (KMP.py:93-128) evaluated in-kernel (plain RBF block or the finite-difference
@@ -200,16 +203,52 @@ int kmpx_gmm_finalize(const double* stats, double n_total, int first, int d, int
                       const double* shift, double* weights, double* log_weights, double* means,
                       double* covs, double* prec_chol, double* log_det, int* info, void* stream);
 
+/* kmpx_gmm_finalize (first = 0) with sklearn's stopping rule on the device (mixture/_base.py:265-278):
+ * em_state = {done, n_iter, lower, converged} (doubles, device); lower = stats[K*F] / n_total is compared with the stored
+ * one, |delta| < tol or n_iter == max_iter sets done; once done the call leaves the parameters untouched, so passes can
+ * be enqueued in batches with one read of em_state per batch. */
+int kmpx_gmm_finalize_check(const double* stats, double n_total, int d, int K, double reg,
+                            const double* shift, double* weights, double* log_weights, double* means,
+                            double* covs, double* prec_chol, double* log_det, int* info,
+                            double tol, int max_iter, double* em_state, void* stream);
+
 /* ---- K7 (sklearn mode): the k-means initialisation of the GMM
- *      (sklearn/cluster/_kmeans.py:180-278,630-758, _k_means_lloyd.pyx:23-230).  The RandomState stream and
- *      the cumulative-sum sampling stay on the host; distances, minima, potentials, assignment and centre
- *      sums are device kernels. */
+ *      (sklearn/cluster/_kmeans.py:180-278,630-758, _k_means_lloyd.pyx:23-230).  Only the RandomState stream stays on
+ *      the host; sampling, distances, minima, potentials, the greedy choice, assignment, centre sums, centre update and
+ *      the stopping rules are device kernels.  Rows may be partitioned over ranks (n_before rows in front of this
+ *      rank's n, n_total in all); the exchanges between the kernels are the caller's (torch.distributed / NCCL). */
 int kmpx_rows_center_sqnorm(double* X, long long n, int d, const double* mean, double* x_sq, void* stream);
 /* dist[t][i] = min(closest[i], max(0, |c_t|^2 - 2 c_t.x_i + |x_i|^2)), pot[t] = sum_i dist[t][i];
  * closest may be NULL (first centre).  cand [T] are row indices into X. */
 int kmpx_kpp_candidates(const double* X, const double* x_sq, long long n, int d, const int* cand, int T,
                         const double* closest, double* dist, double* pot, void* ws, long long ws_bytes,
                         void* stream);
+/* k-means++ draw, replaces  searchsorted(cumsum(closest), uniform(T) * pot)  (_kmeans.py:227-231): u [T] uniform draws,
+ * pot the current potential (device scalar), before {hi, lo} the double-double potential of the ranks in front (NULL: 0).
+ * cand[t] = LOCAL row index of draw t or -1 when another rank owns it; flag[t] = 1 when the draw lies within the
+ * rounding uncertainty of numpy's sequential cumulative sum / BLAS potential (the caller repeats it with numpy). */
+long long kmpx_kpp_sample_workspace_bytes(long long n);
+int kmpx_kpp_sample(const double* closest, long long n, const double* u, int T, const double* pot,
+                    const double* before, long long n_before, long long n_total, int last_rank,
+                    long long* cand, int* flag, void* ws, long long ws_bytes, void* stream);
+/* rows [T][d+2] = [X[cand[t]], 1, n_before + cand[t]] for owned draws, zeros otherwise (summed over the ranks by the caller) */
+int kmpx_kpp_gather_rows(const double* X, int d, const long long* cand, int T, long long n_before, double* rows,
+                         void* stream);
+/* kmpx_kpp_candidates for candidate ROWS [T][d+2]; pot [T][2] = this rank's potentials in double-double */
+int kmpx_kpp_candidates_rows(const double* X, const double* x_sq, long long n, int d, const double* rows, int T,
+                             const double* closest, double* dist, double* pot, void* ws, long long ws_bytes,
+                             void* stream);
+/* greedy choice (_kmeans.py:245-251): pots [R][T][2] per-rank potentials; best = first minimum of their rank-ordered
+ * sums (force_best >= 0 overrides); writes pot_out, before_out {hi, lo} for the next draw, centers[c], center_ids[c],
+ * best_out, flag (two different candidates within rounding slack), and closest[i] = dist[best][i] when dist != NULL. */
+int kmpx_kpp_choose(const double* pots, int R, int T, int rank, const double* rows, int d, int c, long long n_total,
+                    int force_best, const double* dist, long long n, double* pot_out, double* before_out,
+                    double* centers, long long* center_ids, int* best_out, int* flag, double* closest, void* stream);
+/* Lloyd centre update + stopping rules (_kmeans.py:700-737): stats = packed hard-label statistics (kmpx_gmm_label_stats,
+ * summed over the ranks), n_changed_total device scalar (double), state = {done, n_iter, strict, empty}; a no-op once
+ * done or when a cluster is empty (state[3], the host relocates). */
+int kmpx_lloyd_update(const double* stats, int K, int d, double* centers, const double* tol_abs,
+                      const double* n_changed_total, int* n_changed_local, int max_iter, int* state, void* stream);
 /* labels[i] = argmin_j(|c_j|^2 - 2 x_i.c_j) (first minimum); n_changed += (labels != labels_prev). */
 int kmpx_kmeans_assign(const double* X, long long n, int d, int K, const double* centers,
                        const int* labels_prev, int* labels, int* n_changed, void* stream);

@@ -26,6 +26,7 @@ _SIGNATURES = {
     'kmpx_launch_count': [],
     'kmpx_debug_phases': [_p, _i],
     'kmpx_debug_set': [_i],
+    'kmpx_debug_exp': [_p, _p, _ll, _i, _p],
     'kmpx_kernel_build': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _d, _d, _i, _i, _i, _p],
     'kmpx_potrf_workspace_bytes': [_i, _i],
     'kmpx_potrf': [_p, _i, _ll, _p, _i, _i, _p, _p, _ll, _p],
@@ -54,9 +55,16 @@ _SIGNATURES = {
     'kmpx_gmm_em_pass': [_p, _ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p],
     'kmpx_gmm_label_stats': [_p, _ll, _i, _i, _p, _p, _p, _p, _ll, _p],
     'kmpx_gmm_finalize': [_p, _d, _i, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    'kmpx_gmm_finalize_check': [_p, _d, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _p, _p],
     'kmpx_rows_center_sqnorm': [_p, _ll, _i, _p, _p, _p],
     'kmpx_kpp_candidates': [_p, _p, _ll, _i, _p, _i, _p, _p, _p, _p, _ll, _p],
     'kmpx_kmeans_assign': [_p, _ll, _i, _i, _p, _p, _p, _p, _p],
+    'kmpx_kpp_sample_workspace_bytes': [_ll],
+    'kmpx_kpp_sample': [_p, _ll, _p, _i, _p, _p, _ll, _ll, _i, _p, _p, _p, _ll, _p],
+    'kmpx_kpp_gather_rows': [_p, _i, _p, _i, _ll, _p, _p],
+    'kmpx_kpp_candidates_rows': [_p, _p, _ll, _i, _p, _i, _p, _p, _p, _p, _ll, _p],
+    'kmpx_kpp_choose': [_p, _i, _i, _i, _p, _i, _i, _ll, _i, _p, _ll, _p, _p, _p, _p, _p, _p, _p, _p],
+    'kmpx_lloyd_update': [_p, _i, _i, _p, _p, _p, _p, _i, _p, _p],
     'kmpx_refkmeans_assign': [_p, _ll, _i, _i, _p, _p, _p],
     'kmpx_refkmeans_update': [_p, _ll, _i, _i, _p, _p, _p],
     'kmpx_quat_normalize': [_p, _p, _ll, _p],
@@ -73,6 +81,7 @@ _RESTYPES = {
     'kmpx_trtri_workspace_bytes': _ll,
     'kmpx_inverse_workspace_bytes': _ll,
     'kmpx_gmm_workspace_bytes': _ll,
+    'kmpx_kpp_sample_workspace_bytes': _ll,
     'kmpx_inc_workspace_doubles': _ll,
     'kmpx_inc_grouped_workspace_doubles': _ll,
     'kmpx_kmp_predict_gemm_workspace_bytes': _ll,

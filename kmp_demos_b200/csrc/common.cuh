@@ -139,6 +139,32 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     const double res = __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
     return x < -708.0 ? 0.0 : (x != x ? x : res);            // NaN propagates (select, still branch-free)
 }
+// Table-driven variant for kernels that keep a 32-entry table of 2^(j/32) in shared memory (fill_exp2_table): with
+// x = (32 k + j) ln2/32 + r, |r| <= ln2/64, a degree-6 polynomial reaches 3e-18 truncation error, so an exponential costs
+// 11 dependent FP64 operations + one shared-memory load instead of 18.  exp(x) = 2^k * T[j] * p(r); error ~1 ulp (the
+// table entries are correctly rounded).  Same domain rules as exp_nonpos: x < -708 -> 0, NaN propagates, no overflow check.
+constexpr int kExpTabN = 32;
+__device__ __forceinline__ void fill_exp2_table(double* tab, int tid, int nthreads) {
+    for (int j = tid; j < kExpTabN; j += nthreads) tab[j] = exp2((double)j / kExpTabN);   // library exp2: correctly rounded here
+}
+__device__ __forceinline__ double exp_tab(double x, const double* tab) {
+    const double shift = 6755399441055744.0;
+    const double t = fma(x, 46.16624130844682903551, shift);                 // 32 / ln 2
+    const int n = __double2loint(t);
+    const double kd = t - shift;
+    double r = fma(kd, -2.16608493865351192653e-02, x);                      // ln2/32 split like exp_nonpos (hi has 33 bits)
+    r = fma(kd, -5.96317165397058656257e-12, r);
+    double q = 1.388888888888889e-03;                                        // 1/6!
+    q = fma(q, r, 8.333333333333333e-03);
+    q = fma(q, r, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const double tj = tab[n & (kExpTabN - 1)];
+    q = fma(q * r, tj, tj);                                                  // T (1 + r p(r))
+    const double res = __hiloint2double(__double2hiint(q) + ((n >> 5) << 20), __double2loint(q));
+    return x < -708.0 ? 0.0 : (x != x ? x : res);
+}
 // rbf() with the branch-free exponential (plain kernel, hot loops that evaluate many coefficients per thread)
 template <typename P1, typename P2>
 __device__ __forceinline__ double rbf_fast(P1 s1, P2 s2, int I, double sigma_f) {

@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
     double* s_Phi = s_R + (size_t)ETS * ldr;      // [ETS][ldf]
     double* s_red = s_Phi + (size_t)ETS * ldf;    // [EPARTS][ETS] max / sum exchange
     int* s_arg = reinterpret_cast<int*>(s_red + EPARTS * ETS);   // [EPARTS][ETS]
+    double* s_etab = s_red + EPARTS * ETS + EPARTS * ETS / 2;     // [32] table of exp_tab
+    fill_exp2_table(s_etab, threadIdx.x, ETHREADS);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
                     if (kbeg + kk < kend) {
                         double e[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) e[u] = exp_nonpos(wl[kk + u] - m);          // -inf beyond kend -> 0
+                        for (int u = 0; u < 4; ++u) e[u] = exp_tab(wl[kk + u] - m, s_etab);      // -inf beyond kend -> 0
 #pragma unroll
                         for (int u = 0; u < 4; ++u) { wl[kk + u] = e[u]; se += e[u]; }
                     }
@@ -184,11 +186,11 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
                 for (; k + 4 <= kend; k += 4) {
                     double e[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) e[u] = exp_nonpos(Rrow[k + u] - m);
+                    for (int u = 0; u < 4; ++u) e[u] = exp_tab(Rrow[k + u] - m, s_etab);
 #pragma unroll
                     for (int u = 0; u < 4; ++u) { Rrow[k + u] = e[u]; se += e[u]; }
                 }
-                for (; k < kend; ++k) { const double e = exp_nonpos(Rrow[k] - m); Rrow[k] = e; se += e; }
+                for (; k < kend; ++k) { const double e = exp_tab(Rrow[k] - m, s_etab); Rrow[k] = e; se += e; }
             }
             s_red[half * ETS + s_loc] = se;
             __syncthreads();
@@ -266,12 +268,26 @@ __global__ void k_gmm_reduce(const double* partials, int nctas, int K, int KP, i
 struct FinArgs {
     const double* stats; double n_total; int first, d, K; double reg; const double* shift;
     double *weights, *log_weights, *means, *covs, *prec_chol, *log_det; int* info;
+    double* em_state; double tol; int max_iter;   // optional device-side loop control, see kmpx_gmm_finalize_check
 };
 
 // One thread per component (K <= 1024, d <= 16).
 __global__ void k_gmm_finalize(FinArgs p) {
     __shared__ double s_nk[1024];
     const int k = threadIdx.x, d = p.d, K = p.K, F = gmm_F(d);
+    // sklearn's loop (mixture/_base.py:265-278) on the device: em_state = {done, n_iter, lower, converged}.  Once done,
+    // the M-step is not applied any more, so the host may enqueue passes in batches and read the state once per batch.
+    if (p.em_state) {
+        if (p.em_state[0] != 0.0) return;
+        __syncthreads();                       // every thread has read `done` before thread 0 may set it
+        if (k == 0) {
+            const double lower = p.stats[(size_t)K * F] / p.n_total, prev = p.em_state[2];
+            const double it = p.em_state[1] + 1.0;
+            p.em_state[1] = it; p.em_state[2] = lower;
+            if (fabs(lower - prev) < p.tol) { p.em_state[0] = 1.0; p.em_state[3] = 1.0; }
+            else if (it >= (double)p.max_iter) p.em_state[0] = 1.0;
+        }
+    }
     double nk = 0.0;
     if (k < K) { nk = p.stats[(size_t)k * F] + 10.0 * 2.220446049250313e-16; s_nk[k] = nk; }
     __syncthreads();
@@ -335,7 +351,7 @@ static size_t em_smem(int d, int K) {
     const int F = gmm_F(d), FP = pad8(F), KP = pad8(K), TRI = d * (d + 1) / 2;
     const int poff = (d + 2) & ~1, prec = (poff + TRI + 1) & ~1;       // parameter record of k_gmm_em
     size_t dbl = (size_t)K * prec + ((d + 1) & ~1) + (size_t)ETS * d + (size_t)ETS * ld_conflict_free(KP) +
-                 (size_t)ETS * ld_conflict_free(FP) + 2 * EPARTS * ETS;
+                 (size_t)ETS * ld_conflict_free(FP) + 2 * EPARTS * ETS + kExpTabN;
     return dbl * sizeof(double);
 }
 
@@ -415,7 +431,20 @@ extern "C" int kmpx_gmm_finalize(const double* stats, double n_total, int first,
     if (d < 1 || d > 16) return fail_arg(4, "d must be in 1..16");
     if (K < 1 || K > 1024) return fail_arg(5, "K must be in 1..1024");
     if (!weights || !log_weights || !means || !covs || !prec_chol || !log_det) return fail_arg(8, "output arrays are NULL");
-    FinArgs p{stats, n_total, first, d, K, reg, shift, weights, log_weights, means, covs, prec_chol, log_det, info};
+    FinArgs p{stats, n_total, first, d, K, reg, shift, weights, log_weights, means, covs, prec_chol, log_det, info, nullptr, 0.0, 0};
+    k_gmm_finalize<<<1, ((K + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(p);
+    return check_launch("k_gmm_finalize");
+}
+
+extern "C" int kmpx_gmm_finalize_check(const double* stats, double n_total, int d, int K, double reg,
+                                       const double* shift, double* weights, double* log_weights, double* means,
+                                       double* covs, double* prec_chol, double* log_det, int* info,
+                                       double tol, int max_iter, double* em_state, void* stream) {
+    if (!stats || !em_state) return fail_arg(1, "stats / em_state is NULL");
+    if (d < 1 || d > 16) return fail_arg(4, "d must be in 1..16");
+    if (K < 1 || K > 1024) return fail_arg(5, "K must be in 1..1024");
+    if (!weights || !log_weights || !means || !covs || !prec_chol || !log_det) return fail_arg(8, "output arrays are NULL");
+    FinArgs p{stats, n_total, 0, d, K, reg, shift, weights, log_weights, means, covs, prec_chol, log_det, info, em_state, tol, max_iter};
     k_gmm_finalize<<<1, ((K + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(p);
     return check_launch("k_gmm_finalize");
 }

@@ -24,7 +24,7 @@ struct GmrArgs {
 // shared layout per component: [prior, logc, muI (I), Linv (I*I), muO (O), G (O*I), Sc (O*O)]
 __host__ __device__ inline int gmr_stride(int I, int O) { return 2 + I + I * I + O + O * I + O * O; }
 
-template <int O>
+template <int O, bool SMALLK>       // SMALLK: K <= 8, the scalar-input path keeps the exponents in registers
 __global__ void __launch_bounds__(128) k_gmr(GmrArgs p) {
     extern __shared__ double sh[];
     const int I = p.I, K = p.K, d = I + O;
@@ -110,20 +110,42 @@ __global__ void __launch_bounds__(128) k_gmr(GmrArgs p) {
         }
         __syncthreads();
         constexpr double kSkip = 41.58883083359672;      // 60 ln 2
+        constexpr int CB = 4;                            // components per block: CB x 2 queries = 8 independent exp chains
+        double* etab = rec + (size_t)K * RS;
+        fill_exp2_table(etab, threadIdx.x, blockDim.x);
+        __syncthreads();
         const long long span = (long long)gridDim.x * blockDim.x;
         for (long long m0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; m0 < p.M; m0 += 2 * span) {
             const long long m1 = m0 + span;
             const bool two = m1 < p.M;
             double x[2] = {p.x[m0], two ? p.x[m1] : 0.0};
             double mx[2] = {-INFINITY, -INFINITY};
-            for (int k = 0; k < K; ++k) {
-                const double* r = rec + (size_t)k * RS;
+            // K <= 8 (every mixture of the reference's demos): the exponents stay in registers between the two passes
+            constexpr int KR = 8;
+            constexpr bool keep = SMALLK;
+            double er[SMALLK ? KR : 1][2];
+            if constexpr (keep) {
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const double z = fma(r[0], x[u], r[1]);
-                    mx[u] = fmax(mx[u], fma(-z, z, r[2]));
+                for (int k = 0; k < KR; ++k) {
+                    const double* r = rec + (size_t)min(k, K - 1) * RS;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const double z = fma(r[0], x[u], r[1]);
+                        er[k][u] = fma(-z, z, r[2]);
+                        mx[u] = fmax(mx[u], er[k][u]);
+                    }
+                }
+            } else {
+                for (int k = 0; k < K; ++k) {
+                    const double* r = rec + (size_t)k * RS;
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const double z = fma(r[0], x[u], r[1]);
+                        mx[u] = fmax(mx[u], fma(-z, z, r[2]));
+                    }
                 }
             }
+            const double thr[2] = {mx[0] - kSkip, mx[1] - kSkip};
             double mean[2][O], sec[2][NP], hsum[2] = {0.0, 0.0};
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -132,33 +154,66 @@ __global__ void __launch_bounds__(128) k_gmr(GmrArgs p) {
 #pragma unroll
                 for (int t = 0; t < NP; ++t) sec[u][t] = 0.0;
             }
-            for (int k = 0; k < K; ++k) {
-                const double* r = rec + (size_t)k * RS;
-                double e[2]; bool act[2];
+            auto block = [&](int k0, const double (&e)[CB][2]) {
+                bool act[CB][2]; bool any = false;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const double z = fma(r[0], x[u], r[1]);
-                    e[u] = fma(-z, z, r[2]);
-                    act[u] = !(e[u] < mx[u] - kSkip);               // a NaN query stays active and propagates, as in the reference
-                }
-                if (__any_sync(0xffffffffu, act[0] || act[1])) {
+                for (int j = 0; j < CB; ++j)
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        const double h = act[u] ? exp_nonpos(e[u]) : 0.0;
-                        hsum[u] += h + kRealMin;
-                        double mk[O];
-#pragma unroll
-                        for (int o = 0; o < O; ++o) { mk[o] = fma(r[3 + O + o], x[u], r[3 + o]); mean[u][o] = fma(h, mk[o], mean[u][o]); }
-                        int t = 0;
-#pragma unroll
-                        for (int o = 0; o < O; ++o)
-#pragma unroll
-                            for (int q = o; q < O; ++q) { sec[u][t] = fma(h, fma(mk[o], mk[q], r[3 + 2 * O + t]), sec[u][t]); ++t; }
+                        // a NaN query stays active and propagates, as in the reference
+                        act[j][u] = (k0 + j < K) && !(e[j][u] < thr[u]);
+                        any = any || act[j][u];
                     }
-                } else {
-                    hsum[0] += kRealMin; hsum[1] += kRealMin;
+                if (!__any_sync(0xffffffffu, any)) return;
+                double h[CB][2];
+#pragma unroll
+                for (int j = 0; j < CB; ++j)
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) h[j][u] = exp_tab(e[j][u], etab);
+#pragma unroll
+                for (int j = 0; j < CB; ++j) {
+                    if (k0 + j < K) {
+                        const double* r = rec + (size_t)(k0 + j) * RS;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const double hh = act[j][u] ? h[j][u] : 0.0;
+                            hsum[u] += hh;
+                            double mk[O];
+#pragma unroll
+                            for (int o = 0; o < O; ++o) { mk[o] = fma(r[3 + O + o], x[u], r[3 + o]); mean[u][o] = fma(hh, mk[o], mean[u][o]); }
+                            int t = 0;
+#pragma unroll
+                            for (int o = 0; o < O; ++o)
+#pragma unroll
+                                for (int q = o; q < O; ++q) { sec[u][t] = fma(hh, fma(mk[o], mk[q], r[3 + 2 * O + t]), sec[u][t]); ++t; }
+                        }
+                    }
+                }
+            };
+            if constexpr (keep) {
+#pragma unroll
+                for (int k0 = 0; k0 < KR; k0 += CB) {
+                    if (k0 < K) {
+                        double e[CB][2];
+#pragma unroll
+                        for (int j = 0; j < CB; ++j) { e[j][0] = er[k0 + j][0]; e[j][1] = er[k0 + j][1]; }
+                        block(k0, e);
+                    }
+                }
+            } else {
+                for (int k0 = 0; k0 < K; k0 += CB) {
+                    double e[CB][2];
+#pragma unroll
+                    for (int j = 0; j < CB; ++j) {
+                        const double* r = rec + (size_t)min(k0 + j, K - 1) * RS;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) { const double z = fma(r[0], x[u], r[1]); e[j][u] = fma(-z, z, r[2]); }
+                    }
+                    block(k0, e);
                 }
             }
+            // every component adds REALMIN to the normaliser (GaussianMixtureModel.py:90); h + REALMIN == h unless h < 2^-970
+            hsum[0] += K * kRealMin; hsum[1] += K * kRealMin;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 if (u == 1 && !two) break;
@@ -222,12 +277,18 @@ __global__ void __launch_bounds__(128) k_gmr(GmrArgs p) {
 
 template <int O>
 static int launch_gmr(const GmrArgs& p, cudaStream_t st) {
-    const size_t smem = (size_t)p.K * (gmr_stride(p.I, O) + 3 + 2 * O + O * (O + 1) / 2) * sizeof(double);
+    const size_t smem = ((size_t)p.K * (gmr_stride(p.I, O) + 3 + 2 * O + O * (O + 1) / 2) + kExpTabN) * sizeof(double);
     if (smem > 200 * 1024) { snprintf(g_err, sizeof(g_err), "kmpx: too many mixture components for k_gmr"); return -4; }
-    KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_gmr<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr k_gmr"));
+    if (p.K <= 8 && p.I == 1) {
+        KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_gmr<O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr k_gmr"));
+        const long long blocks8 = (p.M + 255) / 256;
+        k_gmr<O, true><<<(int)(blocks8 < num_sms() * 16 ? blocks8 : num_sms() * 16), 128, smem, st>>>(p);
+        return check_launch("k_gmr");
+    }
+    KMPX_TRY(check_cuda(cudaFuncSetAttribute(k_gmr<O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "attr k_gmr"));
     const long long blocks = (p.M + 255) / 256;             // two queries per thread on the scalar-input path
     const int grid = (int)(blocks < num_sms() * 16 ? blocks : num_sms() * 16);
-    k_gmr<O><<<grid, 128, smem, st>>>(p);
+    k_gmr<O, false><<<grid, 128, smem, st>>>(p);
     return check_launch("k_gmr");
 }
 

@@ -120,24 +120,35 @@ class EMEngine:
         if update:
             self._finalize(first=False)
 
-    def run(self, tol=1e-3, max_iter=100, fixed_iters=None):
-        """sklearn's loop (sklearn/mixture/_base.py:265-278): stop when |delta mean log-lik| < tol.
+    def run(self, tol=1e-3, max_iter=100, fixed_iters=None, check_every=None):
+        """sklearn's loop (sklearn/mixture/_base.py:265-278): stop when |delta mean log-lik| < tol.  The comparison runs
+        on the device (kmpx_gmm_finalize_check): passes are enqueued `check_every` at a time and the host reads the
+        4-double loop state once per batch (a pass enqueued after convergence leaves the parameters untouched).
         fixed_iters runs exactly that many passes without reading anything back (benchmarks)."""
+        torch = self.torch
         if fixed_iters is not None:
             for _ in range(fixed_iters):
                 self.em_pass()
             return fixed_iters, float(self.stats[-1].item()) / self.n_total, False
-        lower = -np.inf
-        converged = False
-        n_iter = 0
-        for it in range(1, max_iter + 1):
-            prev = lower
-            self.em_pass()
-            lower = float(self.stats[-1].item()) / self.n_total
-            n_iter = it
-            if abs(lower - prev) < tol:
-                converged = True
+        if check_every is None:
+            # one read per pass costs ~20 us: irrelevant next to a pass over millions of rows, dominant for a few hundred
+            check_every = 1 if self.n * self.K >= 20_000_000 else 8
+        state = torch.tensor([0.0, 0.0, -float('inf'), 0.0], dtype=torch.float64, device=self.X.device)
+        st = None
+        while True:
+            for _ in range(check_every):
+                _lib.call('kmpx_gmm_em_pass', _lib.ptr(self.X), self.n, self.d, self.K, _lib.ptr(self.shift),
+                          _lib.ptr(self.log_weights), _lib.ptr(self.means), _lib.ptr(self.prec_chol), _lib.ptr(self.log_det),
+                          _lib.ptr(self.stats), None, None, _lib.ptr(self.ws), self.ws_bytes, _lib.stream())
+                self._allreduce()
+                _lib.call('kmpx_gmm_finalize_check', _lib.ptr(self.stats), self.n_total, self.d, self.K, self.reg,
+                          _lib.ptr(self.shift), _lib.ptr(self.weights), _lib.ptr(self.log_weights), _lib.ptr(self.means),
+                          _lib.ptr(self.covs), _lib.ptr(self.prec_chol), _lib.ptr(self.log_det), _lib.ptr(self.info),
+                          float(tol), int(max_iter), _lib.ptr(state), _lib.stream())
+            st = state.cpu().numpy()
+            if st[0] != 0.0:
                 break
+        n_iter, lower, converged = int(st[1]), float(st[2]), bool(st[3] != 0.0)
         if int(self.info.abs().max().item()) != 0:
             raise ValueError("Fitting the mixture model failed because some components have ill-defined empirical "
                              "covariance (for instance caused by singleton or collapsed samples). Try to decrease the "
@@ -145,115 +156,270 @@ class EMEngine:
         return n_iter, lower, converged
 
 
-def kmeans_init_labels(X, K, rs, max_iter=300, tol=1e-4):
-    """``KMeans(n_clusters=K, n_init=1, random_state=rs).fit(X).labels_`` with the sample-sized work on the device.
-    X: (n,d) CUDA tensor (not modified).  Returns int32 CUDA labels, the Lloyd iteration count and the
-    data mean (CUDA, (d,)) that the statistics pass produced on the way."""
+class _Ranks:
+    """The optional process group behind a row-partitioned fit: rank / world and the three exchanges the k-means
+    initialisation needs (sum, gather of equal-sized blocks, gather of ragged row vectors to the host)."""
+
+    def __init__(self, group):
+        self.group = group
+        if group is None:
+            self.rank, self.world = 0, 1
+        else:
+            import torch.distributed as dist
+            self.dist = dist
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def sum_(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def gather(self, t):
+        """(world, *t.shape) tensor holding every rank's t."""
+        if self.world == 1:
+            return t.unsqueeze(0)
+        out = t.new_empty((self.world,) + tuple(t.shape))
+        self.dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group)
+        return out
+
+    def gather_rows_host(self, t, counts):
+        """Concatenation over the ranks of the leading-dimension slices t[:counts[rank]] as a numpy array (single rank:
+        through a pinned staging buffer that is kept for the next call)."""
+        if self.world == 1:
+            import torch
+            buf = getattr(self, '_pinned', None)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = self._pinned = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            buf.copy_(t)
+            return buf.numpy()
+        per = max(counts)
+        pad = t.new_zeros((per,) + tuple(t.shape[1:]))
+        pad[:t.shape[0]] = t
+        allr = self.gather(pad).cpu().numpy()
+        return np.concatenate([allr[r, :counts[r]] for r in range(self.world)])
+
+
+def _first_center(rs, n_total):
+    """``rs.choice(n_total, p=ones/n_total)`` (sklearn/cluster/_kmeans.py:228) without materialising the n_total-long
+    probability vector: numpy draws ONE uniform u and returns searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right'), i.e.
+    floor(u * n_total) unless u lies within the rounding error of that cumulative sum (< 4 (n+2) eps) of a boundary -
+    then the literal call is replayed from the saved generator state."""
+    state = rs.get_state()
+    u = rs.random_sample()
+    pos = u * n_total
+    idx = int(np.floor(pos))
+    margin = min(pos - idx, idx + 1 - pos) / n_total
+    if margin <= 4.0 * (n_total + 2) * np.finfo(float).eps or idx >= n_total:
+        rs.set_state(state)
+        w = np.ones(n_total)
+        idx = int(rs.choice(n_total, p=w / w.sum()))
+    return idx
+
+
+def kmeans_init_labels(X, K, rs, max_iter=300, tol=1e-4, group=None, n_total=None, n_before=0, host_sampling=False):
+    """``KMeans(n_clusters=K, n_init=1, random_state=rs).fit(X).labels_`` on the device, optionally with the rows
+    partitioned over the ranks of `group` (this rank holds rows n_before .. n_before + n of n_total; every rank passes
+    an identical `rs`).  X: (n,d) CUDA tensor (not modified).  The host keeps the RandomState stream only; k-means++
+    sampling, greedy choice, Lloyd updates and stopping rules are kernels, the host reads one small flag block per
+    centre / per batch of Lloyd iterations.  A k-means++ draw the device cannot decide provably the way numpy's
+    sequential cumsum does (kmpx_kpp_sample) is repeated on the host with numpy's own expressions; host_sampling=True
+    forces that path for every centre (tests).  Returns int32 CUDA labels of the local rows, the Lloyd iteration count,
+    the data mean (CUDA, (d,)) and a dict of counters."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     dev = X.device
-    f64, i32 = torch.float64, torch.int32
+    f64, i32, i64 = torch.float64, torch.int32, torch.int64
     n, d = X.shape
+    rk = _Ranks(group)
+    n_total = int(n_total if n_total is not None else n)
+    counts = [n] if rk.world == 1 else [int(v) for v in rk.gather(torch.tensor([n], dtype=i64, device=dev)).view(-1).tolist()]
     st = _lib.stream()
-    ws_bytes = max(int(lib.kmpx_gmm_workspace_bytes(int(n), d, max(K, 1))), 148 * 4 * 8 * 8)
+    ws_bytes = max(int(lib.kmpx_gmm_workspace_bytes(int(n), d, max(K, 1))), 148 * 4 * 16 * 8,
+                   int(lib.kmpx_kpp_sample_workspace_bytes(int(n))))
     ws = torch.empty(ws_bytes // 8 + 1, dtype=f64, device=dev)
     F = 1 + d + d * (d + 1) // 2
     zeros_lab = torch.zeros(n, dtype=i32, device=dev)
-    # data mean and per-feature variance from one statistics pass (K=1)
+    # ---- data mean, centring, per-feature variance -> Lloyd tolerance (sklearn/cluster/_kmeans.py:1486-1496, 285-295)
     st1 = torch.zeros(F + 1, dtype=f64, device=dev)
     _lib.call('kmpx_gmm_label_stats', _lib.ptr(X), n, d, 1, None, _lib.ptr(zeros_lab), _lib.ptr(st1), _lib.ptr(ws), ws_bytes, st)
-    s1 = st1.cpu().numpy()
-    mean = s1[1:1 + d] / n
+    rk.sum_(st1)
+    mean_dev = (st1[1:1 + d] / n_total).contiguous()
     Xc = X.clone()
     x_sq = torch.empty(n, dtype=f64, device=dev)
-    mean_dev = torch.as_tensor(mean, device=dev)
     _lib.call('kmpx_rows_center_sqnorm', _lib.ptr(Xc), n, d, _lib.ptr(mean_dev), _lib.ptr(x_sq), st)
     _lib.call('kmpx_gmm_label_stats', _lib.ptr(Xc), n, d, 1, None, _lib.ptr(zeros_lab), _lib.ptr(st1), _lib.ptr(ws), ws_bytes, st)
-    s1 = st1.cpu().numpy()
-    diag_idx = np.cumsum([0] + [d - i for i in range(d - 1)])
-    var = s1[1 + d + diag_idx] / n - (s1[1:1 + d] / n) ** 2
-    tol_abs = float(np.mean(var) * tol)
+    rk.sum_(st1)
+    diag_idx = torch.as_tensor(np.cumsum([0] + [d - i for i in range(d - 1)]) + 1 + d, device=dev)
+    var = st1[diag_idx] / n_total - (st1[1:1 + d] / n_total) ** 2
+    tol_dev = (var.mean() * tol).reshape(1).contiguous()
     # ---- k-means++ (sklearn/cluster/_kmeans.py:180-278)
-    n_trials = 2 + int(np.log(K))
-    w = np.ones(n)
-    center_ids = np.full(K, -1, dtype=np.int64)
-    center_ids[0] = rs.choice(n, p=w / w.sum())
-    cand = torch.as_tensor(np.array([center_ids[0]], dtype=np.int32), device=dev)
-    dist = torch.empty((max(n_trials, 1), n), dtype=f64, device=dev)
-    pot_dev = torch.empty(8, dtype=f64, device=dev)
-    _lib.call('kmpx_kpp_candidates', _lib.ptr(Xc), _lib.ptr(x_sq), n, d, _lib.ptr(cand), 1, None, _lib.ptr(dist),
-              _lib.ptr(pot_dev), _lib.ptr(ws), ws_bytes, st)
-    closest = dist[0].clone()
-    pot = float(pot_dev[0].item())
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    T = 2 + int(np.log(K))
+    gid0 = _first_center(rs, n_total)
+    U = rs.uniform(size=(max(K - 1, 1), T)) if K > 1 else np.zeros((1, T))
+    U_dev = torch.as_tensor(U, device=dev)
+    cand = torch.full((8,), -1, dtype=i64, device=dev)
+    flags = torch.zeros(9, dtype=i32, device=dev)           # [0:T] draws, [8] greedy choice
+    rows = torch.zeros((8, d + 2), dtype=f64, device=dev)
+    dist = torch.empty((T, n), dtype=f64, device=dev)
+    closest = [torch.empty(n, dtype=f64, device=dev), torch.empty(n, dtype=f64, device=dev)]
+    pot_l = torch.zeros((T, 2), dtype=f64, device=dev)
+    pot_dev = torch.zeros(1, dtype=f64, device=dev)
+    before = torch.zeros(2, dtype=f64, device=dev)
+    centers = torch.zeros((K, d), dtype=f64, device=dev)
+    center_ids = torch.full((K,), -1, dtype=i64, device=dev)
+    best = torch.zeros(1, dtype=i32, device=dev)
+    info = {'kpp_host_draws': 0, 'kpp_host_choices': 0, 'lloyd_relocations': 0}
+
+    def local_of(gids):
+        """global row indices -> this rank's local indices (-1: another rank owns the row)"""
+        g = np.asarray(gids, dtype=np.int64)
+        loc = np.where((g >= n_before) & (g < n_before + n), g - n_before, -1)
+        out = np.full(8, -1, dtype=np.int64)
+        out[:len(loc)] = loc
+        return torch.as_tensor(out, device=dev)
+
+    def evaluate(cand_t, t_cnt, cur):
+        """candidate rows -> everybody; distances / per-rank potentials of this rank's rows"""
+        _lib.call('kmpx_kpp_gather_rows', _lib.ptr(Xc), d, _lib.ptr(cand_t), t_cnt, n_before, _lib.ptr(rows), st)
+        rk.sum_(rows)
+        _lib.call('kmpx_kpp_candidates_rows', _lib.ptr(Xc), _lib.ptr(x_sq), n, d, _lib.ptr(rows), t_cnt,
+                  _lib.ptr(closest[cur]) if cur is not None else None, _lib.ptr(dist), _lib.ptr(pot_l), _lib.ptr(ws), ws_bytes, st)
+        return rk.gather(pot_l[:t_cnt].contiguous())
+
+    def choose(pots, t_cnt, c, nxt, force=-1):
+        _lib.call('kmpx_kpp_choose', _lib.ptr(pots), rk.world, t_cnt, rk.rank, _lib.ptr(rows), d, c, n_total, force,
+                  _lib.ptr(dist), n, _lib.ptr(pot_dev), _lib.ptr(before), _lib.ptr(centers), _lib.ptr(center_ids),
+                  _lib.ptr(best), _lib.ptr(flags[8:]), _lib.ptr(closest[nxt]), st)
+
+    def host_choice(t_cnt):
+        """np.argmin(distance_to_candidates @ ones) with numpy's own product (_kmeans.py:241-245)"""
+        full = rk.gather_rows_host(dist[:t_cnt].t().contiguous(), counts)          # (n_total, T)
+        return int(np.argmin(full.T @ np.ones((n_total, 1))))
+
+    pots = evaluate(local_of([gid0]), 1, None)
+    choose(pots, 1, 0, 0)
+    cur = 0
+    host_ones = host_cum = None
     for c in range(1, K):
-        rand_vals = rs.uniform(size=n_trials) * pot
-        cum = np.cumsum(closest.cpu().numpy())
-        cids = np.searchsorted(cum, rand_vals)
-        np.clip(cids, None, n - 1, out=cids)
-        cand = torch.as_tensor(cids.astype(np.int32), device=dev)
-        _lib.call('kmpx_kpp_candidates', _lib.ptr(Xc), _lib.ptr(x_sq), n, d, _lib.ptr(cand), n_trials, _lib.ptr(closest),
-                  _lib.ptr(dist), _lib.ptr(pot_dev), _lib.ptr(ws), ws_bytes, st)
-        pots = pot_dev[:n_trials].cpu().numpy()
-        best = int(np.argmin(pots))
-        pot = float(pots[best])
-        closest = dist[best].clone()
-        center_ids[c] = cids[best]
-    centers = Xc[torch.as_tensor(center_ids, device=dev)].contiguous()          # (K,d) gather of the chosen rows
+        nxt = 1 - cur
+        if not host_sampling:
+            _lib.call('kmpx_kpp_sample', _lib.ptr(closest[cur]), n, _lib.ptr(U_dev[c - 1]), T, _lib.ptr(pot_dev), _lib.ptr(before),
+                      n_before, n_total, int(rk.rank == rk.world - 1), _lib.ptr(cand), _lib.ptr(flags), _lib.ptr(ws), ws_bytes, st)
+            pots = evaluate(cand, T, cur)                    # speculative: queued before the flags are read
+            choose(pots, T, c, nxt)
+            fl = rk.sum_(flags.clone()).cpu().numpy() if rk.world > 1 else flags.cpu().numpy()
+            redraw = bool(fl[:T].any())
+        else:
+            redraw, fl = True, None
+        if redraw:
+            # the draw lies within numpy's own rounding uncertainty: numpy's expressions decide (_kmeans.py:227-233)
+            info['kpp_host_draws'] += 1
+            full = rk.gather_rows_host(closest[cur], counts)
+            if host_ones is None:
+                host_ones, host_cum = np.ones(n_total), np.empty(n_total)
+            rand_vals = U[c - 1] * (full @ host_ones)
+            cids = np.searchsorted(np.cumsum(full, out=host_cum), rand_vals)
+            np.clip(cids, None, n_total - 1, out=cids)
+            pots = evaluate(local_of(cids), T, cur)
+            choose(pots, T, c, nxt)
+            fl = rk.sum_(flags.clone()).cpu().numpy() if rk.world > 1 else flags.cpu().numpy()
+        if fl[8]:
+            info['kpp_host_choices'] += 1
+            choose(pots, T, c, nxt, force=host_choice(T))
+        cur = nxt
     # ---- Lloyd (sklearn/cluster/_kmeans.py:630-758)
+    ev[1].record()
     labels = torch.full((n,), -1, dtype=i32, device=dev)
     labels_new = torch.empty(n, dtype=i32, device=dev)
     n_changed = torch.zeros(1, dtype=i32, device=dev)
     stats = torch.zeros(stats_len(K, d), dtype=f64, device=dev)
-    strict = False
-    n_iter = 0
-    for it in range(max_iter):
-        n_changed.zero_()
+    state = torch.zeros(4, dtype=i32, device=dev)
+    batch = 1 if n * K >= 20_000_000 else 8
+
+    def iteration():
+        nonlocal labels, labels_new
         _lib.call('kmpx_kmeans_assign', _lib.ptr(Xc), n, d, K, _lib.ptr(centers), _lib.ptr(labels), _lib.ptr(labels_new),
                   _lib.ptr(n_changed), st)
         _lib.call('kmpx_gmm_label_stats', _lib.ptr(Xc), n, d, K, None, _lib.ptr(labels_new), _lib.ptr(stats), _lib.ptr(ws),
                   ws_bytes, st)
-        sh = stats.cpu().numpy()[:-1].reshape(K, F)
-        cnt = sh[:, 0].copy()
-        sums = sh[:, 1:1 + d].copy()
-        old = centers.cpu().numpy()
-        if np.any(cnt == 0):
-            sums, cnt = _relocate_empty(Xc, labels_new, old, sums, cnt)
-        new = np.empty_like(old)
-        amax = int(np.argmax(cnt))
-        for j in range(K):
-            new[j] = sums[j] * (1.0 / cnt[j]) if cnt[j] > 0 else np.nan
-        for j in range(K):
-            if not cnt[j] > 0:
-                new[j] = new[amax]
-        shift_tot = float(((new - old) ** 2).sum())
-        centers = torch.as_tensor(new, device=dev)
+        stats[-1:].copy_(n_changed)                           # travels with the sums through the one all-reduce
+        rk.sum_(stats)
+        _lib.call('kmpx_lloyd_update', _lib.ptr(stats), K, d, _lib.ptr(centers), _lib.ptr(tol_dev), _lib.ptr(stats[-1:]),
+                  _lib.ptr(n_changed), int(max_iter), _lib.ptr(state), st)
         labels, labels_new = labels_new, labels
-        n_iter = it + 1
-        if int(n_changed.item()) == 0:
-            strict = True
+
+    while True:
+        for _ in range(batch):
+            iteration()
+        s_host = state.cpu().numpy()
+        if s_host[3]:
+            # an empty cluster (rare): this iteration's update is done on the host with sklearn's relocation rule.
+            # The surplus iterations of the batch were no-ops, so labels / stats are those of the flagged iteration,
+            # except for the label-change count, which is recovered from one more assignment against the kept labels
+            info['lloyd_relocations'] += 1
+            _lib.call('kmpx_kmeans_assign', _lib.ptr(Xc), n, d, K, _lib.ptr(centers), None, _lib.ptr(labels_new), None, st)
+            _lib.call('kmpx_gmm_label_stats', _lib.ptr(Xc), n, d, K, None, _lib.ptr(labels_new), _lib.ptr(stats), _lib.ptr(ws),
+                      ws_bytes, st)
+            stats[-1:].zero_()
+            rk.sum_(stats)
+            sh = stats.cpu().numpy()[:-1].reshape(K, F)
+            cnt, sums = sh[:, 0].copy(), sh[:, 1:1 + d].copy()
+            old = centers.cpu().numpy()
+            sums, cnt = _relocate_empty(Xc, labels_new, old, sums, cnt, rk, n_before)
+            new = np.empty_like(old)
+            amax = int(np.argmax(cnt))
+            for j in range(K):
+                new[j] = sums[j] * (1.0 / cnt[j]) if cnt[j] > 0 else np.nan
+            for j in range(K):
+                if not cnt[j] > 0:
+                    new[j] = new[amax]
+            centers.copy_(torch.as_tensor(new, device=dev))
+            it_done = int(s_host[1]) + 1
+            shift_tot = float(((new - old) ** 2).sum())
+            finished = shift_tot <= float(tol_dev.item()) or it_done >= max_iter
+            state.copy_(torch.tensor([int(finished), it_done, 0, 0], dtype=i32, device=dev))
+            labels, labels_new = labels_new, labels
+            batch = 1                                         # a relocating fit is checked every iteration from here on
+            if finished:
+                break
+            continue
+        if s_host[0]:
             break
-        if shift_tot <= tol_abs:
-            break
-    if not strict:
-        _lib.call('kmpx_kmeans_assign', _lib.ptr(Xc), n, d, K, _lib.ptr(centers), None, _lib.ptr(labels_new), None, st)
-        labels = labels_new
-    return labels, n_iter, mean_dev
+    n_iter = int(state[1].item())
+    # labels of the final centres (equal to the last assignment after strict convergence, sklearn's extra E-step otherwise)
+    _lib.call('kmpx_kmeans_assign', _lib.ptr(Xc), n, d, K, _lib.ptr(centers), None, _lib.ptr(labels_new), None, st)
+    ev[2].record(); ev[2].synchronize()
+    info.update(center_ids=center_ids, kpp_ms=ev[0].elapsed_time(ev[1]), lloyd_ms=ev[1].elapsed_time(ev[2]))
+    return labels_new, n_iter, mean_dev, info
 
 
-def _relocate_empty(Xc, labels, centers_old, sums, cnt):
+def _relocate_empty(Xc, labels, centers_old, sums, cnt, rk=None, n_before=0):
     """sklearn's _relocate_empty_clusters_dense (_k_means_common.pyx:167-211): an empty cluster takes the sample
-    farthest from its own centre.  Rare; the distances are one fused device expression."""
+    farthest from its own centre.  Rare; the distances are one fused device expression, with row-partitioned data
+    every rank contributes its local top candidates and all ranks apply the same global selection."""
     torch = _lib.require_cuda()
     empty = np.where(cnt == 0)[0]
     c_old = torch.as_tensor(centers_old, device=Xc.device)
     d2 = ((Xc - c_old[labels.long()]) ** 2).sum(dim=1)
-    if float(d2.max().item()) == 0.0:
+    k = min(len(empty), d2.numel())
+    top = torch.topk(d2, k)
+    rec = torch.zeros((len(empty), Xc.shape[1] + 3), dtype=torch.float64, device=Xc.device)     # [d2, global row, label, x]
+    rec[:k, 0] = top.values
+    rec[:k, 1] = (top.indices + n_before).double()
+    rec[:k, 2] = labels[top.indices].double()
+    rec[:k, 3:] = Xc[top.indices]
+    if rk is not None and rk.world > 1:
+        rec[k:, 0] = -1.0
+        rec = rk.gather(rec).reshape(-1, rec.shape[1])
+    rec = rec.cpu().numpy()
+    order = np.lexsort((rec[:, 1], -rec[:, 0]))[:len(empty)]       # farthest first, ties by global row index
+    rec = rec[order]
+    if rec[0, 0] == 0.0:
         return sums, cnt
-    far = torch.topk(d2, len(empty)).indices.cpu().numpy()
-    lab = labels.cpu().numpy()
-    Xh = Xc[torch.as_tensor(far, device=Xc.device)].cpu().numpy()
-    for e, f, x in zip(empty, far, Xh):
-        old = lab[f]
+    for e, r in zip(empty, rec):
+        old, x = int(r[2]), r[3:]
         sums[old] -= x
         sums[e] = x
         cnt[e] = 1.0
@@ -327,20 +493,36 @@ class GaussianMixtureModel:
         """data: (n_samples, n_features).  Same result as sklearn's GaussianMixture(random_state=420).fit."""
         torch = _lib.require_cuda()
         data = np.ascontiguousarray(data, dtype=np.float64)
-        n, d = data.shape
+        self.fit_device(torch.as_tensor(data, device='cuda'))
+
+    def fit_device(self, X, group=None, n_total=None, n_before=0, timings=None) -> None:
+        """fit() on a CUDA tensor X (n, d); with `group` the rows are partitioned over its ranks (this rank holds rows
+        n_before .. n_before + n of n_total): k-means initialisation and EM exchange only packed sums over NCCL, every
+        rank ends with identical parameters.  timings: optional dict that receives the device times of init / EM."""
+        torch = _lib.require_cuda()
+        n, d = X.shape
         K = self.n_components
-        if n < K:
-            raise ValueError(f"Expected n_samples >= n_components but got n_components = {K}, n_samples = {n}")
+        n_total = int(n_total if n_total is not None else n)
+        if n_total < K:
+            raise ValueError(f"Expected n_samples >= n_components but got n_components = {K}, n_samples = {n_total}")
         if not 1 <= d <= 8 or not 1 <= K <= 128:
             raise ValueError(f"the device EM kernels cover 1 <= n_features <= 8 and 1 <= n_components <= 128 "
                              f"(got n_features = {d}, n_components = {K})")
         self.n_features = d
-        X = torch.as_tensor(data, device='cuda')
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timings is not None else None
+        if ev:
+            ev[0].record()
         rs = np.random.RandomState(420)
-        labels, _, shift = kmeans_init_labels(X, K, rs)
-        eng = EMEngine(X, K, self.diag_reg_factor, shift=shift)
+        labels, km_iter, shift, km_info = kmeans_init_labels(X, K, rs, group=group, n_total=n_total, n_before=n_before)
+        if ev:
+            ev[1].record()
+        eng = EMEngine(X, K, self.diag_reg_factor, shift=shift, group=group, n_total=n_total)
         eng.init_from_labels(labels)
         n_iter, lower, converged = eng.run(tol=1e-3, max_iter=100)
+        if ev:
+            ev[2].record(); ev[2].synchronize()
+            timings.update(init_ms=ev[0].elapsed_time(ev[1]), em_ms=ev[1].elapsed_time(ev[2]), kmeans_iterations=km_iter,
+                           em_iterations=n_iter, **{k: v for k, v in km_info.items() if k != 'center_ids'})
         m = self.model
         m.weights_ = eng.weights.cpu().numpy()
         m.means_ = eng.means.cpu().numpy()

@@ -193,6 +193,16 @@ def em_partitioned(rank, world, dev, dgemm_tflops, n=10_000_000, K=64, d=7, iter
            'tflops_8d': flops / ms * 1e-9, 'frac_fp64': flops / ms * 1e-9 / (dgemm_tflops * world) if dgemm_tflops else None,
            'frac_hbm': 8.0 * n * d / ms * 1e-6 / (peaks() * world),
            'loglik_per_row': float(eng.stats[-1].item()) / n, 'info_max': int(eng.info.abs().max().item())}
+    # GaussianMixtureModel.fit end to end on the same rows (k-means++ / Lloyd initialisation + EM to sklearn's
+    # convergence rule), device times of the two stages
+    from .mixture import GaussianMixtureModel
+    gm = GaussianMixtureModel(n_components=K, diag_reg_factor=1e-6)
+    gm.logger.disabled = True
+    tm = {}
+    gm.fit_device(X[lo:hi], group=dist.group.WORLD if world > 1 else None, n_total=n, n_before=lo, timings=tm)
+    tm['init_share'] = tm['init_ms'] / (tm['init_ms'] + tm['em_ms'])
+    tm['lower_bound'] = float(gm.model.lower_bound_)
+    out['fit_end_to_end'] = tm
     if world > 1:
         us = sorted(a.elapsed_time(b) * 1e3 for a, b in eng.allreduce_events)
         out['allreduce_us_median'] = us[len(us) // 2]

@@ -255,6 +255,25 @@ def test_inverse_gauss_jordan(T):
     assert int(info[0].item()) > 0
 
 
+def test_branch_free_exponentials_are_accurate_to_an_ulp_or_two(T):
+    """exp_nonpos / exp_tab (common.cuh) against the correctly rounded exp of mpmath-grade numpy long doubles."""
+    from kmp_demos_b200 import _lib
+    rng = np.random.default_rng(3)
+    x = np.concatenate([-rng.random(200000) * 50.0, -10.0 ** rng.uniform(-12, 2.8, 100000), rng.random(50000) * 20.0,
+                        [0.0, -0.0, -708.0, -707.9, -1e-320, -745.0, -1e4, -np.inf, np.nan]])
+    xd = T.as_tensor(x, device='cuda')
+    ref = np.exp(x.astype(np.longdouble))
+    for mode in (0, 1):
+        y = T.empty_like(xd)
+        _lib.call('kmpx_debug_exp', _lib.ptr(xd), _lib.ptr(y), x.size, mode, _lib.stream())
+        y = y.cpu().numpy()
+        ok = np.isfinite(x) & (x >= -708.0)
+        ulp = np.spacing(np.exp(x[ok]))
+        err = np.abs(y[ok].astype(np.longdouble) - ref[ok]) / ulp
+        assert float(err.max()) < 2.0, (mode, float(err.max()))
+        assert np.all(y[np.isfinite(x) & (x < -708.0)] == 0.0) and y[-2] == 0.0 and np.isnan(y[-1])
+
+
 def test_gmr_matches_reference(T, golden):
     from kmp_demos_b200.mixture import GaussianMixtureModel
     z = golden('small_cases.npz')

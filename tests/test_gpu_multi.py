@@ -60,6 +60,50 @@ def test_partitioned_em_with_nccl_allreduce_equals_single_gpu(tmp_path):
     assert out['err_means'] < 1e-12 and out['err_covs'] < 1e-12 and out['err_weights'] < 1e-12
 
 
+_WORKER_FIT = r'''
+import os, sys, json
+sys.path.insert(0, os.environ["KMP_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from kmp_demos_b200 import dist as kd, workloads as wl
+from kmp_demos_b200.mixture import GaussianMixtureModel
+rank, world, local = kd.init_process_group("nccl")
+dev = torch.device("cuda", local)
+z = np.load(os.path.join(os.environ["KMP_ROOT"], "tests", "golden", "gmm_synth.npz"))
+n, K = int(z["n"]), int(z["K"])
+X, _, _ = wl.cfg5_samples(n, K=K, d=7, seed=int(z["seed"]))
+lo, hi = kd.shard_range(n, rank, world)
+g = GaussianMixtureModel(n_components=K, diag_reg_factor=1e-6)
+g.logger.disabled = True
+g.fit_device(torch.as_tensor(X[lo:hi], device=dev), group=dist.group.WORLD, n_total=n, n_before=lo)
+rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+out = dict(n_iter=int(g.model.n_iter_), n_iter_ref=int(z["n_iter"]), err_priors=rel(g.priors, z["priors"]),
+           err_means=rel(g.means, z["means"]), err_covs=rel(g.covariances, z["covs"]))
+if rank == 0:
+    print("RESULT " + json.dumps(out))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_row_partitioned_fit_with_distributed_kmeans_init_equals_sklearn(tmp_path):
+    """GaussianMixtureModel.fit_device on rows split over 2 GPUs (k-means++ / Lloyd / EM exchange packed sums only)
+    reproduces the reference wrapper's sklearn fit of the whole data set: same EM iteration count, parameters
+    1e-9 / 1e-7."""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    script = tmp_path / 'worker_fit.py'
+    script.write_text(_WORKER_FIT)
+    env = dict(os.environ, KMP_ROOT=ROOT, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+                        '127.0.0.1', '--master-port', '29635', str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('RESULT ')][0][7:])
+    assert out['n_iter'] == out['n_iter_ref']
+    assert out['err_priors'] < 1e-9 and out['err_means'] < 1e-9 and out['err_covs'] < 1e-7
+
+
 _WORKER_F3 = r'''
 import os, sys, json
 sys.path.insert(0, os.environ["KMP_ROOT"])

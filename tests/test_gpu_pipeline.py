@@ -128,6 +128,22 @@ def test_gmm_fit_cfg5_shape_k64(golden):
     assert abs(gmm.bic(X) - float(z['bic'])) < 1e-9 * abs(float(z['bic']))
 
 
+def test_kmeans_init_device_sampling_equals_host_sampling(golden):
+    """k-means++ on the device (double-double prefix sums + provable-decision flags, kmpx_kpp_sample) picks the rows
+    numpy's sequential cumsum / searchsorted picks: same centre indices, Lloyd iteration count and labels as the path
+    that repeats every draw on the host with numpy's own expressions."""
+    import torch
+    from kmp_demos_b200.mixture import kmeans_init_labels
+    for (n, K, seed) in ((20000, 16, 3), (5003, 5, 11), (257, 64, 2)):
+        X, _, _ = wl.cfg5_samples(n, K=max(K, 8), d=7, seed=seed)
+        Xd = torch.as_tensor(X, device='cuda')
+        la, ia, _, fa = kmeans_init_labels(Xd, K, np.random.RandomState(420))
+        lb, ib, _, fb = kmeans_init_labels(Xd, K, np.random.RandomState(420), host_sampling=True)
+        assert torch.equal(fa['center_ids'], fb['center_ids']), (n, K)
+        assert ia == ib and torch.equal(la, lb)
+        assert fb['kpp_host_draws'] == K - 1 and fa['kpp_host_draws'] <= 1
+
+
 def test_cfg3_batch_vs_reference_and_vs_single(golden):
     """cfg 3 sample: batched adaptation == the reference's per-problem results; batch == one-by-one bit for bit."""
     from kmp_demos_b200.batch import KMPBatch
