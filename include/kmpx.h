@@ -53,7 +53,8 @@ int kmpx_debug_phases(long long* out_host, int reset);
  *   bit 1 (2)  skip the cp.async loads of k_potrf_small / k_trtri_small
  *   bit 2 (4)  skip the kappa panel fill of the fused predict;  bit 3 (8) skip its per-chunk reductions
  *   bit 4 (16) force the cp.async factor kernels instead of the TMA ones;  bit 5 (32) no L2 prefetch in the TMA factor kernels
- *   bit 6 (64) per-category timing printout of the blocked large-n Cholesky (host side) */
+ *   bit 6 (64) per-category timing printout of the blocked large-n Cholesky (host side)
+ *   bit 7 (128) route NT products through the cp.async GEMM instead of the TMA-fed persistent one (results stay correct) */
 int kmpx_debug_set(int flags);
 /* y[i] = exp(x[i]) through the branch-free exponentials of the hot kernels (mode 0: exp_nonpos, 1: table-driven exp_tab);
  * accuracy probe for the tests, x and y are device arrays. */

@@ -130,6 +130,10 @@ __global__ void __launch_bounds__(GTHREADS) k_dgemm(GemmArgs p) {
 
 int launch_dgemm(int transA, int transB, const GemmArgs& p, int batch, cudaStream_t st) {
     if (p.m <= 0 || p.n <= 0) return 0;
+    if (!transA && transB) {                       // NT: the TMA-fed persistent kernel when the operands qualify
+        const int rc = launch_dgemm_nt_tma(p, batch, st);
+        if (rc != 1) return rc;
+    }
     constexpr size_t smem = (size_t)GSTAGES * 2 * GTILE * sizeof(double);
     static bool attr_done[kMaxDevices] = {};          // the attribute is per device
     const int dev = current_device();

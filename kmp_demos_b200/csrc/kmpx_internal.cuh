@@ -40,6 +40,7 @@ bool predict_stream_applicable(const PredictArgs& p);
 int launch_predict_stream(PredictArgs& p, cudaStream_t st);
 
 int launch_dgemm(int transA, int transB, const GemmArgs& p, int batch, cudaStream_t st);
+int launch_dgemm_nt_tma(const GemmArgs& p, int batch, cudaStream_t st);   // 0 launched, 1 not applicable, else error
 int launch_potrf_small(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
                        int info_offset, int info_accumulate, cudaStream_t st);
 int launch_trtri_small(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, cudaStream_t st);

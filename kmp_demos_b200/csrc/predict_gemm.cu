@@ -1,8 +1,9 @@
 // K4 for one LARGE system (cfg 4 of BASELINE.json: N = 8192, n = 16384, 100 000 queries): the posterior covariance as
 // plain DMMA GEMMs instead of the fused streaming kernel.
-//   kappa[j][m] = k(s*_m, s_j)                              (N x Mc, once per chunk of Mc queries)
-//   V_a = Linv[a Ns :, a Ns : a Ns + N] * kappa             (k_dgemm, tri = 2: the operand is lower triangular, k-tiles
-//                                                            right of the diagonal tile are skipped)
+//   kappaT[m][j] = k(s*_m, s_j)                             (Mc x N, query-major, once per chunk of Mc queries)
+//   V_a = Linv[a Ns :, a Ns : a Ns + N] * kappaT^T          (NT product on the TMA-fed k_dgemm_nt_tma, tri = 2: the
+//                                                            operand is lower triangular, k-tiles right of the diagonal
+//                                                            tile are skipped)
 //   xi, Sigma: column reductions of V_a (.) V_b and V_a (.) w over the rows, two passes with a fixed order
 // The fused kernel (predict_stream.cu) regenerates the kappa tile for every 128-row tile of Linv and hands every
 // 16 columns over through a CTA barrier; here the same O^2 Ns^2 M flops run at the rate of k_dgemm (128 x 128 x 32
@@ -15,11 +16,12 @@ namespace kmpx {
 constexpr int PG_RB = 64;       // row blocks of the first reduction pass
 constexpr int PG_T = 128;       // queries per CTA of the reduction kernels
 
-__global__ void __launch_bounds__(256) k_pg_kappa(const double* s, int N, int I, const double* sq, int M, int ldk, double sigma_f, double* kappa) {
+// kappaT[m][j], m < Mc (rows beyond the M live queries are zero), j < ldk (columns beyond N are zero)
+__global__ void __launch_bounds__(256) k_pg_kappa(const double* s, int N, int I, const double* sq, int M, int Mc, int ldk, double sigma_f, double* kappa) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)N * ldk) return;
-    const int j = (int)(idx / ldk), m = (int)(idx - (long long)j * ldk);
-    kappa[idx] = m < M ? rbf(sq + (size_t)m * I, s + (size_t)j * I, I, sigma_f, 0.0, 0.0) : 0.0;
+    if (idx >= (long long)Mc * ldk) return;
+    const int m = (int)(idx / ldk), j = (int)(idx - (long long)m * ldk);
+    kappa[idx] = (m < M && j < N) ? rbf(sq + (size_t)m * I, s + (size_t)j * I, I, sigma_f, 0.0, 0.0) : 0.0;
 }
 
 // partial[rb][t][m] over the rows of block rb:  t = q00, (q01, q11,) mu0 (, mu1)
@@ -67,7 +69,7 @@ static long long pg_ws_doubles(int N, int O, int Mc) {
     const long long Ns = comp_stride(N), n = (long long)O * Ns, nt = O * (O + 1) / 2 + O;
     long long v = 0;
     for (int a = 0; a < O; ++a) v += (n - a * Ns) * Mc;
-    return (long long)N * Mc + v + (long long)PG_RB * nt * Mc;
+    return (long long)comp_stride(N) * Mc + v + (long long)PG_RB * nt * Mc;
 }
 
 }  // namespace kmpx
@@ -92,17 +94,18 @@ extern "C" int kmpx_kmp_predict_gemm(const double* F, int lda, const double* w, 
     while (Mc > PG_T && pg_ws_doubles(N, O, Mc) * (long long)sizeof(double) > ws_bytes) Mc -= PG_T;
     if (pg_ws_doubles(N, O, Mc) * (long long)sizeof(double) > ws_bytes) return fail_arg(13, "workspace too small (kmpx_kmp_predict_gemm_workspace_bytes)");
     double* kappa = ws;
-    double* V[2] = {kappa + (size_t)N * Mc, nullptr};
+    const int ldk = comp_stride(N);
+    double* V[2] = {kappa + (size_t)ldk * Mc, nullptr};
     if (O == 2) V[1] = V[0] + (size_t)n * Mc;
     double* partial = (O == 2 ? V[1] + (size_t)Ns * Mc : V[0] + (size_t)n * Mc);
     const int rows_per_block = ceil_div(n, PG_RB);
     for (int m_off = 0; m_off < M; m_off += Mc) {
         const int mc = M - m_off < Mc ? M - m_off : Mc;
-        k_pg_kappa<<<ceil_div((long long)N * Mc, 256), 256, 0, st>>>(s, N, I, sq + (size_t)m_off * I, mc, Mc, sigma_f, kappa);
+        k_pg_kappa<<<ceil_div((long long)ldk * Mc, 256), 256, 0, st>>>(s, N, I, sq + (size_t)m_off * I, mc, Mc, ldk, sigma_f, kappa);
         KMPX_TRY(check_launch("k_pg_kappa"));
         for (int a = 0; a < O; ++a) {
-            GemmArgs g{n - a * Ns, Mc, N, 1.0, F + (size_t)a * Ns * lda + (size_t)a * Ns, lda, 0, kappa, Mc, 0, 0.0, V[a], Mc, 0, 2};
-            KMPX_TRY(launch_dgemm(0, 0, g, 1, st));
+            GemmArgs g{n - a * Ns, Mc, N, 1.0, F + (size_t)a * Ns * lda + (size_t)a * Ns, lda, 0, kappa, ldk, 0, 0.0, V[a], Mc, 0, 2};
+            KMPX_TRY(launch_dgemm(0, 1, g, 1, st));
         }
         dim3 grid(Mc / PG_T, PG_RB);
         if (O == 1) k_pg_reduce<1><<<grid, PG_T, 0, st>>>(V[0], nullptr, w, n, Ns, Mc, rows_per_block, partial);

@@ -120,6 +120,52 @@ def test_dgemm_triangular_modes(T):
     assert rel_err(Cd.cpu().numpy(), A2 @ Bl) < 1e-13
 
 
+def test_dgemm_nt_tma_persistent_batched_and_triangular(T):
+    """The TMA-fed persistent NT kernel (dgemm_tma.cu): more tiles than SMs, ragged edges, ring wrap-around (k = 300),
+    strided batch, lower-tile mode (tri = 1) and triangular-operand mode (tri = 2), beta = 0 and beta != 0; the debug
+    flag 128 routes the same call through the cp.async kernel, which must agree to rounding."""
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(7)
+    g = T.Generator(device='cuda'); g.manual_seed(5)
+    m, n, k = 2065, 1930, 300
+    A = T.randn((m, k), generator=g, dtype=T.float64, device='cuda'); B = T.randn((n, k), generator=g, dtype=T.float64, device='cuda')
+    C0 = T.randn((m, n), generator=g, dtype=T.float64, device='cuda')
+    C = C0.clone()
+    _lib.call('kmpx_dgemm', 0, 1, m, n, k, 0.75, _lib.ptr(A), k, 0, _lib.ptr(B), k, 0, 2.0, _lib.ptr(C), n, 0, 1, 0, _lib.stream())
+    ref = 0.75 * A @ B.T + 2.0 * C0
+    assert float((C - ref).abs().max() / ref.abs().max()) < 1e-13
+    lib.kmpx_debug_set(128)
+    C2 = C0.clone()
+    _lib.call('kmpx_dgemm', 0, 1, m, n, k, 0.75, _lib.ptr(A), k, 0, _lib.ptr(B), k, 0, 2.0, _lib.ptr(C2), n, 0, 1, 0, _lib.stream())
+    lib.kmpx_debug_set(0)
+    assert float((C - C2).abs().max() / ref.abs().max()) < 1e-14
+    # strided batch, beta = 0
+    nb, mb, kb = 5, 260, 72
+    Ab = T.randn((nb, mb, kb), generator=g, dtype=T.float64, device='cuda'); Bb = T.randn((nb, 200, kb), generator=g, dtype=T.float64, device='cuda')
+    Cb = T.full((nb, mb, 200), float('nan'), dtype=T.float64, device='cuda')
+    _lib.call('kmpx_dgemm', 0, 1, mb, 200, kb, 1.0, _lib.ptr(Ab), kb, mb * kb, _lib.ptr(Bb), kb, 200 * kb, 0.0, _lib.ptr(Cb), 200, mb * 200, nb, 0,
+              _lib.stream())
+    refb = T.bmm(Ab, Bb.transpose(1, 2))
+    assert float((Cb - refb).abs().max() / refb.abs().max()) < 1e-13
+    # tri = 1: lower tiles of a symmetric rank-k update, rectangular tail (m > n)
+    m1, n1 = 1500, 1100
+    P = T.randn((m1, 256), generator=g, dtype=T.float64, device='cuda')
+    S0 = T.randn((m1, n1), generator=g, dtype=T.float64, device='cuda'); S = S0.clone()
+    _lib.call('kmpx_dgemm', 0, 1, m1, n1, 256, -1.0, _lib.ptr(P), 256, 0, _lib.ptr(P), 256, 0, 1.0, _lib.ptr(S), n1, 0, 1, 1, _lib.stream())
+    refs = S0 - P @ P[:n1].T
+    low = T.tril(T.ones((m1, n1), dtype=T.bool, device='cuda'))
+    assert float(((S - refs) * low).abs().max() / refs.abs().max()) < 1e-13
+    # tri = 2: lower-triangular A (explicit zeros above the diagonal), k range cut at the diagonal tile
+    mt = 1000
+    Lw = T.tril(T.randn((mt, mt), generator=g, dtype=T.float64, device='cuda'))
+    Kt = T.randn((384, mt), generator=g, dtype=T.float64, device='cuda')
+    V = T.empty((mt, 384), dtype=T.float64, device='cuda')
+    _lib.call('kmpx_dgemm', 0, 1, mt, 384, mt, 1.0, _lib.ptr(Lw), mt, 0, _lib.ptr(Kt), mt, 0, 0.0, _lib.ptr(V), 384, 0, 1, 2, _lib.stream())
+    refv = Lw @ Kt.T
+    assert float((V - refv).abs().max() / refv.abs().max()) < 1e-13
+
+
 def _spd(rng, n):
     M = rng.normal(size=(n, n))
     return M @ M.T / n + np.eye(n)
