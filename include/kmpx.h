@@ -124,7 +124,7 @@ int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kin
                      double sigma_f, double alpha_kmp, int time_driven,
                      double* xi, double* sigma_out, void* stream);
 /* The same prediction for ONE large system (n > KMPX_SMALL_MAX, plain kernel, O <= 2, symmetric factor) as DMMA GEMMs:
- * kappa (N x Mc) once per chunk of queries, V_a = Linv[a Ns:, a Ns: a Ns + N] kappa with kmpx_dgemm's triangular mode,
+ * kappa^T (Mc x N) once per chunk of queries, V_a = Linv[a Ns:, a Ns: a Ns + N] kappa with kmpx_dgemm's triangular mode,
  * column reductions for xi / sigma.  F as left by kmpx_trtri for n > KMPX_SMALL_MAX (strict upper triangle zero).
  * The workspace decides the chunk size Mc (a multiple of 128; 8192 queries of cfg 4 need 2.2 GB). */
 long long kmpx_kmp_predict_gemm_workspace_bytes(int N, int O, int Mc);
@@ -276,7 +276,9 @@ int kmpx_quat_from_rotvec(const double* r, double* q, long long M, void* stream)
 /* ---- dense fp64 GEMM on DMMA (the building block of the blocked factorisations; exported for tests and
  *      for the lazily materialised `_estimator`).  C = alpha*op(A)*op(B) + beta*C, row-major, strided batch.
  *      tri: 0 none; 1 compute only tiles with row >= col of C (SYRK-like); 2 op(A) is lower-triangular
- *      (skip k > row); 3 op(B) is lower-triangular (skip k < col).  */
+ *      (skip k > row); 3 op(B) is lower-triangular (skip k < col); 4 (NT form only) B [n][k] is lower-triangular with
+ *      explicit zeros above the diagonal (skip k > col).  The NT form runs on a TMA-fed persistent kernel when rows and
+ *      batches are 16-byte aligned (dgemm_tma.cu), everything else on the cp.async kernel (dgemm.cu).  */
 int kmpx_dgemm(int transA, int transB, int m, int n, int k, double alpha, const double* A, int lda,
                long long strideA, const double* B, int ldb, long long strideB, double beta, double* C,
                int ldc, long long strideC, int batch, int tri, void* stream);

@@ -170,9 +170,10 @@ extern "C" int kmpx_dgemm(int transA, int transB, int m, int n, int k, double al
     if ((strideA & 1) || (strideB & 1)) return fail_arg(9, "batch strides must be even");
     if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return fail_arg(7, "A and B must be 16-byte aligned");
     if (batch <= 0 || batch > 65535) return fail_arg(17, "batch must be in 1..65535");
-    if (tri < 0 || tri > 3) return fail_arg(18, "tri must be in 0..3");
+    if (tri < 0 || tri > 4) return fail_arg(18, "tri must be in 0..4");
+    if (tri == 4 && !(transB && !transA)) return fail_arg(18, "tri=4 needs the NT form");
     if (tri == 2 && transA) return fail_arg(18, "tri=2 needs op(A)=A");
     if (tri == 3 && transB) return fail_arg(18, "tri=3 needs op(B)=B");
-    GemmArgs p{m, n, k, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC, tri};
+    GemmArgs p{m, n, k, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC, tri, 0};
     return launch_dgemm(transA, transB, p, batch, (cudaStream_t)stream);
 }

@@ -47,8 +47,10 @@ __device__ __forceinline__ void tile_coords(const TmaGemmArgs& p, int t, int& tm
         tm = tri_rows + u / p.tiles_n; tn = u - (u / p.tiles_n) * p.tiles_n;
     }
 }
-__device__ __forceinline__ int tile_k_tiles(const TmaGemmArgs& p, int tm) {
-    const int kend = p.tri == 2 ? min(p.k, (tm + 1) * HBM_) : p.k;
+__device__ __forceinline__ int tile_k_tiles(const TmaGemmArgs& p, int tm, int tn) {
+    // tri = 2: A lower triangular (k <= row);  tri = 4: B lower triangular (B[n][k] = 0 for k > n, the transposed
+    // inverse of a Cholesky block): the k range ends at the diagonal tile of the triangular operand
+    const int kend = p.tri == 2 ? min(p.k, (tm + 1) * HBM_) : (p.tri == 4 ? min(p.k, (tn + 1) * HBN) : p.k);
     return (kend + HBK - 1) / HBK;
 }
 
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) k_dgemm_nt_tma(const __grid_const
             const int z = t / p.tiles_per_mat;
             int tm, tn;
             tile_coords(p, t - z * p.tiles_per_mat, tm, tn);
-            const int nk = tile_k_tiles(p, tm);
+            const int nk = tile_k_tiles(p, tm, tn);
             for (int kt = 0; kt < nk; ++kt) {
                 if (wrapped) mbar_wait(empty0 + 8 * stage, par ^ 1);
                 const uint32_t bar = full0 + 8 * stage;
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) k_dgemm_nt_tma(const __grid_const
         int tm, tn;
         tile_coords(p, t - z * p.tiles_per_mat, tm, tn);
         const int m0 = tm * HBM_, n0 = tn * HBN;
-        const int nk = tile_k_tiles(p, tm);
+        const int nk = tile_k_tiles(p, tm, tn);
         double* C = p.C + (size_t)z * p.strideC;
         const bool interior = vec_ok && m0 + HBM_ <= p.m && n0 + HBN <= p.n;
         if (p.beta != 0.0 && interior) {
@@ -208,7 +210,8 @@ static int make_operand_map(CUtensorMap* map, const double* A, int ld, long long
 }
 
 // The NT product through the TMA kernel when the operands qualify (16-byte aligned rows and batches, tri in {0,1,2});
-// returns 1 when the caller has to take the cp.async kernel instead.
+// returns 1 when the caller has to take the cp.async kernel instead.  tri = 4 (B lower triangular) exists only here: the
+// cp.async kernel treats it as a dense product (the skipped k-tiles hold zeros).
 int launch_dgemm_nt_tma(const GemmArgs& g, int batch, cudaStream_t st) {
     if (g_host_dbg & 128) return 1;
     if (g.tri == 3 || g.k < 8 || g.m < 8 || g.n < 8) return 1;
@@ -230,7 +233,9 @@ int launch_dgemm_nt_tma(const GemmArgs& g, int batch, cudaStream_t st) {
     p.tiles_total = (int)total;
     static SmemCache cache;
     KMPX_TRY(ensure_dyn_smem(k_dgemm_nt_tma, HSMEM, cache, "k_dgemm_nt_tma"));
-    const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
+    int sms = num_sms() - (g.reserve_sms > 0 ? g.reserve_sms : 0);
+    if (sms < 1) sms = 1;
+    const int grid = p.tiles_total < sms ? p.tiles_total : sms;
     k_dgemm_nt_tma<<<grid, HTHREADS, HSMEM, st>>>(mapA, mapB, p);
     return check_launch("k_dgemm_nt_tma");
 }

@@ -86,15 +86,19 @@ static int potrf_large(double* A, int lda, int n, int* info, double* ws, cudaStr
         const int m = n - k - nb;
         if (m <= 0) break;
         double* A21 = A + (size_t)(k + nb) * lda + k;
-        GemmArgs g1{m, nb, nb, 1.0, A21, lda, 0, Dinv[step & 1], LNB, 0, 0.0, panel, LNB, 0, 0};
+        GemmArgs g1{m, nb, nb, 1.0, A21, lda, 0, Dinv[step & 1], LNB, 0, 0.0, panel, LNB, 0, 4};   // Dinv is lower triangular with zeros above
         mark();
-        KMPX_TRY(launch_dgemm(0, 1, g1, 1, st));                               // panel = A21 * Dinv^T
+        KMPX_TRY(launch_dgemm(0, 1, g1, 1, st));                               // panel = A21 * Dinv^T (dense copy)
         mark();
-        KMPX_TRY(copy_block(panel, LNB, A21, lda, m, nb, st));
+        // L21 itself goes back into A on the side stream, off the critical path: nothing reads A21 again before the
+        // factorisation is complete (the trailing updates take the dense panel)
+        KMPX_TRY(check_cuda(cudaEventRecord(g_side.ev_main, st), "cudaEventRecord"));
+        KMPX_TRY(check_cuda(cudaStreamWaitEvent(g_side.s, g_side.ev_main, 0), "cudaStreamWaitEvent"));
+        KMPX_TRY(copy_block(panel, LNB, A21, lda, m, nb, g_side.s));
         mark();
         double* A22 = A + (size_t)(k + nb) * lda + k + nb;
         const int nb2 = m < LNB ? m : LNB;
-        GemmArgs g2{m, nb2, nb, -1.0, panel, LNB, 0, panel, LNB, 0, 1.0, A22, lda, 0, 1};
+        GemmArgs g2{m, nb2, nb, -1.0, panel, LNB, 0, panel, LNB, 0, 1.0, A22, lda, 0, 1, 4};
         KMPX_TRY(launch_dgemm(0, 1, g2, 1, st));                               // look-ahead: next block column
         mark();
         KMPX_TRY(check_cuda(cudaEventRecord(g_side.ev_main, st), "cudaEventRecord"));
@@ -104,7 +108,9 @@ static int potrf_large(double* A, int lda, int n, int* info, double* ws, cudaStr
         if (m > nb2) {
             const int m2 = m - nb2;
             double* P2 = panel + (size_t)nb2 * LNB;
-            GemmArgs g3{m2, m2, nb, -1.0, P2, LNB, 0, P2, LNB, 0, 1.0, A22 + (size_t)nb2 * lda + nb2, lda, 0, 1};
+            // the persistent GEMM leaves a few SMs to the side stream's single-CTA factor / inverse kernels: a grid that
+            // holds every SM for the whole update would serialise them behind it
+            GemmArgs g3{m2, m2, nb, -1.0, P2, LNB, 0, P2, LNB, 0, 1.0, A22 + (size_t)nb2 * lda + nb2, lda, 0, 1, 4};
             KMPX_TRY(launch_dgemm(0, 1, g3, 1, st));                           // rest of the trailing update (lower tiles)
         }
         mark();

@@ -19,6 +19,7 @@ struct FactorArgs {
 struct GemmArgs {
     int m, n, k; double alpha; const double* A; int lda; long long strideA;
     const double* B; int ldb; long long strideB; double beta; double* C; int ldc; long long strideC; int tri;
+    int reserve_sms;           // persistent kernels leave this many SMs to concurrent streams (0 when omitted)
 };
 struct AlphaArgs {
     const double* F; int lda; long long strideA; const int* n_pts; int n_max, O, batch, layout;
