@@ -82,11 +82,80 @@ def factorise(s, xi, sigma, lam, sigma_f, time_driven, layout=_lib.LAYOUT_COMPON
                   _lib.ptr(w), lda, _lib.ptr(alpha), st)
         kind = 0
     else:
-        A = general_inverse(A, n, lda)
+        Ainv = None
+        if not force_general:
+            Ainv = _woodbury_inverse(A, s_dev, g_host, N, I, O, n, lda, lam, sigma_f, time_driven, layout)
+        A = Ainv if Ainv is not None else general_inverse(A, n, lda)
         _lib.call('kmpx_apply_inverse', _lib.ptr(A), lda, n * lda, None, N, O, 1, layout, _lib.ptr(y_dev),
                   _lib.ptr(w), lda, _lib.ptr(alpha), st)
         kind = 1
     return _Factorisation(A, lda, kind, w, alpha, s_dev, N, I, O)
+
+
+def _woodbury_inverse(A, s_dev, g_host, N, I, O, n, lda, lam, sigma_f, time_driven, layout, newton_steps=1):
+    """Inverse of a system whose covariance blocks are non-symmetric at a FEW points (the un-listed via-point covariance
+    of demos.py:251,285) without the O(n) sequential pivots of Gauss-Jordan: A = S + P W P^T with S the
+    system of the symmetrised blocks (Cholesky kernels: potrf, trtri, Linv^T Linv on the DMMA GEMM) and W = lam * skew
+    parts on the r = O * (#asymmetric points) rows P selects, so
+        A^-1 = S^-1 - S^-1 P W (I + P^T S^-1 P W)^-1 P^T S^-1          (r x r solve on the host),
+    followed by Newton-Schulz refinement X <- X + X (I - A X) against the full non-symmetric A, which restores the
+    accuracy of a backward-stable LU inverse (what numpy.linalg.inv delivers at KMP.py:157).  Returns None when the
+    symmetrised system is not positive definite or too many points are asymmetric (the caller falls back to
+    Gauss-Jordan).  A: the full non-symmetric system (n x lda, device); returns A^-1 in the same layout."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = A.device
+    st = _lib.stream()
+    skew = 0.5 * (g_host - np.transpose(g_host, (0, 2, 1)))
+    scale = float(np.max(np.abs(g_host)))
+    pts = np.where(np.max(np.abs(skew), axis=(1, 2)) > 1e-12 * scale)[0]
+    if len(pts) == 0 or len(pts) * O > 64:
+        return None
+    g_sym = torch.as_tensor(np.ascontiguousarray(g_host - skew), dtype=torch.float64, device=dev)
+    S = torch.empty((n, lda), dtype=torch.float64, device=dev)
+    _lib.call('kmpx_kernel_build', _lib.ptr(s_dev), _lib.ptr(g_sym), None, _lib.ptr(S), 1, N, I, O, lda, n * lda,
+              float(sigma_f), float(lam), int(bool(time_driven)), layout, _lib.UPLO_LOWER, st)
+    info = torch.zeros(1, dtype=torch.int32, device=dev)
+    nbytes = max(int(lib.kmpx_potrf_workspace_bytes(n, 1)), int(lib.kmpx_trtri_workspace_bytes(n, 1)))
+    ws = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=dev)
+    _lib.call('kmpx_potrf', _lib.ptr(S), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
+    if int(info.item()) != 0:
+        return None
+    _lib.call('kmpx_trtri', _lib.ptr(S), lda, n * lda, None, n, 1, _lib.ptr(ws), nbytes, st)
+    S[:, :n].tril_()                                               # small systems keep garbage above the diagonal
+    S[:, n:].zero_()
+    X = torch.zeros((n, lda), dtype=torch.float64, device=dev)
+    _lib.call('kmpx_dgemm', 1, 0, n, n, n, 1.0, _lib.ptr(S), lda, 0, _lib.ptr(S), lda, 0, 0.0, _lib.ptr(X), lda, 0, 1, 0, st)   # S^-1
+    # rows of the system the asymmetric points occupy, in the layout's order, and W on them
+    Ns = (N + 1) // 2 * 2
+    row_of = (lambda i, a: i * O + a) if layout == _lib.LAYOUT_POINT else (lambda i, a: a * Ns + i)
+    idx = np.array([row_of(int(i), a) for i in pts for a in range(O)], dtype=np.int64)
+    r = len(idx)
+    W = np.zeros((r, r))
+    for q, i in enumerate(pts):
+        W[q * O:(q + 1) * O, q * O:(q + 1) * O] = lam * skew[i]
+    idx_d = torch.as_tensor(idx, device=dev)
+    Sc = X[:, idx_d][:n].contiguous()                              # S^-1 P   (n x r)
+    Sr = X[idx_d, :].contiguous()                                  # P^T S^-1 (r x lda)
+    core = Sr[:, idx_d].cpu().numpy()                              # P^T S^-1 P
+    M = W @ np.linalg.inv(np.eye(r) + core @ W)
+    r2 = r + (r & 1)                                               # even leading dimensions for the GEMM
+    Mp = np.zeros((r2, r2)); Mp[:r, :r] = M
+    Scp = torch.zeros((n, r2), dtype=torch.float64, device=dev); Scp[:, :r] = Sc
+    left = torch.empty((n, r2), dtype=torch.float64, device=dev)
+    Md = torch.as_tensor(Mp, device=dev)
+    _lib.call('kmpx_dgemm', 0, 0, n, r2, r2, 1.0, _lib.ptr(Scp), r2, 0, _lib.ptr(Md), r2, 0, 0.0, _lib.ptr(left), r2, 0, 1, 0, st)
+    right = torch.zeros((r2, lda), dtype=torch.float64, device=dev)
+    right[:r] = Sr
+    _lib.call('kmpx_dgemm', 0, 0, n, n, r2, -1.0, _lib.ptr(left), r2, 0, _lib.ptr(right), lda, 0, 1.0, _lib.ptr(X), lda, 0, 1, 0, st)
+    R = torch.empty_like(X)
+    for _ in range(newton_steps):
+        R.zero_()
+        R[:, :n].fill_diagonal_(1.0)
+        _lib.call('kmpx_dgemm', 0, 0, n, n, n, -1.0, _lib.ptr(A), lda, 0, _lib.ptr(X), lda, 0, 1.0, _lib.ptr(R), lda, 0, 1, 0, st)
+        X0 = X.clone()
+        _lib.call('kmpx_dgemm', 0, 0, n, n, n, 1.0, _lib.ptr(X0), lda, 0, _lib.ptr(R), lda, 0, 1.0, _lib.ptr(X), lda, 0, 1, 0, st)
+    return X
 
 
 def general_inverse(A, n, lda, newton_steps=2):
