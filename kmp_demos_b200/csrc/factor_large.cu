@@ -41,8 +41,8 @@ static int copy_block(const double* src, int ld_src, double* dst, int ld_dst, in
     return check_launch("k_copy_block");
 }
 
-// workspace layout (doubles): Dinv[2] [LNB][LNB] | panel [n][LNB]
-static long long large_ws_doubles(int n) { return 2LL * LNB * LNB + (long long)round_up(n, 2) * LNB; }
+// workspace layout (doubles): Dinv[2] [LNB][LNB] | panel[2] [n][LNB]
+static long long large_ws_doubles(int n) { return 2LL * LNB * LNB + 2LL * round_up(n, 2) * LNB; }
 
 struct SideStream {
     cudaStream_t s = nullptr; cudaEvent_t ev_main = nullptr, ev_side = nullptr;
@@ -68,48 +68,57 @@ static int diag_factor(double* D, int lda, int nb, double* Dinv, int* info, int 
     return launch_trtri_small(Dinv, LNB, 0, nullptr, nb, 1, st);
 }
 
-// Right-looking blocked Cholesky with one step of look-ahead: while the bulk of the trailing update of step s runs
-// on the caller's stream, the next diagonal block is factorised and inverted (single-CTA kernels) on a side stream.
+// Right-looking blocked Cholesky with one step of look-ahead, two streams:
+//   main stream   look-ahead(s): block column s+1 of the trailing matrix -= P_s P_s^T      (m x 256, K = 256)
+//                 trailing(s):   the rest of the trailing matrix -= P_s P_s^T               (lower tiles, persistent GEMM
+//                                that leaves a few SMs to the side stream)
+//   side stream   after look-ahead(s): factor + invert the diagonal block s+1 (single-CTA kernels), then the panel
+//                 P_{s+1} = A21 * Dinv^T (into the other of two dense panel buffers) and the write-back of L21 into A.
+//                 The panel GEMM's CTAs are scheduled as the trailing update's persistent CTAs run out of tiles, i.e. it
+//                 fills the tail of trailing(s) instead of following it.
+// look-ahead(s+1) on the main stream waits for the side stream.
 static int potrf_large(double* A, int lda, int n, int* info, double* ws, cudaStream_t st) {
     double* Dinv[2] = {ws, ws + (size_t)LNB * LNB};
-    double* panel = ws + 2 * (size_t)LNB * LNB;
+    double* panel[2] = {ws + 2 * (size_t)LNB * LNB, ws + 2 * (size_t)LNB * LNB + (size_t)round_up(n, 2) * LNB};
     KMPX_TRY(g_side.ensure());
     if (info) { k_set_int<<<1, 32, 0, st>>>(info, 0, 1); KMPX_TRY(check_launch("k_set_int")); }
-    KMPX_TRY(diag_factor(A, lda, n < LNB ? n : LNB, Dinv[0], info, 0, st));
     // profiling aid (kmpx_debug_set bit 6): per-category device time on the caller's stream
     const bool prof = (g_host_dbg & 64) != 0;
     std::vector<cudaEvent_t> evs;
     auto mark = [&]() { if (prof) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); evs.push_back(e); } };
+    // diagonal block k, its inverse, the panel below it and the write-back of L21: everything step `step` needs before its
+    // look-ahead, on stream `s`
+    auto prepare = [&](int step, cudaStream_t s) -> int {
+        const int k = step * LNB;
+        const int nb = n - k < LNB ? n - k : LNB;
+        KMPX_TRY(diag_factor(A + (size_t)k * lda + k, lda, nb, Dinv[step & 1], info, k, s));
+        const int m = n - k - nb;
+        if (m <= 0) return 0;
+        double* A21 = A + (size_t)(k + nb) * lda + k;
+        GemmArgs g1{m, nb, nb, 1.0, A21, lda, 0, Dinv[step & 1], LNB, 0, 0.0, panel[step & 1], LNB, 0, 4, 0};   // Dinv: zeros above the diagonal
+        KMPX_TRY(launch_dgemm(0, 1, g1, 1, s));                                // P = A21 * Dinv^T (dense copy)
+        return copy_block(panel[step & 1], LNB, A21, lda, m, nb, s);          // L21 in place (nothing reads it again)
+    };
+    KMPX_TRY(prepare(0, st));
     int step = 0;
     for (int k = 0; k < n; k += LNB, ++step) {
         const int nb = n - k < LNB ? n - k : LNB;
         const int m = n - k - nb;
         if (m <= 0) break;
-        double* A21 = A + (size_t)(k + nb) * lda + k;
-        GemmArgs g1{m, nb, nb, 1.0, A21, lda, 0, Dinv[step & 1], LNB, 0, 0.0, panel, LNB, 0, 4};   // Dinv is lower triangular with zeros above
-        mark();
-        KMPX_TRY(launch_dgemm(0, 1, g1, 1, st));                               // panel = A21 * Dinv^T (dense copy)
-        mark();
-        // L21 itself goes back into A on the side stream, off the critical path: nothing reads A21 again before the
-        // factorisation is complete (the trailing updates take the dense panel)
-        KMPX_TRY(check_cuda(cudaEventRecord(g_side.ev_main, st), "cudaEventRecord"));
-        KMPX_TRY(check_cuda(cudaStreamWaitEvent(g_side.s, g_side.ev_main, 0), "cudaStreamWaitEvent"));
-        KMPX_TRY(copy_block(panel, LNB, A21, lda, m, nb, g_side.s));
-        mark();
+        double* P = panel[step & 1];
         double* A22 = A + (size_t)(k + nb) * lda + k + nb;
         const int nb2 = m < LNB ? m : LNB;
-        GemmArgs g2{m, nb2, nb, -1.0, panel, LNB, 0, panel, LNB, 0, 1.0, A22, lda, 0, 1, 4};
+        mark();
+        GemmArgs g2{m, nb2, nb, -1.0, P, LNB, 0, P, LNB, 0, 1.0, A22, lda, 0, 1, 4};
         KMPX_TRY(launch_dgemm(0, 1, g2, 1, st));                               // look-ahead: next block column
         mark();
         KMPX_TRY(check_cuda(cudaEventRecord(g_side.ev_main, st), "cudaEventRecord"));
         KMPX_TRY(check_cuda(cudaStreamWaitEvent(g_side.s, g_side.ev_main, 0), "cudaStreamWaitEvent"));
-        KMPX_TRY(diag_factor(A22, lda, nb2, Dinv[(step + 1) & 1], info, k + nb, g_side.s));
+        KMPX_TRY(prepare(step + 1, g_side.s));
         KMPX_TRY(check_cuda(cudaEventRecord(g_side.ev_side, g_side.s), "cudaEventRecord"));
         if (m > nb2) {
             const int m2 = m - nb2;
-            double* P2 = panel + (size_t)nb2 * LNB;
-            // the persistent GEMM leaves a few SMs to the side stream's single-CTA factor / inverse kernels: a grid that
-            // holds every SM for the whole update would serialise them behind it
+            double* P2 = P + (size_t)nb2 * LNB;
             GemmArgs g3{m2, m2, nb, -1.0, P2, LNB, 0, P2, LNB, 0, 1.0, A22 + (size_t)nb2 * lda + nb2, lda, 0, 1, 4};
             KMPX_TRY(launch_dgemm(0, 1, g3, 1, st));                           // rest of the trailing update (lower tiles)
         }
@@ -119,10 +128,10 @@ static int potrf_large(double* A, int lda, int n, int* info, double* ws, cudaStr
     }
     if (prof && !evs.empty()) {
         cudaStreamSynchronize(st);
-        double tot[6] = {0, 0, 0, 0, 0, 0};       // panel gemm, copy, look-ahead gemm, trailing gemm, wait for the side stream, (between steps)
-        for (size_t i = 0; i + 1 < evs.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); tot[i % 6] += ms; }
-        fprintf(stderr, "potrf_large n=%d: panel %.2f ms, copy %.2f, look-ahead %.2f, trailing %.2f, side wait %.2f, step gap %.2f\n", n,
-                tot[0], tot[1], tot[2], tot[3], tot[4], tot[5]);
+        double tot[4] = {0, 0, 0, 0};       // look-ahead gemm, trailing gemm, wait for the side stream, (between steps)
+        for (size_t i = 0; i + 1 < evs.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, evs[i], evs[i + 1]); tot[i % 4] += ms; }
+        fprintf(stderr, "potrf_large n=%d: look-ahead %.2f ms, trailing %.2f, side wait (diag + panel) %.2f, step gap %.2f\n", n,
+                tot[0], tot[1], tot[2], tot[3]);
         for (cudaEvent_t e : evs) cudaEventDestroy(e);
     }
     return 0;
