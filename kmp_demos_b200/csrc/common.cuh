@@ -181,6 +181,20 @@ __device__ __forceinline__ double rbf_fast(P1 s1, P2 s2, int I, double sigma_f) 
     return exp_nonpos(-sigma_f * r2);
 }
 
+// rbf_fast with the table-driven exponential (tab: fill_exp2_table in shared memory)
+template <typename P1, typename P2>
+__device__ __forceinline__ double rbf_tab(P1 s1, P2 s2, int I, double sigma_f, const double* tab) {
+    double r2;
+    if (I == 1) { const double d = fabs(s1[0] - s2[0]); r2 = d * d; }
+    else {
+        double acc = 0.0;
+        for (int t = 0; t < I; ++t) { const double d = s1[t] - s2[t]; acc += d * d; }
+        const double r = sqrt(acc);                            // norm first, then squared, as the reference does
+        r2 = r * r;
+    }
+    return exp_tab(-sigma_f * r2, tab);
+}
+
 // The coefficient block of one kernel evaluation: plain -> c[0]; time-driven -> c = {ktt, ktdt, kdtt, kdtdt}
 // by forward differences with dt = 1e-3 added to every input coordinate (KMP.py:113-123).
 template <typename P1, typename P2>

@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(256) k_kernel_build(BuildArgs p) {
 // division.  Each store is 16 bytes; for fixed (i, a, b) a warp writes 512 contiguous bytes.
 template <bool TD, bool BULK>
 __global__ void __launch_bounds__(256) k_kernel_build_comp(BuildArgs p) {
+    __shared__ double etab[kExpTabN];
+    if (!TD) { fill_exp2_table(etab, threadIdx.x, 256); __syncthreads(); }
     const int bidx = blockIdx.z;
     const int N = p.n_pts ? p.n_pts[bidx] : p.n_max;
     const int Ns = comp_stride(N);
@@ -114,8 +116,8 @@ __global__ void __launch_bounds__(256) k_kernel_build_comp(BuildArgs p) {
 #pragma unroll
         for (int r = 0; r < kBuildRows / 8; ++r) {
             const double* si = s + (size_t)min(ibase + warp + 8 * r, N - 1) * p.I;
-            pre[r][0] = rbf_fast(si, s + (size_t)min(j0, N - 1) * p.I, p.I, p.sigma_f);
-            pre[r][1] = rbf_fast(si, s + (size_t)min(j0 + 1, N - 1) * p.I, p.I, p.sigma_f);
+            pre[r][0] = rbf_tab(si, s + (size_t)min(j0, N - 1) * p.I, p.I, p.sigma_f, etab);
+            pre[r][1] = rbf_tab(si, s + (size_t)min(j0 + 1, N - 1) * p.I, p.I, p.sigma_f, etab);
         }
     }
 #pragma unroll (BULK ? kBuildRows / 8 : 1)
@@ -140,8 +142,8 @@ __global__ void __launch_bounds__(256) k_kernel_build_comp(BuildArgs p) {
                 if (BULK) { e0 = pre[r][0]; e1 = pre[r][1]; }
                 else {
                     const double* si = s + (size_t)i * p.I;
-                    e0 = rbf_fast(si, s + (size_t)j0 * p.I, p.I, p.sigma_f);
-                    e1 = rbf_fast(si, s + (size_t)min(j0 + 1, N - 1) * p.I, p.I, p.sigma_f);
+                    e0 = rbf_tab(si, s + (size_t)j0 * p.I, p.I, p.sigma_f, etab);
+                    e1 = rbf_tab(si, s + (size_t)min(j0 + 1, N - 1) * p.I, p.I, p.sigma_f, etab);
                 }
                 co[0][0] = e0;
                 co[1][0] = (j0 + 1 < N && (!lower || j0 + 1 <= i)) ? e1 : 0.0;

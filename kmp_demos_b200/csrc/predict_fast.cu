@@ -40,7 +40,7 @@ constexpr int QSTAGE_ELEMS = RC * QK;
 
 template <int O> struct FastCfg { static constexpr int NT = O * (O + 1) / 2 + O; };
 
-struct FastSmem { size_t rings, panel, racc, wsh, sqs, bars, total; };     // byte offsets from the 1 KB aligned base
+struct FastSmem { size_t rings, panel, racc, wsh, sqs, etab, bars, total; };     // byte offsets from the 1 KB aligned base
 __host__ __device__ inline FastSmem fast_smem_layout(int O, int I, int n_max_pts, int ldp) {
     const int nt = O * (O + 1) / 2 + O;
     const int n_sys_max = O * comp_stride(n_max_pts);
@@ -50,7 +50,8 @@ __host__ __device__ inline FastSmem fast_smem_layout(int O, int I, int n_max_pts
     L.racc = L.panel + (size_t)QT * ldp * 8;
     L.wsh = L.racc + (size_t)QWARPS * nt * QT * 8;
     L.sqs = L.wsh + (size_t)round_up(n_sys_max, 2) * 8;
-    L.bars = L.sqs + (size_t)round_up(QT * I, 2) * 8;
+    L.etab = L.sqs + (size_t)round_up(QT * I, 2) * 8;
+    L.bars = L.etab + (size_t)kExpTabN * 8;
     L.total = L.bars + (size_t)2 * QWARPS * QST * 8 + 1024 /* alignment slack */;
     return L;
 }
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
     double* racc = reinterpret_cast<double*>(base + lay.racc);          // [QWARPS][NT][QT]
     double* wsh = reinterpret_cast<double*>(base + lay.wsh);            // [n_sys_max]
     double* sqs = reinterpret_cast<double*>(base + lay.sqs);            // [QT][I]
+    double* etab = reinterpret_cast<double*>(base + lay.etab);          // [32] table of exp_tab
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + lay.bars);      // full[QWARPS][QST], empty[QWARPS][QST]
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + QWARPS * QST);
 
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
     }
     for (int idx = tid; idx < n_sys_max; idx += PTHREADS) wsh[idx] = idx < n ? w[idx] : 0.0;
     for (int idx = tid; idx < QWARPS * NT * QT; idx += PTHREADS) racc[idx] = 0.0;
+    fill_exp2_table(etab, tid, PTHREADS);
     // producer cursors (lanes 0, 1 of the four producer warps: two streams each); the first tiles are requested now
     // so that they land while the panel is evaluated
     const bool is_producer = warp >= QWARPS && lane < 2;
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) k_kmp_predict_fast(const __grid_c
 #pragma unroll
                 for (int u = 0; u < FILL_J; ++u) {
                     const double* sp = s + (size_t)min(j0 + 32 * u, N - 1) * I;
-                    if (ONE) { const double d = fabs(sqs[m] - sp[0]); e[u] = exp_nonpos(-p.sigma_f * (d * d)); }
+                    if (ONE) { const double d = fabs(sqs[m] - sp[0]); e[u] = exp_tab(-p.sigma_f * (d * d), etab); }
                     else e[u] = rbf_fast(sqs + m * I, sp, I, p.sigma_f);
                 }
                 const int pj = (j0 & ~6) | ((j0 & 2) << 1) | ((j0 & 4) >> 1);       // the same permutation applies to j0 + 32 u
