@@ -85,6 +85,16 @@ long long kmpx_trtri_workspace_bytes(int n_max, int batch);
 int kmpx_trtri(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch,
                void* ws, long long ws_bytes, void* stream);
 
+/* ---- K1 + K2 + K3 fused for the small plain-kernel systems (O <= 2, N <= ~204: cfg 1 / cfg 3).  Replaces KMP.fit's
+ *      N^2 loop and numpy.linalg.inv, KMP.py:146-157, in ONE kernel: the matrix is generated from (s, sigma) inside shared
+ *      memory and factorised / inverted there exploiting that the cross-component blocks lambda * Sigma_ab are diagonal
+ *      (factor_struct.cuh).  F receives L^-1 in the component-major order exactly as kmpx_potrf + kmpx_trtri leave it
+ *      (lower triangle; the strict upper triangle is scratch).  info[b] = 0 or the 1-based index of the first non-positive
+ *      pivot.  sigma blocks must be symmetric (the caller routes non-symmetric ones to the general path). */
+int kmpx_factor_struct_applicable(int n_max_pts, int I, int O);
+int kmpx_factor_struct(const double* s, const double* sigma, const int* n_pts, double* F, int lda, long long strideF,
+                       int n_max_pts, int I, int O, int batch, double sigma_f, double lambda, int* info, void* stream);
+
 /* ---- K3a: w = Linv * P y and alpha = P^T Linv^T w  (= (K+lambda Sigma)^{-1} mu, the reference's
  *      `_estimator @ Y`, KMP.py:185-187).  y, alpha are point-major [batch][n_max][O]; P is the permutation
  *      to `layout`; w [batch][ldw] is kept in system order for the predict kernel. */

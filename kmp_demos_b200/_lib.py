@@ -28,6 +28,8 @@ _SIGNATURES = {
     'kmpx_debug_set': [_i],
     'kmpx_debug_exp': [_p, _p, _ll, _i, _p],
     'kmpx_kernel_build': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _d, _d, _i, _i, _i, _p],
+    'kmpx_factor_struct_applicable': [_i, _i, _i],
+    'kmpx_factor_struct': [_p, _p, _p, _p, _i, _ll, _i, _i, _i, _i, _d, _d, _p, _p],
     'kmpx_potrf_workspace_bytes': [_i, _i],
     'kmpx_potrf': [_p, _i, _ll, _p, _i, _i, _p, _p, _ll, _p],
     'kmpx_trtri_workspace_bytes': [_i, _i],

@@ -29,6 +29,10 @@ class KMPBatch:
         self.tol, self.time_driven_kernel, self.chunk = float(adaptation_tol), bool(time_driven_kernel), int(chunk)
         self._bufs = {}
         self._base = None
+        # plain kernel, O <= 2, N <= ~204: one fused shared-memory-resident fit kernel (factor_struct.cuh) instead of
+        # build + potrf + trtri.  Correct and tested, but measured ~20 % SLOWER than the TMA pipeline on the cfg-3 shape
+        # (DESIGN.md 3.4), hence opt-in
+        self.fused_fit = False
         self.events = None        # set to a list to collect (kernel name, start, end) CUDA events per launch
 
     # ------------------------------------------------------------------ data staging
@@ -106,6 +110,8 @@ class KMPBatch:
         st = _lib.stream()
         td = int(self.time_driven_kernel)
         strideA = n_max * lda
+        # the covariance blocks handed to this path are symmetric by contract (GMR output, via-point covariances)
+        fused_fit = (not self.time_driven_kernel) and self.fused_fit and bool(lib.kmpx_factor_struct_applicable(n_max_pts, I, O))
         copy_stream = None
         if host_xi is not None or host_sigma is not None:
             if getattr(self, '_copy_stream', None) is None:
@@ -118,11 +124,16 @@ class KMPBatch:
             self._launch('kmpx_waypoint_insert', _lib.ptr(b['s']), _lib.ptr(b['y']), _lib.ptr(b['g']), None, N0,
                       _lib.ptr(base_of[c0:]), _lib.ptr(via_s[c0:]), _lib.ptr(via_xi[c0:]), _lib.ptr(via_sigma[c0:]), P,
                       self.tol, _lib.ptr(s), _lib.ptr(y), _lib.ptr(g), _lib.ptr(npc), n_max_pts, I, O, bc, st)
-            self._launch('kmpx_sys_sizes', _lib.ptr(npc), O, _lib.LAYOUT_COMPONENT, bc, _lib.ptr(n_sys), st)
-            self._launch('kmpx_kernel_build', _lib.ptr(s), _lib.ptr(g), _lib.ptr(npc), _lib.ptr(A), bc, n_max_pts, I, O, lda,
-                      strideA, self.sigma_f, self.l, td, _lib.LAYOUT_COMPONENT, _lib.UPLO_LOWER, st)
-            self._launch('kmpx_potrf', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, _lib.ptr(info[c0:]), None, 0, st)
-            self._launch('kmpx_trtri', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, None, 0, st)
+            if fused_fit:
+                # build + Cholesky + triangular inverse in one shared-memory-resident kernel (factor_struct.cuh)
+                self._launch('kmpx_factor_struct', _lib.ptr(s), _lib.ptr(g), _lib.ptr(npc), _lib.ptr(A), lda, strideA, n_max_pts, I, O,
+                             bc, self.sigma_f, self.l, _lib.ptr(info[c0:]), st)
+            else:
+                self._launch('kmpx_sys_sizes', _lib.ptr(npc), O, _lib.LAYOUT_COMPONENT, bc, _lib.ptr(n_sys), st)
+                self._launch('kmpx_kernel_build', _lib.ptr(s), _lib.ptr(g), _lib.ptr(npc), _lib.ptr(A), bc, n_max_pts, I, O, lda,
+                             strideA, self.sigma_f, self.l, td, _lib.LAYOUT_COMPONENT, _lib.UPLO_LOWER, st)
+                self._launch('kmpx_potrf', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, _lib.ptr(info[c0:]), None, 0, st)
+                self._launch('kmpx_trtri', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, None, 0, st)
             # alpha = A^-1 mu is only needed by the mean-only predict; the fused mean+covariance kernel takes w
             self._launch('kmpx_solve_alpha', _lib.ptr(A), lda, strideA, _lib.ptr(npc), n_max_pts, O, bc,
                       _lib.LAYOUT_COMPONENT, _lib.ptr(y), _lib.ptr(w), lda, None if want_cov else _lib.ptr(al), st)

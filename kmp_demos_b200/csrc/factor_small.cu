@@ -566,6 +566,7 @@ __global__ void __launch_bounds__(256) k_solve_alpha(AlphaArgs p) {
 
 }  // namespace kmpx
 #include "factor_tma.cuh"
+#include "factor_struct.cuh"
 namespace kmpx {
 
 int debug_set(int flags) { g_host_dbg = flags; return check_cuda(cudaMemcpyToSymbol(g_dbg, &flags, sizeof(int)), "cudaMemcpyToSymbol"); }
@@ -630,5 +631,19 @@ int launch_solve_alpha(const AlphaArgs& p, cudaStream_t st) {
 
 }  // namespace kmpx
 
+extern "C" int kmpx_factor_struct_applicable(int n_max_pts, int I, int O) {
+    return kmpx::factor_struct_applicable(n_max_pts, I, O, 2, 0, nullptr) ? 1 : 0;
+}
+extern "C" int kmpx_factor_struct(const double* s, const double* sigma, const int* n_pts, double* F, int lda, long long strideF,
+                                  int n_max_pts, int I, int O, int batch, double sigma_f, double lambda, int* info, void* stream) {
+    using namespace kmpx;
+    if (!s || !sigma || !F) return fail_arg(1, "s / sigma / F is NULL");
+    if (batch <= 0) return fail_arg(10, "batch must be > 0");
+    if (!factor_struct_applicable(n_max_pts, I, O, lda, strideF, F))
+        return fail_arg(7, "kmpx_factor_struct covers the plain kernel with O <= 2, aligned F and N <= ~204 (kmpx_factor_struct_applicable)");
+    if (lda < O * comp_stride(n_max_pts)) return fail_arg(5, "lda < system size");
+    StructArgs p{s, sigma, n_pts, F, lda, strideF, n_max_pts, I, O, batch, sigma_f, lambda, info, 0};
+    return launch_factor_struct(p, (cudaStream_t)stream);
+}
 extern "C" int kmpx_debug_phases(long long* out_host, int reset) { return kmpx::debug_phases(out_host, reset); }
 extern "C" int kmpx_debug_set(int flags) { return kmpx::debug_set(flags); }

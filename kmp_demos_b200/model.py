@@ -30,6 +30,9 @@ logging.basicConfig(
 )
 
 
+USE_FUSED_FIT = False
+
+
 def _roundup(v, m):
     return (v + m - 1) // m * m
 
@@ -64,20 +67,31 @@ def factorise(s, xi, sigma, lam, sigma_f, time_driven, layout=_lib.LAYOUT_COMPON
     general = force_general or (asym > 1e-12 * scale)
     A = torch.empty((n, lda), dtype=torch.float64, device=dev)
     st = _lib.stream()
-    _lib.call('kmpx_kernel_build', _lib.ptr(s_dev), _lib.ptr(g_dev), None, _lib.ptr(A), 1, N, I, O, lda, n * lda,
-              float(sigma_f), float(lam), int(bool(time_driven)), layout,
-              _lib.UPLO_FULL if general else _lib.UPLO_LOWER, st)
+    # symmetric blocks, plain kernel, O <= 2, N <= ~204 (cfg 1 / cfg 3): build + Cholesky + inverse in ONE shared-memory-
+    # resident kernel (factor_struct.cuh) - opt-in through USE_FUSED_FIT, like KMPBatch.fused_fit
+    fused = USE_FUSED_FIT and (not general) and (not time_driven) and layout == _lib.LAYOUT_COMPONENT and \
+        bool(lib.kmpx_factor_struct_applicable(N, I, O))
+    if not fused:
+        _lib.call('kmpx_kernel_build', _lib.ptr(s_dev), _lib.ptr(g_dev), None, _lib.ptr(A), 1, N, I, O, lda, n * lda,
+                  float(sigma_f), float(lam), int(bool(time_driven)), layout,
+                  _lib.UPLO_FULL if general else _lib.UPLO_LOWER, st)
     info = torch.zeros(1, dtype=torch.int32, device=dev)
     w = torch.zeros(lda, dtype=torch.float64, device=dev)
     alpha = torch.empty((N, O), dtype=torch.float64, device=dev)
     if not general:
-        nbytes = max(int(lib.kmpx_potrf_workspace_bytes(n, 1)), int(lib.kmpx_trtri_workspace_bytes(n, 1)))
-        ws = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=dev)
-        _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
-        if int(info.item()) != 0:
-            # not positive definite: the reference's LU inverse would still go through -> general path
-            return factorise(s, xi, sigma, lam, sigma_f, time_driven, layout, force_general=True)
-        _lib.call('kmpx_trtri', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(ws), nbytes, st)
+        if fused:
+            _lib.call('kmpx_factor_struct', _lib.ptr(s_dev), _lib.ptr(g_dev), None, _lib.ptr(A), lda, n * lda, N, I, O, 1,
+                      float(sigma_f), float(lam), _lib.ptr(info), st)
+            if int(info.item()) != 0:
+                return factorise(s, xi, sigma, lam, sigma_f, time_driven, layout, force_general=True)
+        else:
+            nbytes = max(int(lib.kmpx_potrf_workspace_bytes(n, 1)), int(lib.kmpx_trtri_workspace_bytes(n, 1)))
+            ws = torch.empty(max(nbytes, 8) // 8, dtype=torch.float64, device=dev)
+            _lib.call('kmpx_potrf', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(info), _lib.ptr(ws), nbytes, st)
+            if int(info.item()) != 0:
+                # not positive definite: the reference's LU inverse would still go through -> general path
+                return factorise(s, xi, sigma, lam, sigma_f, time_driven, layout, force_general=True)
+            _lib.call('kmpx_trtri', _lib.ptr(A), lda, n * lda, None, n, 1, _lib.ptr(ws), nbytes, st)
         _lib.call('kmpx_solve_alpha', _lib.ptr(A), lda, n * lda, None, N, O, 1, layout, _lib.ptr(y_dev),
                   _lib.ptr(w), lda, _lib.ptr(alpha), st)
         kind = 0

@@ -171,6 +171,56 @@ def _spd(rng, n):
     return M @ M.T / n + np.eye(n)
 
 
+@pytest.mark.parametrize('O', [1, 2])
+def test_factor_struct_equals_potrf_trtri(T, O):
+    """The fused shared-memory-resident fit (k_factor_struct: build + Cholesky + inverse exploiting the diagonal
+    cross-component blocks) leaves the same L^-1 (component-major, lower triangle) as kmpx_kernel_build + kmpx_potrf +
+    kmpx_trtri, on a ragged batch including odd N (identity padding rows) and tiny systems; a non-SPD problem is
+    reported through info."""
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(11 + O)
+    sizes = [202, 201, 200, 33, 64, 1, 7, 100, 204, 31, 32, 65, 129, 193]
+    B, nmax = len(sizes), 204
+    assert lib.kmpx_factor_struct_applicable(nmax, 1, O) == 1
+    n_sys_max = int(lib.kmpx_sys_size(nmax, O, _lib.LAYOUT_COMPONENT))
+    lda = (n_sys_max + 7) // 8 * 8
+    s = np.zeros((B, nmax, 1)); sig = np.zeros((B, nmax, O, O))
+    for b, N in enumerate(sizes):
+        s[b, :N, 0] = 0.01 * np.arange(1, N + 1) + 0.002 * rng.random(N)
+        Bm = rng.normal(size=(N, O, O)) * 0.3
+        sig[b, :N] = np.einsum('nab,ncb->nac', Bm, Bm) + 0.05 * np.eye(O)
+    sd, gd = dev(T, s), dev(T, sig)
+    npts = dev(T, np.array(sizes, dtype=np.int32))
+    st = _lib.stream()
+    A = T.full((B, n_sys_max, lda), float('nan'), dtype=T.float64, device='cuda')
+    _lib.call('kmpx_kernel_build', _lib.ptr(sd), _lib.ptr(gd), _lib.ptr(npts), _lib.ptr(A), B, nmax, 1, O, lda, n_sys_max * lda,
+              200.0, 0.5, 0, _lib.LAYOUT_COMPONENT, _lib.UPLO_LOWER, st)
+    nsys = T.empty(B, dtype=T.int32, device='cuda')
+    _lib.call('kmpx_sys_sizes', _lib.ptr(npts), O, _lib.LAYOUT_COMPONENT, B, _lib.ptr(nsys), st)
+    info = T.full((B,), -1, dtype=T.int32, device='cuda')
+    _lib.call('kmpx_potrf', _lib.ptr(A), lda, n_sys_max * lda, _lib.ptr(nsys), n_sys_max, B, _lib.ptr(info), None, 0, st)
+    _lib.call('kmpx_trtri', _lib.ptr(A), lda, n_sys_max * lda, _lib.ptr(nsys), n_sys_max, B, None, 0, st)
+    assert int(info.abs().max().item()) == 0
+    F = T.full((B, n_sys_max, lda), float('nan'), dtype=T.float64, device='cuda')
+    info2 = T.full((B,), -1, dtype=T.int32, device='cuda')
+    _lib.call('kmpx_factor_struct', _lib.ptr(sd), _lib.ptr(gd), _lib.ptr(npts), _lib.ptr(F), lda, n_sys_max * lda, nmax, 1, O, B,
+              200.0, 0.5, _lib.ptr(info2), st)
+    assert int(info2.abs().max().item()) == 0
+    Ah, Fh = A.cpu().numpy(), F.cpu().numpy()
+    for b, N in enumerate(sizes):
+        n = int(nsys[b].item())
+        ref, got = np.tril(Ah[b, :n, :n]), np.tril(Fh[b, :n, :n])
+        assert np.all(np.isfinite(got)), (N, np.argwhere(~np.isfinite(got))[:4])
+        assert np.max(np.abs(got - ref)) < 1e-11 * np.max(np.abs(ref)), (N, float(np.max(np.abs(got - ref))), float(np.max(np.abs(ref))))
+    # a system that is not positive definite (negative covariance block) is flagged, not silently factorised
+    sig_bad = sig.copy(); sig_bad[0, 5] = -50.0 * np.eye(O)
+    _lib.call('kmpx_factor_struct', _lib.ptr(sd), _lib.ptr(dev(T, sig_bad)), _lib.ptr(npts), _lib.ptr(F), lda, n_sys_max * lda, nmax, 1, O, B,
+              200.0, 0.5, _lib.ptr(info2), st)
+    ih = info2.cpu().numpy()
+    assert ih[0] > 0 and np.all(ih[1:] == 0)
+
+
 def test_potrf_trtri_small_ragged_batch(T):
     from kmp_demos_b200 import _lib
     rng = np.random.default_rng(3)

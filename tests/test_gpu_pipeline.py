@@ -144,6 +144,29 @@ def test_kmeans_init_device_sampling_equals_host_sampling(golden):
         assert fb['kpp_host_draws'] == K - 1 and fa['kpp_host_draws'] <= 1
 
 
+def test_fused_fit_kernel_through_the_pipeline(golden):
+    """KMPBatch.fused_fit = True (k_factor_struct instead of build + potrf + trtri) reproduces the reference's cfg-3
+    results and agrees with the default pipeline to rounding."""
+    from kmp_demos_b200.batch import KMPBatch
+    zl, z = golden('letters_ref.npz'), golden('cfg3_sample.npz')
+    c = wl.CFG1
+    t = wl.cfg1_kmp_grid(200)
+    base_of, vs, vp, vv = [], [], [], []
+    for r in range(len(z['letter'])):
+        li, si = int(z['letter'][r]), int(z['set_idx'][r])
+        a, b, cc = wl.cfg3_via_sets(li, zl['gmr_mu'][li], si + 1)
+        base_of.append(li); vs.append(a[si]); vp.append(b[si]); vv.append(cc[si])
+    res = []
+    for fused in (False, True):
+        kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=16)
+        kb.fused_fit = fused
+        kb.set_base(np.broadcast_to(t, (26, 1, 200)), zl['gmr_mu'], zl['gmr_sigma'])
+        res.append(kb.fit_predict(np.array(base_of), np.array(vs), np.array(vp), np.array(vv), z['queries']))
+    for r in range(len(z['letter'])):
+        assert rel_err(res[1][0][r], z['xi'][r]) < MEAN_TOL and rel_err(res[1][1][r], z['sigma'][r]) < COV_TOL, r
+    assert rel_err(res[1][0], res[0][0]) < 1e-10 and rel_err(res[1][1], res[0][1]) < 1e-9
+
+
 def test_cfg3_batch_vs_reference_and_vs_single(golden):
     """cfg 3 sample: batched adaptation == the reference's per-problem results; batch == one-by-one bit for bit."""
     from kmp_demos_b200.batch import KMPBatch
