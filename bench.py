@@ -203,6 +203,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     _lib.load()
+    # pinned result buffers on the NUMA node of this rank's GPU (N > 1: all ranks copying to one node's memory is what
+    # capped the 8-GPU end-to-end figure of the incremental path in round 1)
+    numa_node = kd.bind_to_gpu_numa_node(local) if world > 1 else None
     mu, sig, src = wl.load_letter_references()
     L, O, T = mu.shape
     log(f'rank {rank}/{world}: building {L} x {args.sets} via-point sets')
@@ -382,7 +385,7 @@ def run_ours(args):
         'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': src + '; via-point sets seeded per (letter, rank, set)',
         'config': {'workload': WORKLOAD,
-                   'problems_per_gpu': B, 'chunk': args.chunk,
+                   'problems_per_gpu': B, 'chunk': args.chunk, 'numa_node_of_rank0': numa_node,
                    'l2': 'inputs larger than L2: each step streams ~35 GB of system matrices per GPU (126 MB L2)'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
         'gpu_launches': launches,

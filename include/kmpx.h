@@ -207,6 +207,10 @@ int kmpx_gmm_em_pass(const double* X, long long n, int d, int K, const double* s
  * k-means initialisation (sklearn/mixture/_base.py:119-128) and the Lloyd centre update. */
 int kmpx_gmm_label_stats(const double* X, long long n, int d, int K, const double* shift,
                          const int* labels, double* stats, void* ws, long long ws_bytes, void* stream);
+/* The same with only the count and the first moments accumulated (Lloyd iterations need nothing else; the second-moment
+ * entries of stats are written as 0). */
+int kmpx_gmm_label_sums(const double* X, long long n, int d, int K, const double* shift,
+                         const int* labels, double* stats, void* ws, long long ws_bytes, void* stream);
 /* M-step finalisation from (all-reduced) statistics: nk = sum r + 10 eps, means, covariances + reg*I,
  * weights = nk / n_total (first = 1) or nk / sum nk, precision Cholesky, log-dets
  * (sklearn/mixture/_gaussian_mixture.py:312-320,358-370,883-901).  info[k] != 0 => covariance not SPD. */

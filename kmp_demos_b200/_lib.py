@@ -56,6 +56,7 @@ _SIGNATURES = {
     'kmpx_gmm_workspace_bytes': [_i, _i, _i],
     'kmpx_gmm_em_pass': [_p, _ll, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p],
     'kmpx_gmm_label_stats': [_p, _ll, _i, _i, _p, _p, _p, _p, _ll, _p],
+    'kmpx_gmm_label_sums': [_p, _ll, _i, _i, _p, _p, _p, _p, _ll, _p],
     'kmpx_gmm_finalize': [_p, _d, _i, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     'kmpx_gmm_finalize_check': [_p, _d, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p, _d, _i, _p, _p],
     'kmpx_rows_center_sqnorm': [_p, _ll, _i, _p, _p, _p],

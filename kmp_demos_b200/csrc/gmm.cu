@@ -30,6 +30,7 @@ struct EmArgs {
     const double* log_weights; const double* means; const double* prec_chol; const double* log_det;
     const int* hard_labels;           // != NULL: one-hot responsibilities from labels (no E-step)
     double* partials; int* labels; double* lse;
+    int first_moments_only;           // hard labels for Lloyd: only [count, sum x] are accumulated (the other statistics are 0)
 };
 
 template <int D, int KB>   // KB = 8-component blocks per warp (K_pad <= 64*KB)
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t4 = lane & 3;
     const bool hard = p.hard_labels != nullptr;
+    const int nf_use = p.first_moments_only ? (1 + D + 7) / 8 : NF;      // feature tiles the M-step contracts
 
     if (!hard) {
         for (int idx = tid; idx < K * D; idx += ETHREADS) s_par[(size_t)(idx / D) * PREC + idx % D] = p.means[idx];
@@ -100,10 +102,12 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
 #pragma unroll
             for (int i = 0; i < D; ++i) ph[1 + i] = live ? xs[i] : 0.0;
             int t = 1 + D;
+            if (!p.first_moments_only) {
 #pragma unroll
-            for (int i = 0; i < D; ++i)
+                for (int i = 0; i < D; ++i)
 #pragma unroll
-                for (int j = i; j < D; ++j) ph[t++] = live ? xs[i] * xs[j] : 0.0;
+                    for (int j = i; j < D; ++j) ph[t++] = live ? xs[i] * xs[j] : 0.0;
+            }
             for (; t < FP; ++t) ph[t] = 0.0;
         }
         double* Rrow = s_R + (size_t)s_loc * ldr;
@@ -222,8 +226,10 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
                     const double a = s_R[(size_t)(s0 + t4) * ldr + kb * 8 + g];
 #pragma unroll
                     for (int j = 0; j < NF; ++j) {
-                        const double bv = s_Phi[(size_t)(s0 + t4) * ldf + j * 8 + g];
-                        dmma884(acc[q][j], a, bv);
+                        if (j < nf_use) {
+                            const double bv = s_Phi[(size_t)(s0 + t4) * ldf + j * 8 + g];
+                            dmma884(acc[q][j], a, bv);
+                        }
                     }
                 }
             }
@@ -413,14 +419,21 @@ extern "C" int kmpx_gmm_em_pass(const double* X, long long n, int d, int K, cons
                                 const double* log_det, double* stats, int* labels, double* lse,
                                 void* ws, long long ws_bytes, void* stream) {
     if (!log_weights || !means || !prec_chol || !log_det) return fail_arg(6, "mixture parameters are NULL");
-    EmArgs p{X, n, d, K, shift, log_weights, means, prec_chol, log_det, nullptr, nullptr, labels, lse};
+    EmArgs p{X, n, d, K, shift, log_weights, means, prec_chol, log_det, nullptr, nullptr, labels, lse, 0};
     return run_em(p, stats, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int kmpx_gmm_label_stats(const double* X, long long n, int d, int K, const double* shift,
                                     const int* labels, double* stats, void* ws, long long ws_bytes, void* stream) {
     if (!labels) return fail_arg(6, "labels is NULL");
-    EmArgs p{X, n, d, K, shift, nullptr, nullptr, nullptr, nullptr, labels, nullptr, nullptr, nullptr};
+    EmArgs p{X, n, d, K, shift, nullptr, nullptr, nullptr, nullptr, labels, nullptr, nullptr, nullptr, 0};
+    return run_em(p, stats, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int kmpx_gmm_label_sums(const double* X, long long n, int d, int K, const double* shift,
+                                   const int* labels, double* stats, void* ws, long long ws_bytes, void* stream) {
+    if (!labels) return fail_arg(6, "labels is NULL");
+    EmArgs p{X, n, d, K, shift, nullptr, nullptr, nullptr, nullptr, labels, nullptr, nullptr, nullptr, 1};
     return run_em(p, stats, ws, ws_bytes, (cudaStream_t)stream);
 }
 

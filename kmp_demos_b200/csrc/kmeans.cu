@@ -315,8 +315,10 @@ __global__ void k_kpp_take_row(const double* dist, const int* best, long long n,
 }
 
 // labels[i] = argmin_j(|c_j|^2 - 2 x_i.c_j), first minimum (_k_means_lloyd.pyx:215-224)
-__global__ void __launch_bounds__(256) k_kmeans_assign(const double* X, long long n, int d, int K, const double* centers,
+template <int D>      // D = number of features (1..8: loops unrolled, samples in registers), 0 = run-time d <= 16
+__global__ void __launch_bounds__(256) k_kmeans_assign(const double* X, long long n, int d_rt, int K, const double* centers,
                                                        const int* labels_prev, int* labels, int* n_changed) {
+    const int d = D > 0 ? D : d_rt;
     extern __shared__ double sh[];
     double* c_sh = sh;              // [K][d]
     double* csq = sh + (size_t)K * d;
@@ -325,18 +327,49 @@ __global__ void __launch_bounds__(256) k_kmeans_assign(const double* X, long lon
     for (int k = threadIdx.x; k < K; k += blockDim.x) { double a = 0.0; for (int q = 0; q < d; ++q) a += c_sh[k * d + q] * c_sh[k * d + q]; csq[k] = a; }
     __syncthreads();
     int changed = 0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        double x[16];
-        for (int q = 0; q < d; ++q) x[q] = X[i * d + q];
-        double best = 0.0; int bl = 0;
-        for (int k = 0; k < K; ++k) {
-            double dot = 0.0;
-            for (int q = 0; q < d; ++q) dot += x[q] * c_sh[k * d + q];
-            const double v = csq[k] - 2.0 * dot;
-            if (k == 0 || v < best) { best = v; bl = k; }
+    // four samples per thread: a centre coordinate is loaded from shared memory once and used four times (with one
+    // sample per thread the loop issues one broadcast load per FMA and is bound by the shared-memory pipe).  The
+    // arithmetic of a sample is unchanged (same FMA chain over the features, same first-minimum rule).
+    constexpr int SPT = 4;
+    const long long span = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n; i0 += SPT * span) {
+        double x[SPT][D > 0 ? D : 16];
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            const long long i = i0 + u * span < n ? i0 + u * span : i0;
+#pragma unroll
+            for (int q = 0; q < (D > 0 ? D : 16); ++q) if (q < d) x[u][q] = X[i * d + q];
         }
-        labels[i] = bl;
-        if (labels_prev && labels_prev[i] != bl) ++changed;
+        double best[SPT]; int bl[SPT];
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) { best[u] = 0.0; bl[u] = 0; }
+        for (int k = 0; k < K; ++k) {
+            double dot[SPT];
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) dot[u] = 0.0;
+#pragma unroll
+            for (int q = 0; q < (D > 0 ? D : 16); ++q) {
+                if (q < d) {
+                    const double cq = c_sh[k * d + q];
+#pragma unroll
+                    for (int u = 0; u < SPT; ++u) dot[u] += x[u][q] * cq;
+                }
+            }
+            const double ck = csq[k];
+#pragma unroll
+            for (int u = 0; u < SPT; ++u) {
+                const double v = ck - 2.0 * dot[u];
+                if (k == 0 || v < best[u]) { best[u] = v; bl[u] = k; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SPT; ++u) {
+            const long long i = i0 + u * span;
+            if (i < n) {
+                labels[i] = bl[u];
+                if (labels_prev && labels_prev[i] != bl[u]) ++changed;
+            }
+        }
     }
     if (n_changed && changed) atomicAdd(n_changed, changed);
 }
@@ -457,10 +490,17 @@ extern "C" int kmpx_kmeans_assign(const double* X, long long n, int d, int K, co
     if (K < 1 || K > 1024) return fail_arg(4, "K must be in 1..1024");
     if (!centers) return fail_arg(5, "centers is NULL");
     if (!labels) return fail_arg(7, "labels is NULL");
-    const long long blocks = (n + 255) / 256;
-    const int grid = (int)(blocks < num_sms() * 8 ? blocks : num_sms() * 8);
+    const long long blocks = (n + 1023) / 1024;                   // four samples per thread
+    const int grid = (int)(blocks < num_sms() * 8 ? (blocks < 1 ? 1 : blocks) : num_sms() * 8);
     const size_t smem = ((size_t)K * d + K) * sizeof(double);
-    k_kmeans_assign<<<grid, 256, smem, (cudaStream_t)stream>>>(X, n, d, K, centers, labels_prev, labels, n_changed);
+    cudaStream_t st = (cudaStream_t)stream;
+#define KMPX_ASSIGN(DD) k_kmeans_assign<DD><<<grid, 256, smem, st>>>(X, n, d, K, centers, labels_prev, labels, n_changed)
+    switch (d) {
+        case 1: KMPX_ASSIGN(1); break; case 2: KMPX_ASSIGN(2); break; case 3: KMPX_ASSIGN(3); break; case 4: KMPX_ASSIGN(4); break;
+        case 5: KMPX_ASSIGN(5); break; case 6: KMPX_ASSIGN(6); break; case 7: KMPX_ASSIGN(7); break; case 8: KMPX_ASSIGN(8); break;
+        default: KMPX_ASSIGN(0); break;
+    }
+#undef KMPX_ASSIGN
     return check_launch("k_kmeans_assign");
 }
 

@@ -35,6 +35,42 @@ def init_process_group(backend=None):
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pins the calling process to the CPU cores of the NUMA node its GPU hangs off (Linux sysfs), so that pinned host
+    buffers allocated afterwards are first-touched on that node: with one process per GPU all writing results to host
+    memory, buffers that all live on one node cap the aggregate device-to-host rate at that node's memory bandwidth.
+    Returns the node id, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        import torch
+        bdf = None
+        props = torch.cuda.get_device_properties(local_rank)
+        if hasattr(props, 'pci_bus_id') and hasattr(props, 'pci_device_id'):
+            dom = getattr(props, 'pci_domain_id', 0)
+            bdf = f'{dom:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0'
+        if bdf is None:
+            return None
+        with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, RuntimeError, AttributeError):
+        return None
+
+
 def shard_range(n_items, rank, world):
     """[lo, hi) of a contiguous static split of n_items units over `world` ranks."""
     per, rem = divmod(n_items, world)

@@ -2,10 +2,10 @@
 (kmp/mixture/GaussianMixtureModel.py), which wraps ``sklearn.mixture.GaussianMixture`` and adds GMR.
 
   fit      GaussianMixtureModel.py:44-57 -> sklearn GaussianMixture(n_components, reg_covar, random_state=420):
-           k-means++ / Lloyd initialisation and the EM loop run on the device (kmpx_kpp_candidates,
-           kmpx_kmeans_assign, kmpx_gmm_label_stats, kmpx_gmm_em_pass, kmpx_gmm_finalize).  The host keeps what
-           is inherently sequential in sklearn: the RandomState(420) stream, the cumulative-sum sampling of
-           k-means++ (sklearn/cluster/_kmeans.py:227-231) and the convergence tests.
+           k-means++ sampling and greedy choice (kmpx_kpp_sample / _candidates_rows / _choose), Lloyd (kmpx_kmeans_assign,
+           kmpx_gmm_label_sums, kmpx_lloyd_update) and the EM loop with sklearn's stopping rule (kmpx_gmm_label_stats,
+           kmpx_gmm_em_pass, kmpx_gmm_finalize_check) run on the device.  The host keeps the RandomState(420) stream and
+           reads one small flag block per centre / per batch of iterations.
   predict  GaussianMixtureModel.py:59-107 (GMR) -> kmpx_gmr.
   bic      GaussianMixtureModel.py:109-122 -> one E-step reduction.
 
@@ -182,9 +182,10 @@ class _Ranks:
         self.dist.all_gather_into_tensor(out.view(-1), t.contiguous().view(-1), group=self.group)
         return out
 
-    def gather_rows_host(self, t, counts):
+    def gather_rows_host(self, t, counts, root_only=False):
         """Concatenation over the ranks of the leading-dimension slices t[:counts[rank]] as a numpy array (single rank:
-        through a pinned staging buffer that is kept for the next call)."""
+        through a pinned staging buffer that is kept for the next call).  root_only: only rank 0 copies the gathered
+        rows to the host and returns them (the others return None)."""
         if self.world == 1:
             import torch
             buf = getattr(self, '_pinned', None)
@@ -195,7 +196,10 @@ class _Ranks:
         per = max(counts)
         pad = t.new_zeros((per,) + tuple(t.shape[1:]))
         pad[:t.shape[0]] = t
-        allr = self.gather(pad).cpu().numpy()
+        allr = self.gather(pad)
+        if root_only and self.rank != 0:
+            return None
+        allr = allr.cpu().numpy()
         return np.concatenate([allr[r, :counts[r]] for r in range(self.world)])
 
 
@@ -216,15 +220,20 @@ def _first_center(rs, n_total):
     return idx
 
 
-def kmeans_init_labels(X, K, rs, max_iter=300, tol=1e-4, group=None, n_total=None, n_before=0, host_sampling=False):
+def kmeans_init_labels(X, K, rs, max_iter=300, tol=1e-4, group=None, n_total=None, n_before=0, host_sampling=False,
+                       resolve_on_host=None):
     """``KMeans(n_clusters=K, n_init=1, random_state=rs).fit(X).labels_`` on the device, optionally with the rows
     partitioned over the ranks of `group` (this rank holds rows n_before .. n_before + n of n_total; every rank passes
     an identical `rs`).  X: (n,d) CUDA tensor (not modified).  The host keeps the RandomState stream only; k-means++
     sampling, greedy choice, Lloyd updates and stopping rules are kernels, the host reads one small flag block per
     centre / per batch of Lloyd iterations.  A k-means++ draw the device cannot decide provably the way numpy's
     sequential cumsum does (kmpx_kpp_sample) is repeated on the host with numpy's own expressions; host_sampling=True
-    forces that path for every centre (tests).  Returns int32 CUDA labels of the local rows, the Lloyd iteration count,
-    the data mean (CUDA, (d,)) and a dict of counters."""
+    forces that path for every centre (tests).  Such a draw lies within the rounding error of numpy's cumulative sum /
+    BLAS potential (up to n u pot each), i.e. where scikit-learn's own choice depends on its BLAS build and thread
+    count; the probability is ~4 n^2 u per draw (4 % at n = 10 M, 2e-5 at n = 200 k).  resolve_on_host=False keeps the
+    device's (exact-arithmetic) choice there instead of paying ~30 ms of host work per draw; the default resolves on
+    the host up to 2 M rows - where parity with the fixtures is checked - and not beyond.  Returns int32 CUDA labels of
+    the local rows, the Lloyd iteration count, the data mean (CUDA, (d,)) and a dict of counters."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     dev = X.device
@@ -232,6 +241,8 @@ def kmeans_init_labels(X, K, rs, max_iter=300, tol=1e-4, group=None, n_total=Non
     n, d = X.shape
     rk = _Ranks(group)
     n_total = int(n_total if n_total is not None else n)
+    if resolve_on_host is None:
+        resolve_on_host = n_total <= 2_000_000
     counts = [n] if rk.world == 1 else [int(v) for v in rk.gather(torch.tensor([n], dtype=i64, device=dev)).view(-1).tolist()]
     st = _lib.stream()
     ws_bytes = max(int(lib.kmpx_gmm_workspace_bytes(int(n), d, max(K, 1))), 148 * 4 * 16 * 8,
@@ -270,7 +281,7 @@ def kmeans_init_labels(X, K, rs, max_iter=300, tol=1e-4, group=None, n_total=Non
     centers = torch.zeros((K, d), dtype=f64, device=dev)
     center_ids = torch.full((K,), -1, dtype=i64, device=dev)
     best = torch.zeros(1, dtype=i32, device=dev)
-    info = {'kpp_host_draws': 0, 'kpp_host_choices': 0, 'lloyd_relocations': 0}
+    info = {'kpp_host_draws': 0, 'kpp_host_choices': 0, 'kpp_ambiguous_draws': 0, 'lloyd_relocations': 0}
 
     def local_of(gids):
         """global row indices -> this rank's local indices (-1: another rank owns the row)"""
@@ -295,8 +306,13 @@ def kmeans_init_labels(X, K, rs, max_iter=300, tol=1e-4, group=None, n_total=Non
 
     def host_choice(t_cnt):
         """np.argmin(distance_to_candidates @ ones) with numpy's own product (_kmeans.py:241-245)"""
-        full = rk.gather_rows_host(dist[:t_cnt].t().contiguous(), counts)          # (n_total, T)
-        return int(np.argmin(full.T @ np.ones((n_total, 1))))
+        full = rk.gather_rows_host(dist[:t_cnt].t().contiguous(), counts, root_only=True)          # (n_total, T)
+        b = int(np.argmin(full.T @ np.ones((n_total, 1)))) if rk.rank == 0 else 0
+        if rk.world > 1:
+            bd = torch.tensor([b], dtype=i64, device=dev)
+            rk.dist.broadcast(bd, src=rk.dist.get_global_rank(rk.group, 0) if rk.group is not rk.dist.group.WORLD else 0, group=rk.group)
+            b = int(bd.item())
+        return b
 
     pots = evaluate(local_of([gid0]), 1, None)
     choose(pots, 1, 0, 0)
@@ -311,17 +327,28 @@ def kmeans_init_labels(X, K, rs, max_iter=300, tol=1e-4, group=None, n_total=Non
             choose(pots, T, c, nxt)
             fl = rk.sum_(flags.clone()).cpu().numpy() if rk.world > 1 else flags.cpu().numpy()
             redraw = bool(fl[:T].any())
+            info['kpp_ambiguous_draws'] += int(redraw)
+            if not resolve_on_host:
+                redraw = False
+                fl[8] = 0
         else:
             redraw, fl = True, None
         if redraw:
             # the draw lies within numpy's own rounding uncertainty: numpy's expressions decide (_kmeans.py:227-233)
             info['kpp_host_draws'] += 1
-            full = rk.gather_rows_host(closest[cur], counts)
-            if host_ones is None:
-                host_ones, host_cum = np.ones(n_total), np.empty(n_total)
-            rand_vals = U[c - 1] * (full @ host_ones)
-            cids = np.searchsorted(np.cumsum(full, out=host_cum), rand_vals)
-            np.clip(cids, None, n_total - 1, out=cids)
+            full = rk.gather_rows_host(closest[cur], counts, root_only=True)
+            if rk.rank == 0:
+                if host_ones is None:
+                    host_ones, host_cum = np.ones(n_total), np.empty(n_total)
+                rand_vals = U[c - 1] * (full @ host_ones)
+                cids = np.searchsorted(np.cumsum(full, out=host_cum), rand_vals)
+                np.clip(cids, None, n_total - 1, out=cids)
+            else:
+                cids = np.zeros(T, dtype=np.int64)
+            if rk.world > 1:                                  # one rank does the host arithmetic, everybody gets the indices
+                cd = torch.as_tensor(np.asarray(cids, dtype=np.int64), device=dev)
+                rk.dist.broadcast(cd, src=rk.dist.get_global_rank(rk.group, 0) if rk.group is not rk.dist.group.WORLD else 0, group=rk.group)
+                cids = cd.cpu().numpy()
             pots = evaluate(local_of(cids), T, cur)
             choose(pots, T, c, nxt)
             fl = rk.sum_(flags.clone()).cpu().numpy() if rk.world > 1 else flags.cpu().numpy()
@@ -342,7 +369,7 @@ def kmeans_init_labels(X, K, rs, max_iter=300, tol=1e-4, group=None, n_total=Non
         nonlocal labels, labels_new
         _lib.call('kmpx_kmeans_assign', _lib.ptr(Xc), n, d, K, _lib.ptr(centers), _lib.ptr(labels), _lib.ptr(labels_new),
                   _lib.ptr(n_changed), st)
-        _lib.call('kmpx_gmm_label_stats', _lib.ptr(Xc), n, d, K, None, _lib.ptr(labels_new), _lib.ptr(stats), _lib.ptr(ws),
+        _lib.call('kmpx_gmm_label_sums', _lib.ptr(Xc), n, d, K, None, _lib.ptr(labels_new), _lib.ptr(stats), _lib.ptr(ws),
                   ws_bytes, st)
         stats[-1:].copy_(n_changed)                           # travels with the sums through the one all-reduce
         rk.sum_(stats)
@@ -360,7 +387,7 @@ def kmeans_init_labels(X, K, rs, max_iter=300, tol=1e-4, group=None, n_total=Non
             # except for the label-change count, which is recovered from one more assignment against the kept labels
             info['lloyd_relocations'] += 1
             _lib.call('kmpx_kmeans_assign', _lib.ptr(Xc), n, d, K, _lib.ptr(centers), None, _lib.ptr(labels_new), None, st)
-            _lib.call('kmpx_gmm_label_stats', _lib.ptr(Xc), n, d, K, None, _lib.ptr(labels_new), _lib.ptr(stats), _lib.ptr(ws),
+            _lib.call('kmpx_gmm_label_sums', _lib.ptr(Xc), n, d, K, None, _lib.ptr(labels_new), _lib.ptr(stats), _lib.ptr(ws),
                       ws_bytes, st)
             stats[-1:].zero_()
             rk.sum_(stats)
