@@ -205,7 +205,8 @@ def run_ours(args):
     _lib.load()
     # pinned result buffers on the NUMA node of this rank's GPU (N > 1: all ranks copying to one node's memory is what
     # capped the 8-GPU end-to-end figure of the incremental path in round 1)
-    numa_node = kd.bind_to_gpu_numa_node(local) if world > 1 else None
+    numa_node = kd.bind_to_gpu_numa_node(local, world) if world > 1 else (None, 'single rank')
+    log(f'rank {rank}: NUMA binding {numa_node}')
     mu, sig, src = wl.load_letter_references()
     L, O, T = mu.shape
     log(f'rank {rank}/{world}: building {L} x {args.sets} via-point sets')

@@ -4,8 +4,12 @@
 //
 // One pass over the samples produces the sufficient statistics {sum r, sum r x', sum r x' x'^T} per
 // component and sum log p(x); responsibilities are never written to HBM.
-//   E-step : one (sample, quarter of the components) per thread; parameters broadcast from shared memory;
-//            y = (x - mu_k) P_k with P_k upper-triangular, log-sum-exp over the components.
+//   E-step : log p_k(x) = Phi(x) . theta_k with the same feature row Phi = [1, x', vech(x' x'^T)] the M-step contracts and
+//            theta_k the coefficients of the expanded quadratic form (built per CTA from mu_k and the precision factor
+//            P_k): one (64 x FP) x (FP x K) product per tile on DMMA.  Warp w owns the samples 8 w .. 8 w + 7 and ALL
+//            components, so the log-sum-exp, the arg-max and the normalisation need quad shuffles only - no shared-
+//            memory exchange, no CTA barrier inside the E-step.  x' = x - shift (the data mean) keeps the cancellation
+//            of the expanded form at ~1e-11 in log p, three orders below what parity needs.
 //   M-step : stats[k][f] += sum_s R[s][k] * Phi[s][f] with Phi = [1, x', vech(x' x'^T)]  -- a
 //            (K x TS) x (TS x F) contraction per tile on DMMA, accumulators persistent in registers.
 //   Per-CTA partial sums are combined in CTA order by a second kernel => bitwise reproducible.
@@ -39,13 +43,12 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
     constexpr int FP = (F + 7) & ~7;
     constexpr int NF = FP / 8;
     constexpr int TRI = D * (D + 1) / 2;
-    constexpr int POFF = (D + 2) & ~1;                 // offset of the packed precision factor inside a parameter record (even)
-    constexpr int PREC = (POFF + TRI + 1) & ~1;        // doubles per record (even)
     extern __shared__ __align__(16) double smem[];
     const int K = p.K, KP = pad8(K);
     const int ldr = ld_conflict_free(KP), ldf = ld_conflict_free(FP);
-    double* s_par = smem;                         // [K][PREC]: mu (D), c = log_det + log_weight - D/2 log(2 pi), pad, packed upper triangle (row order)
-    double* s_shift = s_par + (size_t)K * PREC;   // [D] (+1 pad: what follows stays 16-byte aligned)
+    const int ldt = ld_conflict_free(KP);
+    double* s_theta = smem;                       // [FP][ldt]: k-major B operand of the E-step product (columns >= K are zero)
+    double* s_shift = s_theta + (size_t)FP * ldt; // [D] (+1 pad: what follows stays 16-byte aligned)
     double* s_x = s_shift + ((D + 1) & ~1);       // [ETS][D]
     double* s_R = s_x + (size_t)ETS * D;          // [ETS][ldr]
     double* s_Phi = s_R + (size_t)ETS * ldr;      // [ETS][ldf]
@@ -60,14 +63,44 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
     const int nf_use = p.first_moments_only ? (1 + D + 7) / 8 : NF;      // feature tiles the M-step contracts
 
     if (!hard) {
-        for (int idx = tid; idx < K * D; idx += ETHREADS) s_par[(size_t)(idx / D) * PREC + idx % D] = p.means[idx];
-        for (int idx = tid; idx < K * TRI; idx += ETHREADS) {
-            const int k = idx / TRI; int t = idx - k * TRI, i = 0;
-            const int t0 = t;
-            while (t >= D - i) { t -= D - i; ++i; }
-            s_par[(size_t)k * PREC + POFF + t0] = p.prec_chol[((size_t)k * D + i) * D + i + t];
+        // theta_k from (mu_k, P_k): Lambda = P P^T, mu' = mu - shift,
+        //   log p = [c - mu'^T Lambda mu' / 2] + (Lambda mu')^T x' - sum_i Lambda_ii x'_i^2 / 2 - sum_{i<j} Lambda_ij x'_i x'_j
+        for (int idx = tid; idx < FP * ldt; idx += ETHREADS) s_theta[idx] = 0.0;
+        __syncthreads();
+        for (int k = tid; k < K; k += ETHREADS) {
+            double P[D][D], Lm[D][D], mu[D], lmu[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                mu[i] = p.means[(size_t)k * D + i] - (p.shift ? p.shift[i] : 0.0);
+#pragma unroll
+                for (int j = 0; j < D; ++j) P[i][j] = j >= i ? p.prec_chol[((size_t)k * D + i) * D + j] : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int c = 0; c < D; ++c) a += P[i][c] * P[j][c];
+                    Lm[i][j] = a;
+                }
+            double quad = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double a = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) a += Lm[i][j] * mu[j];
+                lmu[i] = a; quad += a * mu[i];
+            }
+            s_theta[k] = p.log_det[k] + p.log_weights[k] - 0.5 * D * kLog2Pi - 0.5 * quad;
+#pragma unroll
+            for (int i = 0; i < D; ++i) s_theta[(size_t)(1 + i) * ldt + k] = lmu[i];
+            int t = 1 + D;
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = i; j < D; ++j) { s_theta[(size_t)t * ldt + k] = (i == j) ? -0.5 * Lm[i][i] : -Lm[i][j]; ++t; }
         }
-        for (int k = tid; k < K; k += ETHREADS) s_par[(size_t)k * PREC + D] = p.log_det[k] + p.log_weights[k] - 0.5 * D * kLog2Pi;
     }
     for (int i = tid; i < D; i += ETHREADS) s_shift[i] = p.shift ? p.shift[i] : 0.0;
     __syncthreads();
@@ -93,22 +126,23 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
         double x[D];
 #pragma unroll
         for (int i = 0; i < D; ++i) x[i] = s_x[s_loc * D + i];
-        if (half == 0) {                                         // Phi row = [1, x', vech(x' x'^T)]
-            double xs[D];
+        {                                                        // Phi row = [1, x', vech(x' x'^T)]: the four threads of a
+            double xs[D];                                        // sample write every fourth feature
 #pragma unroll
             for (int i = 0; i < D; ++i) xs[i] = x[i] - s_shift[i];
             double* ph = s_Phi + (size_t)s_loc * ldf;
-            ph[0] = live ? 1.0 : 0.0;
+            if (half == 0) ph[0] = live ? 1.0 : 0.0;
 #pragma unroll
-            for (int i = 0; i < D; ++i) ph[1 + i] = live ? xs[i] : 0.0;
+            for (int i = 0; i < D; ++i) if (((1 + i) & 3) == half) ph[1 + i] = live ? xs[i] : 0.0;
             int t = 1 + D;
             if (!p.first_moments_only) {
 #pragma unroll
                 for (int i = 0; i < D; ++i)
 #pragma unroll
-                    for (int j = i; j < D; ++j) ph[t++] = live ? xs[i] * xs[j] : 0.0;
+                    for (int j = i; j < D; ++j) { if ((t & 3) == half) ph[t] = live ? xs[i] * xs[j] : 0.0; ++t; }
             }
-            for (; t < FP; ++t) ph[t] = 0.0;
+#pragma unroll
+            for (int tt = 1 + D; tt < FP; ++tt) if (tt >= t && (tt & 3) == half) ph[tt] = 0.0;
         }
         double* Rrow = s_R + (size_t)s_loc * ldr;
         if (hard) {
@@ -116,104 +150,65 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
             for (int k = kbeg; k < kend; ++k) Rrow[k] = (k == lab) ? 1.0 : 0.0;
             if (half == EPARTS - 1) for (int k = K; k < KP; ++k) Rrow[k] = 0.0;
         } else {
-            // Weighted log-probabilities of this thread's components.  For K <= 64 (KB == 1: at most 16 components per
-            // thread) they stay in registers through the max / exp / normalise passes and R is written once: with the
-            // rows of s_R as scratch the kernel was bound by the shared-memory pipe (85 % of its wavefronts, a third of
-            // them bank conflicts of the 8-byte accesses with stride ldr), not by FP64.
-            constexpr int KREG = KB == 1 ? 16 : 1;
-            double wl[KREG];
-            double mx = -INFINITY; int am = kbeg;
-            auto weighted_logp = [&](int k) {
-                // the parameters of a component are one 16-byte aligned record [mu (D), c, pad, pc (TRI)] read with 16-byte
-                // broadcast loads: with 8-byte loads the shared-memory pipe, not the FP64 pipe, limits this loop
-                double par[PREC];
-                const double2* pr = reinterpret_cast<const double2*>(s_par + (size_t)k * PREC);
+            __syncthreads();                                     // the Phi rows of this tile are complete
+            // ---- E-step on the tensor pipe: warp w, samples 8 w + g, all components.  lp[j][e] = weighted log-probability
+            //      of component 8 j + 2 t4 + e (accumulator layout of an 8 x 8 DMMA tile).
+            constexpr int NTE = 8 * KB;                          // component tiles of 8 (K_pad <= 64 KB)
+            const int nte = KP >> 3;
+            double lp[NTE][2];
 #pragma unroll
-                for (int t = 0; t < PREC / 2; ++t) { const double2 v = pr[t]; par[2 * t] = v.x; par[2 * t + 1] = v.y; }
-                double df[D], y[D];
+            for (int j = 0; j < NTE; ++j) { lp[j][0] = 0.0; lp[j][1] = 0.0; }
+            const double* arow = s_Phi + (size_t)(8 * warp + g) * ldf + t4;
+            const double* brow = s_theta + (size_t)t4 * ldt + g;
 #pragma unroll
-                for (int i = 0; i < D; ++i) { df[i] = x[i] - par[i]; y[i] = 0.0; }
-                int t = 0;
+            for (int ks = 0; ks < FP / 4; ++ks) {
+                const double a = arow[4 * ks];
 #pragma unroll
-                for (int i = 0; i < D; ++i)
-#pragma unroll
-                    for (int j = i; j < D; ++j) y[j] += df[i] * par[POFF + t++];
-                double q = 0.0;
-#pragma unroll
-                for (int j = 0; j < D; ++j) q += y[j] * y[j];
-                return par[D] - 0.5 * q;
-            };
-            if (KB == 1) {
-#pragma unroll
-                for (int kk = 0; kk < KREG; ++kk) {
-                    const int k = kbeg + kk;
-                    double wlp = -INFINITY;
-                    if (k < kend) {
-                        wlp = weighted_logp(k);
-                        if (wlp > mx) { mx = wlp; am = k; }
-                    }
-                    wl[kk] = wlp;
-                }
-            } else {
-                for (int k = kbeg; k < kend; ++k) {
-                    const double wlp = weighted_logp(k);
-                    Rrow[k] = wlp;
-                    if (wlp > mx) { mx = wlp; am = k; }
-                }
+                for (int j = 0; j < NTE; ++j)
+                    if (j < nte) dmma884(lp[j], a, brow[(size_t)4 * ks * ldt + 8 * j]);
             }
-            s_red[half * ETS + s_loc] = mx; s_arg[half * ETS + s_loc] = am;
-            __syncthreads();
-            double m = s_red[s_loc];
-            int amax = s_arg[s_loc];
+            // first maximum over the components (np.argmax rule), quad-wide
+            double mx = -INFINITY; int am = 0;
 #pragma unroll
-            for (int q = 1; q < EPARTS; ++q) {                   // first maximum wins (parts are in component order)
-                const double mq = s_red[q * ETS + s_loc];
-                if (mq > m) { m = mq; amax = s_arg[q * ETS + s_loc]; }
+            for (int j = 0; j < NTE; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 8 * j + 2 * t4 + e;
+                    if (k >= K) lp[j][e] = -INFINITY;
+                    if (lp[j][e] > mx) { mx = lp[j][e]; am = k; }
+                }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const double mo = __shfl_xor_sync(0xffffffffu, mx, o);
+                const int ao = __shfl_xor_sync(0xffffffffu, am, o);
+                if (mo > mx || (mo == mx && ao < am)) { mx = mo; am = ao; }
             }
-            __syncthreads();
+            // exponentials as four interleaved branch-free chains (arguments <= 0; -inf beyond K gives 0)
             double se = 0.0;
-            // four interleaved branch-free exponentials (the arguments are <= 0); one at a time through the library exp
-            // the chains serialise and the E-step becomes FP64-latency bound
-            if (KB == 1) {
 #pragma unroll
-                for (int kk = 0; kk < KREG; kk += 4) {
-                    if (kbeg + kk < kend) {
-                        double e[4];
+            for (int j = 0; j < NTE; j += 2) {
+                if (j < nte) {
+                    double e4[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) e[u] = exp_tab(wl[kk + u] - m, s_etab);      // -inf beyond kend -> 0
+                    for (int u = 0; u < 4; ++u) e4[u] = exp_tab(lp[j + (u >> 1)][u & 1] - mx, s_etab);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) { wl[kk + u] = e[u]; se += e[u]; }
-                    }
+                    for (int u = 0; u < 4; ++u) { lp[j + (u >> 1)][u & 1] = e4[u]; se += e4[u]; }
                 }
-            } else {
-                int k = kbeg;
-                for (; k + 4 <= kend; k += 4) {
-                    double e[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) e[u] = exp_tab(Rrow[k + u] - m, s_etab);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { Rrow[k + u] = e[u]; se += e[u]; }
-                }
-                for (; k < kend; ++k) { const double e = exp_tab(Rrow[k] - m, s_etab); Rrow[k] = e; se += e; }
             }
-            s_red[half * ETS + s_loc] = se;
-            __syncthreads();
-            double tot = 0.0;
+            se += __shfl_xor_sync(0xffffffffu, se, 1);
+            se += __shfl_xor_sync(0xffffffffu, se, 2);
+            const int srow = 8 * warp + g;
+            const bool live_r = srow < cnt;
+            const double inv = live_r ? 1.0 / se : 0.0;
+            double* Rr = s_R + (size_t)srow * ldr + 2 * t4;
 #pragma unroll
-            for (int q = 0; q < EPARTS; ++q) tot += s_red[q * ETS + s_loc];
-            const double inv = live ? 1.0 / tot : 0.0;
-            if (KB == 1) {
-#pragma unroll
-                for (int kk = 0; kk < KREG; ++kk) if (kbeg + kk < kend) Rrow[kbeg + kk] = wl[kk] * inv;
-            } else {
-                for (int k = kbeg; k < kend; ++k) Rrow[k] *= inv;
-            }
-            if (half == EPARTS - 1) for (int k = K; k < KP; ++k) Rrow[k] = 0.0;
-            if (half == 0 && live) {
-                const double l = m + log(tot);
+            for (int j = 0; j < NTE; ++j)
+                if (j < nte) *reinterpret_cast<double2*>(Rr + 8 * j) = make_double2(lp[j][0] * inv, lp[j][1] * inv);
+            if (t4 == 0 && live_r) {
+                const double l = mx + log(se);
                 ll_acc += l;
-                if (p.lse) p.lse[base + s_loc] = l;
-                if (p.labels) p.labels[base + s_loc] = amax;
+                if (p.lse) p.lse[base + srow] = l;
+                if (p.labels) p.labels[base + srow] = am;
             }
         }
         __syncthreads();
@@ -250,7 +245,7 @@ __global__ void __launch_bounds__(ETHREADS, 2) k_gmm_em(EmArgs p) {
         }
     }
     __syncthreads();
-    if (half == 0) s_red[s_loc] = ll_acc;
+    if (t4 == 0) s_red[8 * warp + g] = ll_acc;                // one accumulator per sample slot of the tile, summed in slot order
     __syncthreads();
     if (tid == 0) { double t = 0.0; for (int i = 0; i < ETS; ++i) t += s_red[i]; part[(size_t)KP * FP] = t; }
 }
@@ -355,8 +350,8 @@ static int em_grid(long long n) {
 }
 static size_t em_smem(int d, int K) {
     const int F = gmm_F(d), FP = pad8(F), KP = pad8(K), TRI = d * (d + 1) / 2;
-    const int poff = (d + 2) & ~1, prec = (poff + TRI + 1) & ~1;       // parameter record of k_gmm_em
-    size_t dbl = (size_t)K * prec + ((d + 1) & ~1) + (size_t)ETS * d + (size_t)ETS * ld_conflict_free(KP) +
+    (void)TRI;
+    size_t dbl = (size_t)FP * ld_conflict_free(KP) + ((d + 1) & ~1) + (size_t)ETS * d + (size_t)ETS * ld_conflict_free(KP) +
                  (size_t)ETS * ld_conflict_free(FP) + 2 * EPARTS * ETS + kExpTabN;
     return dbl * sizeof(double);
 }

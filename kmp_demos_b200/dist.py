@@ -35,40 +35,51 @@ def init_process_group(backend=None):
     return rank, world, local
 
 
-def bind_to_gpu_numa_node(local_rank):
-    """Pins the calling process to the CPU cores of the NUMA node its GPU hangs off (Linux sysfs), so that pinned host
-    buffers allocated afterwards are first-touched on that node: with one process per GPU all writing results to host
-    memory, buffers that all live on one node cap the aggregate device-to-host rate at that node's memory bandwidth.
-    Returns the node id, or None when the topology cannot be read (nothing is changed then)."""
+def _cpulist(spec):
+    cpus = set()
+    for part in spec.strip().split(','):
+        if '-' in part:
+            a, b = part.split('-')
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local_rank, local_world=1):
+    """Pins the calling process to the CPU cores of one NUMA node, so that pinned host buffers allocated afterwards are
+    first-touched there: with one process per GPU all writing results to host memory, buffers that all live on one node
+    cap the aggregate device-to-host rate at that node's memory bandwidth.  The node is the one the GPU hangs off
+    (sysfs numa_node of its PCI function) when the container exposes it, else the ranks are spread evenly over the
+    nodes that are visible.  Returns (node id, how) or (None, reason); nothing is changed in the latter case."""
+    try:
+        nodes = sorted(int(d[4:]) for d in os.listdir('/sys/devices/system/node') if d.startswith('node') and d[4:].isdigit())
+    except OSError:
+        return None, 'no /sys/devices/system/node'
+    if len(nodes) < 2:
+        return None, f'{len(nodes)} NUMA node(s) visible'
+    node, how = None, ''
     try:
         import torch
-        bdf = None
         props = torch.cuda.get_device_properties(local_rank)
-        if hasattr(props, 'pci_bus_id') and hasattr(props, 'pci_device_id'):
-            dom = getattr(props, 'pci_domain_id', 0)
-            bdf = f'{dom:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0'
-        if bdf is None:
-            return None
+        bdf = f'{getattr(props, "pci_domain_id", 0):04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0'
         with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as fh:
-            node = int(fh.read().strip())
-        if node < 0:
-            return None
-        with open(f'/sys/devices/system/node/node{node}/cpulist') as fh:
-            spec = fh.read().strip()
-        cpus = set()
-        for part in spec.split(','):
-            if '-' in part:
-                a, b = part.split('-')
-                cpus.update(range(int(a), int(b) + 1))
-            elif part:
-                cpus.add(int(part))
-        allowed = cpus & set(os.sched_getaffinity(0))
-        if not allowed:
-            return None
-        os.sched_setaffinity(0, allowed)
-        return node
+            v = int(fh.read().strip())
+        if v in nodes:
+            node, how = v, f'sysfs numa_node of {bdf}'
     except (OSError, ValueError, RuntimeError, AttributeError):
-        return None
+        pass
+    if node is None:
+        node, how = nodes[(local_rank * len(nodes)) // max(local_world, 1) % len(nodes)], 'ranks spread over the visible nodes'
+    try:
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as fh:
+            allowed = _cpulist(fh.read()) & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None, f'no allowed core on node {node}'
+        os.sched_setaffinity(0, allowed)
+    except (OSError, ValueError):
+        return None, 'cpulist unreadable'
+    return node, how
 
 
 def shard_range(n_items, rank, world):
