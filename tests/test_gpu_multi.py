@@ -27,12 +27,12 @@ shift = torch.as_tensor(X.mean(axis=0), device=dev)
 lo, hi = kd.shard_range(n, rank, world)
 eng = EMEngine(torch.as_tensor(X[lo:hi], device=dev), K, 1e-6, shift=shift, group=dist.group.WORLD, n_total=n)
 eng.init_from_labels(torch.as_tensor(lab[lo:hi], device=dev))
-n_iter, lower, conv = eng.run(tol=1e-3, max_iter=100)
+n_iter, lower, conv = eng.run(tol=1e-3, max_iter=100, check_every=1)      # one all-reduce per executed pass
 out = dict(n_iter=n_iter, lower=lower, allreduces=eng.allreduce_count)
 if rank == 0:
     ref = EMEngine(torch.as_tensor(X, device=dev), K, 1e-6, shift=shift)
     ref.init_from_labels(torch.as_tensor(lab, device=dev))
-    n2, lower2, _ = ref.run(tol=1e-3, max_iter=100)
+    n2, lower2, _ = ref.run(tol=1e-3, max_iter=100, check_every=1)
     rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
     out.update(n_iter_ref=n2, lower_ref=lower2, err_means=rel(eng.means, ref.means), err_covs=rel(eng.covs, ref.covs),
                err_weights=rel(eng.weights, ref.weights))
