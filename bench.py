@@ -453,14 +453,14 @@ def run_ours(args):
 
 
 def strong_chunk(b_local, chunk):
-    """Systems resident at once for a shard of b_local problems: the factor kernels run one CTA per SM (148), so a
-    shard is cut into near-equal chunks whose sizes are multiples of 148 where the shard allows it (3 328 problems at
-    N = 8 -> one chunk, 22.5 waves: the partial wave costs < 1 % of a step)."""
+    """Systems resident at once for a shard of b_local problems: the factor kernels run twelve problems per SM (1776
+    warp slots), so a shard is cut into near-equal chunks whose sizes are multiples of 1776 where the shard allows it
+    (3 328 problems at N = 8 -> one chunk)."""
     if b_local <= chunk:
         return b_local
     n_chunks = -(-b_local // chunk)
     per = -(-b_local // n_chunks)
-    return -(-per // 148) * 148
+    return min(chunk, -(-per // 1776) * 1776)
 
 
 _RESULT = []      # the JSON line(s) of this process, printed by main() once stdout is restored
@@ -473,7 +473,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--sets', type=int, default=N_SETS, help='via-point sets per letter (1024 = the named config)')
-    ap.add_argument('--chunk', type=int, default=4440, help='systems resident at once (a multiple of the 148 SMs: the factor kernels run one CTA per SM)')
+    ap.add_argument('--chunk', type=int, default=5328,
+                    help='systems resident at once (a multiple of 12 x 148 = 1776: the factor kernels run twelve problems per SM)')
     ap.add_argument('--no-extras', action='store_true')
     args = ap.parse_args()
     # stdout carries exactly one JSON line: whatever libraries write to file descriptor 1 while the run is on (NCCL's

@@ -85,6 +85,19 @@ long long kmpx_trtri_workspace_bytes(int n_max, int batch);
 int kmpx_trtri(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch,
                void* ws, long long ws_bytes, void* stream);
 
+/* ---- K2 / K3, warp-per-problem variants for LARGE batches of small systems (64 <= n_max <= KMPX_SMALL_MAX; cfg 3).
+ *      Same mathematics and result layout as kmpx_potrf / kmpx_trtri (KMP.py:157), but a warp owns a problem from the
+ *      first block column to the last (factor_wpp.cuh): twelve independent problems per SM hide each other's latency,
+ *      which pays once the batch holds several problems per warp slot (batch >~ 4 * 148).  Differences to kmpx_trtri:
+ *      the strict upper triangle of every problem is used as scratch and holds finite garbage afterwards.
+ *      struct_o: 0, or 2 for component-major KMP systems with two outputs and the plain kernel (kmpx_kernel_build with
+ *      O = 2, KMPX_LAYOUT_COMPONENT: A = [[A00, D], [D, A11]], D diagonal, component stride n_sys[b] / 2) - blocks of
+ *      the factor that are exactly zero are then skipped; the results are bit-identical to struct_o = 0. */
+int kmpx_factor_wpp_applicable(const double* A, int lda, long long strideA, int n_max, int batch);
+int kmpx_potrf_wpp(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
+                   int struct_o, void* stream);
+int kmpx_trtri_wpp(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, int struct_o, void* stream);
+
 /* ---- K1 + K2 + K3 fused for the small plain-kernel systems (O <= 2, N <= ~204: cfg 1 / cfg 3).  Replaces KMP.fit's
  *      N^2 loop and numpy.linalg.inv, KMP.py:146-157, in ONE kernel: the matrix is generated from (s, sigma) inside shared
  *      memory and factorised / inverted there exploiting that the cross-component blocks lambda * Sigma_ab are diagonal

@@ -75,6 +75,9 @@ _SIGNATURES = {
     'kmpx_quat_log': [_p, _p, _ll, _p],
     'kmpx_quat_mul': [_p, _p, _i, _i, _p, _ll, _p],
     'kmpx_quat_from_rotvec': [_p, _p, _ll, _p],
+    'kmpx_factor_wpp_applicable': [_p, _i, _ll, _i, _i],
+    'kmpx_potrf_wpp': [_p, _i, _ll, _p, _i, _i, _p, _i, _p],
+    'kmpx_trtri_wpp': [_p, _i, _ll, _p, _i, _i, _i, _p],
     'kmpx_dgemm': [_i, _i, _i, _i, _i, _d, _p, _i, _ll, _p, _i, _ll, _d, _p, _i, _ll, _i, _i, _p],
 }
 _RESTYPES = {

@@ -18,13 +18,16 @@ def _roundup(v, m):
     return (v + m - 1) // m * m
 
 
+WARP_MIN_BATCH = 4 * 148     # problems per call from which the warp-per-problem factor kernels are taken ('auto')
+
+
 class KMPBatch:
     """Batched fit+predict of KMP problems that share base trajectories and a query grid.
 
     Parameters mirror ``KMP`` (l, alpha, sigma_f, adaptation_tol, time_driven_kernel).  ``chunk`` bounds the
     number of systems resident at once (each is n^2 doubles)."""
 
-    def __init__(self, l=0.5, alpha=40.0, sigma_f=1.0, adaptation_tol=0.0005, time_driven_kernel=False, chunk=4440):
+    def __init__(self, l=0.5, alpha=40.0, sigma_f=1.0, adaptation_tol=0.0005, time_driven_kernel=False, chunk=5328):
         self.l, self.alpha, self.sigma_f = float(l), float(alpha), float(sigma_f)
         self.tol, self.time_driven_kernel, self.chunk = float(adaptation_tol), bool(time_driven_kernel), int(chunk)
         self._bufs = {}
@@ -33,6 +36,12 @@ class KMPBatch:
         # build + potrf + trtri.  Correct and tested, but measured ~20 % SLOWER than the TMA pipeline on the cfg-3 shape
         # (DESIGN.md 3.4), hence opt-in
         self.fused_fit = False
+        # Cholesky + triangular inverse of the batched path: 'cta' = one CTA per problem (factor_tma.cuh), 'warp' = one
+        # warp per problem, twelve independent problems per SM (factor_wpp.cuh; 1.8x faster on a cfg-3 chunk, but it needs
+        # a few problems per warp slot to pay), 'auto' = 'warp' when the call holds >= WARP_MIN_BATCH problems.  The
+        # choice is made once per call from the total batch, never per chunk, so that a problem takes the same kernel -
+        # and yields the same bits - whichever chunk it falls into.
+        self.factor_mode = 'auto'
         self.events = None        # set to a list to collect (kernel name, start, end) CUDA events per launch
 
     # ------------------------------------------------------------------ data staging
@@ -112,6 +121,11 @@ class KMPBatch:
         strideA = n_max * lda
         # the covariance blocks handed to this path are symmetric by contract (GMR output, via-point covariances)
         fused_fit = (not self.time_driven_kernel) and self.fused_fit and bool(lib.kmpx_factor_struct_applicable(n_max_pts, I, O))
+        if self.factor_mode not in ('auto', 'cta', 'warp'):
+            raise ValueError("factor_mode must be 'auto', 'cta' or 'warp'")
+        warp_fit = (not fused_fit) and self.factor_mode != 'cta' and (self.factor_mode == 'warp' or B >= WARP_MIN_BATCH) \
+            and bool(lib.kmpx_factor_wpp_applicable(_lib.ptr(A), lda, strideA, n_max, Bc))
+        struct_o = 2 if (O == 2 and not self.time_driven_kernel) else 0      # [[A00, D], [D, A11]] with D diagonal
         copy_stream = None
         if host_xi is not None or host_sigma is not None:
             if getattr(self, '_copy_stream', None) is None:
@@ -132,8 +146,12 @@ class KMPBatch:
                 self._launch('kmpx_sys_sizes', _lib.ptr(npc), O, _lib.LAYOUT_COMPONENT, bc, _lib.ptr(n_sys), st)
                 self._launch('kmpx_kernel_build', _lib.ptr(s), _lib.ptr(g), _lib.ptr(npc), _lib.ptr(A), bc, n_max_pts, I, O, lda,
                              strideA, self.sigma_f, self.l, td, _lib.LAYOUT_COMPONENT, _lib.UPLO_LOWER, st)
-                self._launch('kmpx_potrf', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, _lib.ptr(info[c0:]), None, 0, st)
-                self._launch('kmpx_trtri', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, None, 0, st)
+                if warp_fit:
+                    self._launch('kmpx_potrf_wpp', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, _lib.ptr(info[c0:]), struct_o, st)
+                    self._launch('kmpx_trtri_wpp', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, struct_o, st)
+                else:
+                    self._launch('kmpx_potrf', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, _lib.ptr(info[c0:]), None, 0, st)
+                    self._launch('kmpx_trtri', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, None, 0, st)
             # alpha = A^-1 mu is only needed by the mean-only predict; the fused mean+covariance kernel takes w
             self._launch('kmpx_solve_alpha', _lib.ptr(A), lda, strideA, _lib.ptr(npc), n_max_pts, O, bc,
                       _lib.LAYOUT_COMPONENT, _lib.ptr(y), _lib.ptr(w), lda, None if want_cov else _lib.ptr(al), st)

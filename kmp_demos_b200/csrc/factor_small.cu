@@ -567,6 +567,7 @@ __global__ void __launch_bounds__(256) k_solve_alpha(AlphaArgs p) {
 }  // namespace kmpx
 #include "factor_tma.cuh"
 #include "factor_struct.cuh"
+#include "factor_wpp.cuh"
 namespace kmpx {
 
 int debug_set(int flags) { g_host_dbg = flags; return check_cuda(cudaMemcpyToSymbol(g_dbg, &flags, sizeof(int)), "cudaMemcpyToSymbol"); }
@@ -644,6 +645,30 @@ extern "C" int kmpx_factor_struct(const double* s, const double* sigma, const in
     if (lda < O * comp_stride(n_max_pts)) return fail_arg(5, "lda < system size");
     StructArgs p{s, sigma, n_pts, F, lda, strideF, n_max_pts, I, O, batch, sigma_f, lambda, info, 0};
     return launch_factor_struct(p, (cudaStream_t)stream);
+}
+extern "C" int kmpx_factor_wpp_applicable(const double* A, int lda, long long strideA, int n_max, int batch) {
+    return kmpx::wpp_applicable(A, lda, strideA, n_max, batch) ? 1 : 0;
+}
+extern "C" int kmpx_potrf_wpp(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
+                              int struct_o, void* stream) {
+    using namespace kmpx;
+    if (!A) return fail_arg(1, "matrix is NULL");
+    if (batch <= 0) return fail_arg(6, "batch must be > 0");
+    if (lda < n_max) return fail_arg(2, "lda < n_max");
+    if (struct_o != 0 && struct_o != 2) return fail_arg(8, "struct_o must be 0 or 2");
+    if (!wpp_applicable(A, lda, strideA, n_max, batch))
+        return fail_arg(5, "kmpx_potrf_wpp needs 64 <= n_max <= KMPX_SMALL_MAX, even lda / strideA and a 16-byte aligned matrix");
+    return launch_potrf_wpp(A, lda, strideA, n_sys, n_max, batch, info, struct_o, (cudaStream_t)stream);
+}
+extern "C" int kmpx_trtri_wpp(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, int struct_o, void* stream) {
+    using namespace kmpx;
+    if (!L) return fail_arg(1, "matrix is NULL");
+    if (batch <= 0) return fail_arg(6, "batch must be > 0");
+    if (lda < n_max) return fail_arg(2, "lda < n_max");
+    if (struct_o != 0 && struct_o != 2) return fail_arg(7, "struct_o must be 0 or 2");
+    if (!wpp_applicable(L, lda, strideA, n_max, batch))
+        return fail_arg(5, "kmpx_trtri_wpp needs 64 <= n_max <= KMPX_SMALL_MAX, even lda / strideA and a 16-byte aligned matrix");
+    return launch_trtri_wpp(L, lda, strideA, n_sys, n_max, batch, struct_o, (cudaStream_t)stream);
 }
 extern "C" int kmpx_debug_phases(long long* out_host, int reset) { return kmpx::debug_phases(out_host, reset); }
 extern "C" int kmpx_debug_set(int flags) { return kmpx::debug_set(flags); }

@@ -289,6 +289,100 @@ def test_potrf_tma_reports_first_bad_pivot(T):
     assert rel_err(np.tril(A[2].cpu().numpy()), np.linalg.cholesky(good)) < 1e-13
 
 
+def _struct_spd(rng, N):
+    """Component-major two-output KMP system [[A00, D], [D, A11]] with diagonal D (padding rows identity): what
+    kmpx_kernel_build writes for O = 2 and the plain kernel."""
+    Ns = (N + 1) // 2 * 2
+    A = np.eye(2 * Ns)
+    t = np.sort(rng.uniform(0, 1, N))
+    K = np.exp(-30.0 * (t[:, None] - t[None, :]) ** 2)
+    for a in range(2):
+        A[a * Ns:a * Ns + N, a * Ns:a * Ns + N] = K + np.diag(rng.uniform(0.5, 1.5, N))
+    d = rng.uniform(-0.3, 0.3, N)
+    A[Ns:Ns + N, :N] += np.diag(d)
+    A[:N, Ns:Ns + N] += np.diag(d)
+    return A
+
+
+@pytest.mark.parametrize('variant_flags', [0, 128, 256])
+@pytest.mark.parametrize('nmax,lda,sizes', [(404, 408, [64, 65, 96, 100, 257, 333, 402, 404, 1, 5, 31, 32, 33] * 3),
+                                            (202, 202, [200, 202, 128]), (512, 512, [512, 511, 497, 481, 480, 300, 64])])
+def test_potrf_trtri_warp_per_problem_ragged(T, nmax, lda, sizes, variant_flags):
+    """kmpx_potrf_wpp / kmpx_trtri_wpp (factor_wpp.cuh; all three tile variants) on ragged batches with NaN everywhere
+    outside the lower triangles: factor and inverse against numpy, rows beyond a system untouched."""
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    A = T.full((len(sizes), nmax, lda), float('nan'), dtype=T.float64, device='cuda')
+    mats = []
+    for b, n in enumerate(sizes):
+        S = _spd(rng, n)
+        mats.append(S)
+        A[b, :n, :n] = dev(T, np.tril(S) + np.triu(np.full((n, n), np.nan), 1))
+    n_sys = dev(T, np.array(sizes, dtype=np.int32))
+    info = T.full((len(sizes),), -3, dtype=T.int32, device='cuda')
+    assert lib.kmpx_factor_wpp_applicable(_lib.ptr(A), lda, nmax * lda, nmax, len(sizes)) == 1
+    lib.kmpx_debug_set(variant_flags)
+    try:
+        _lib.call('kmpx_potrf_wpp', _lib.ptr(A), lda, nmax * lda, _lib.ptr(n_sys), nmax, len(sizes), _lib.ptr(info), 0, _lib.stream())
+        Lh = A.cpu().numpy()
+        _lib.call('kmpx_trtri_wpp', _lib.ptr(A), lda, nmax * lda, _lib.ptr(n_sys), nmax, len(sizes), 0, _lib.stream())
+        Xh = A.cpu().numpy()
+    finally:
+        lib.kmpx_debug_set(0)
+    assert info.cpu().numpy().tolist() == [0] * len(sizes)
+    for b, n in enumerate(sizes):
+        assert rel_err(np.tril(Lh[b, :n, :n]), np.linalg.cholesky(mats[b])) < 1e-13, n
+        assert rel_err(np.tril(Xh[b, :n, :n]), np.linalg.inv(np.linalg.cholesky(mats[b]))) < 1e-12, n
+        assert np.all(np.isnan(Xh[b, n:, :])), 'rows beyond the system must stay untouched'
+
+
+@pytest.mark.parametrize('variant_flags', [0, 128, 256])
+def test_warp_per_problem_structure_skipping_is_bit_identical(T, variant_flags):
+    """struct_o = 2 only drops products with exact zeros of the component-major two-output system: same bits as
+    struct_o = 0, and the inverse agrees with numpy."""
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(22)
+    Ns_list = [202, 201, 200, 150, 37]
+    sizes = [2 * ((N + 1) // 2 * 2) for N in Ns_list]
+    nmax = max(sizes)
+    lda = nmax + 4
+    mats = [_struct_spd(rng, N) for N in Ns_list]
+    out = []
+    lib.kmpx_debug_set(variant_flags)
+    try:
+        for struct_o in (0, 2):
+            A = T.full((len(sizes), nmax, lda), float('nan'), dtype=T.float64, device='cuda')
+            for b, n in enumerate(sizes):
+                A[b, :n, :n] = dev(T, np.tril(mats[b]) + np.triu(np.full((n, n), np.nan), 1))
+            n_sys = dev(T, np.array(sizes, dtype=np.int32))
+            info = T.zeros(len(sizes), dtype=T.int32, device='cuda')
+            _lib.call('kmpx_potrf_wpp', _lib.ptr(A), lda, nmax * lda, _lib.ptr(n_sys), nmax, len(sizes), _lib.ptr(info), struct_o, _lib.stream())
+            _lib.call('kmpx_trtri_wpp', _lib.ptr(A), lda, nmax * lda, _lib.ptr(n_sys), nmax, len(sizes), struct_o, _lib.stream())
+            assert info.cpu().numpy().tolist() == [0] * len(sizes)
+            out.append(A.cpu().numpy())
+    finally:
+        lib.kmpx_debug_set(0)
+    for b, n in enumerate(sizes):
+        assert np.array_equal(np.tril(out[0][b, :n, :n]), np.tril(out[1][b, :n, :n])), n
+        assert rel_err(np.tril(out[1][b, :n, :n]), np.linalg.inv(np.linalg.cholesky(mats[b]))) < 1e-12, n
+
+
+def test_potrf_warp_per_problem_reports_first_bad_pivot(T):
+    from kmp_demos_b200 import _lib
+    rng = np.random.default_rng(23)
+    n = 160
+    good = _spd(rng, n)
+    bad = good.copy(); bad[100, 100] = -5.0
+    bad0 = good.copy(); bad0[0, 0] = 0.0
+    A = dev(T, np.stack([good, bad, good, bad0]))
+    info = T.zeros(4, dtype=T.int32, device='cuda')
+    _lib.call('kmpx_potrf_wpp', _lib.ptr(A), n, n * n, None, n, 4, _lib.ptr(info), 0, _lib.stream())
+    assert info.cpu().numpy().tolist() == [0, 101, 0, 1]
+    assert rel_err(np.tril(A[2].cpu().numpy()), np.linalg.cholesky(good)) < 1e-13
+
+
 def test_potrf_reports_first_bad_pivot(T):
     from kmp_demos_b200 import _lib
     rng = np.random.default_rng(4)

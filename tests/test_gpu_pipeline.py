@@ -167,6 +167,39 @@ def test_fused_fit_kernel_through_the_pipeline(golden):
     assert rel_err(res[1][0], res[0][0]) < 1e-10 and rel_err(res[1][1], res[0][1]) < 1e-9
 
 
+def test_warp_per_problem_fit_through_the_pipeline(golden):
+    """KMPBatch.factor_mode = 'warp' (kmpx_potrf_wpp / kmpx_trtri_wpp with the two-output structure flag instead of the
+    CTA-per-problem kernels) reproduces the reference's cfg-3 results, agrees with the 'cta' pipeline to rounding, ignores
+    NaN-poisoned storage, and is independent of the chunking (a problem takes the same kernel in every chunk)."""
+    from kmp_demos_b200.batch import KMPBatch
+    zl, z = golden('letters_ref.npz'), golden('cfg3_sample.npz')
+    c = wl.CFG1
+    t = wl.cfg1_kmp_grid(200)
+    base_of, vs, vp, vv = [], [], [], []
+    for r in range(len(z['letter'])):
+        li, si = int(z['letter'][r]), int(z['set_idx'][r])
+        a, b, cc = wl.cfg3_via_sets(li, zl['gmr_mu'][li], si + 1)
+        base_of.append(li); vs.append(a[si]); vp.append(b[si]); vv.append(cc[si])
+    args = (np.array(base_of), np.array(vs), np.array(vp), np.array(vv), z['queries'])
+    res = {}
+    for mode, chunk in (('cta', 16), ('warp', 16), ('warp', 7)):
+        kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=chunk)
+        kb.factor_mode = mode
+        kb.set_base(np.broadcast_to(t, (26, 1, 200)), zl['gmr_mu'], zl['gmr_sigma'])
+        res[(mode, chunk)] = kb.fit_predict(*args)
+        if (mode, chunk) == ('warp', 7):
+            for key, buf in kb._bufs.items():
+                if key[0] in ('A', 'w', 'alpha'):
+                    buf.fill_(float('nan'))
+            res['poisoned'] = kb.fit_predict(*args)
+    xi, sg = res[('warp', 16)]
+    for r in range(len(z['letter'])):
+        assert rel_err(xi[r], z['xi'][r]) < MEAN_TOL and rel_err(sg[r], z['sigma'][r]) < COV_TOL, r
+    assert rel_err(xi, res[('cta', 16)][0]) < 1e-10 and rel_err(sg, res[('cta', 16)][1]) < 1e-9
+    assert np.array_equal(xi, res[('warp', 7)][0]) and np.array_equal(sg, res[('warp', 7)][1])
+    assert np.array_equal(xi, res['poisoned'][0]) and np.array_equal(sg, res['poisoned'][1])
+
+
 def test_cfg3_batch_vs_reference_and_vs_single(golden):
     """cfg 3 sample: batched adaptation == the reference's per-problem results; batch == one-by-one bit for bit."""
     from kmp_demos_b200.batch import KMPBatch
