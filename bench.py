@@ -402,7 +402,7 @@ def run_ours(args):
         for v in kern.values():
             v['share'] = v['ms_per_step'] / tot
         line['kernels'] = kern
-        pred = per['kmpx_kmp_predict']
+        pred = per.get('kmpx_kmp_predict_persistent') or per['kmpx_kmp_predict']
         n_launch = len(pred)
         # algorithmic flops of the fused predict: triangular V = Linv k*^T (O^2 Ns^2 M) + Gram/mean reduction
         Ns = np.ceil(n_host / 2) * 2

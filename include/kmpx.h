@@ -146,6 +146,18 @@ int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kin
                      int batch, const double* sq, long long stride_sq, int M,
                      double sigma_f, double alpha_kmp, int time_driven,
                      double* xi, double* sigma_out, void* stream);
+/* kmpx_kmp_predict for LARGE batches (many (problem, query tile) pairs per SM): same arguments and mathematics; where
+ * the fast path applies (plain kernel, O <= 2, factor_kind 0) persistent CTAs walk tiles of 40 queries with the kappa panel
+ * of the next tile evaluated, and the results of the previous one written, while the tensor pipe contracts the current
+ * one (predict_pers.cu).  Results agree with kmpx_kmp_predict to rounding (the summation order over the rows differs);
+ * a problem's bits do not depend on the batch it sits in.  Falls back to kmpx_kmp_predict's kernels elsewhere.
+ * Measured 6 % slower than kmpx_kmp_predict on the cfg-3 shape (the smaller tile costs more in the streaming loop than
+ * the hidden prologue saves): an experiment kept for reference, not what KMPBatch calls by default. */
+int kmpx_kmp_predict_persistent(const double* F, int lda, long long strideA, int factor_kind,
+                                const double* w, int ldw, const double* s, const int* n_pts, int n_max, int I, int O,
+                                int batch, const double* sq, long long stride_sq, int M,
+                                double sigma_f, double alpha_kmp, int time_driven,
+                                double* xi, double* sigma_out, void* stream);
 /* The same prediction for ONE large system (n > KMPX_SMALL_MAX, plain kernel, O <= 2, symmetric factor) as DMMA GEMMs:
  * kappa^T (Mc x N) once per chunk of queries, V_a = Linv[a Ns:, a Ns: a Ns + N] kappa with kmpx_dgemm's triangular mode,
  * column reductions for xi / sigma.  F as left by kmpx_trtri for n > KMPX_SMALL_MAX (strict upper triangle zero).

@@ -41,6 +41,7 @@ _SIGNATURES = {
     'kmpx_sys_size': [_i, _i, _i],
     'kmpx_sys_sizes': [_p, _i, _i, _i, _p, _p],
     'kmpx_kmp_predict': [_p, _i, _ll, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _ll, _i, _d, _d, _i, _p, _p, _p],
+    'kmpx_kmp_predict_persistent': [_p, _i, _ll, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _ll, _i, _d, _d, _i, _p, _p, _p],
     'kmpx_inc_workspace_doubles': [_i, _i, _i],
     'kmpx_inc_base': [_p, _i, _ll, _p, _p, _i, _i, _i, _i, _p, _i, _d, _p, _p, _p],
     'kmpx_inc_adapt': [_p, _p, _i, _ll, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _i, _d, _d, _d, _d, _i, _p, _i,

@@ -42,6 +42,11 @@ class KMPBatch:
         # choice is made once per call from the total batch, never per chunk, so that a problem takes the same kernel -
         # and yields the same bits - whichever chunk it falls into.
         self.factor_mode = 'auto'
+        # fused mean + covariance predict: 'tile' = one CTA per tile of 64 queries (predict_fast.cu, the default);
+        # 'persistent' = persistent CTAs over tiles of 40 queries with double-buffered kappa panels (predict_pers.cu):
+        # built to hide the panel evaluation and the epilogue, correct, but measured 6 % SLOWER on the cfg-3 shape
+        #  - opt-in, kept as the measurement behind that paragraph.
+        self.predict_mode = 'tile'
         self.events = None        # set to a list to collect (kernel name, start, end) CUDA events per launch
 
     # ------------------------------------------------------------------ data staging
@@ -126,6 +131,9 @@ class KMPBatch:
         warp_fit = (not fused_fit) and self.factor_mode != 'cta' and (self.factor_mode == 'warp' or B >= WARP_MIN_BATCH) \
             and bool(lib.kmpx_factor_wpp_applicable(_lib.ptr(A), lda, strideA, n_max, Bc))
         struct_o = 2 if (O == 2 and not self.time_driven_kernel) else 0      # [[A00, D], [D, A11]] with D diagonal
+        if self.predict_mode not in ('tile', 'persistent'):
+            raise ValueError("predict_mode must be 'tile' or 'persistent'")
+        predict_entry = 'kmpx_kmp_predict_persistent' if self.predict_mode == 'persistent' else 'kmpx_kmp_predict'
         copy_stream = None
         if host_xi is not None or host_sigma is not None:
             if getattr(self, '_copy_stream', None) is None:
@@ -161,7 +169,7 @@ class KMPBatch:
             for q0, q1 in ((bc * i // parts, bc * (i + 1) // parts) for i in range(parts)):
                 nb = q1 - q0
                 if want_cov:
-                    self._launch('kmpx_kmp_predict', _lib.ptr(A[q0:]), lda, strideA, 0, _lib.ptr(w[q0:]), lda, _lib.ptr(s[q0:]),
+                    self._launch(predict_entry, _lib.ptr(A[q0:]), lda, strideA, 0, _lib.ptr(w[q0:]), lda, _lib.ptr(s[q0:]),
                               _lib.ptr(npc[q0:]), n_max_pts, I, O, nb, _lib.ptr(queries), 0, M, self.sigma_f, self.alpha, td,
                               _lib.ptr(xi[c0 + q0:]), _lib.ptr(sg[c0 + q0:]), st)
                 else:

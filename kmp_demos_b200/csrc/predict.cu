@@ -386,11 +386,11 @@ static int launch_predict(PredictArgs& p, cudaStream_t st) {
 
 using namespace kmpx;
 
-extern "C" int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kind,
-                                const double* w, int ldw, const double* s, const int* n_pts, int n_max, int I, int O,
-                                int batch, const double* sq, long long stride_sq, int M,
-                                double sigma_f, double alpha_kmp, int time_driven,
-                                double* xi, double* sigma_out, void* stream) {
+static int predict_dispatch(const double* F, int lda, long long strideA, int factor_kind,
+                            const double* w, int ldw, const double* s, const int* n_pts, int n_max, int I, int O,
+                            int batch, const double* sq, long long stride_sq, int M,
+                            double sigma_f, double alpha_kmp, int time_driven,
+                            double* xi, double* sigma_out, int persistent, void* stream) {
     if (!F) return fail_arg(1, "F is NULL");
     if (lda & 1) return fail_arg(2, "lda must be even");
     if (strideA & 1) return fail_arg(3, "strideA must be even");
@@ -408,10 +408,28 @@ extern "C" int kmpx_kmp_predict(const double* F, int lda, long long strideA, int
     if ((reinterpret_cast<uintptr_t>(F) & 15) != 0) return fail_arg(1, "F must be 16-byte aligned");
     PredictArgs p{F, lda, strideA, factor_kind, w, ldw, s, n_pts, n_max, I, O, batch, sq, stride_sq, M,
                   sigma_f, alpha_kmp, time_driven, xi, sigma_out, 0, 0, g_host_dbg};
+    if (persistent && predict_pers_applicable(p)) return launch_predict_pers(p, (cudaStream_t)stream);
     if (predict_fast_applicable(p)) return launch_predict_fast(p, (cudaStream_t)stream);
     if (predict_stream_applicable(p)) return launch_predict_stream(p, (cudaStream_t)stream);
     if (O <= 2) return launch_predict<64>(p, (cudaStream_t)stream);
     return launch_predict<32>(p, (cudaStream_t)stream);
+}
+
+extern "C" int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kind,
+                                const double* w, int ldw, const double* s, const int* n_pts, int n_max, int I, int O,
+                                int batch, const double* sq, long long stride_sq, int M,
+                                double sigma_f, double alpha_kmp, int time_driven,
+                                double* xi, double* sigma_out, void* stream) {
+    return predict_dispatch(F, lda, strideA, factor_kind, w, ldw, s, n_pts, n_max, I, O, batch, sq, stride_sq, M, sigma_f, alpha_kmp,
+                            time_driven, xi, sigma_out, 0, stream);
+}
+extern "C" int kmpx_kmp_predict_persistent(const double* F, int lda, long long strideA, int factor_kind,
+                                           const double* w, int ldw, const double* s, const int* n_pts, int n_max, int I, int O,
+                                           int batch, const double* sq, long long stride_sq, int M,
+                                           double sigma_f, double alpha_kmp, int time_driven,
+                                           double* xi, double* sigma_out, void* stream) {
+    return predict_dispatch(F, lda, strideA, factor_kind, w, ldw, s, n_pts, n_max, I, O, batch, sq, stride_sq, M, sigma_f, alpha_kmp,
+                            time_driven, xi, sigma_out, 1, stream);
 }
 
 extern "C" int kmpx_kmp_predict_mean(const double* alpha, const double* s, const int* n_pts, int n_max, int I, int O,

@@ -182,9 +182,12 @@ def test_warp_per_problem_fit_through_the_pipeline(golden):
         base_of.append(li); vs.append(a[si]); vp.append(b[si]); vv.append(cc[si])
     args = (np.array(base_of), np.array(vs), np.array(vp), np.array(vv), z['queries'])
     res = {}
-    for mode, chunk in (('cta', 16), ('warp', 16), ('warp', 7)):
+    for mode, chunk in (('cta', 16), ('warp', 16), ('warp', 7), ('persistent', 16)):
         kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=chunk)
-        kb.factor_mode = mode
+        if mode == 'persistent':            # the opt-in persistent predict kernel (predict_pers.cu) on top of the 'cta' fit
+            kb.predict_mode = 'persistent'
+        else:
+            kb.factor_mode = mode
         kb.set_base(np.broadcast_to(t, (26, 1, 200)), zl['gmr_mu'], zl['gmr_sigma'])
         res[(mode, chunk)] = kb.fit_predict(*args)
         if (mode, chunk) == ('warp', 7):
@@ -198,6 +201,10 @@ def test_warp_per_problem_fit_through_the_pipeline(golden):
     assert rel_err(xi, res[('cta', 16)][0]) < 1e-10 and rel_err(sg, res[('cta', 16)][1]) < 1e-9
     assert np.array_equal(xi, res[('warp', 7)][0]) and np.array_equal(sg, res[('warp', 7)][1])
     assert np.array_equal(xi, res['poisoned'][0]) and np.array_equal(sg, res['poisoned'][1])
+    xp, sp = res[('persistent', 16)]
+    assert rel_err(xp, res[('cta', 16)][0]) < 1e-12 and rel_err(sp, res[('cta', 16)][1]) < 1e-11
+    for r in range(len(z['letter'])):
+        assert rel_err(xp[r], z['xi'][r]) < MEAN_TOL and rel_err(sp[r], z['sigma'][r]) < COV_TOL, r
 
 
 def test_cfg3_batch_vs_reference_and_vs_single(golden):
