@@ -97,6 +97,11 @@ int kmpx_factor_wpp_applicable(const double* A, int lda, long long strideA, int 
 int kmpx_potrf_wpp(double* A, int lda, long long strideA, const int* n_sys, int n_max, int batch, int* info,
                    int struct_o, void* stream);
 int kmpx_trtri_wpp(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, int struct_o, void* stream);
+/* kmpx_trtri_wpp that also leaves w = Linv y' (the w of kmpx_solve_alpha, system order, [batch][ldw]) - formed from the
+ * blocks of the inverse while they are on chip, which saves the extra pass over Linv.  Component-major systems only:
+ * n_max = O * (n_max_pts rounded up to even); y point-major [batch][n_max_pts][O], n_pts [batch] (NULL with n_sys NULL). */
+int kmpx_trtri_wpp_solve(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, int struct_o,
+                         const double* y, const int* n_pts, int n_max_pts, int O, double* w, int ldw, void* stream);
 
 /* ---- K1 + K2 + K3 fused for the small plain-kernel systems (O <= 2, N <= ~204: cfg 1 / cfg 3).  Replaces KMP.fit's
  *      N^2 loop and numpy.linalg.inv, KMP.py:146-157, in ONE kernel: the matrix is generated from (s, sigma) inside shared

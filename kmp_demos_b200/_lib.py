@@ -79,6 +79,7 @@ _SIGNATURES = {
     'kmpx_factor_wpp_applicable': [_p, _i, _ll, _i, _i],
     'kmpx_potrf_wpp': [_p, _i, _ll, _p, _i, _i, _p, _i, _p],
     'kmpx_trtri_wpp': [_p, _i, _ll, _p, _i, _i, _i, _p],
+    'kmpx_trtri_wpp_solve': [_p, _i, _ll, _p, _i, _i, _i, _p, _p, _i, _i, _p, _i, _p],
     'kmpx_dgemm': [_i, _i, _i, _i, _i, _d, _p, _i, _ll, _p, _i, _ll, _d, _p, _i, _ll, _i, _i, _p],
 }
 _RESTYPES = {

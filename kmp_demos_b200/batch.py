@@ -156,12 +156,17 @@ class KMPBatch:
                              strideA, self.sigma_f, self.l, td, _lib.LAYOUT_COMPONENT, _lib.UPLO_LOWER, st)
                 if warp_fit:
                     self._launch('kmpx_potrf_wpp', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, _lib.ptr(info[c0:]), struct_o, st)
-                    self._launch('kmpx_trtri_wpp', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, struct_o, st)
+                    if want_cov:       # w = Linv y' falls out of the inverse (no pass of its own)
+                        self._launch('kmpx_trtri_wpp_solve', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, struct_o,
+                                     _lib.ptr(y), _lib.ptr(npc), n_max_pts, O, _lib.ptr(w), lda, st)
+                    else:
+                        self._launch('kmpx_trtri_wpp', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, struct_o, st)
                 else:
                     self._launch('kmpx_potrf', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, _lib.ptr(info[c0:]), None, 0, st)
                     self._launch('kmpx_trtri', _lib.ptr(A), lda, strideA, _lib.ptr(n_sys), n_max, bc, None, 0, st)
             # alpha = A^-1 mu is only needed by the mean-only predict; the fused mean+covariance kernel takes w
-            self._launch('kmpx_solve_alpha', _lib.ptr(A), lda, strideA, _lib.ptr(npc), n_max_pts, O, bc,
+            if not (warp_fit and want_cov):
+                self._launch('kmpx_solve_alpha', _lib.ptr(A), lda, strideA, _lib.ptr(npc), n_max_pts, O, bc,
                       _lib.LAYOUT_COMPONENT, _lib.ptr(y), _lib.ptr(w), lda, None if want_cov else _lib.ptr(al), st)
             # with host outputs the predict of the LAST chunk is launched in four parts, so that only the copy of the last
             # quarter is left when the compute stream is done (the copies of earlier chunks overlap with the next chunk)

@@ -668,7 +668,23 @@ extern "C" int kmpx_trtri_wpp(double* L, int lda, long long strideA, const int* 
     if (struct_o != 0 && struct_o != 2) return fail_arg(7, "struct_o must be 0 or 2");
     if (!wpp_applicable(L, lda, strideA, n_max, batch))
         return fail_arg(5, "kmpx_trtri_wpp needs 64 <= n_max <= KMPX_SMALL_MAX, even lda / strideA and a 16-byte aligned matrix");
-    return launch_trtri_wpp(L, lda, strideA, n_sys, n_max, batch, struct_o, (cudaStream_t)stream);
+    return launch_trtri_wpp(L, lda, strideA, n_sys, n_max, batch, struct_o, WppSolve{nullptr, nullptr, 0, 0, nullptr, 0}, (cudaStream_t)stream);
+}
+extern "C" int kmpx_trtri_wpp_solve(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, int struct_o,
+                                    const double* y, const int* n_pts, int n_max_pts, int O, double* w, int ldw, void* stream) {
+    using namespace kmpx;
+    if (!L) return fail_arg(1, "matrix is NULL");
+    if (batch <= 0) return fail_arg(6, "batch must be > 0");
+    if (lda < n_max) return fail_arg(2, "lda < n_max");
+    if (struct_o != 0 && struct_o != 2) return fail_arg(7, "struct_o must be 0 or 2");
+    if (!y) return fail_arg(8, "y is NULL");
+    if (O <= 0 || n_max_pts <= 0 || comp_stride(n_max_pts) * O != n_max) return fail_arg(10, "n_max must be the component-major system size of (n_max_pts, O)");
+    if (!n_sys != !n_pts) return fail_arg(9, "n_sys and n_pts must both be given (ragged batch) or both be NULL");
+    if (!w) return fail_arg(12, "w is NULL");
+    if (ldw < n_max) return fail_arg(13, "ldw < n_max");
+    if (!wpp_applicable(L, lda, strideA, n_max, batch))
+        return fail_arg(5, "kmpx_trtri_wpp_solve needs 64 <= n_max <= KMPX_SMALL_MAX, even lda / strideA and a 16-byte aligned matrix");
+    return launch_trtri_wpp(L, lda, strideA, n_sys, n_max, batch, struct_o, WppSolve{y, n_pts, n_max_pts, O, w, ldw}, (cudaStream_t)stream);
 }
 extern "C" int kmpx_debug_phases(long long* out_host, int reset) { return kmpx::debug_phases(out_host, reset); }
 extern "C" int kmpx_debug_set(int flags) { return kmpx::debug_set(flags); }

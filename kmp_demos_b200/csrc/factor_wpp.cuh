@@ -430,8 +430,17 @@ __device__ __forceinline__ bool wpp_trtri_pass(int k0, int q, int n, int ktot, W
     return true;
 }
 
+// Optional by-product of the inverse:  w = Linv y'  (what kmpx_solve_alpha computes in a pass of its own), accumulated block
+// column by block column from the pieces of X while they are in registers / shared memory.  y: point-major targets
+// [batch][n_max_pts][O]; the systems are component-major (row = a Ns + i, padding rows carry y' = 0).  y == nullptr: off.
+struct WppSolve { const double* y; const int* n_pts; int n_max_pts, O; double* w; int ldw; };
+__device__ __forceinline__ double wpp_rhs(const WppSolve& sv, const double* yb, int N, int Ns, int c) {
+    const int a = c / Ns, i = c - a * Ns;
+    return (a < sv.O && i < N) ? yb[(size_t)i * sv.O + a] : 0.0;
+}
+
 template <int V>
-__global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __grid_constant__ CUtensorMap tmap, FactorArgs p, int struct_o) {
+__global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __grid_constant__ CUtensorMap tmap, FactorArgs p, int struct_o, WppSolve sv) {
     using C = WppCfg<V>;
     constexpr int U = C::U;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -448,6 +457,11 @@ __global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __gri
         const int struct_ns = struct_o == 2 ? n >> 1 : 0;
         double* L = p.A + (size_t)b * p.strideA;
         const int nblk = (n + NB - 1) / NB;
+        const bool solve = sv.y != nullptr;
+        const double* yb = solve ? sv.y + (size_t)b * sv.n_max_pts * sv.O : nullptr;
+        double* wb = solve ? sv.w + (size_t)b * sv.ldw : nullptr;
+        const int svN = solve ? (sv.n_pts ? sv.n_pts[b] : sv.n_max_pts) : 0;
+        const int svNs = solve ? n / sv.O : 1;          // component stride of this problem
         // the columns n .. round8(n)-1 (inside the tensor) are streamed with the last k-tile of a row: make them finite
         if (n < p.n_max) {
             const int cw = min(p.n_max, (n + 7) / 8 * 8) - n;
@@ -468,6 +482,14 @@ __global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __gri
             wpp_trinv32(D, rcp_chain(D[lane * WLD + lane]), lane);
             for (int r = 0; r < kb; ++r)
                 if (lane < kb) L[(size_t)(k0 + r) * p.lda + k0 + lane] = D[r * WLD + lane];
+            // w[k0 + r] = X_jj[r][:] y'[k0 ..]: the first contribution to these rows (later steps add those of the block columns to the left)
+            double ylane = 0.0;          // y'[k0 + lane]
+            if (solve) {
+                ylane = (k0 + lane < n) ? wpp_rhs(sv, yb, svN, svNs, k0 + lane) : 0.0;
+                double dot = 0.0;
+                for (int c = 0; c < 32; ++c) dot = fma(D[lane * WLD + c], __shfl_sync(0xffffffffu, ylane, c), dot);
+                if (lane < kb) wb[k0 + lane] = dot;
+            }
             if (m > 0) {
                 wpp_extract_frags<false>(D, F, lane);
                 wpp_fence_smem_to_tma();
@@ -547,6 +569,17 @@ __global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __gri
                                 for (int jj = 0; jj < 4; ++jj)
                                     *reinterpret_cast<double2*>(L + (size_t)r * p.lda + k0 + jj * 8 + 2 * t4) = make_double2(-acc[c][i][jj][0], -acc[c][i][jj][1]);
                             }
+                            if (solve) {          // w[r] += X21[r][:] y'[k0 ..] = -(acc row) . y'
+                                double part = 0.0;
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    part = fma(acc[c][i][jj][0], __shfl_sync(0xffffffffu, ylane, jj * 8 + 2 * t4), part);
+                                    part = fma(acc[c][i][jj][1], __shfl_sync(0xffffffffu, ylane, jj * 8 + 2 * t4 + 1), part);
+                                }
+                                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                                if (t4 == 0 && r < n) wb[r] -= part;
+                            }
                         }
                     }
                 }
@@ -579,10 +612,10 @@ inline int launch_potrf_wpp_v(const CUtensorMap& map, const FactorArgs& p, int s
     return check_launch("k_potrf_wpp");
 }
 template <int V>
-inline int launch_trtri_wpp_v(const CUtensorMap& map, const FactorArgs& p, int struct_o, cudaStream_t st) {
+inline int launch_trtri_wpp_v(const CUtensorMap& map, const FactorArgs& p, int struct_o, const WppSolve& sv, cudaStream_t st) {
     static SmemCache smem_set;
     KMPX_TRY(ensure_dyn_smem(k_trtri_wpp<V>, WppCfg<V>::SMEM, smem_set, "k_trtri_wpp"));
-    k_trtri_wpp<V><<<wpp_grid<V>(p.batch), WppCfg<V>::THREADS, WppCfg<V>::SMEM, st>>>(map, p, struct_o);
+    k_trtri_wpp<V><<<wpp_grid<V>(p.batch), WppCfg<V>::THREADS, WppCfg<V>::SMEM, st>>>(map, p, struct_o, sv);
     return check_launch("k_trtri_wpp");
 }
 inline int wpp_variant(int dflt) { return (dflt + ((g_host_dbg >> 7) & 3)) % 3; }
@@ -597,14 +630,15 @@ inline int launch_potrf_wpp(double* A, int lda, long long strideA, const int* n_
         default: return launch_potrf_wpp_v<2>(map, p, struct_o, st);
     }
 }
-inline int launch_trtri_wpp(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, int struct_o, cudaStream_t st) {
+inline int launch_trtri_wpp(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, int struct_o, const WppSolve& sv,
+                            cudaStream_t st) {
     CUtensorMap map;
     KMPX_TRY(make_batch_map(&map, L, lda, strideA, n_max, batch, NB));
     FactorArgs p{L, lda, strideA, n_sys, n_max, batch, nullptr, 0, 0};
     switch (wpp_variant(WPP_V_TRTRI)) {
-        case 0: return launch_trtri_wpp_v<0>(map, p, struct_o, st);
-        case 1: return launch_trtri_wpp_v<1>(map, p, struct_o, st);
-        default: return launch_trtri_wpp_v<2>(map, p, struct_o, st);
+        case 0: return launch_trtri_wpp_v<0>(map, p, struct_o, sv, st);
+        case 1: return launch_trtri_wpp_v<1>(map, p, struct_o, sv, st);
+        default: return launch_trtri_wpp_v<2>(map, p, struct_o, sv, st);
     }
 }
 

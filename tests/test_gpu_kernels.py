@@ -369,6 +369,46 @@ def test_warp_per_problem_structure_skipping_is_bit_identical(T, variant_flags):
         assert rel_err(np.tril(out[1][b, :n, :n]), np.linalg.inv(np.linalg.cholesky(mats[b]))) < 1e-12, n
 
 
+@pytest.mark.parametrize('variant_flags', [0, 128, 256])
+def test_trtri_warp_per_problem_with_fused_solve(T, variant_flags):
+    """kmpx_trtri_wpp_solve leaves w = Linv y' next to the inverse (ragged component-major two-output systems, y point-major)."""
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(24)
+    pts = [202, 201, 200, 150, 37, 202]
+    O = 2
+    n_max_pts = max(pts)
+    nmax = O * ((n_max_pts + 1) // 2 * 2)
+    lda = nmax + 4
+    sizes = [O * ((N + 1) // 2 * 2) for N in pts]
+    mats = [_struct_spd(rng, N) for N in pts]
+    A = T.full((len(pts), nmax, lda), float('nan'), dtype=T.float64, device='cuda')
+    for b, n in enumerate(sizes):
+        A[b, :n, :n] = dev(T, np.tril(mats[b]) + np.triu(np.full((n, n), np.nan), 1))
+    y = rng.normal(size=(len(pts), n_max_pts, O))
+    yd = dev(T, y)
+    n_sys, n_pts = dev(T, np.array(sizes, dtype=np.int32)), dev(T, np.array(pts, dtype=np.int32))
+    info = T.zeros(len(pts), dtype=T.int32, device='cuda')
+    w = T.full((len(pts), lda), float('nan'), dtype=T.float64, device='cuda')
+    lib.kmpx_debug_set(variant_flags)
+    try:
+        _lib.call('kmpx_potrf_wpp', _lib.ptr(A), lda, nmax * lda, _lib.ptr(n_sys), nmax, len(pts), _lib.ptr(info), 2, _lib.stream())
+        _lib.call('kmpx_trtri_wpp_solve', _lib.ptr(A), lda, nmax * lda, _lib.ptr(n_sys), nmax, len(pts), 2,
+                  _lib.ptr(yd), _lib.ptr(n_pts), n_max_pts, O, _lib.ptr(w), lda, _lib.stream())
+    finally:
+        lib.kmpx_debug_set(0)
+    assert info.cpu().numpy().tolist() == [0] * len(pts)
+    Xh, wh = A.cpu().numpy(), w.cpu().numpy()
+    for b, (N, n) in enumerate(zip(pts, sizes)):
+        Ns = n // O
+        ys = np.zeros(n)
+        for a in range(O):
+            ys[a * Ns:a * Ns + N] = y[b, :N, a]
+        Linv = np.linalg.inv(np.linalg.cholesky(mats[b]))
+        assert rel_err(np.tril(Xh[b, :n, :n]), Linv) < 1e-12, N
+        assert rel_err(wh[b, :n], Linv @ ys) < 1e-12, N
+
+
 def test_potrf_warp_per_problem_reports_first_bad_pivot(T):
     from kmp_demos_b200 import _lib
     rng = np.random.default_rng(23)
