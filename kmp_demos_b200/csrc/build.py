@@ -9,7 +9,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['api.cu', 'kernel_build.cu', 'factor_small.cu', 'factor_large.cu', 'dgemm.cu', 'dgemm_tma.cu', 'predict.cu', 'predict_fast.cu', 'predict_pers.cu', 'predict_stream.cu',
+SOURCES = ['api.cu', 'kernel_build.cu', 'factor_small.cu', 'factor_large.cu', 'dgemm.cu', 'dgemm_tma.cu', 'predict.cu', 'predict_fast.cu', 'predict_tab.cu', 'predict_pers.cu', 'predict_stream.cu',
            'inverse_gj.cu', 'gmm.cu', 'kmeans.cu', 'gmr.cu', 'quat.cu', 'incremental.cu', 'predict_gemm.cu']
 HEADERS = ['common.cuh', 'dmma_tile.cuh', 'kmpx_internal.cuh', 'factor_tma.cuh', 'factor_struct.cuh', 'factor_wpp.cuh', 'tma_util.cuh', os.path.join('..', '..', 'include', 'kmpx.h')]
 LIB = os.path.join(HERE, 'libkmpx.so')

@@ -37,6 +37,8 @@ struct PredictArgs {
 };
 bool predict_fast_applicable(const PredictArgs& p);
 int launch_predict_fast(PredictArgs& p, cudaStream_t st);
+bool predict_tab_applicable(const PredictArgs& p);
+int launch_predict_tab(PredictArgs& p, cudaStream_t st);
 bool predict_pers_applicable(const PredictArgs& p);
 int launch_predict_pers(PredictArgs& p, cudaStream_t st);
 bool predict_stream_applicable(const PredictArgs& p);

@@ -409,6 +409,7 @@ static int predict_dispatch(const double* F, int lda, long long strideA, int fac
     PredictArgs p{F, lda, strideA, factor_kind, w, ldw, s, n_pts, n_max, I, O, batch, sq, stride_sq, M,
                   sigma_f, alpha_kmp, time_driven, xi, sigma_out, 0, 0, g_host_dbg};
     if (persistent && predict_pers_applicable(p)) return launch_predict_pers(p, (cudaStream_t)stream);
+    if (predict_tab_applicable(p)) return launch_predict_tab(p, (cudaStream_t)stream);
     if (predict_fast_applicable(p)) return launch_predict_fast(p, (cudaStream_t)stream);
     if (predict_stream_applicable(p)) return launch_predict_stream(p, (cudaStream_t)stream);
     if (O <= 2) return launch_predict<64>(p, (cudaStream_t)stream);

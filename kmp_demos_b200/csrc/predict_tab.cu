@@ -1,0 +1,453 @@
+// K4 fast path, table-driven form: plain RBF kernel, O <= 2, symmetric factor (the cfg-1/3 shape of BASELINE.json).
+//
+// Same mathematics, CTA shape (64 queries of one problem, kappa panel resident in shared memory, eight MMA warps with
+// private 2-stage TMA rings fed by a producer warpgroup), warp tile and reductions as k_kmp_predict_fast (predict_fast.cu).
+// What changes is everything an MMA warp does BETWEEN its DMMAs.  Measured with clock64 on one MMA warp of that kernel
+// (112 k cycles in the streaming loop): 81 k in full stages - at the pipe's rate, two warps per scheduler saturate it - but
+// 13 k in the cursor arithmetic between two stages (which chunk, which output, which k-block, how many columns are valid:
+// ~570 cycles of dependent integer code per stage), 9 k in the per-chunk reductions, 5 k waiting for tiles and 5 k in the
+// rolled loop of the short last k-blocks; a single warp reaches only ~57 % of its scheduler's DMMA rate, so whatever one warp
+// spends outside its DMMA loop is only half covered by its partner.  Here
+//   * the stage sequence of every warp - and the assignment of the 16-row chunks to the warps - is a pure function of
+//     (O, N): the host tabulates it once per (device, O, n_max) for every N (8 bytes per stage: row, column, k-steps, flags),
+//     the CTA copies its row of the table into shared memory, and producer lanes and MMA warps just walk it;
+//   * the assignment is longest-first by a cycle model of stages and reductions, refined by moves and swaps off the most
+//     loaded warp (the boustrophedon deal left 5 % between the first and the last warp);
+//   * chunks of the first component block (V_1 = 0) reduce only the two sums that are not identically zero;
+//   * the short last k-block runs its boxes (two k-steps each) unrolled.
+// Results are bitwise reproducible and independent of the batch a problem sits in (the schedule depends on (O, N) only).
+// Algorithmic flops per problem: O^2 Ns^2 M (+ lower-order reductions); F is streamed from L2 once per CTA.
+#include "dmma_tile.cuh"
+#include "kmpx_internal.cuh"
+#include "tma_util.cuh"
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <type_traits>
+#include <vector>
+
+namespace kmpx {
+
+constexpr int TQT = 64;          // queries per CTA
+constexpr int TRC = 16;          // rows of Linv per chunk
+constexpr int TQK = 32;          // k per stage: 8 k-steps of 4 = 128 DMMA per warp between two ring hand-overs
+constexpr int TST = 2;           // ring stages per warp
+constexpr int TWARPS = 8;        // MMA warps
+constexpr int TTHR = TWARPS * 32;
+constexpr int TALL = TTHR + 128;              // + producer warpgroup (setmaxnreg works on groups of four warps)
+constexpr int TMAXST = 48;       // stages per warp the table holds (n_sys <= ~600; larger systems take k_kmp_predict_fast)
+constexpr int TSTAGE_BYTES = TRC * TQK * 8;   // 4 boxes of 16 rows x 64 B
+constexpr int TSTAGE_ELEMS = TRC * TQK;
+constexpr int TROW = 8 + TWARPS * TMAXST * 2; // ints per table row: stage counts per warp, then [warp][stage]{d0, d1}
+
+// stage descriptor: d0 = r0 | a << 12 | chunk_end << 13 | has_v1 << 14 | nst << 16;  d1 = k offset in the panel | col0 << 16
+__host__ __device__ inline int tdesc0(int r0, int a, int chunk_end, int has_v1, int nst) { return r0 | (a << 12) | (chunk_end << 13) | (has_v1 << 14) | (nst << 16); }
+
+struct TabSmem { size_t rings, panel, racc, wsh, sqs, etab, sched, bars, total; };
+__host__ __device__ inline TabSmem tab_smem_layout(int O, int I, int n_max_pts, int ldp) {
+    const int nt = O * (O + 1) / 2 + O;
+    const int n_sys_max = O * comp_stride(n_max_pts);
+    TabSmem L;
+    L.rings = 0;
+    L.panel = (size_t)TWARPS * TST * TSTAGE_BYTES;
+    L.racc = L.panel + (size_t)TQT * ldp * 8;
+    L.wsh = L.racc + (size_t)TWARPS * nt * TQT * 8;
+    L.sqs = L.wsh + (size_t)round_up(n_sys_max, 2) * 8;
+    L.etab = L.sqs + (size_t)round_up(TQT * I, 2) * 8;
+    L.sched = L.etab + (size_t)kExpTabN * 8;
+    L.bars = L.sched + (size_t)TROW * 4;
+    L.total = L.bars + (size_t)2 * TWARPS * TST * 8 + 1024 /* alignment slack */;
+    return L;
+}
+
+// ---- host: the schedule of one (O, N).  Returns false when a warp would need more than TMAXST stages.
+static bool tab_schedule_host(int O, int N, int* row) {
+    const int Ns = comp_stride(N), n = O * Ns;
+    const int nchunks = (n + TRC - 1) / TRC;
+    struct Stage { int d0, d1; };
+    std::vector<std::vector<Stage>> st(nchunks);
+    std::vector<int> cost(nchunks), order(nchunks), owner(nchunks);
+    for (int c = 0; c < nchunks; ++c) {
+        const int r0 = c * TRC;
+        int cyc = 0, has_v1 = 0;
+        for (int a = 0; a < O; ++a) {
+            int jm = r0 + TRC - a * Ns;
+            jm = jm < 0 ? 0 : (jm > N ? N : jm);
+            if (jm > 0 && a == 1) has_v1 = 1;
+            for (int kb = 0; kb * TQK < jm; ++kb) {
+                const int kv = jm - kb * TQK;
+                const int nst = kv >= TQK ? TQK / 4 : 2 * ((kv + 7) >> 3);
+                st[c].push_back({tdesc0(r0, a, 0, 0, nst), (kb * TQK) | ((a * Ns) << 16)});
+                cyc += nst * 32 * 16 / 16 + 120;              // 16 DMMAs per k-step at one per 32 cycles and warp; hand-over
+            }
+        }
+        for (auto& sgm : st[c]) sgm.d0 |= has_v1 << 14;
+        if (!st[c].empty()) st[c].back().d0 |= 1 << 13;
+        cost[c] = cyc + (has_v1 ? 700 : 330);
+        order[c] = c;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+    long long load[TWARPS] = {0};
+    for (int k = 0; k < nchunks; ++k) {
+        int best = 0;
+        for (int w = 1; w < TWARPS; ++w) if (load[w] < load[best]) best = w;
+        owner[order[k]] = best;
+        load[best] += cost[order[k]];
+    }
+    // local search: move a chunk off, or swap a chunk of, the most loaded warp while that lowers the maximum
+    for (int iter = 0; iter < 400; ++iter) {
+        int hi = 0;
+        for (int w = 1; w < TWARPS; ++w) if (load[w] > load[hi]) hi = w;
+        long long best_gain = 0;
+        int bi = -1, bj = -1, bw = -1;
+        for (int i = 0; i < nchunks; ++i) {
+            if (owner[i] != hi) continue;
+            for (int w = 0; w < TWARPS; ++w) {
+                if (w == hi) continue;
+                const long long after = std::max(load[hi] - cost[i], load[w] + cost[i]);
+                if (load[hi] - after > best_gain) { best_gain = load[hi] - after; bi = i; bj = -1; bw = w; }
+                for (int j = 0; j < nchunks; ++j) {
+                    if (owner[j] != w || cost[j] >= cost[i]) continue;
+                    const long long after2 = std::max(load[hi] - cost[i] + cost[j], load[w] + cost[i] - cost[j]);
+                    if (load[hi] - after2 > best_gain) { best_gain = load[hi] - after2; bi = i; bj = j; bw = w; }
+                }
+            }
+        }
+        if (bi < 0) break;
+        load[hi] -= cost[bi]; load[bw] += cost[bi]; owner[bi] = bw;
+        if (bj >= 0) { load[bw] -= cost[bj]; load[hi] += cost[bj]; owner[bj] = hi; }
+    }
+    int cnt[TWARPS] = {0};
+    for (int k = 0; k < nchunks; ++k) {             // every warp takes its chunks longest first
+        const int c = order[k], w = owner[c];
+        for (const auto& sgm : st[c]) {
+            if (cnt[w] >= TMAXST) return false;
+            row[8 + (w * TMAXST + cnt[w]) * 2] = sgm.d0;
+            row[8 + (w * TMAXST + cnt[w]) * 2 + 1] = sgm.d1;
+            ++cnt[w];
+        }
+    }
+    for (int w = 0; w < TWARPS; ++w) row[w] = cnt[w];
+    return true;
+}
+// device copy of the table for (O, n_max), built on first use (per device; never freed: 3 KB per N).  *out = nullptr when
+// some N <= n_max does not fit the table (the caller then takes k_kmp_predict_fast).
+static int tab_sched_table(int O, int n_max, const int** out) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int>, int*> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_tuple(current_device(), O, n_max);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        std::vector<int> host((size_t)(n_max + 1) * TROW, 0);
+        bool ok = true;
+        for (int N = 1; N <= n_max && ok; ++N) ok = tab_schedule_host(O, N, host.data() + (size_t)N * TROW);
+        int* dptr = nullptr;
+        if (ok) {
+            KMPX_TRY(check_cuda(cudaMalloc(&dptr, host.size() * sizeof(int)), "cudaMalloc (predict schedule table)"));
+            KMPX_TRY(check_cuda(cudaMemcpy(dptr, host.data(), host.size() * sizeof(int), cudaMemcpyHostToDevice), "cudaMemcpy (predict schedule table)"));
+        }
+        it = cache.emplace(key, dptr).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+template <int O>
+__global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_constant__ CUtensorMap tmap, PredictArgs p, TabSmem lay, const int* sched_tab) {
+    constexpr int NT = O * (O + 1) / 2 + O;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int b = blockIdx.y, m0 = blockIdx.x * TQT;
+    const int I = p.I;
+    const int N = p.n_pts ? p.n_pts[b] : p.n_max;
+    const int Ns = comp_stride(N);
+    const int n = O * Ns;
+    const int ldp = p.ldp;
+    const int n_sys_max = O * comp_stride(p.n_max);
+
+    unsigned char* base = smem_align1k(smem_raw);
+    double* rings = reinterpret_cast<double*>(base + lay.rings);        // [TWARPS][TST][16 x 32 swizzled]
+    double* panel = reinterpret_cast<double*>(base + lay.panel);        // [TQT][ldp], columns in k-step order
+    double* racc = reinterpret_cast<double*>(base + lay.racc);          // [TWARPS][NT][TQT]
+    double* wsh = reinterpret_cast<double*>(base + lay.wsh);            // [n_sys_max]
+    double* sqs = reinterpret_cast<double*>(base + lay.sqs);            // [TQT][I]
+    double* etab = reinterpret_cast<double*>(base + lay.etab);          // [32] table of exp_tab
+    int* sched = reinterpret_cast<int*>(base + lay.sched);                // this N's row of the schedule table
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + lay.bars);      // full[TWARPS][TST], empty[TWARPS][TST]
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TWARPS * TST);
+
+    if (tid == 0) {
+        for (int i = 0; i < TWARPS * TST; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------- prologue: ALL twelve warps (the register split
+    //      between the roles is made afterwards, so the producer warps' lanes work on the kappa panel too)
+    const double* s = p.s + (size_t)b * p.n_max * I;
+    const double* sq = p.sq + (size_t)b * p.stride_sq;
+    const double* w = p.w + (size_t)b * p.ldw;
+    for (int idx = tid; idx < TQT * I; idx += TALL) {
+        const int m = idx / I;
+        sqs[idx] = (m0 + m < p.M) ? sq[(size_t)(m0 + m) * I + (idx - m * I)] : 0.0;
+    }
+    for (int idx = tid; idx < n_sys_max; idx += TALL) wsh[idx] = idx < n ? w[idx] : 0.0;
+    for (int idx = tid; idx < TWARPS * NT * TQT; idx += TALL) racc[idx] = 0.0;
+    fill_exp2_table(etab, tid, TALL);
+    for (int idx = tid; idx < TROW; idx += TALL) sched[idx] = sched_tab[(size_t)N * TROW + idx];
+    __syncthreads();          // the schedule is complete (the producers need it before the panel is evaluated)
+    // producer cursors (lanes 0, 1 of the four producer warps: two streams each); the first tiles are requested now
+    // so that they land while the panel is evaluated
+    const bool is_producer = warp >= TWARPS && lane < 2;
+    const int cw = is_producer ? (warp - TWARPS) * 2 + lane : 0;
+    const int* pdesc = sched + 8 + cw * TMAXST * 2;
+    const int pcount = is_producer ? sched[cw] : 0;
+    int pk = 0;
+    int pstage = 0;
+    uint32_t ppar = 0;
+    bool pwrapped = false;
+    auto produce_one = [&]() {
+        const uint32_t bi = 8 * (cw * TST + pstage);
+        const uint32_t bar = full0 + bi;
+        mbar_expect_tx(bar, TSTAGE_BYTES);
+        const uint32_t dst = smem_u32(rings + (size_t)(cw * TST + pstage) * TSTAGE_ELEMS);
+        const int d0 = pdesc[2 * pk], d1 = pdesc[2 * pk + 1];
+        const int col = (d1 >> 16) + (d1 & 0xffff), prow = d0 & 0xfff;
+#pragma unroll
+        for (int q = 0; q < TQK / 8; ++q) tma_load_box(dst + q * (TRC * 64), &tmap, col + 8 * q, prow, b, bar);
+        ++pk;
+        if (++pstage == TST) { pstage = 0; ppar ^= 1; pwrapped = true; }
+    };
+    if (is_producer) {
+        for (int t = 0; t < TST && pk < pcount; ++t) produce_one();
+    }
+    __syncthreads();          // sqs is complete
+    // kappa panel (the B operand), evaluated while the first Linv tiles are in flight: warp-strided over the queries,
+    // lane-strided over the stored points; column j goes to position (j & ~7) | swap_bits_1_2(j & 7)  (k-step order).
+    // A dependent FP64 operation costs 40-60 cycles here and an exp is a chain of ~25 of them, so every lane keeps
+    // FILL_J independent chains in flight (seven columns of one query; fourteen were measured slower); indices are
+    // clamped and the results selected, and the exponential itself is branch-free (exp_nonpos), so the chains interleave.
+    constexpr int FILL_J = 7, FILL_WARPS = TALL / 32;
+    auto fill = [&](auto one_dim) {         // the I == 1 test is hoisted: a branch inside the chain body would serialise the chains
+        constexpr bool ONE = decltype(one_dim)::value;
+        for (int m = warp; m < TQT && !(p.dbg & 4); m += FILL_WARPS) {
+            const bool live = m0 + m < p.M;
+            for (int j0 = lane; j0 < ldp - 4; j0 += 32 * FILL_J) {       // ldp - 4 is a multiple of 32
+                double e[FILL_J];
+#pragma unroll
+                for (int u = 0; u < FILL_J; ++u) {
+                    const double* sp = s + (size_t)min(j0 + 32 * u, N - 1) * I;
+                    if (ONE) { const double d = fabs(sqs[m] - sp[0]); e[u] = exp_tab(-p.sigma_f * (d * d), etab); }
+                    else e[u] = rbf_fast(sqs + m * I, sp, I, p.sigma_f);
+                }
+                const int pj = (j0 & ~6) | ((j0 & 2) << 1) | ((j0 & 4) >> 1);       // the same permutation applies to j0 + 32 u
+#pragma unroll
+                for (int u = 0; u < FILL_J; ++u) {
+                    const int j = j0 + 32 * u;
+                    if (j < ldp - 4) panel[(size_t)m * ldp + pj + 32 * u] = (j < N && live) ? e[u] : 0.0;
+                }
+            }
+        }
+    };
+    if (I == 1) fill(std::true_type{}); else fill(std::false_type{});
+    __syncthreads();          // panel, wsh, racc are complete
+
+    if (warp >= TWARPS) {
+        // ---- producers: one lane per MMA warp runs that warp's tile cursor and issues its TMA boxes
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+        if (lane >= 2) return;
+        while (pk < pcount) {
+            const uint32_t bi = 8 * (cw * TST + pstage);
+            if (pwrapped && !mbar_test(empty0 + bi, ppar ^ 1)) { __nanosleep(100); continue; }   // polling must not eat the MMA warps' issue slots
+            produce_one();
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+
+    // ---------------------------------------------------------------- per-warp streaming loop
+    const double* ring = rings + (size_t)warp * TST * TSTAGE_ELEMS;
+    double* my_racc = racc + (size_t)warp * NT * TQT;
+    // per-lane constants of the swizzled 8-column boxes: element offset of (row g, k-step h) and the logical column
+    const int sw = (g >> 1) & 3, c0 = (t4 >> 1) << 1;
+    const int o0 = g * 8 + ((c0 ^ sw) << 1) + (t4 & 1);
+    const int o1 = g * 8 + (((c0 | 1) ^ sw) << 1) + (t4 & 1);
+    const int cm0 = (t4 & 1) | ((t4 & 2) << 1);          // k-step 0 uses the columns {0,1,4,5} of a box, k-step 1 {2,3,6,7}
+    const int* cdesc = sched + 8 + warp * TMAXST * 2;
+    const int ccount = sched[warp];
+    int stage = 0;
+    uint32_t par = 0;
+    double acc0[2][8][2], acc1[2][8][2];
+    zero_acc(acc0);
+    zero_acc(acc1);
+    // chunk complete: reduce the V tile over its 16 rows straight from the accumulators (products, then a 3-step reduce-scatter
+    // over the 8 row lanes: lane g ends up owning the column block j == g).  Sums t: O == 1: 0 = q00, 1 = mu0;
+    // O == 2: 0 = q00, 1 = q01, 2 = q11, 3 = mu0, 4 = mu1.  HAS_V1 = false (first component block, V_1 = 0): the sums with V_1 are skipped.
+    auto reduce = [&](int row0, auto has_v1) {
+        constexpr bool HAS_V1 = decltype(has_v1)::value;
+        double wv[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { const int r = row0 + i * 8 + g; wv[i] = r < n ? wsh[r] : 0.0; }
+        const bool g2 = (lane & 16) != 0, g1 = (lane & 8) != 0, g0 = (lane & 4) != 0;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const bool needs_v1 = O == 2 && (t == 1 || t == 2 || t == 4);
+            if (needs_v1 && !HAS_V1) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double val[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const double v0 = acc0[i][j][e];
+                        const double v1 = HAS_V1 ? acc1[i][j][e] : 0.0;
+                        if (O == 1) sum += t == 0 ? v0 * v0 : v0 * wv[i];
+                        else sum += t == 0 ? v0 * v0 : (t == 1 ? v0 * v1 : (t == 2 ? v1 * v1 : (t == 3 ? v0 * wv[i] : v1 * wv[i])));
+                    }
+                    val[j] = sum;
+                }
+                double s4[4], s2[2];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const double keep = g2 ? val[jj + 4] : val[jj];
+                    const double send = g2 ? val[jj] : val[jj + 4];
+                    s4[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const double keep = g1 ? s4[jj + 2] : s4[jj];
+                    const double send = g1 ? s4[jj] : s4[jj + 2];
+                    s2[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                const double keep = g0 ? s2[1] : s2[0];
+                const double send = g0 ? s2[0] : s2[1];
+                const double tot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                my_racc[t * TQT + g * 8 + 2 * t4 + e] += tot;
+            }
+        }
+    };
+    for (int ck = 0; ck < ccount; ++ck) {
+        const int d0 = cdesc[2 * ck], d1 = cdesc[2 * ck + 1];
+        const int c_r0 = d0 & 0xfff, c_kcol = d1 & 0xffff, c_col0 = d1 >> 16;
+        const uint32_t bi = 8 * (warp * TST + stage);
+        mbar_wait(full0 + bi, par);
+        const double* tile = ring + stage * TSTAGE_ELEMS;
+        const double* Bs = panel + c_kcol;
+        // last valid point index of the two rows this lane carries in this segment (-1: row outside the system)
+        int lim[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = c_r0 + i * 8 + g;
+            lim[i] = r < n ? min(N - 1, r - c_col0) - c_kcol : -1;
+        }
+        const int nst = (p.dbg & 1) ? 0 : (d0 >> 16);                     // k-steps of 4 that carry data (whole boxes)
+        const bool first = (O == 1 || !(d0 & (1 << 12)));
+        auto kstep = [&](int st, double (&acc)[2][8][2]) {
+            const int q = st >> 1, h = st & 1;
+            const int jl = 8 * q + 2 * h + cm0;                             // logical column of this lane inside the tile
+            double a[2], bf[8];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double v = tile[q * (TRC * 8) + i * 64 + (h ? o1 : o0)];
+                a[i] = jl <= lim[i] ? v : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bf[j] = Bs[(size_t)(j * 8 + g) * ldp + 4 * st + t4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[i][j], a[i], bf[j]);
+        };
+        if (nst == 8) {
+            if (first) {
+#pragma unroll
+                for (int st = 0; st < 8; ++st) kstep(st, acc0);
+            } else {
+#pragma unroll
+                for (int st = 0; st < 8; ++st) kstep(st, acc1);
+            }
+        } else {                                          // last k-block of a segment: only the boxes with data (two k-steps each)
+            if (first) {
+#pragma unroll 1
+                for (int st = 0; st < nst; st += 2) { kstep(st, acc0); kstep(st + 1, acc0); }
+            } else {
+#pragma unroll 1
+                for (int st = 0; st < nst; st += 2) { kstep(st, acc1); kstep(st + 1, acc1); }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + bi);
+        if (++stage == TST) { stage = 0; par ^= 1; }
+        if ((d0 & (1 << 13)) && !(p.dbg & 8)) {
+            // chunk complete: reduce the V tile over its 16 rows straight from the accumulators
+            if (O == 2 && (d0 & (1 << 14))) reduce(c_r0, std::true_type{});
+            else reduce(c_r0, std::false_type{});
+            zero_acc(acc0);
+            zero_acc(acc1);
+        }
+    }
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+
+    // ---------------------------------------------------------------- outputs (reference layout, query last)
+    double* xi = p.xi + (size_t)b * O * p.M;
+    double* sg_out = p.sigma_out ? p.sigma_out + (size_t)b * O * O * p.M : nullptr;
+    constexpr int NPAIR = O * (O + 1) / 2;
+    for (int idx = tid; idx < NT * TQT; idx += TTHR) {
+        const int t = idx / TQT, m = idx - t * TQT;
+        if (m0 + m >= p.M) continue;
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < TWARPS; ++q) v += racc[((size_t)q * NT + t) * TQT + m];
+        if (t >= NPAIR) {
+            xi[(size_t)(t - NPAIR) * p.M + m0 + m] = v;
+        } else if (sg_out) {
+            // pair index -> (a <= bb): O == 1: (0,0);  O == 2: 0 -> (0,0), 1 -> (0,1), 2 -> (1,1)
+            const int a = (O == 2 && t == 2) ? 1 : 0;
+            const int bb = (O == 2 && t >= 1) ? 1 : 0;
+            const double val = p.alpha_kmp * ((a == bb ? 1.0 : 0.0) - v);
+            sg_out[((size_t)a * O + bb) * p.M + m0 + m] = val;
+            if (a != bb) sg_out[((size_t)bb * O + a) * p.M + m0 + m] = val;
+        }
+    }
+}
+
+bool predict_tab_applicable(const PredictArgs& p) {
+    if (g_host_dbg & 4096) return false;
+    if (p.time_driven || p.general || p.O > 2) return false;
+    if ((p.lda & 1) || (p.batch > 1 && (p.strideA & 1)) || (reinterpret_cast<uintptr_t>(p.F) & 15)) return false;   // TMA
+    if ((long long)p.O * comp_stride(p.n_max) > 0xfff) return false;                                                 // descriptor fields
+    const int ldp = (int)round_up(p.n_max, TQK) + 4;
+    if (tab_smem_layout(p.O, p.I, p.n_max, ldp).total > 226 * 1024) return false;
+    const int* tab = nullptr;
+    if (tab_sched_table(p.O, p.n_max, &tab) != 0) return false;
+    return tab != nullptr;
+}
+
+int launch_predict_tab(PredictArgs& p, cudaStream_t st) {
+    p.ldp = (int)round_up(p.n_max, TQK) + 4;      // 4 (mod 16) and long enough for the last k-block of a row
+    p.resident = 1;
+    const TabSmem lay = tab_smem_layout(p.O, p.I, p.n_max, p.ldp);
+    const int n_sys_max = p.O * comp_stride(p.n_max);
+    CUtensorMap map;
+    KMPX_TRY(make_batch_map(&map, p.F, p.lda, p.strideA, n_sys_max, p.batch, TRC));
+    const int* tab = nullptr;
+    KMPX_TRY(tab_sched_table(p.O, p.n_max, &tab));
+    dim3 grid(ceil_div(p.M, TQT), p.batch);
+    if (p.O == 1) {
+        static SmemCache set1;
+        KMPX_TRY(ensure_dyn_smem(k_kmp_predict_tab<1>, lay.total, set1, "k_kmp_predict_tab<1>"));
+        k_kmp_predict_tab<1><<<grid, TALL, lay.total, st>>>(map, p, lay, tab);
+    } else {
+        static SmemCache set2;
+        KMPX_TRY(ensure_dyn_smem(k_kmp_predict_tab<2>, lay.total, set2, "k_kmp_predict_tab<2>"));
+        k_kmp_predict_tab<2><<<grid, TALL, lay.total, st>>>(map, p, lay, tab);
+    }
+    return check_launch("k_kmp_predict_tab");
+}
+
+}  // namespace kmpx

@@ -1,0 +1,32 @@
+"""Table-driven predict kernel (predict_tab.cu, default) vs the cursor-driven one (predict_fast.cu, kmpx_debug_set(4096)): agreement and time.
+usage: tab_probe.py [sets per letter] [debug flag sets ...]"""
+import sys, os, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from kmp_demos_b200 import _lib, workloads as wl
+from kmp_demos_b200.batch import KMPBatch
+lib = _lib.load()
+mu, sig, _ = wl.load_letter_references()
+L = 26; c = wl.CFG1
+nset = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+flagsets = [int(a) for a in sys.argv[2:]] or [4096, 0]
+ts, ps, vs = [], [], []
+for li in range(L):
+    t, p, v = wl.cfg3_via_sets(li, mu[li], nset); ts.append(t); ps.append(p); vs.append(v)
+base_of = torch.as_tensor(np.repeat(np.arange(L, dtype=np.int32), nset), device='cuda')
+d_vs = torch.as_tensor(np.concatenate(ts)[:, :, None], device='cuda'); d_vp = torch.as_tensor(np.concatenate(ps), device='cuda'); d_vv = torch.as_tensor(np.concatenate(vs), device='cuda')
+q = torch.as_tensor(np.ascontiguousarray(wl.cfg1_query_grid(1000).T), device='cuda')
+out = {}
+kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], chunk=5328)
+kb.set_base(np.broadcast_to(wl.cfg1_kmp_grid(200), (L, 1, 200)), mu, sig)
+for fl in flagsets:
+    lib.kmpx_debug_set(fl)
+    for rep in range(3):
+        kb.events = []
+        xi, sg, info, _ = kb.run_device(base_of, d_vs, d_vp, d_vv, q); torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for n, a, b in kb.events if n.startswith('kmpx_kmp_predict'))
+    print(f'flags {fl:5d} predict {ms:.3f} ms for {len(base_of)} problems ({ms / len(base_of) * 26624:.1f} ms per 26624)', flush=True)
+    out[fl] = (xi.clone(), sg.clone())
+lib.kmpx_debug_set(0)
+rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+if 0 in out and 4096 in out:
+    print('table vs cursor: mean', rel(out[0][0], out[4096][0]), 'cov', rel(out[0][1], out[4096][1]))
