@@ -88,8 +88,9 @@ int kmpx_trtri(double* L, int lda, long long strideA, const int* n_sys, int n_ma
 /* ---- K2 / K3, warp-per-problem variants for LARGE batches of small systems (64 <= n_max <= KMPX_SMALL_MAX; cfg 3).
  *      Same mathematics and result layout as kmpx_potrf / kmpx_trtri (KMP.py:157), but a warp owns a problem from the
  *      first block column to the last (factor_wpp.cuh): twelve independent problems per SM hide each other's latency,
- *      which pays once the batch holds several problems per warp slot (batch >~ 4 * 148).  Differences to kmpx_trtri:
- *      the strict upper triangle of every problem is used as scratch and holds finite garbage afterwards.
+ *      which pays once the batch holds several problems per warp slot (batch >~ 4 * 148).  kmpx_trtri_wpp writes the
+ *      lower triangle only (plus explicit zeros above the diagonal inside the 32 x 32 diagonal blocks); nothing else of
+ *      a problem's n_max x lda slot is touched.
  *      struct_o: 0, or 2 for component-major KMP systems with two outputs and the plain kernel (kmpx_kernel_build with
  *      O = 2, KMPX_LAYOUT_COMPONENT: A = [[A00, D], [D, A11]], D diagonal, component stride n_sys[b] / 2) - blocks of
  *      the factor that are exactly zero are then skipped; the results are bit-identical to struct_o = 0. */

@@ -17,8 +17,10 @@
 //     inverted inside the warp (lane = row for the Cholesky recurrence, lane = column for the inverse) on a 33-stride
 //     block that borrows the (drained) ring; the inverse then lives in DMMA fragment order in 5 KB of shared memory;
 //     every 32-row unit below is  X = (A - L[unit, :k0] L[k0:k0+32, :k0]^T) Dinv^T;
-//   * trtri, block column jb (right to left):  T = L21 Dinv is written TRANSPOSED into the mirror position of L21 in
-//     the strict upper triangle (scratch), so that  X21 = -X22 T  is the same NT contraction (B rows = rows of T^T);
+//   * trtri, block column jb (right to left):  X21 = -(X22 L21) Dinv  with the row units taken bottom-up: unit u needs the
+//     rows k < 32 (u + 1) of L21, so what it overwrites is never read again in the step; L21 ITSELF is the k-major B
+//     operand (boxes of 8 rows x 8 columns, whose 64-byte swizzle makes the k-major fragment reads conflict-free), the
+//     accumulator is multiplied by Dinv from registers like potrf's panel - no T = L21 Dinv, no scratch, no transposition;
 //   * struct_o == 2 declares the component-major KMP system of two outputs (A = [[A00, D], [D, A11]] with D diagonal,
 //     component stride n / 2): L21 = D L11^-T is upper triangular, so k-tiles and whole units that are exactly
 //     zero are skipped (the results are bit-identical to the unskipped run: only products with exact zeros are dropped).
@@ -439,8 +441,42 @@ __device__ __forceinline__ double wpp_rhs(const WppSolve& sv, const double* yb, 
     return (a < sv.O && i < N) ? yb[(size_t)i * sv.O + a] : 0.0;
 }
 
+// acc[c] += (A rows of unit c) * B over the 8 k of one stage, B given K-MAJOR: four boxes of 8 k-rows x 8 columns (the rows
+// r0 + 8 t .. of L21 itself, 64-byte swizzle).  Lane (g, t4) reads B[k][8 j + g] with k = {0,1,4,5}[t4] (step 0) /
+// {2,3,6,7}[t4] (step 1) - the k order of the A fragments; the swizzle puts the four rows of a half-warp into distinct banks.
+// kvalid < 8 (last tile of a ragged / structurally short k-range): fragments of k >= kvalid are zeroed in registers.
+template <int U>
+__device__ __forceinline__ void wpp_tile_mma_kmajor(double (&acc)[U][4][4][2], const double* tile, int o0, int o1, int ob0, int ob1,
+                                                    int kk0, bool live0, bool live1, int kvalid) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int o = s ? o1 : o0, ob = s ? ob1 : ob0;
+        const bool kok = kk0 + 2 * s < kvalid;
+        double bf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double v = tile[j * 64 + ob]; bf[j] = kok ? v : 0.0; }
+#pragma unroll
+        for (int c = 0; c < U; ++c) {
+            if (c == 0 ? live0 : live1) {
+                double a[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const double v = tile[(1 + c) * WPP_BOX_ELEMS + i * 64 + o]; a[i] = kok ? v : 0.0; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[c][i][j], a[i], bf[j]);
+            }
+        }
+    }
+}
+
+// tmap: boxes of 32 rows x 8 columns (A rows = rows of X22);  tmapb: boxes of 8 rows x 8 columns (k-major B = L21 itself).
+// X21 = -(X22 L21) Dinv, the row units taken BOTTOM-UP: unit u needs the rows k < 32 (u + 1) of L21 - its own and those above -
+// so what it overwrites is never read again in this step, and neither T = L21 Dinv nor any scratch outside the lower
+// triangle is needed.
 template <int V>
-__global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __grid_constant__ CUtensorMap tmap, FactorArgs p, int struct_o, WppSolve sv) {
+__global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapb,
+                                                                     FactorArgs p, int struct_o, WppSolve sv) {
     using C = WppCfg<V>;
     constexpr int U = C::U;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -451,6 +487,10 @@ __global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __gri
     double* D = ring.stage0;
     int o0, o1;
     swz_offsets(lane, o0, o1);
+    // k index of this lane inside a k-tile (k-step 0; + 2 for k-step 1) and its offsets in a k-major box
+    const int kk0 = (t4 & 1) + 4 * (t4 >> 1);
+    const int ob0 = kk0 * 8 + (((g >> 1) ^ ((kk0 >> 1) & 3)) << 1) + (g & 1);
+    const int ob1 = (kk0 + 2) * 8 + (((g >> 1) ^ (((kk0 + 2) >> 1) & 3)) << 1) + (g & 1);
 
     for (int b = warp * gridDim.x + blockIdx.x; b < p.batch; b += gridDim.x * C::WARPS) {
         const int n = p.n_sys ? p.n_sys[b] : p.n_max;
@@ -462,17 +502,11 @@ __global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __gri
         double* wb = solve ? sv.w + (size_t)b * sv.ldw : nullptr;
         const int svN = solve ? (sv.n_pts ? sv.n_pts[b] : sv.n_max_pts) : 0;
         const int svNs = solve ? n / sv.O : 1;          // component stride of this problem
-        // the columns n .. round8(n)-1 (inside the tensor) are streamed with the last k-tile of a row: make them finite
-        if (n < p.n_max) {
-            const int cw = min(p.n_max, (n + 7) / 8 * 8) - n;
-            for (int idx = lane; idx < n * cw; idx += 32) L[(size_t)(idx / cw) * p.lda + n + idx % cw] = 0.0;
-        }
         for (int jb = nblk - 1; jb >= 0; --jb) {
             const int k0 = jb * NB, kb = min(NB, n - k0);
             const int r0 = k0 + NB;
             const int m = n - k0 - kb;                       // rows below the diagonal block
             // ---- inverse of the diagonal block (the ring is drained), written back with an explicit zero upper triangle
-            if (m > 0) wpp_prefetch_block(L, p.lda, r0, k0, n, lane);
             for (int r = 0; r < 32; ++r) {
                 double v = (r == lane) ? 1.0 : 0.0;
                 if (r < kb && lane < kb) v = lane <= r ? L[(size_t)(k0 + r) * p.lda + k0 + lane] : 0.0;
@@ -494,66 +528,39 @@ __global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __gri
                 wpp_extract_frags<false>(D, F, lane);
                 wpp_fence_smem_to_tma();
                 __syncwarp();
-                // rows of T beyond the component stride vanish (struct_ns: L[r][k0 .. k0+31] = 0 for r - struct_ns >= k0 + 32)
+                // rows of L21 beyond the component stride vanish (struct_ns: L[r][k0 .. k0+31] = 0 for r - struct_ns >= k0 + 32)
                 const int mt = struct_ns > 0 ? min(m, struct_ns) : m;
-                const int nch = (m + NB - 1) / NB, ncht = (mt + NB - 1) / NB;
+                const int ktot = (mt + 7) >> 3;
+                const int np = ((m + NB - 1) / NB + U - 1) / U;          // passes of U units
                 double acc[U][4][4][2];
-                // ---- T = L21 Dinv, stored transposed at the mirror position (rows k0.., columns r0..) of the upper triangle
-                for (int u = 0; u < ncht; ++u) {
-                    const int row0 = r0 + u * NB;
-                    if (u + 1 < ncht) wpp_prefetch_block(L, p.lda, row0 + NB, k0, n, lane);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = row0 + i * 8 + g;
-                        const double* src = L + (size_t)min(r, n - 1) * p.lda + k0 + 2 * t4;
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const double2 v = *reinterpret_cast<const double2*>(src + jj * 8);
-                            acc[0][i][jj][0] = r < n ? v.x : 0.0; acc[0][i][jj][1] = r < n ? v.y : 0.0;
-                        }
-                    }
-                    wpp_chunk_mul<false>(acc[0], F, lane);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = row0 + i * 8 + g;          // column of the mirror block
-                        if (r < n) {
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                                for (int e = 0; e < 2; ++e) L[(size_t)(k0 + jj * 8 + 2 * t4 + e) * p.lda + r] = acc[0][i][jj][e];
-                        }
-                    }
-                }
-                fence_global_to_tma();
-                __syncwarp();
-                // ---- X21 = -X22 T
-                const int ktot = (min(mt, ncht * NB) + 7) >> 3;
-                int pq = 0, pt = 0;
+                int pq = np - 1, pt = 0;
                 WppPass pp;
-                bool pvalid = wpp_trtri_pass<U>(k0, 0, n, ktot, pp);
+                bool pvalid = wpp_trtri_pass<U>(k0, pq, n, ktot, pp);
                 auto pump = [&]() {
                     while (pvalid && ring.has_room()) {
                         if (lane == 0) {
                             const bool a0 = pt < pp.t0hi, a1 = pp.arow1 >= 0;
                             uint32_t bar;
                             const uint32_t dst = ring.arm(1 + a0 + a1, bar);
-                            tma_load_box(dst, &tmap, r0 + 8 * pt, pp.brow, b, bar);
+#pragma unroll
+                            for (int jn = 0; jn < 4; ++jn) tma_load_box(dst + jn * 512, &tmapb, k0 + 8 * jn, r0 + 8 * pt, b, bar);
                             if (a0) tma_load_box(dst + WPP_BOX_BYTES, &tmap, r0 + 8 * pt, pp.arow0, b, bar);
                             if (a1) tma_load_box(dst + 2 * WPP_BOX_BYTES, &tmap, r0 + 8 * pt, pp.arow1, b, bar);
                         }
                         ++ring.issued;
-                        if (++pt >= pp.thi) { pt = 0; ++pq; pvalid = wpp_trtri_pass<U>(k0, pq, n, ktot, pp); }
+                        if (++pt >= pp.thi) { pt = 0; --pq; pvalid = pq >= 0 && wpp_trtri_pass<U>(k0, pq, n, ktot, pp); }
                     }
                 };
                 WppPass ps;
-                for (int q = 0; wpp_trtri_pass<U>(k0, q, n, ktot, ps); ++q) {
+                for (int q = np - 1; q >= 0; --q) {
+                    wpp_trtri_pass<U>(k0, q, n, ktot, ps);
                     const bool live1 = ps.arow1 >= 0;
 #pragma unroll
                     for (int c = 0; c < U; ++c) zero_acc(acc[c]);
                     for (int t = 0; t < ps.thi; ++t) {
                         pump();
                         const double* tile = ring.wait_tile();
-                        if (!(g_dbg & 1)) wpp_tile_mma<U, false>(acc, tile, o0, o1, t < ps.t0hi, live1);
+                        if (!(g_dbg & 1)) wpp_tile_mma_kmajor<U>(acc, tile, o0, o1, ob0, ob1, kk0, t < ps.t0hi, live1, mt - 8 * t);
                         ring.release_tile();
                     }
                     pump();
@@ -561,6 +568,7 @@ __global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __gri
                     for (int c = 0; c < U; ++c) {
                         if (c == 1 && !live1) break;
                         const int row0 = c ? ps.arow1 : ps.arow0;
+                        wpp_chunk_mul<false>(acc[c], F, lane);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int r = row0 + i * 8 + g;
@@ -583,7 +591,6 @@ __global__ void __launch_bounds__(WppCfg<V>::THREADS, 1) k_trtri_wpp(const __gri
                         }
                     }
                 }
-                (void)nch;
             }
             fence_global_to_tma();
             __syncwarp();
@@ -612,10 +619,10 @@ inline int launch_potrf_wpp_v(const CUtensorMap& map, const FactorArgs& p, int s
     return check_launch("k_potrf_wpp");
 }
 template <int V>
-inline int launch_trtri_wpp_v(const CUtensorMap& map, const FactorArgs& p, int struct_o, const WppSolve& sv, cudaStream_t st) {
+inline int launch_trtri_wpp_v(const CUtensorMap& map, const CUtensorMap& mapb, const FactorArgs& p, int struct_o, const WppSolve& sv, cudaStream_t st) {
     static SmemCache smem_set;
     KMPX_TRY(ensure_dyn_smem(k_trtri_wpp<V>, WppCfg<V>::SMEM, smem_set, "k_trtri_wpp"));
-    k_trtri_wpp<V><<<wpp_grid<V>(p.batch), WppCfg<V>::THREADS, WppCfg<V>::SMEM, st>>>(map, p, struct_o, sv);
+    k_trtri_wpp<V><<<wpp_grid<V>(p.batch), WppCfg<V>::THREADS, WppCfg<V>::SMEM, st>>>(map, mapb, p, struct_o, sv);
     return check_launch("k_trtri_wpp");
 }
 inline int wpp_variant(int dflt) { return (dflt + ((g_host_dbg >> 7) & 3)) % 3; }
@@ -632,13 +639,14 @@ inline int launch_potrf_wpp(double* A, int lda, long long strideA, const int* n_
 }
 inline int launch_trtri_wpp(double* L, int lda, long long strideA, const int* n_sys, int n_max, int batch, int struct_o, const WppSolve& sv,
                             cudaStream_t st) {
-    CUtensorMap map;
+    CUtensorMap map, mapb;
     KMPX_TRY(make_batch_map(&map, L, lda, strideA, n_max, batch, NB));
+    KMPX_TRY(make_batch_map(&mapb, L, lda, strideA, n_max, batch, 8));
     FactorArgs p{L, lda, strideA, n_sys, n_max, batch, nullptr, 0, 0};
     switch (wpp_variant(WPP_V_TRTRI)) {
-        case 0: return launch_trtri_wpp_v<0>(map, p, struct_o, sv, st);
-        case 1: return launch_trtri_wpp_v<1>(map, p, struct_o, sv, st);
-        default: return launch_trtri_wpp_v<2>(map, p, struct_o, sv, st);
+        case 0: return launch_trtri_wpp_v<0>(map, mapb, p, struct_o, sv, st);
+        case 1: return launch_trtri_wpp_v<1>(map, mapb, p, struct_o, sv, st);
+        default: return launch_trtri_wpp_v<2>(map, mapb, p, struct_o, sv, st);
     }
 }
 
