@@ -416,7 +416,8 @@ def run_ours(args):
             tpath = os.path.join(ROOT, 'profiles', cand)
             if os.path.isfile(tpath):
                 with open(tpath) as fh:
-                    tk = json.load(fh)['k_kmp_predict_fast']
+                    tj = json.load(fh)
+                    tk = tj.get('k_kmp_predict_tab') or tj['k_kmp_predict_fast']
                 traffic = (tk['dram_bytes_read'] + tk['dram_bytes_write']) * (B * args.steps / n_launch) / tk['problems_per_launch']
                 traffic_src = f'static: profiles/{cand} (ncu --set full of this kernel), scaled to the problems per launch'
                 break
