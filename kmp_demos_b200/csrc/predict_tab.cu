@@ -233,6 +233,36 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
     constexpr int FILL_J = 7, FILL_WARPS = TALL / 32;
     auto fill = [&](auto one_dim) {         // the I == 1 test is hoisted: a branch inside the chain body would serialise the chains
         constexpr bool ONE = decltype(one_dim)::value;
+        if (ONE && ldp - 4 <= 32 * FILL_J) {
+            // scalar inputs, N <= 224: a lane owns the same FILL_J stored points for every query, so they are loaded once, and
+            // two queries are evaluated per batch: 2 FILL_J independent chains per lane (the panel is latency bound: each warp
+            // walks ~1000 dependent-chain instructions whatever the other warps do)
+            double sj[FILL_J];
+#pragma unroll
+            for (int u = 0; u < FILL_J; ++u) sj[u] = s[min(lane + 32 * u, N - 1)];
+            const int pj = (lane & ~6) | ((lane & 2) << 1) | ((lane & 4) >> 1);
+            for (int ma = warp; ma < TQT && !(p.dbg & 4); ma += 2 * FILL_WARPS) {
+                const int mb = ma + FILL_WARPS;
+                const double qa = sqs[ma], qb = sqs[min(mb, TQT - 1)];
+                double ea[FILL_J], eb[FILL_J];
+#pragma unroll
+                for (int u = 0; u < FILL_J; ++u) {
+                    const double da = fabs(qa - sj[u]), db = fabs(qb - sj[u]);
+                    ea[u] = exp_tab(-p.sigma_f * (da * da), etab);
+                    eb[u] = exp_tab(-p.sigma_f * (db * db), etab);
+                }
+                const bool la = m0 + ma < p.M, lb = mb < TQT && m0 + mb < p.M;
+#pragma unroll
+                for (int u = 0; u < FILL_J; ++u) {
+                    const int j = lane + 32 * u;
+                    if (j < ldp - 4) {
+                        panel[(size_t)ma * ldp + pj + 32 * u] = (j < N && la) ? ea[u] : 0.0;
+                        if (mb < TQT) panel[(size_t)mb * ldp + pj + 32 * u] = (j < N && lb) ? eb[u] : 0.0;
+                    }
+                }
+            }
+            return;
+        }
         for (int m = warp; m < TQT && !(p.dbg & 4); m += FILL_WARPS) {
             const bool live = m0 + m < p.M;
             for (int j0 = lane; j0 < ldp - 4; j0 += 32 * FILL_J) {       // ldp - 4 is a multiple of 32
