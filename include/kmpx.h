@@ -56,6 +56,9 @@ int kmpx_debug_phases(long long* out_host, int reset);
  *   bit 6 (64) per-category timing printout of the blocked large-n Cholesky (host side)
  *   bit 7 (128) route NT products through the cp.async GEMM instead of the TMA-fed persistent one (results stay correct) */
 int kmpx_debug_set(int flags);
+/* k-steps executed / scheduled by the table-driven predict kernel since the last reset (out_host[2]), counted while
+ * kmpx_debug_set(32768) is on: how much of the dense contraction the 2^-60 kappa-block skipping left. */
+int kmpx_debug_predict_stats(long long* out_host, int reset);
 /* y[i] = exp(x[i]) through the branch-free exponentials of the hot kernels (mode 0: exp_nonpos, 1: table-driven exp_tab);
  * accuracy probe for the tests, x and y are device arrays. */
 int kmpx_debug_exp(const double* x, double* y, long long n, int mode, void* stream);

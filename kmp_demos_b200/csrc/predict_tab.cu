@@ -29,6 +29,8 @@
 
 namespace kmpx {
 
+__device__ unsigned long long g_pstats[2];      // k-steps executed / scheduled by k_kmp_predict_tab, counted under kmpx_debug_set(32768)
+
 constexpr int TQT = 64;          // queries per CTA
 constexpr int TRC = 16;          // rows of Linv per chunk
 constexpr int TQK = 32;          // k per stage: 8 k-steps of 4 = 128 DMMA per warp between two ring hand-overs
@@ -39,6 +41,7 @@ constexpr int TALL = TTHR + 128;              // + producer warpgroup (setmaxnre
 constexpr int TMAXST = 48;       // stages per warp the table holds (n_sys <= ~600; larger systems take k_kmp_predict_fast)
 constexpr int TSTAGE_BYTES = TRC * TQK * 8;   // 4 boxes of 16 rows x 64 B
 constexpr int TSTAGE_ELEMS = TRC * TQK;
+constexpr double kKappaSkip = 3.3881317890172014e-21;     // 2^-68: kappa boxes whose every entry is below this are skipped (see the kernel)
 constexpr int TROW = 8 + TWARPS * TMAXST * 2; // ints per table row: stage counts per warp, then [warp][stage]{d0, d1}
 
 // stage descriptor: d0 = r0 | a << 12 | chunk_end << 13 | has_v1 << 14 | nst << 16;  d1 = k offset in the panel | col0 << 16
@@ -56,7 +59,7 @@ __host__ __device__ inline TabSmem tab_smem_layout(int O, int I, int n_max_pts, 
     L.sqs = L.wsh + (size_t)round_up(n_sys_max, 2) * 8;
     L.etab = L.sqs + (size_t)round_up(TQT * I, 2) * 8;
     L.sched = L.etab + (size_t)kExpTabN * 8;
-    L.bars = L.sched + (size_t)TROW * 4;
+    L.bars = L.sched + (size_t)(TROW + 8) * 4;          // + the kappa box masks of the tile
     L.total = L.bars + (size_t)2 * TWARPS * TST * 8 + 1024 /* alignment slack */;
     return L;
 }
@@ -179,7 +182,9 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + lay.bars);      // full[TWARPS][TST], empty[TWARPS][TST]
     const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TWARPS * TST);
 
+    unsigned* kmask = reinterpret_cast<unsigned*>(sched + TROW);          // bit q of word q / 32: the columns 8 q .. 8 q + 7 of the kappa panel carry data
     if (tid == 0) {
+        for (int i = 0; i < 8; ++i) kmask[i] = 0u;
         for (int i = 0; i < TWARPS * TST; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -231,6 +236,7 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
     // FILL_J independent chains in flight (seven columns of one query; fourteen were measured slower); indices are
     // clamped and the results selected, and the exponential itself is branch-free (exp_nonpos), so the chains interleave.
     constexpr int FILL_J = 7, FILL_WARPS = TALL / 32;
+    unsigned kflags = 0u;
     auto fill = [&](auto one_dim) {         // the I == 1 test is hoisted: a branch inside the chain body would serialise the chains
         constexpr bool ONE = decltype(one_dim)::value;
         if (ONE && ldp - 4 <= 32 * FILL_J) {
@@ -256,8 +262,10 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
                 for (int u = 0; u < FILL_J; ++u) {
                     const int j = lane + 32 * u;
                     if (j < ldp - 4) {
-                        panel[(size_t)ma * ldp + pj + 32 * u] = (j < N && la) ? ea[u] : 0.0;
-                        if (mb < TQT) panel[(size_t)mb * ldp + pj + 32 * u] = (j < N && lb) ? eb[u] : 0.0;
+                        const double va = (j < N && la) ? ea[u] : 0.0, vb = (j < N && lb) ? eb[u] : 0.0;
+                        panel[(size_t)ma * ldp + pj + 32 * u] = va;
+                        if (mb < TQT) panel[(size_t)mb * ldp + pj + 32 * u] = vb;
+                        if (va >= kKappaSkip || vb >= kKappaSkip) kflags |= 1u << ((lane >> 3) + 4 * u);
                     }
                 }
             }
@@ -277,19 +285,38 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
 #pragma unroll
                 for (int u = 0; u < FILL_J; ++u) {
                     const int j = j0 + 32 * u;
-                    if (j < ldp - 4) panel[(size_t)m * ldp + pj + 32 * u] = (j < N && live) ? e[u] : 0.0;
+                    if (j < ldp - 4) {
+                        const double v = (j < N && live) ? e[u] : 0.0;
+                        panel[(size_t)m * ldp + pj + 32 * u] = v;
+                        if (v >= kKappaSkip) atomicOr(kmask + (j >> 8), 1u << ((j >> 3) & 31));
+                    }
                 }
             }
         }
     };
     if (I == 1) fill(std::true_type{}); else fill(std::false_type{});
-    __syncthreads();          // panel, wsh, racc are complete
+    kflags = __reduce_or_sync(0xffffffffu, kflags);
+    if (lane == 0 && kflags) atomicOr(kmask, kflags);
+    __syncthreads();          // panel, wsh, racc and the kappa box masks are complete
+    // RBF locality: a box of 8 stored points whose kappa is below 2^-68 for all 64 queries of the tile contributes at most
+    // 2^-68 |Linv row|_1 <= 2^-60 max|Linv row| to an entry of V (n <= 256 terms) - 1/128 of ONE rounding error of a retained
+    // term of that size, i.e. far inside the error of the dense sum itself.  Stages without a live box are skipped by
+    // producer and consumer alike (not the first TST of a warp: those are requested before the panel exists); partly live
+    // stages run their live boxes.  kmpx_debug_set(8192) keeps everything.
+    const bool keep_all = (p.dbg & 8192) != 0;
+    auto live_boxes = [&](int kcol, int nst) -> unsigned {      // live boxes among the nst / 2 boxes with data of the stage at column kcol
+        const unsigned have = (1u << (nst >> 1)) - 1u;
+        if (keep_all) return have;
+        const int q = kcol >> 3;                                  // kcol is a multiple of 32: the four boxes sit in one word
+        return (kmask[q >> 5] >> (q & 31)) & have;
+    };
 
     if (warp >= TWARPS) {
         // ---- producers: one lane per MMA warp runs that warp's tile cursor and issues its TMA boxes
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
         if (lane >= 2) return;
         while (pk < pcount) {
+            if (pk >= TST && live_boxes(pdesc[2 * pk + 1] & 0xffff, pdesc[2 * pk] >> 16) == 0u) { ++pk; continue; }
             const uint32_t bi = 8 * (cw * TST + pstage);
             if (pwrapped && !mbar_test(empty0 + bi, ppar ^ 1)) { __nanosleep(100); continue; }   // polling must not eat the MMA warps' issue slots
             produce_one();
@@ -361,9 +388,17 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
             }
         }
     };
+    bool touched = false;          // a stage of the current chunk ran
+    int ks_run = 0, ks_all = 0;
     for (int ck = 0; ck < ccount; ++ck) {
         const int d0 = cdesc[2 * ck], d1 = cdesc[2 * ck + 1];
         const int c_r0 = d0 & 0xfff, c_kcol = d1 & 0xffff, c_col0 = d1 >> 16;
+        ks_all += d0 >> 16;
+        const unsigned live = live_boxes(c_kcol, d0 >> 16);
+        const bool run = ck < TST || live != 0u;
+        if (run) {
+        touched = true;
+        ks_run += 2 * __popc(live);
         const uint32_t bi = 8 * (warp * TST + stage);
         mbar_wait(full0 + bi, par);
         const double* tile = ring + stage * TSTAGE_ELEMS;
@@ -393,7 +428,7 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dmma884(acc[i][j], a[i], bf[j]);
         };
-        if (nst == 8) {
+        if (live == 0xfu && nst == 8) {
             if (first) {
 #pragma unroll
                 for (int st = 0; st < 8; ++st) kstep(st, acc0);
@@ -401,26 +436,31 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
 #pragma unroll
                 for (int st = 0; st < 8; ++st) kstep(st, acc1);
             }
-        } else {                                          // last k-block of a segment: only the boxes with data (two k-steps each)
+        } else {                                          // short last k-block / partly live stage: only the live boxes (two k-steps each)
             if (first) {
 #pragma unroll 1
-                for (int st = 0; st < nst; st += 2) { kstep(st, acc0); kstep(st + 1, acc0); }
+                for (int st = 0; st < nst; st += 2) if ((live >> (st >> 1)) & 1u) { kstep(st, acc0); kstep(st + 1, acc0); }
             } else {
 #pragma unroll 1
-                for (int st = 0; st < nst; st += 2) { kstep(st, acc1); kstep(st + 1, acc1); }
+                for (int st = 0; st < nst; st += 2) if ((live >> (st >> 1)) & 1u) { kstep(st, acc1); kstep(st + 1, acc1); }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + bi);
         if (++stage == TST) { stage = 0; par ^= 1; }
-        if ((d0 & (1 << 13)) && !(p.dbg & 8)) {
-            // chunk complete: reduce the V tile over its 16 rows straight from the accumulators
-            if (O == 2 && (d0 & (1 << 14))) reduce(c_r0, std::true_type{});
-            else reduce(c_r0, std::false_type{});
-            zero_acc(acc0);
-            zero_acc(acc1);
+        }   // run
+        if (d0 & (1 << 13)) {
+            if (touched && !(p.dbg & 8)) {
+                // chunk complete: reduce the V tile over its 16 rows straight from the accumulators
+                if (O == 2 && (d0 & (1 << 14))) reduce(c_r0, std::true_type{});
+                else reduce(c_r0, std::false_type{});
+                zero_acc(acc0);
+                zero_acc(acc1);
+            }
+            touched = false;
         }
     }
+    if (lane == 0 && (p.dbg & 32768)) { atomicAdd(&g_pstats[0], (unsigned long long)ks_run); atomicAdd(&g_pstats[1], (unsigned long long)ks_all); }
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
 
     // ---------------------------------------------------------------- outputs (reference layout, query last)
@@ -446,11 +486,19 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
     }
 }
 
+int debug_predict_stats(long long* out, int reset) {
+    unsigned long long v[2];
+    KMPX_TRY(check_cuda(cudaMemcpyFromSymbol(v, g_pstats, sizeof(v)), "cudaMemcpyFromSymbol"));
+    out[0] = (long long)v[0]; out[1] = (long long)v[1];
+    if (reset) { unsigned long long z[2] = {0, 0}; KMPX_TRY(check_cuda(cudaMemcpyToSymbol(g_pstats, z, sizeof(z)), "cudaMemcpyToSymbol")); }
+    return 0;
+}
+
 bool predict_tab_applicable(const PredictArgs& p) {
     if (g_host_dbg & 4096) return false;
     if (p.time_driven || p.general || p.O > 2) return false;
     if ((p.lda & 1) || (p.batch > 1 && (p.strideA & 1)) || (reinterpret_cast<uintptr_t>(p.F) & 15)) return false;   // TMA
-    if ((long long)p.O * comp_stride(p.n_max) > 0xfff) return false;                                                 // descriptor fields
+    if ((long long)p.O * comp_stride(p.n_max) > 0xfff || p.n_max > 1024) return false;                                // descriptor fields, 32-bit k-block mask
     const int ldp = (int)round_up(p.n_max, TQK) + 4;
     if (tab_smem_layout(p.O, p.I, p.n_max, ldp).total > 226 * 1024) return false;
     const int* tab = nullptr;
@@ -481,3 +529,5 @@ int launch_predict_tab(PredictArgs& p, cudaStream_t st) {
 }
 
 }  // namespace kmpx
+
+extern "C" int kmpx_debug_predict_stats(long long* out_host, int reset) { return kmpx::debug_predict_stats(out_host, reset); }

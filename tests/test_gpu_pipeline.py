@@ -207,6 +207,39 @@ def test_warp_per_problem_fit_through_the_pipeline(golden):
         assert rel_err(xp[r], z['xi'][r]) < MEAN_TOL and rel_err(sp[r], z['sigma'][r]) < COV_TOL, r
 
 
+def test_predict_kappa_box_skipping_stays_inside_rounding(golden):
+    """The fused predict kernel drops boxes of 8 stored points whose kernel coefficients are below 2^-68 for a whole tile of
+    64 queries (RBF locality).  Against the same kernel with every stage kept (kmpx_debug_set(8192)): in-range queries agree to
+    ~1e-16 norm-wise, and on a query grid that reaches far outside the data (tiles with no live box at all) mean and
+    covariance still agree - far queries give mean 0 and covariance alpha * I up to the dropped 1e-21 terms."""
+    from kmp_demos_b200 import _lib
+    from kmp_demos_b200.batch import KMPBatch
+    lib = _lib.load()
+    zl, z = golden('letters_ref.npz'), golden('cfg3_sample.npz')
+    c = wl.CFG1
+    t = wl.cfg1_kmp_grid(200)
+    base_of, vs, vp, vv = [], [], [], []
+    for r in range(12):
+        li, si = int(z['letter'][r]), int(z['set_idx'][r])
+        a, b, cc = wl.cfg3_via_sets(li, zl['gmr_mu'][li], si + 1)
+        base_of.append(li); vs.append(a[si]); vp.append(b[si]); vv.append(cc[si])
+    kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], time_driven_kernel=False, chunk=16)
+    kb.set_base(np.broadcast_to(t, (26, 1, 200)), zl['gmr_mu'], zl['gmr_sigma'])
+    for queries in (wl.cfg1_query_grid(1000), np.linspace(-6.0, 8.0, 1500).reshape(1, -1)):
+        args = (np.array(base_of), np.array(vs), np.array(vp), np.array(vv), queries)
+        xi1, sg1 = kb.fit_predict(*args)
+        lib.kmpx_debug_set(8192)
+        try:
+            xi0, sg0 = kb.fit_predict(*args)
+        finally:
+            lib.kmpx_debug_set(0)
+        assert rel_err(xi1, xi0) < 1e-14 and rel_err(sg1, sg0) < 1e-14
+        assert np.all(np.isfinite(xi1)) and np.all(np.isfinite(sg1))
+    far = np.abs(queries[0] - 1.0) > 3.0                      # further than any kernel support from the data in [0.01, 2]
+    assert np.max(np.abs(xi1[:, :, far])) < 1e-15
+    assert np.max(np.abs(sg1[:, 0, 0, far] - c['alpha'])) < 1e-12 and np.max(np.abs(sg1[:, 0, 1, far])) < 1e-12
+
+
 def test_cfg3_batch_vs_reference_and_vs_single(golden):
     """cfg 3 sample: batched adaptation == the reference's per-problem results; batch == one-by-one bit for bit."""
     from kmp_demos_b200.batch import KMPBatch

@@ -1,6 +1,6 @@
 """Table-driven predict kernel (predict_tab.cu, default) vs the cursor-driven one (predict_fast.cu, kmpx_debug_set(4096)): agreement and time.
 usage: tab_probe.py [sets per letter] [debug flag sets ...]"""
-import sys, os, numpy as np, torch
+import sys, os, ctypes, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from kmp_demos_b200 import _lib, workloads as wl
 from kmp_demos_b200.batch import KMPBatch
@@ -24,9 +24,11 @@ for fl in flagsets:
         kb.events = []
         xi, sg, info, _ = kb.run_device(base_of, d_vs, d_vp, d_vv, q); torch.cuda.synchronize()
     ms = sum(a.elapsed_time(b) for n, a, b in kb.events if n.startswith('kmpx_kmp_predict'))
-    print(f'flags {fl:5d} predict {ms:.3f} ms for {len(base_of)} problems ({ms / len(base_of) * 26624:.1f} ms per 26624)', flush=True)
+    st = (ctypes.c_longlong * 2)(); lib.kmpx_debug_predict_stats(st, 1)
+    print(f'flags {fl:5d} predict {ms:.3f} ms for {len(base_of)} problems ({ms / len(base_of) * 26624:.1f} ms per 26624); k-steps executed / scheduled {st[0] / max(st[1], 1):.3f}', flush=True)
     out[fl] = (xi.clone(), sg.clone())
 lib.kmpx_debug_set(0)
 rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
-if 0 in out and 4096 in out:
-    print('table vs cursor: mean', rel(out[0][0], out[4096][0]), 'cov', rel(out[0][1], out[4096][1]))
+for a in out:
+    if a != flagsets[0]:
+        print(f'flags {a} vs {flagsets[0]}: mean', rel(out[a][0], out[flagsets[0]][0]), 'cov', rel(out[a][1], out[flagsets[0]][1]))
