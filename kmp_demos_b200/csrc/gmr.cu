@@ -114,11 +114,17 @@ __global__ void __launch_bounds__(128) k_gmr(GmrArgs p) {
         double* etab = rec + (size_t)K * RS;
         fill_exp2_table(etab, threadIdx.x, blockDim.x);
         __syncthreads();
+        // a thread takes two ADJACENT queries (a warp 64 consecutive ones): on a sorted query grid the lanes of a warp then
+        // share their active components and whole blocks of components are skipped; 16-byte loads / stores when M is even
         const long long span = (long long)gridDim.x * blockDim.x;
-        for (long long m0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; m0 < p.M; m0 += 2 * span) {
-            const long long m1 = m0 + span;
+        const bool vec2 = (p.M & 1) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.mu) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(p.sigma) & 15) == 0;
+        for (long long m0 = 2 * (blockIdx.x * (long long)blockDim.x + threadIdx.x); m0 < p.M; m0 += 2 * span) {
+            const long long m1 = m0 + 1;
             const bool two = m1 < p.M;
-            double x[2] = {p.x[m0], two ? p.x[m1] : 0.0};
+            double x[2];
+            if (vec2) { const double2 xv = *reinterpret_cast<const double2*>(p.x + m0); x[0] = xv.x; x[1] = xv.y; }
+            else { x[0] = p.x[m0]; x[1] = two ? p.x[m1] : 0.0; }
             double mx[2] = {-INFINITY, -INFINITY};
             // K <= 8 (every mixture of the reference's demos): the exponents stay in registers between the two passes
             constexpr int KR = 8;
@@ -214,22 +220,46 @@ __global__ void __launch_bounds__(128) k_gmr(GmrArgs p) {
             }
             // every component adds REALMIN to the normaliser (GaussianMixtureModel.py:90); h + REALMIN == h unless h < 2^-970
             hsum[0] += K * kRealMin; hsum[1] += K * kRealMin;
+            double cv[2][NP];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                if (u == 1 && !two) break;
-                const long long m = u ? m1 : m0;
                 const double inv = 1.0 / hsum[u];
 #pragma unroll
                 for (int o = 0; o < O; ++o) mean[u][o] *= inv;
                 int t = 0;
 #pragma unroll
+                for (int o = 0; o < O; ++o)
+#pragma unroll
+                    for (int q = o; q < O; ++q) { cv[u][t] = sec[u][t] * inv + (o == q ? p.reg : 0.0) - mean[u][o] * mean[u][q]; ++t; }
+            }
+            if (vec2) {
+                int t = 0;
+#pragma unroll
                 for (int o = 0; o < O; ++o) {
-                    p.mu[(size_t)o * p.M + m] = mean[u][o];
+                    *reinterpret_cast<double2*>(p.mu + (size_t)o * p.M + m0) = make_double2(mean[0][o], mean[1][o]);
 #pragma unroll
                     for (int q = o; q < O; ++q) {
-                        const double v = sec[u][t++] * inv + (o == q ? p.reg : 0.0) - mean[u][o] * mean[u][q];
-                        p.sigma[((size_t)o * O + q) * p.M + m] = v;
-                        if (q != o) p.sigma[((size_t)q * O + o) * p.M + m] = v;
+                        const double2 v = make_double2(cv[0][t], cv[1][t]);
+                        ++t;
+                        *reinterpret_cast<double2*>(p.sigma + ((size_t)o * O + q) * p.M + m0) = v;
+                        if (q != o) *reinterpret_cast<double2*>(p.sigma + ((size_t)q * O + o) * p.M + m0) = v;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (u == 1 && !two) break;
+                    const long long m = u ? m1 : m0;
+                    int t = 0;
+#pragma unroll
+                    for (int o = 0; o < O; ++o) {
+                        p.mu[(size_t)o * p.M + m] = mean[u][o];
+#pragma unroll
+                        for (int q = o; q < O; ++q) {
+                            const double v = cv[u][t++];
+                            p.sigma[((size_t)o * O + q) * p.M + m] = v;
+                            if (q != o) p.sigma[((size_t)q * O + o) * p.M + m] = v;
+                        }
                     }
                 }
             }
