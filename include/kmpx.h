@@ -155,6 +155,13 @@ int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kin
                      int batch, const double* sq, long long stride_sq, int M,
                      double sigma_f, double alpha_kmp, int time_driven,
                      double* xi, double* sigma_out, void* stream);
+/* RBF locality in kmpx_kmp_predict (plain kernel, O <= 2, the table-driven kernel): a box of 8 stored points whose kernel
+ * coefficients k(s*, s_j) are below `threshold` for ALL 64 queries of a tile is treated as zero - its share of the
+ * contraction is skipped.  Default 2^-68: an entry of V = Linv k*^T then loses at most 2^-60 max|Linv row|, 1/128 of one
+ * rounding error of a retained term; with the reference's sigma_f = 200 about half of the contraction of a
+ * cfg-3 problem goes.  threshold = 0 keeps every term.  Process-wide setting, read at launch time. */
+int kmpx_predict_skip_threshold(double threshold);
+
 /* kmpx_kmp_predict for LARGE batches (many (problem, query tile) pairs per SM): same arguments and mathematics; where
  * the fast path applies (plain kernel, O <= 2, factor_kind 0) persistent CTAs walk tiles of 40 queries with the kappa panel
  * of the next tile evaluated, and the results of the previous one written, while the tensor pipe contracts the current

@@ -34,9 +34,11 @@ struct PredictArgs {
     double* xi; double* sigma_out;
     int resident; int ldp;   // panel leading dimension (resident mode)
     int dbg;                 // profiling experiments: bit 0 skip MMAs, bit 1 skip loads
+    double kskip;            // kernel coefficients below this for a whole query tile are treated as zero (0: keep everything)
 };
 bool predict_fast_applicable(const PredictArgs& p);
 int launch_predict_fast(PredictArgs& p, cudaStream_t st);
+extern double g_predict_kskip;   // kmpx_predict_skip_threshold
 bool predict_tab_applicable(const PredictArgs& p);
 int launch_predict_tab(PredictArgs& p, cudaStream_t st);
 bool predict_pers_applicable(const PredictArgs& p);

@@ -407,13 +407,19 @@ static int predict_dispatch(const double* F, int lda, long long strideA, int fac
     if (!xi) return fail_arg(19, "xi is NULL");
     if ((reinterpret_cast<uintptr_t>(F) & 15) != 0) return fail_arg(1, "F must be 16-byte aligned");
     PredictArgs p{F, lda, strideA, factor_kind, w, ldw, s, n_pts, n_max, I, O, batch, sq, stride_sq, M,
-                  sigma_f, alpha_kmp, time_driven, xi, sigma_out, 0, 0, g_host_dbg};
+                  sigma_f, alpha_kmp, time_driven, xi, sigma_out, 0, 0, g_host_dbg, g_predict_kskip};
     if (persistent && predict_pers_applicable(p)) return launch_predict_pers(p, (cudaStream_t)stream);
     if (predict_tab_applicable(p)) return launch_predict_tab(p, (cudaStream_t)stream);
     if (predict_fast_applicable(p)) return launch_predict_fast(p, (cudaStream_t)stream);
     if (predict_stream_applicable(p)) return launch_predict_stream(p, (cudaStream_t)stream);
     if (O <= 2) return launch_predict<64>(p, (cudaStream_t)stream);
     return launch_predict<32>(p, (cudaStream_t)stream);
+}
+
+extern "C" int kmpx_predict_skip_threshold(double threshold) {
+    if (!(threshold >= 0.0) || threshold > 1e-12) return fail_arg(1, "threshold must be in [0, 1e-12]");
+    g_predict_kskip = threshold;
+    return 0;
 }
 
 extern "C" int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kind,

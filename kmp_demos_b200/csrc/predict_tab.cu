@@ -41,7 +41,6 @@ constexpr int TALL = TTHR + 128;              // + producer warpgroup (setmaxnre
 constexpr int TMAXST = 48;       // stages per warp the table holds (n_sys <= ~600; larger systems take k_kmp_predict_fast)
 constexpr int TSTAGE_BYTES = TRC * TQK * 8;   // 4 boxes of 16 rows x 64 B
 constexpr int TSTAGE_ELEMS = TRC * TQK;
-constexpr double kKappaSkip = 3.3881317890172014e-21;     // 2^-68: kappa boxes whose every entry is below this are skipped (see the kernel)
 constexpr int TROW = 8 + TWARPS * TMAXST * 2; // ints per table row: stage counts per warp, then [warp][stage]{d0, d1}
 
 // stage descriptor: d0 = r0 | a << 12 | chunk_end << 13 | has_v1 << 14 | nst << 16;  d1 = k offset in the panel | col0 << 16
@@ -237,6 +236,7 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
     // clamped and the results selected, and the exponential itself is branch-free (exp_nonpos), so the chains interleave.
     constexpr int FILL_J = 7, FILL_WARPS = TALL / 32;
     unsigned kflags = 0u;
+    const double kskip = p.kskip;          // 2^-68 by default (kmpx_predict_skip_threshold)
     auto fill = [&](auto one_dim) {         // the I == 1 test is hoisted: a branch inside the chain body would serialise the chains
         constexpr bool ONE = decltype(one_dim)::value;
         if (ONE && ldp - 4 <= 32 * FILL_J) {
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
                         const double va = (j < N && la) ? ea[u] : 0.0, vb = (j < N && lb) ? eb[u] : 0.0;
                         panel[(size_t)ma * ldp + pj + 32 * u] = va;
                         if (mb < TQT) panel[(size_t)mb * ldp + pj + 32 * u] = vb;
-                        if (va >= kKappaSkip || vb >= kKappaSkip) kflags |= 1u << ((lane >> 3) + 4 * u);
+                        if (va >= kskip || vb >= kskip) kflags |= 1u << ((lane >> 3) + 4 * u);
                     }
                 }
             }
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
                     if (j < ldp - 4) {
                         const double v = (j < N && live) ? e[u] : 0.0;
                         panel[(size_t)m * ldp + pj + 32 * u] = v;
-                        if (v >= kKappaSkip) atomicOr(kmask + (j >> 8), 1u << ((j >> 3) & 31));
+                        if (v >= kskip) atomicOr(kmask + (j >> 8), 1u << ((j >> 3) & 31));
                     }
                 }
             }
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
     // term of that size, i.e. far inside the error of the dense sum itself.  Stages without a live box are skipped by
     // producer and consumer alike (not the first TST of a warp: those are requested before the panel exists); partly live
     // stages run their live boxes.  kmpx_debug_set(8192) keeps everything.
-    const bool keep_all = (p.dbg & 8192) != 0;
+    const bool keep_all = (p.dbg & 8192) != 0 || !(p.kskip > 0.0);
     auto live_boxes = [&](int kcol, int nst) -> unsigned {      // live boxes among the nst / 2 boxes with data of the stage at column kcol
         const unsigned have = (1u << (nst >> 1)) - 1u;
         if (keep_all) return have;
