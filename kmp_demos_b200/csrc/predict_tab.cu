@@ -58,7 +58,7 @@ __host__ __device__ inline TabSmem tab_smem_layout(int O, int I, int n_max_pts, 
     L.sqs = L.wsh + (size_t)round_up(n_sys_max, 2) * 8;
     L.etab = L.sqs + (size_t)round_up(TQT * I, 2) * 8;
     L.sched = L.etab + (size_t)kExpTabN * 8;
-    L.bars = L.sched + (size_t)(TROW + 8) * 4;          // + the kappa box masks of the tile
+    L.bars = L.sched + (size_t)(TROW + 8 + 16) * 4;     // + the kappa box masks of the tile and the corners of its query box
     L.total = L.bars + (size_t)2 * TWARPS * TST * 8 + 1024 /* alignment slack */;
     return L;
 }
@@ -202,7 +202,47 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
     for (int idx = tid; idx < TWARPS * NT * TQT; idx += TALL) racc[idx] = 0.0;
     fill_exp2_table(etab, tid, TALL);
     for (int idx = tid; idx < TROW; idx += TALL) sched[idx] = sched_tab[(size_t)N * TROW + idx];
-    __syncthreads();          // the schedule is complete (the producers need it before the panel is evaluated)
+    __syncthreads();          // the schedule and the queries are complete
+    // RBF locality.  k(q, s_j) = exp(-sigma_f |q - s_j|^2) < kskip (2^-68 by default) as soon as s_j is further
+    // than d = sqrt(-ln(kskip) / sigma_f) from the bounding box of the tile's live queries.  A box of 8 stored points that are
+    // all that far contributes at most 2^-68 |Linv row|_1 <= 2^-60 max|Linv row| to an entry of V (n <= 256 terms) - 1/128 of
+    // ONE rounding error of a retained term of that size, far inside the error of the dense sum itself - so it is dead: its
+    // stages are never requested, its panel entries never read.  Bit q of kmask[q / 32]: box q (columns 8 q .. 8 q + 7) is live.
+    const bool keep_all = (p.dbg & 8192) != 0 || !(p.kskip > 0.0);
+    if (!keep_all) {
+        double* qbox = reinterpret_cast<double*>(kmask + 8) ;          // [I] lower and [I] upper corner of the live queries
+        if (warp == 0) {
+            for (int i = 0; i < I; ++i) {
+                double lo = INFINITY, hi = -INFINITY;
+                for (int m = lane; m < TQT; m += 32)
+                    if (m0 + m < p.M) { const double v = sqs[m * I + i]; lo = fmin(lo, v); hi = fmax(hi, v); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+                if (lane == 0) { qbox[i] = lo; qbox[I + i] = hi; }
+            }
+        }
+        __syncthreads();
+        const double lim2 = -log(p.kskip) / p.sigma_f * (1.0 + 1e-9);      // squared distance beyond which k < kskip
+        for (int j0 = warp * 32; j0 < N; j0 += TALL) {
+            const int j = j0 + lane;
+            double d2 = 0.0;
+            if (j < N)
+                for (int i = 0; i < I; ++i) {
+                    const double v = s[(size_t)j * I + i];
+                    const double dd = fmax(fmax(qbox[i] - v, v - qbox[I + i]), 0.0);       // distance to the box along axis i
+                    d2 = fma(dd, dd, d2);
+                }
+            const unsigned near = __ballot_sync(0xffffffffu, j < N && !(d2 > lim2));      // (a NaN coordinate keeps its box)
+            if (lane < 4 && ((near >> (8 * lane)) & 0xffu)) atomicOr(kmask + (j0 >> 8), 1u << (((j0 >> 3) + lane) & 31));
+        }
+        __syncthreads();
+    }
+    auto live_boxes = [&](int kcol, int nst) -> unsigned {      // live boxes among the nst / 2 boxes with data of the stage at column kcol
+        const unsigned have = (1u << (nst >> 1)) - 1u;
+        if (keep_all) return have;
+        const int q = kcol >> 3;                                  // kcol is a multiple of 32: the four boxes sit in one word
+        return (kmask[q >> 5] >> (q & 31)) & have;
+    };
     // producer cursors (lanes 0, 1 of the four producer warps: two streams each); the first tiles are requested now
     // so that they land while the panel is evaluated
     const bool is_producer = warp >= TWARPS && lane < 2;
@@ -226,17 +266,18 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
         if (++pstage == TST) { pstage = 0; ppar ^= 1; pwrapped = true; }
     };
     if (is_producer) {
-        for (int t = 0; t < TST && pk < pcount; ++t) produce_one();
+        for (int t = 0; t < TST && pk < pcount;) {
+            if (live_boxes(pdesc[2 * pk + 1] & 0xffff, pdesc[2 * pk] >> 16) == 0u) { ++pk; continue; }
+            produce_one();
+            ++t;
+        }
     }
-    __syncthreads();          // sqs is complete
     // kappa panel (the B operand), evaluated while the first Linv tiles are in flight: warp-strided over the queries,
     // lane-strided over the stored points; column j goes to position (j & ~7) | swap_bits_1_2(j & 7)  (k-step order).
     // A dependent FP64 operation costs 40-60 cycles here and an exp is a chain of ~25 of them, so every lane keeps
     // FILL_J independent chains in flight (seven columns of one query; fourteen were measured slower); indices are
     // clamped and the results selected, and the exponential itself is branch-free (exp_nonpos), so the chains interleave.
     constexpr int FILL_J = 7, FILL_WARPS = TALL / 32;
-    unsigned kflags = 0u;
-    const double kskip = p.kskip;          // 2^-68 by default (kmpx_predict_skip_threshold)
     auto fill = [&](auto one_dim) {         // the I == 1 test is hoisted: a branch inside the chain body would serialise the chains
         constexpr bool ONE = decltype(one_dim)::value;
         if (ONE && ldp - 4 <= 32 * FILL_J) {
@@ -265,7 +306,6 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
                         const double va = (j < N && la) ? ea[u] : 0.0, vb = (j < N && lb) ? eb[u] : 0.0;
                         panel[(size_t)ma * ldp + pj + 32 * u] = va;
                         if (mb < TQT) panel[(size_t)mb * ldp + pj + 32 * u] = vb;
-                        if (va >= kskip || vb >= kskip) kflags |= 1u << ((lane >> 3) + 4 * u);
                     }
                 }
             }
@@ -288,35 +328,20 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
                     if (j < ldp - 4) {
                         const double v = (j < N && live) ? e[u] : 0.0;
                         panel[(size_t)m * ldp + pj + 32 * u] = v;
-                        if (v >= kskip) atomicOr(kmask + (j >> 8), 1u << ((j >> 3) & 31));
                     }
                 }
             }
         }
     };
     if (I == 1) fill(std::true_type{}); else fill(std::false_type{});
-    kflags = __reduce_or_sync(0xffffffffu, kflags);
-    if (lane == 0 && kflags) atomicOr(kmask, kflags);
-    __syncthreads();          // panel, wsh, racc and the kappa box masks are complete
-    // RBF locality: a box of 8 stored points whose kappa is below 2^-68 for all 64 queries of the tile contributes at most
-    // 2^-68 |Linv row|_1 <= 2^-60 max|Linv row| to an entry of V (n <= 256 terms) - 1/128 of ONE rounding error of a retained
-    // term of that size, i.e. far inside the error of the dense sum itself.  Stages without a live box are skipped by
-    // producer and consumer alike (not the first TST of a warp: those are requested before the panel exists); partly live
-    // stages run their live boxes.  kmpx_debug_set(8192) keeps everything.
-    const bool keep_all = (p.dbg & 8192) != 0 || !(p.kskip > 0.0);
-    auto live_boxes = [&](int kcol, int nst) -> unsigned {      // live boxes among the nst / 2 boxes with data of the stage at column kcol
-        const unsigned have = (1u << (nst >> 1)) - 1u;
-        if (keep_all) return have;
-        const int q = kcol >> 3;                                  // kcol is a multiple of 32: the four boxes sit in one word
-        return (kmask[q >> 5] >> (q & 31)) & have;
-    };
+    __syncthreads();          // panel, wsh, racc are complete
 
     if (warp >= TWARPS) {
         // ---- producers: one lane per MMA warp runs that warp's tile cursor and issues its TMA boxes
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
         if (lane >= 2) return;
         while (pk < pcount) {
-            if (pk >= TST && live_boxes(pdesc[2 * pk + 1] & 0xffff, pdesc[2 * pk] >> 16) == 0u) { ++pk; continue; }
+            if (live_boxes(pdesc[2 * pk + 1] & 0xffff, pdesc[2 * pk] >> 16) == 0u) { ++pk; continue; }
             const uint32_t bi = 8 * (cw * TST + pstage);
             if (pwrapped && !mbar_test(empty0 + bi, ppar ^ 1)) { __nanosleep(100); continue; }   // polling must not eat the MMA warps' issue slots
             produce_one();
@@ -395,7 +420,7 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
         const int c_r0 = d0 & 0xfff, c_kcol = d1 & 0xffff, c_col0 = d1 >> 16;
         ks_all += d0 >> 16;
         const unsigned live = live_boxes(c_kcol, d0 >> 16);
-        const bool run = ck < TST || live != 0u;
+        const bool run = live != 0u;
         if (run) {
         touched = true;
         ks_run += 2 * __popc(live);
