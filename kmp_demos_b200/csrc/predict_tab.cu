@@ -212,14 +212,16 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
     if (!keep_all) {
         double* qbox = reinterpret_cast<double*>(kmask + 8) ;          // [I] lower and [I] upper corner of the live queries
         if (warp == 0) {
+            bool odd = false;           // a NaN / infinite query coordinate: the reference propagates it, so this tile keeps every box
             for (int i = 0; i < I; ++i) {
                 double lo = INFINITY, hi = -INFINITY;
                 for (int m = lane; m < TQT; m += 32)
-                    if (m0 + m < p.M) { const double v = sqs[m * I + i]; lo = fmin(lo, v); hi = fmax(hi, v); }
+                    if (m0 + m < p.M) { const double v = sqs[m * I + i]; lo = fmin(lo, v); hi = fmax(hi, v); odd = odd || !(fabs(v) < INFINITY); }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
                 if (lane == 0) { qbox[i] = lo; qbox[I + i] = hi; }
             }
+            if (__any_sync(0xffffffffu, odd) && lane < 8) kmask[lane] = ~0u;
         }
         __syncthreads();
         const double lim2 = -log(p.kskip) / p.sigma_f * (1.0 + 1e-9);      // squared distance beyond which k < kskip

@@ -238,6 +238,13 @@ def test_predict_kappa_box_skipping_stays_inside_rounding(golden):
     far = np.abs(queries[0] - 1.0) > 3.0                      # further than any kernel support from the data in [0.01, 2]
     assert np.max(np.abs(xi1[:, :, far])) < 1e-15
     assert np.max(np.abs(sg1[:, 0, 0, far] - c['alpha'])) < 1e-12 and np.max(np.abs(sg1[:, 0, 1, far])) < 1e-12
+    # a NaN query propagates as in the reference (its tile keeps every box), and only into its own outputs
+    qn = np.array(queries, copy=True)
+    qn[0, 5] = np.nan; qn[0, 1400] = np.nan                   # one in range of the data's tiles, one in a far tile
+    xin, sgn = kb.fit_predict(np.array(base_of), np.array(vs), np.array(vp), np.array(vv), qn)
+    bad = np.zeros(qn.shape[1], dtype=bool); bad[[5, 1400]] = True
+    assert np.all(np.isnan(xin[:, :, bad])) and np.all(np.isnan(sgn[:, :, :, bad]))
+    assert np.all(np.isfinite(xin[:, :, ~bad])) and rel_err(xin[:, :, ~bad], xi1[:, :, ~bad]) < 1e-14
 
 
 def test_cfg3_batch_vs_reference_and_vs_single(golden):
