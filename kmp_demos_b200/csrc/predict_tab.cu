@@ -14,7 +14,11 @@
 //   * the assignment is longest-first by a cycle model of stages and reductions, refined by moves and swaps off the most
 //     loaded warp (the boustrophedon deal left 5 % between the first and the last warp);
 //   * chunks of the first component block (V_1 = 0) reduce only the two sums that are not identically zero;
-//   * the short last k-block runs its boxes (two k-steps each) unrolled.
+//   * the short last k-block runs its boxes (two k-steps each) unrolled;
+//   * RBF locality: boxes of 8 stored points that are further than sqrt(-ln(2^-68) / sigma_f) from the bounding
+//     box of the tile's queries have kappa < 2^-68 for the whole tile and are skipped - stages without a live box are never
+//     requested, partly live stages run their live boxes; at the reference's sigma_f = 200 half of the contraction goes, and
+//     what is dropped is below the rounding error of what is kept (kmpx_predict_skip_threshold moves or disables the threshold).
 // Results are bitwise reproducible and independent of the batch a problem sits in (the schedule depends on (O, N) only).
 // Algorithmic flops per problem: O^2 Ns^2 M (+ lower-order reductions); F is streamed from L2 once per CTA.
 #include "dmma_tile.cuh"
