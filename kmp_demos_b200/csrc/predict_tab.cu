@@ -467,13 +467,14 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
 #pragma unroll
                 for (int st = 0; st < 8; ++st) kstep(st, acc1);
             }
-        } else {                                          // short last k-block / partly live stage: only the live boxes (two k-steps each)
+        } else {                                          // short last k-block / partly live stage: only the live boxes (two k-steps
+            const unsigned lv = (p.dbg & 1) ? 0u : live;  // each), every box with static offsets (live is already cut to the boxes with data)
             if (first) {
-#pragma unroll 1
-                for (int st = 0; st < nst; st += 2) if ((live >> (st >> 1)) & 1u) { kstep(st, acc0); kstep(st + 1, acc0); }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (lv & (1u << q)) { kstep(2 * q, acc0); kstep(2 * q + 1, acc0); }
             } else {
-#pragma unroll 1
-                for (int st = 0; st < nst; st += 2) if ((live >> (st >> 1)) & 1u) { kstep(st, acc1); kstep(st + 1, acc1); }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (lv & (1u << q)) { kstep(2 * q, acc1); kstep(2 * q + 1, acc1); }
             }
         }
         __syncwarp();
