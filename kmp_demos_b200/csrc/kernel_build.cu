@@ -77,14 +77,16 @@ __global__ void __launch_bounds__(256) k_kernel_build(BuildArgs p) {
 // Component-major fast path (what the factorisation consumes): a thread owns the point pair (i, j..j+1), evaluates
 // the kernel coefficients ONCE and writes them into every (a, b) block - n^2/O^2 exp instead of n^2/O, no integer
 // division.  Each store is 16 bytes; for fixed (i, a, b) a warp writes 512 contiguous bytes.
-template <bool TD, bool BULK>
+// OC: compile-time number of outputs (0: read p.O) - the loops over the (a, b) blocks unroll and their predicates fold, which matters on
+// small systems, where the kernel is bound by instruction issue
+template <bool TD, bool BULK, int OC>
 __global__ void __launch_bounds__(256) k_kernel_build_comp(BuildArgs p) {
     __shared__ double etab[kExpTabN];
     if (!TD) { fill_exp2_table(etab, threadIdx.x, 256); __syncthreads(); }
     const int bidx = blockIdx.z;
     const int N = p.n_pts ? p.n_pts[bidx] : p.n_max;
     const int Ns = comp_stride(N);
-    const int O = p.O, P = TD ? (O >> 1) : O;
+    const int O = OC ? OC : p.O, P = TD ? (O >> 1) : O;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j0 = blockIdx.x * kBuildCols + lane * 2;
     const int ibase = blockIdx.y * kBuildRows;
@@ -154,6 +156,8 @@ __global__ void __launch_bounds__(256) k_kernel_build_comp(BuildArgs p) {
             double* row = A + (size_t)(a * Ns + i) * p.lda;
             for (int b = 0; b < O; ++b) {
                 if (lower && b > a) continue;
+                // compile-time O: lambda * Sigma_i[a][b] once per (row, block), a warp-uniform load outside the element loop
+                const double lsig = (OC && i < N) ? p.lambda * sig[((size_t)i * O + a) * O + b] : 0.0;
                 double v[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -162,7 +166,8 @@ __global__ void __launch_bounds__(256) k_kernel_build_comp(BuildArgs p) {
                     if (i >= N || j0 + e >= N) x = (a == b && dg) ? 1.0 : 0.0;           // identity padding
                     else {
                         x = TD ? (((a % P) == (b % P)) ? co[e][(a / P) * 2 + (b / P)] : 0.0) : ((a == b) ? co[e][0] : 0.0);
-                        if (dg) x += p.lambda * sig[((size_t)i * O + a) * O + b];
+                        if (OC) x = dg ? x + lsig : x;          // (the same sum: lambda * Sigma is added to the diagonal lane only)
+                        else if (dg) x += p.lambda * sig[((size_t)i * O + a) * O + b];
                     }
                     v[e] = x;
                 }
@@ -271,9 +276,11 @@ extern "C" int kmpx_kernel_build(const double* s, const double* sigma, const int
         const int Ns = comp_stride(n_max);
         dim3 grid(ceil_div(Ns, kBuildCols), ceil_div(Ns, kBuildRows), batch);
         if (grid.y > 65535) return fail_arg(6, "n_max too large for one launch");
-        if (time_driven) k_kernel_build_comp<true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-        else if (Ns >= 1024) k_kernel_build_comp<false, true><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-        else k_kernel_build_comp<false, false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        if (time_driven) k_kernel_build_comp<true, false, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        else if (Ns >= 1024) k_kernel_build_comp<false, true, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        else if (O == 2 && !(g_host_dbg & 131072)) k_kernel_build_comp<false, false, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        else if (O == 1 && !(g_host_dbg & 131072)) k_kernel_build_comp<false, false, 1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+        else k_kernel_build_comp<false, false, 0><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
         return check_launch("k_kernel_build_comp");
     }
     dim3 grid(ceil_div(n, kBuildCols), ceil_div(n, kBuildRows), batch);
