@@ -161,6 +161,12 @@ int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kin
  * rounding error of a retained term; with the reference's sigma_f = 200 about half of the contraction of a
  * cfg-3 problem goes.  threshold = 0 keeps every term.  Process-wide setting, read at launch time. */
 int kmpx_predict_skip_threshold(double threshold);
+/* Queries per CTA of the same kernel: 64 (one CTA of eight MMA warps per SM) or 32 (two CTAs of four MMA warps per SM, whose
+ * set-up and epilogue overlap the other CTA's contraction).  0 (default) chooses 32 when boxes are skipped (threshold > 0)
+ * and 64 when every term is kept - measured at cfg 3: 116 vs 120 ms per 26 624 problems with skipping, 185 vs 179 ms
+ * without.  The two shapes sum in different orders (results differ by ~1e-16 norm-wise); the choice never depends on the
+ * batch, so a problem's bits do not depend on its neighbours.  Process-wide setting, read at launch time. */
+int kmpx_predict_tile_queries(int queries);
 
 /* kmpx_kmp_predict for LARGE batches (many (problem, query tile) pairs per SM): same arguments and mathematics; where
  * the fast path applies (plain kernel, O <= 2, factor_kind 0) persistent CTAs walk tiles of 40 queries with the kappa panel

@@ -27,6 +27,7 @@ _SIGNATURES = {
     'kmpx_debug_phases': [_p, _i],
     'kmpx_debug_predict_stats': [_p, _i],
     'kmpx_predict_skip_threshold': [_d],
+    'kmpx_predict_tile_queries': [_i],
     'kmpx_debug_set': [_i],
     'kmpx_debug_exp': [_p, _p, _ll, _i, _p],
     'kmpx_kernel_build': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _ll, _d, _d, _i, _i, _i, _p],

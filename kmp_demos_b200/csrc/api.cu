@@ -6,6 +6,7 @@ thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 int g_host_dbg = 0;   // profiling experiments (kmpx_debug_set)
 double g_predict_kskip = 3.3881317890172014e-21;      // 2^-68, kmpx_predict_skip_threshold
+int g_predict_tile_queries = 0;                       // 0 = automatic, 32, 64: kmpx_predict_tile_queries
 }  // namespace kmpx
 
 extern "C" int kmpx_version(void) { return KMPX_VERSION; }

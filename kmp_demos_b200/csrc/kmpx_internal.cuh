@@ -39,6 +39,7 @@ struct PredictArgs {
 bool predict_fast_applicable(const PredictArgs& p);
 int launch_predict_fast(PredictArgs& p, cudaStream_t st);
 extern double g_predict_kskip;   // kmpx_predict_skip_threshold
+extern int g_predict_tile_queries;   // kmpx_predict_tile_queries
 bool predict_tab_applicable(const PredictArgs& p);
 int launch_predict_tab(PredictArgs& p, cudaStream_t st);
 bool predict_pers_applicable(const PredictArgs& p);

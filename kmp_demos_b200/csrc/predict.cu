@@ -422,6 +422,12 @@ extern "C" int kmpx_predict_skip_threshold(double threshold) {
     return 0;
 }
 
+extern "C" int kmpx_predict_tile_queries(int queries) {
+    if (queries != 0 && queries != 32 && queries != 64) return fail_arg(1, "queries per CTA must be 0 (automatic), 32 or 64");
+    g_predict_tile_queries = queries;
+    return 0;
+}
+
 extern "C" int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kind,
                                 const double* w, int ldw, const double* s, const int* n_pts, int n_max, int I, int O,
                                 int batch, const double* sq, long long stride_sq, int M,

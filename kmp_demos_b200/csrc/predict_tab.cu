@@ -35,23 +35,19 @@ namespace kmpx {
 
 __device__ unsigned long long g_pstats[2];      // k-steps executed / scheduled by k_kmp_predict_tab, counted under kmpx_debug_set(32768)
 
-constexpr int TQT = 64;          // queries per CTA
 constexpr int TRC = 16;          // rows of Linv per chunk
 constexpr int TQK = 32;          // k per stage: 8 k-steps of 4 = 128 DMMA per warp between two ring hand-overs
 constexpr int TST = 2;           // ring stages per warp
-constexpr int TWARPS = 8;        // MMA warps
-constexpr int TTHR = TWARPS * 32;
-constexpr int TALL = TTHR + 128;              // + producer warpgroup (setmaxnreg works on groups of four warps)
-constexpr int TMAXST = 48;       // stages per warp the table holds (n_sys <= ~600; larger systems take k_kmp_predict_fast)
+constexpr int TWST = 384;        // MMA warps x stages per warp the table holds (8 x 48 or 4 x 96: n_sys <= ~600; larger systems take k_kmp_predict_fast)
 constexpr int TSTAGE_BYTES = TRC * TQK * 8;   // 4 boxes of 16 rows x 64 B
 constexpr int TSTAGE_ELEMS = TRC * TQK;
-constexpr int TROW = 8 + TWARPS * TMAXST * 2; // ints per table row: stage counts per warp, then [warp][stage]{d0, d1}
+constexpr int TROW = 8 + TWST * 2;             // ints per table row: stage counts per warp, then [warp][stage]{d0, d1}
 
 // stage descriptor: d0 = r0 | a << 12 | chunk_end << 13 | has_v1 << 14 | nst << 16;  d1 = k offset in the panel | col0 << 16
 __host__ __device__ inline int tdesc0(int r0, int a, int chunk_end, int has_v1, int nst) { return r0 | (a << 12) | (chunk_end << 13) | (has_v1 << 14) | (nst << 16); }
 
 struct TabSmem { size_t rings, panel, racc, wsh, sqs, etab, sched, bars, total; };
-__host__ __device__ inline TabSmem tab_smem_layout(int O, int I, int n_max_pts, int ldp) {
+__host__ __device__ inline TabSmem tab_smem_layout(int O, int I, int n_max_pts, int ldp, int TQT, int TWARPS) {
     const int nt = O * (O + 1) / 2 + O;
     const int n_sys_max = O * comp_stride(n_max_pts);
     TabSmem L;
@@ -68,7 +64,8 @@ __host__ __device__ inline TabSmem tab_smem_layout(int O, int I, int n_max_pts, 
 }
 
 // ---- host: the schedule of one (O, N).  Returns false when a warp would need more than TMAXST stages.
-static bool tab_schedule_host(int O, int N, int* row) {
+static bool tab_schedule_host(int O, int N, int* row, int TWARPS) {
+    const int TMAXST = TWST / TWARPS;
     const int Ns = comp_stride(N), n = O * Ns;
     const int nchunks = (n + TRC - 1) / TRC;
     struct Stage { int d0, d1; };
@@ -94,7 +91,7 @@ static bool tab_schedule_host(int O, int N, int* row) {
         order[c] = c;
     }
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-    long long load[TWARPS] = {0};
+    long long load[8] = {0};
     for (int k = 0; k < nchunks; ++k) {
         int best = 0;
         for (int w = 1; w < TWARPS; ++w) if (load[w] < load[best]) best = w;
@@ -124,7 +121,7 @@ static bool tab_schedule_host(int O, int N, int* row) {
         load[hi] -= cost[bi]; load[bw] += cost[bi]; owner[bi] = bw;
         if (bj >= 0) { load[bw] -= cost[bj]; load[hi] += cost[bj]; owner[bj] = hi; }
     }
-    int cnt[TWARPS] = {0};
+    int cnt[8] = {0};
     for (int k = 0; k < nchunks; ++k) {             // every warp takes its chunks longest first
         const int c = order[k], w = owner[c];
         for (const auto& sgm : st[c]) {
@@ -139,16 +136,16 @@ static bool tab_schedule_host(int O, int N, int* row) {
 }
 // device copy of the table for (O, n_max), built on first use (per device; never freed: 3 KB per N).  *out = nullptr when
 // some N <= n_max does not fit the table (the caller then takes k_kmp_predict_fast).
-static int tab_sched_table(int O, int n_max, const int** out) {
+static int tab_sched_table(int O, int n_max, int NW, const int** out) {
     static std::mutex mu;
-    static std::map<std::tuple<int, int, int>, int*> cache;
+    static std::map<std::tuple<int, int, int, int>, int*> cache;
     std::lock_guard<std::mutex> lock(mu);
-    const auto key = std::make_tuple(current_device(), O, n_max);
+    const auto key = std::make_tuple(current_device(), O, n_max, NW);
     auto it = cache.find(key);
     if (it == cache.end()) {
         std::vector<int> host((size_t)(n_max + 1) * TROW, 0);
         bool ok = true;
-        for (int N = 1; N <= n_max && ok; ++N) ok = tab_schedule_host(O, N, host.data() + (size_t)N * TROW);
+        for (int N = 1; N <= n_max && ok; ++N) ok = tab_schedule_host(O, N, host.data() + (size_t)N * TROW, NW);
         int* dptr = nullptr;
         if (ok) {
             KMPX_TRY(check_cuda(cudaMalloc(&dptr, host.size() * sizeof(int)), "cudaMalloc (predict schedule table)"));
@@ -160,8 +157,14 @@ static int tab_sched_table(int O, int n_max, const int** out) {
     return 0;
 }
 
-template <int O>
-__global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_constant__ CUtensorMap tmap, PredictArgs p, TabSmem lay, const int* sched_tab) {
+// Two CTA shapes: <64 queries, 8 MMA warps> - one CTA of 384 threads per SM - and <32 queries, 4 MMA warps> - two CTAs of 256
+// threads per SM, whose set-up, kappa panel and epilogue overlap the other CTA's DMMA loop.
+template <int O, int TQT, int TWARPS>
+__global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_predict_tab(const __grid_constant__ CUtensorMap tmap, PredictArgs p, TabSmem lay, const int* sched_tab) {
+    constexpr int TTHR = TWARPS * 32;          // MMA threads
+    constexpr int TALL = TTHR + 128;           // + producer warpgroup (setmaxnreg works on groups of four warps)
+    constexpr int TMAXST = TWST / TWARPS;
+    constexpr int NJ = TQT / 8;                // n-tiles of 8 queries per warp tile
     constexpr int NT = O * (O + 1) / 2 + O;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -251,8 +254,9 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
     };
     // producer cursors (lanes 0, 1 of the four producer warps: two streams each); the first tiles are requested now
     // so that they land while the panel is evaluated
-    const bool is_producer = warp >= TWARPS && lane < 2;
-    const int cw = is_producer ? (warp - TWARPS) * 2 + lane : 0;
+    constexpr int PL = TWARPS / 4;             // producer lanes per warp of the producer warpgroup
+    const bool is_producer = warp >= TWARPS && lane < PL;
+    const int cw = is_producer ? (warp - TWARPS) * PL + lane : 0;
     const int* pdesc = sched + 8 + cw * TMAXST * 2;
     const int pcount = is_producer ? sched[cw] : 0;
     int pk = 0;
@@ -344,8 +348,9 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
 
     if (warp >= TWARPS) {
         // ---- producers: one lane per MMA warp runs that warp's tile cursor and issues its TMA boxes
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
-        if (lane >= 2) return;
+        // register split: one CTA of 384 threads at 168 -> 40 / 232;  two CTAs of 256 threads at 128 -> 48 / 208
+        if (TWARPS == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n"); else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;\n");
+        if (lane >= PL) return;
         while (pk < pcount) {
             if (live_boxes(pdesc[2 * pk + 1] & 0xffff, pdesc[2 * pk] >> 16) == 0u) { ++pk; continue; }
             const uint32_t bi = 8 * (cw * TST + pstage);
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
         }
         return;
     }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n");
+    if (TWARPS == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n"); else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
 
     // ---------------------------------------------------------------- per-warp streaming loop
     const double* ring = rings + (size_t)warp * TST * TSTAGE_ELEMS;
@@ -368,7 +373,7 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
     const int ccount = sched[warp];
     int stage = 0;
     uint32_t par = 0;
-    double acc0[2][8][2], acc1[2][8][2];
+    double acc0[2][NJ][2], acc1[2][NJ][2];
     zero_acc(acc0);
     zero_acc(acc1);
     // chunk complete: reduce the V tile over its 16 rows straight from the accumulators (products, then a 3-step reduce-scatter
@@ -386,9 +391,9 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
             if (needs_v1 && !HAS_V1) continue;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                double val[8];
+                double val[NJ];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     double sum = 0.0;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
@@ -399,23 +404,39 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
                     }
                     val[j] = sum;
                 }
-                double s4[4], s2[2];
+                if constexpr (NJ == 8) {
+                    double s4[4], s2[2];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const double keep = g2 ? val[jj + 4] : val[jj];
-                    const double send = g2 ? val[jj] : val[jj + 4];
-                    s4[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                }
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const double keep = g2 ? val[jj + 4] : val[jj];
+                        const double send = g2 ? val[jj] : val[jj + 4];
+                        s4[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const double keep = g1 ? s4[jj + 2] : s4[jj];
-                    const double send = g1 ? s4[jj] : s4[jj + 2];
-                    s2[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const double keep = g1 ? s4[jj + 2] : s4[jj];
+                        const double send = g1 ? s4[jj] : s4[jj + 2];
+                        s2[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+                    const double keep = g0 ? s2[1] : s2[0];
+                    const double send = g0 ? s2[0] : s2[1];
+                    const double tot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    my_racc[t * TQT + g * 8 + 2 * t4 + e] += tot;
+                } else {
+                    // four column blocks: two scatter steps (lane pair (g2, g1) owns block 2 g2 + g1), then a plain sum over g0
+                    double s2[2];
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const double keep = g2 ? val[jj + 2] : val[jj];
+                        const double send = g2 ? val[jj] : val[jj + 2];
+                        s2[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+                    const double keep = g1 ? s2[1] : s2[0];
+                    const double send = g1 ? s2[0] : s2[1];
+                    double tot = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+                    if (!g0) my_racc[t * TQT + (g >> 1) * 8 + 2 * t4 + e] += tot;
                 }
-                const double keep = g0 ? s2[1] : s2[0];
-                const double send = g0 ? s2[0] : s2[1];
-                const double tot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                my_racc[t * TQT + g * 8 + 2 * t4 + e] += tot;
             }
         }
     };
@@ -443,21 +464,21 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
         }
         const int nst = (p.dbg & 1) ? 0 : (d0 >> 16);                     // k-steps of 4 that carry data (whole boxes)
         const bool first = (O == 1 || !(d0 & (1 << 12)));
-        auto kstep = [&](int st, double (&acc)[2][8][2]) {
+        auto kstep = [&](int st, double (&acc)[2][NJ][2]) {
             const int q = st >> 1, h = st & 1;
             const int jl = 8 * q + 2 * h + cm0;                             // logical column of this lane inside the tile
-            double a[2], bf[8];
+            double a[2], bf[NJ];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const double v = tile[q * (TRC * 8) + i * 64 + (h ? o1 : o0)];
                 a[i] = jl <= lim[i] ? v : 0.0;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bf[j] = Bs[(size_t)(j * 8 + g) * ldp + 4 * st + t4];
+            for (int j = 0; j < NJ; ++j) bf[j] = Bs[(size_t)(j * 8 + g) * ldp + 4 * st + t4];
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dmma884(acc[i][j], a[i], bf[j]);
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j], a[i], bf[j]);
         };
         if (live == 0xfu && nst == 8) {
             if (first) {
@@ -493,7 +514,7 @@ __global__ void __launch_bounds__(TALL, 1) k_kmp_predict_tab(const __grid_consta
         }
     }
     if (lane == 0 && (p.dbg & 32768)) { atomicAdd(&g_pstats[0], (unsigned long long)ks_run); atomicAdd(&g_pstats[1], (unsigned long long)ks_all); }
-    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    if (TWARPS == 8) asm volatile("bar.sync 1, 256;\n" ::: "memory"); else asm volatile("bar.sync 1, 128;\n" ::: "memory");
 
     // ---------------------------------------------------------------- outputs (reference layout, query last)
     double* xi = p.xi + (size_t)b * O * p.M;
@@ -526,38 +547,48 @@ int debug_predict_stats(long long* out, int reset) {
     return 0;
 }
 
+// The shape of the CTA: kmpx_predict_tile_queries(32 | 64) or, by default, 32 queries (two CTAs per SM) when kappa boxes are skipped
+// and 64 (one CTA per SM) when everything is kept - a function of the process-wide options only, never of the batch.
+static bool tab_small_shape(const PredictArgs& p) {
+    if (g_predict_tile_queries == 32) return true;
+    if (g_predict_tile_queries == 64) return false;
+    return p.kskip > 0.0 && !(g_host_dbg & 8192);
+}
+
 bool predict_tab_applicable(const PredictArgs& p) {
     if (g_host_dbg & 4096) return false;
     if (p.time_driven || p.general || p.O > 2) return false;
     if ((p.lda & 1) || (p.batch > 1 && (p.strideA & 1)) || (reinterpret_cast<uintptr_t>(p.F) & 15)) return false;   // TMA
     if ((long long)p.O * comp_stride(p.n_max) > 0xfff || p.n_max > 1024) return false;                                // descriptor fields, 32-bit k-block mask
     const int ldp = (int)round_up(p.n_max, TQK) + 4;
-    if (tab_smem_layout(p.O, p.I, p.n_max, ldp).total > 226 * 1024) return false;
+    const bool sm = tab_small_shape(p);
+    if (tab_smem_layout(p.O, p.I, p.n_max, ldp, sm ? 32 : 64, sm ? 4 : 8).total > (size_t)(sm ? 110 : 226) * 1024) return false;
     const int* tab = nullptr;
-    if (tab_sched_table(p.O, p.n_max, &tab) != 0) return false;
+    if (tab_sched_table(p.O, p.n_max, sm ? 4 : 8, &tab) != 0) return false;
     return tab != nullptr;
+}
+
+template <int O, int QTT, int NW>
+static int launch_tab(const CUtensorMap& map, const PredictArgs& p, const TabSmem& lay, const int* tab, cudaStream_t st) {
+    static SmemCache set;
+    KMPX_TRY(ensure_dyn_smem(k_kmp_predict_tab<O, QTT, NW>, lay.total, set, "k_kmp_predict_tab"));
+    dim3 grid(ceil_div(p.M, QTT), p.batch);
+    k_kmp_predict_tab<O, QTT, NW><<<grid, NW * 32 + 128, lay.total, st>>>(map, p, lay, tab);
+    return check_launch("k_kmp_predict_tab");
 }
 
 int launch_predict_tab(PredictArgs& p, cudaStream_t st) {
     p.ldp = (int)round_up(p.n_max, TQK) + 4;      // 4 (mod 16) and long enough for the last k-block of a row
     p.resident = 1;
-    const TabSmem lay = tab_smem_layout(p.O, p.I, p.n_max, p.ldp);
+    const bool sm = tab_small_shape(p);
+    const TabSmem lay = tab_smem_layout(p.O, p.I, p.n_max, p.ldp, sm ? 32 : 64, sm ? 4 : 8);
     const int n_sys_max = p.O * comp_stride(p.n_max);
     CUtensorMap map;
     KMPX_TRY(make_batch_map(&map, p.F, p.lda, p.strideA, n_sys_max, p.batch, TRC));
     const int* tab = nullptr;
-    KMPX_TRY(tab_sched_table(p.O, p.n_max, &tab));
-    dim3 grid(ceil_div(p.M, TQT), p.batch);
-    if (p.O == 1) {
-        static SmemCache set1;
-        KMPX_TRY(ensure_dyn_smem(k_kmp_predict_tab<1>, lay.total, set1, "k_kmp_predict_tab<1>"));
-        k_kmp_predict_tab<1><<<grid, TALL, lay.total, st>>>(map, p, lay, tab);
-    } else {
-        static SmemCache set2;
-        KMPX_TRY(ensure_dyn_smem(k_kmp_predict_tab<2>, lay.total, set2, "k_kmp_predict_tab<2>"));
-        k_kmp_predict_tab<2><<<grid, TALL, lay.total, st>>>(map, p, lay, tab);
-    }
-    return check_launch("k_kmp_predict_tab");
+    KMPX_TRY(tab_sched_table(p.O, p.n_max, sm ? 4 : 8, &tab));
+    if (sm) return p.O == 1 ? launch_tab<1, 32, 4>(map, p, lay, tab, st) : launch_tab<2, 32, 4>(map, p, lay, tab, st);
+    return p.O == 1 ? launch_tab<1, 64, 8>(map, p, lay, tab, st) : launch_tab<2, 64, 8>(map, p, lay, tab, st);
 }
 
 }  // namespace kmpx

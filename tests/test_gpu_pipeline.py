@@ -209,7 +209,7 @@ def test_warp_per_problem_fit_through_the_pipeline(golden):
 
 def test_predict_kappa_box_skipping_stays_inside_rounding(golden):
     """The fused predict kernel drops boxes of 8 stored points whose kernel coefficients are below 2^-68 for a whole tile of
-    64 queries (RBF locality).  Against the same kernel with every term kept (kmpx_predict_skip_threshold(0)): in-range queries agree to
+    32 or 64 queries (RBF locality; both CTA shapes are run).  Against the same kernel with every term kept (kmpx_predict_skip_threshold(0)): in-range queries agree to
     ~1e-16 norm-wise, and on a query grid that reaches far outside the data (tiles with no live box at all) mean and
     covariance still agree - far queries give mean 0 and covariance alpha * I up to the dropped 1e-21 terms."""
     from kmp_demos_b200 import _lib
@@ -227,13 +227,18 @@ def test_predict_kappa_box_skipping_stays_inside_rounding(golden):
     kb.set_base(np.broadcast_to(t, (26, 1, 200)), zl['gmr_mu'], zl['gmr_sigma'])
     for queries in (wl.cfg1_query_grid(1000), np.linspace(-6.0, 8.0, 1500).reshape(1, -1)):
         args = (np.array(base_of), np.array(vs), np.array(vp), np.array(vv), queries)
-        xi1, sg1 = kb.fit_predict(*args)
-        assert lib.kmpx_predict_skip_threshold(0.0) == 0
+        xi1, sg1 = kb.fit_predict(*args)                       # default: boxes skipped, 32-query CTAs
         try:
-            xi0, sg0 = kb.fit_predict(*args)
+            assert lib.kmpx_predict_tile_queries(64) == 0
+            xi2, sg2 = kb.fit_predict(*args)                   # boxes skipped, 64-query CTAs
+            assert lib.kmpx_predict_skip_threshold(0.0) == 0
+            xi0, sg0 = kb.fit_predict(*args)                   # every term kept, 64-query CTAs
+            assert lib.kmpx_predict_tile_queries(32) == 0
+            xi3, sg3 = kb.fit_predict(*args)                   # every term kept, 32-query CTAs
         finally:
-            assert lib.kmpx_predict_skip_threshold(2.0 ** -68) == 0
-        assert rel_err(xi1, xi0) < 1e-14 and rel_err(sg1, sg0) < 1e-14
+            assert lib.kmpx_predict_skip_threshold(2.0 ** -68) == 0 and lib.kmpx_predict_tile_queries(0) == 0
+        for xa, sa in ((xi1, sg1), (xi2, sg2), (xi3, sg3)):
+            assert rel_err(xa, xi0) < 1e-14 and rel_err(sa, sg0) < 1e-14
         assert np.all(np.isfinite(xi1)) and np.all(np.isfinite(sg1))
     far = np.abs(queries[0] - 1.0) > 3.0                      # further than any kernel support from the data in [0.01, 2]
     assert np.max(np.abs(xi1[:, :, far])) < 1e-15

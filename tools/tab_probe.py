@@ -19,7 +19,8 @@ out = {}
 kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], chunk=5328)
 kb.set_base(np.broadcast_to(wl.cfg1_kmp_grid(200), (L, 1, 200)), mu, sig)
 for fl in flagsets:
-    lib.kmpx_debug_set(fl)
+    lib.kmpx_predict_tile_queries(32 if fl & 262144 else (64 if fl & 524288 else 0))     # + 262144: 32-query CTAs, + 524288: 64-query CTAs
+    lib.kmpx_debug_set(fl & ~(262144 | 524288))
     for rep in range(3):
         kb.events = []
         xi, sg, info, _ = kb.run_device(base_of, d_vs, d_vp, d_vv, q); torch.cuda.synchronize()
@@ -27,7 +28,7 @@ for fl in flagsets:
     st = (ctypes.c_longlong * 2)(); lib.kmpx_debug_predict_stats(st, 1)
     print(f'flags {fl:5d} predict {ms:.3f} ms for {len(base_of)} problems ({ms / len(base_of) * 26624:.1f} ms per 26624); k-steps executed / scheduled {st[0] / max(st[1], 1):.3f}', flush=True)
     out[fl] = (xi.clone(), sg.clone())
-lib.kmpx_debug_set(0)
+lib.kmpx_debug_set(0); lib.kmpx_predict_tile_queries(0)
 rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
 for a in out:
     if a != flagsets[0]:
