@@ -263,22 +263,24 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
     int pstage = 0;
     uint32_t ppar = 0;
     bool pwrapped = false;
-    auto produce_one = [&]() {
+    auto produce_one = [&](unsigned live) {          // only the live boxes of the stage travel
         const uint32_t bi = 8 * (cw * TST + pstage);
         const uint32_t bar = full0 + bi;
-        mbar_expect_tx(bar, TSTAGE_BYTES);
+        mbar_expect_tx(bar, __popc(live) * (TRC * 64));
         const uint32_t dst = smem_u32(rings + (size_t)(cw * TST + pstage) * TSTAGE_ELEMS);
         const int d0 = pdesc[2 * pk], d1 = pdesc[2 * pk + 1];
         const int col = (d1 >> 16) + (d1 & 0xffff), prow = d0 & 0xfff;
 #pragma unroll
-        for (int q = 0; q < TQK / 8; ++q) tma_load_box(dst + q * (TRC * 64), &tmap, col + 8 * q, prow, b, bar);
+        for (int q = 0; q < TQK / 8; ++q)
+            if (live & (1u << q)) tma_load_box(dst + q * (TRC * 64), &tmap, col + 8 * q, prow, b, bar);
         ++pk;
         if (++pstage == TST) { pstage = 0; ppar ^= 1; pwrapped = true; }
     };
     if (is_producer) {
         for (int t = 0; t < TST && pk < pcount;) {
-            if (live_boxes(pdesc[2 * pk + 1] & 0xffff, pdesc[2 * pk] >> 16) == 0u) { ++pk; continue; }
-            produce_one();
+            const unsigned lv = live_boxes(pdesc[2 * pk + 1] & 0xffff, pdesc[2 * pk] >> 16);
+            if (lv == 0u) { ++pk; continue; }
+            produce_one(lv);
             ++t;
         }
     }
@@ -352,10 +354,12 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
         if (TWARPS == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n"); else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;\n");
         if (lane >= PL) return;
         while (pk < pcount) {
-            if (live_boxes(pdesc[2 * pk + 1] & 0xffff, pdesc[2 * pk] >> 16) == 0u) { ++pk; continue; }
+            const unsigned lv = live_boxes(pdesc[2 * pk + 1] & 0xffff, pdesc[2 * pk] >> 16);
+            if (lv == 0u) { ++pk; continue; }
             const uint32_t bi = 8 * (cw * TST + pstage);
-            if (pwrapped && !mbar_test(empty0 + bi, ppar ^ 1)) { __nanosleep(100); continue; }   // polling must not eat the MMA warps' issue slots
-            produce_one();
+            if (PL == 1) { if (pwrapped) mbar_wait(empty0 + bi, ppar ^ 1); }      // one stream per producer warp: the hardware-suspended wait
+            else if (pwrapped && !mbar_test(empty0 + bi, ppar ^ 1)) { __nanosleep(100); continue; }   // polling must not eat the MMA warps' issue slots
+            produce_one(lv);
         }
         return;
     }
