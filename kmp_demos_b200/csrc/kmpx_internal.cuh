@@ -35,6 +35,7 @@ struct PredictArgs {
     int resident; int ldp;   // panel leading dimension (resident mode)
     int dbg;                 // profiling experiments: bit 0 skip MMAs, bit 1 skip loads
     double kskip;            // kernel coefficients below this for a whole query tile are treated as zero (0: keep everything)
+    double kskip_d2;         // -ln(kskip) / sigma_f: the squared distance beyond which k < kskip (set by the launcher)
 };
 bool predict_fast_applicable(const PredictArgs& p);
 int launch_predict_fast(PredictArgs& p, cudaStream_t st);

@@ -25,6 +25,7 @@
 #include "kmpx_internal.cuh"
 #include "tma_util.cuh"
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -201,6 +202,13 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
     const double* s = p.s + (size_t)b * p.n_max * I;
     const double* sq = p.sq + (size_t)b * p.stride_sq;
     const double* w = p.w + (size_t)b * p.ldw;
+    // scalar inputs, N <= 224: every lane keeps "its" FILL_J stored points in registers from here on - the loads are in flight
+    // while the queries, w and the schedule arrive, and both the box mask and the kappa panel are evaluated from them
+    constexpr int FILL_J = 7, FILL_WARPS = TALL / 32;
+    const bool s_in_regs = I == 1 && ldp - 4 <= 32 * FILL_J;
+    double sj[FILL_J];
+#pragma unroll
+    for (int u = 0; u < FILL_J; ++u) sj[u] = s_in_regs ? s[min(lane + 32 * u, N - 1)] : 0.0;
     for (int idx = tid; idx < TQT * I; idx += TALL) {
         const int m = idx / I;
         sqs[idx] = (m0 + m < p.M) ? sq[(size_t)(m0 + m) * I + (idx - m * I)] : 0.0;
@@ -216,7 +224,28 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
     // ONE rounding error of a retained term of that size, far inside the error of the dense sum itself - so it is dead: its
     // stages are never requested, its panel entries never read.  Bit q of kmask[q / 32]: box q (columns 8 q .. 8 q + 7) is live.
     const bool keep_all = (p.dbg & 8192) != 0 || !(p.kskip > 0.0);
-    if (!keep_all) {
+    if (!keep_all && s_in_regs) {
+        // one warp: the interval of the tile's live queries, then the 4 boxes of each group of 32 stored points from one ballot
+        if (warp == 0) {
+            double lo = INFINITY, hi = -INFINITY;
+            bool odd = false;           // a NaN / infinite query: the reference propagates it, so this tile keeps every box
+            for (int m = lane; m < TQT; m += 32)
+                if (m0 + m < p.M) { const double v = sqs[m]; lo = fmin(lo, v); hi = fmax(hi, v); odd = odd || !(fabs(v) < INFINITY); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+            unsigned word = 0u;
+#pragma unroll
+            for (int u = 0; u < FILL_J; ++u) {
+                const double dd = fmax(fmax(lo - sj[u], sj[u] - hi), 0.0);
+                const unsigned near = __ballot_sync(0xffffffffu, lane + 32 * u < N && !(dd * dd > p.kskip_d2));      // (a NaN coordinate keeps its box)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if ((near >> (8 * k)) & 0xffu) word |= 1u << (4 * u + k);
+            }
+            if (__any_sync(0xffffffffu, odd)) { if (lane < 8) kmask[lane] = ~0u; }
+            else if (lane == 0) kmask[0] = word;
+        }
+        __syncthreads();
+    } else if (!keep_all) {
         double* qbox = reinterpret_cast<double*>(kmask + 8) ;          // [I] lower and [I] upper corner of the live queries
         if (warp == 0) {
             bool odd = false;           // a NaN / infinite query coordinate: the reference propagates it, so this tile keeps every box
@@ -231,7 +260,7 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
             if (__any_sync(0xffffffffu, odd) && lane < 8) kmask[lane] = ~0u;
         }
         __syncthreads();
-        const double lim2 = -log(p.kskip) / p.sigma_f * (1.0 + 1e-9);      // squared distance beyond which k < kskip
+        const double lim2 = p.kskip_d2;      // squared distance beyond which k < kskip
         for (int j0 = warp * 32; j0 < N; j0 += TALL) {
             const int j = j0 + lane;
             double d2 = 0.0;
@@ -289,16 +318,12 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
     // A dependent FP64 operation costs 40-60 cycles here and an exp is a chain of ~25 of them, so every lane keeps
     // FILL_J independent chains in flight (seven columns of one query; fourteen were measured slower); indices are
     // clamped and the results selected, and the exponential itself is branch-free (exp_nonpos), so the chains interleave.
-    constexpr int FILL_J = 7, FILL_WARPS = TALL / 32;
     auto fill = [&](auto one_dim) {         // the I == 1 test is hoisted: a branch inside the chain body would serialise the chains
         constexpr bool ONE = decltype(one_dim)::value;
-        if (ONE && ldp - 4 <= 32 * FILL_J) {
+        if (ONE && s_in_regs) {
             // scalar inputs, N <= 224: a lane owns the same FILL_J stored points for every query, so they are loaded once, and
             // two queries are evaluated per batch: 2 FILL_J independent chains per lane (the panel is latency bound: each warp
             // walks ~1000 dependent-chain instructions whatever the other warps do)
-            double sj[FILL_J];
-#pragma unroll
-            for (int u = 0; u < FILL_J; ++u) sj[u] = s[min(lane + 32 * u, N - 1)];
             const int pj = (lane & ~6) | ((lane & 2) << 1) | ((lane & 4) >> 1);
             for (int ma = warp; ma < TQT && !(p.dbg & 4); ma += 2 * FILL_WARPS) {
                 const int mb = ma + FILL_WARPS;
@@ -584,6 +609,7 @@ static int launch_tab(const CUtensorMap& map, const PredictArgs& p, const TabSme
 int launch_predict_tab(PredictArgs& p, cudaStream_t st) {
     p.ldp = (int)round_up(p.n_max, TQK) + 4;      // 4 (mod 16) and long enough for the last k-block of a row
     p.resident = 1;
+    p.kskip_d2 = p.kskip > 0.0 ? -std::log(p.kskip) / p.sigma_f * (1.0 + 1e-9) : INFINITY;     // squared distance beyond which k < kskip
     const bool sm = tab_small_shape(p);
     const TabSmem lay = tab_smem_layout(p.O, p.I, p.n_max, p.ldp, sm ? 32 : 64, sm ? 4 : 8);
     const int n_sys_max = p.O * comp_stride(p.n_max);

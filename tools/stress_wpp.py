@@ -60,9 +60,9 @@ while time.time() - t0 < budget:
     # (means of queries far from every stored point are ~1e-30 in the dense kernel and exactly 0 with the skipping: floor the scale)
     rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-6))
     worst_fit = max(worst_fit, rel(res['warp'][0], res['cta'][0]), rel(res['warp'][1], res['cta'][1]))
-    lib.kmpx_predict_skip_threshold(0.0)
+    lib.kmpx_predict_skip_threshold(0.0); lib.kmpx_predict_tile_queries(32)       # every term kept, same CTA shape (same summation order)
     dense = kb.fit_predict(base_of, via_s, via_xi, via_sigma, q)
-    lib.kmpx_predict_skip_threshold(2.0 ** -68)
+    lib.kmpx_predict_skip_threshold(2.0 ** -68); lib.kmpx_predict_tile_queries(0)
     worst_skip = max(worst_skip, rel(res['warp'][0], dense[0]), rel(res['warp'][1], dense[1]))
     rounds += 1
 print(f'{rounds} random KMPBatch problems: warp vs cta fit worst {worst_fit:.2e}, skipping vs dense predict worst {worst_skip:.2e}')
