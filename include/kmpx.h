@@ -156,7 +156,7 @@ int kmpx_kmp_predict(const double* F, int lda, long long strideA, int factor_kin
                      double sigma_f, double alpha_kmp, int time_driven,
                      double* xi, double* sigma_out, void* stream);
 /* RBF locality in kmpx_kmp_predict (plain kernel, O <= 2, the table-driven kernel): a box of 8 stored points whose kernel
- * coefficients k(s*, s_j) are below `threshold` for ALL 64 queries of a tile is treated as zero - its share of the
+ * coefficients k(s*, s_j) are below `threshold` for ALL queries of a tile (32 or 64, below) is treated as zero - its share of the
  * contraction is skipped.  Default 2^-68: an entry of V = Linv k*^T then loses at most 2^-60 max|Linv row|, 1/128 of one
  * rounding error of a retained term; with the reference's sigma_f = 200 about half of the contraction of a
  * cfg-3 problem goes.  threshold = 0 keeps every term.  Process-wide setting, read at launch time. */
