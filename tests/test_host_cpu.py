@@ -39,6 +39,11 @@ def test_argument_validation_without_gpu():
     assert rc == -8
     assert lib.kmpx_sys_size(201, 2, _lib.LAYOUT_COMPONENT) == 404 and lib.kmpx_sys_size(201, 2, _lib.LAYOUT_POINT) == 402
     assert lib.kmpx_potrf_workspace_bytes(512, 1) == 0 and lib.kmpx_potrf_workspace_bytes(16384, 1) > 0
+    # process-wide options of the fused predict kernel: range-checked, and restored to their defaults here
+    assert lib.kmpx_predict_tile_queries(48) == -1 and b'32 or 64' in lib.kmpx_last_error()
+    assert lib.kmpx_predict_tile_queries(32) == 0 and lib.kmpx_predict_tile_queries(64) == 0 and lib.kmpx_predict_tile_queries(0) == 0
+    assert lib.kmpx_predict_skip_threshold(1e-3) == -1 and lib.kmpx_predict_skip_threshold(float('nan')) == -1
+    assert lib.kmpx_predict_skip_threshold(2.0 ** -68) == 0
 
 
 def test_product_path_fails_loudly_without_gpu():
