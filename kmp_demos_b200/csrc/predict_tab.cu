@@ -1,7 +1,9 @@
 // K4 fast path, table-driven form: plain RBF kernel, O <= 2, symmetric factor (the cfg-1/3 shape of BASELINE.json).
 //
-// Same mathematics, CTA shape (64 queries of one problem, kappa panel resident in shared memory, eight MMA warps with
-// private 2-stage TMA rings fed by a producer warpgroup), warp tile and reductions as k_kmp_predict_fast (predict_fast.cu).
+// Same mathematics, CTA structure (a tile of queries of one problem, kappa panel resident in shared memory, MMA warps with
+// private 2-stage TMA rings fed by a producer warpgroup), warp tile and reductions as k_kmp_predict_fast (predict_fast.cu),
+// in two shapes: 64 queries / eight MMA warps / one CTA per SM, and 32 queries / four MMA warps / two CTAs per SM (the
+// default when kappa boxes are skipped: one CTA's set-up, panel and epilogue run under the other's contraction).
 // What changes is everything an MMA warp does BETWEEN its DMMAs.  Measured with clock64 on one MMA warp of that kernel
 // (112 k cycles in the streaming loop): 81 k in full stages - at the pipe's rate, two warps per scheduler saturate it - but
 // 13 k in the cursor arithmetic between two stages (which chunk, which output, which k-block, how many columns are valid:
@@ -17,8 +19,9 @@
 //   * the short last k-block runs its boxes (two k-steps each) unrolled;
 //   * RBF locality: boxes of 8 stored points that are further than sqrt(-ln(2^-68) / sigma_f) from the bounding
 //     box of the tile's queries have kappa < 2^-68 for the whole tile and are skipped - stages without a live box are never
-//     requested, partly live stages run their live boxes; at the reference's sigma_f = 200 half of the contraction goes, and
-//     what is dropped is below the rounding error of what is kept (kmpx_predict_skip_threshold moves or disables the threshold).
+//     requested, partly live stages request and run their live boxes only; at the reference's sigma_f = 200 half of the
+//     contraction goes, and what is dropped is below the rounding error of what is kept (kmpx_predict_skip_threshold moves
+//     or disables the threshold).
 // Results are bitwise reproducible and independent of the batch a problem sits in (the schedule depends on (O, N) only).
 // Algorithmic flops per problem: O^2 Ns^2 M (+ lower-order reductions); F is streamed from L2 once per CTA.
 #include "dmma_tile.cuh"
