@@ -53,6 +53,44 @@ def test_kmp_fit_predict_matches_oracle(I, O, N, M, sigma_f, lam, alpha, td, see
     assert np.max(np.abs(sg - sr)) < tol_c * slack * max(np.max(np.abs(sr)), alpha), (np.max(np.abs(sg - sr)), cond)
 
 
+@settings(max_examples=12, **COMMON)
+@given(I=st.integers(1, 2), O=st.integers(1, 2), N=st.integers(2, 230), M=st.integers(1, 150),
+       sigma_f=st.sampled_from([0.5, 5.0, 50.0, 200.0, 1000.0]), seed=st.integers(0, 2 ** 31 - 1))
+def test_fused_predict_both_cta_shapes_match_oracle(I, O, N, M, sigma_f, seed):
+    """The table-driven fused predict kernel (plain kernel, O <= 2) in both CTA shapes - 32 queries with two CTAs per SM and
+    64 queries with one (kmpx_predict_tile_queries) - with the kappa-box skipping on, on queries that reach outside the
+    data: each == the restatement of KMP.py:160-194, and the two shapes agree to rounding."""
+    from kmp.model import KMP
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(seed)
+    s = np.sort(rng.random((I, N)), axis=1) * 2.0
+    mu = rng.normal(size=(O, N)) * 3.0
+    sig = _spd_blocks(rng, N, O)
+    q = rng.random((I, M)) * 4.0 - 1.0
+    A = orc.kmp_matrix(s, sig, 0.5, sigma_f, False)
+    cond = np.linalg.cond(A)
+    if not np.isfinite(cond) or cond > 1e10:
+        return
+    xr, sr = orc.kmp_predict(np.linalg.inv(A), s, mu, q, 40.0, sigma_f, False)
+    k = KMP(l=0.5, alpha=40.0, sigma_f=sigma_f, time_driven_kernel=False)
+    k._logger.disabled = True
+    k.fit(s, mu, sig)
+    out = {}
+    try:
+        for tile in (32, 64):
+            assert lib.kmpx_predict_tile_queries(tile) == 0
+            out[tile] = k.predict(q)
+    finally:
+        assert lib.kmpx_predict_tile_queries(0) == 0
+    slack = max(1.0, cond / 1e5)
+    for tile, (xi, sg) in out.items():
+        assert np.max(np.abs(xi - xr)) < 1e-9 * slack * max(np.max(np.abs(xr)), 1.0), (tile, np.max(np.abs(xi - xr)), cond)
+        assert np.max(np.abs(sg - sr)) < 1e-7 * slack * 40.0, (tile, np.max(np.abs(sg - sr)), cond)
+    assert np.max(np.abs(out[32][0] - out[64][0])) < 1e-11 * slack * max(np.max(np.abs(xr)), 1.0)
+    assert np.max(np.abs(out[32][1] - out[64][1])) < 1e-11 * slack * 40.0
+
+
 @settings(max_examples=20, **COMMON)
 @given(O=st.integers(1, 3), N=st.integers(3, 30), P=st.integers(1, 4), seed=st.integers(0, 2 ** 31 - 1),
        near=st.lists(st.booleans(), min_size=4, max_size=4))
