@@ -42,7 +42,7 @@ class KMPBatch:
         # choice is made once per call from the total batch, never per chunk, so that a problem takes the same kernel -
         # and yields the same bits - whichever chunk it falls into.
         self.factor_mode = 'auto'
-        # fused mean + covariance predict: 'tile' = one CTA per tile of 64 queries (predict_fast.cu, the default);
+        # fused mean + covariance predict: 'tile' = one CTA per tile of 32 or 64 queries (predict_tab.cu, the default);
         # 'persistent' = persistent CTAs over tiles of 40 queries with double-buffered kappa panels (predict_pers.cu):
         # built to hide the panel evaluation and the epilogue, correct, but measured 6 % SLOWER on the cfg-3 shape
         #  - opt-in, kept as the measurement behind that paragraph.
