@@ -7,6 +7,7 @@ from kmp_demos_b200.batch import KMPBatch
 lib = _lib.load()
 mu, sig, _ = wl.load_letter_references()
 L = 26; c = wl.CFG1
+NB = int(os.environ.get('TAB_PROBE_N', '200'))          # stored points of the base trajectories
 nset = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 flagsets = [int(a) for a in sys.argv[2:]] or [4096, 0]
 ts, ps, vs = [], [], []
@@ -17,7 +18,7 @@ d_vs = torch.as_tensor(np.concatenate(ts)[:, :, None], device='cuda'); d_vp = to
 q = torch.as_tensor(np.ascontiguousarray(wl.cfg1_query_grid(1000).T), device='cuda')
 out = {}
 kb = KMPBatch(l=c['lam'], alpha=c['alpha'], sigma_f=c['sigma_f'], chunk=5328)
-kb.set_base(np.broadcast_to(wl.cfg1_kmp_grid(200), (L, 1, 200)), mu, sig)
+kb.set_base(np.broadcast_to(wl.cfg1_kmp_grid(NB), (L, 1, NB)), np.ascontiguousarray(mu[:, :, :NB]), np.ascontiguousarray(sig[..., :NB]))
 for fl in flagsets:
     lib.kmpx_predict_tile_queries(32 if fl & 262144 else (64 if fl & 524288 else 0))     # + 262144: 32-query CTAs, + 524288: 64-query CTAs
     lib.kmpx_debug_set(fl & ~(262144 | 524288))
