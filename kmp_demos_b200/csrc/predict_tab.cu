@@ -50,7 +50,7 @@ constexpr int TROW = 8 + TWST * 2;             // ints per table row: stage coun
 // stage descriptor: d0 = r0 | a << 12 | chunk_end << 13 | has_v1 << 14 | nst << 16;  d1 = k offset in the panel | col0 << 16
 __host__ __device__ inline int tdesc0(int r0, int a, int chunk_end, int has_v1, int nst) { return r0 | (a << 12) | (chunk_end << 13) | (has_v1 << 14) | (nst << 16); }
 
-struct TabSmem { size_t rings, panel, racc, wsh, sqs, etab, sched, bars, total; };
+struct TabSmem { size_t rings, panel, racc, wsh, sqs, etab, sched, clist, bars, total; };
 __host__ __device__ inline TabSmem tab_smem_layout(int O, int I, int n_max_pts, int ldp, int TQT, int TWARPS) {
     const int nt = O * (O + 1) / 2 + O;
     const int n_sys_max = O * comp_stride(n_max_pts);
@@ -62,7 +62,8 @@ __host__ __device__ inline TabSmem tab_smem_layout(int O, int I, int n_max_pts, 
     L.sqs = L.wsh + (size_t)round_up(n_sys_max, 2) * 8;
     L.etab = L.sqs + (size_t)round_up(TQT * I, 2) * 8;
     L.sched = L.etab + (size_t)kExpTabN * 8;
-    L.bars = L.sched + (size_t)(TROW + 8 + 16) * 4;     // + the kappa box masks of the tile and the corners of its query box
+    L.clist = L.sched + (size_t)(TROW + 8 + 16) * 4;    // + the kappa box masks of the tile and the corners of its query box
+    L.bars = L.clist + (size_t)TWST * 2 * 4;            // the live stages of every MMA warp, compacted per tile
     L.total = L.bars + (size_t)2 * TWARPS * TST * 8 + 1024 /* alignment slack */;
     return L;
 }
@@ -284,6 +285,32 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
         const int q = kcol >> 3;                                  // kcol is a multiple of 32: the four boxes sit in one word
         return (kmask[q >> 5] >> (q & 31)) & have;
     };
+    // Every MMA warp compacts ITS stage list under the tile's mask once: {d0 | live boxes << 20, d1} of the live stages only, the
+    // chunk-end flag moved to the last live stage of each chunk - so the streaming loop neither visits dead stages nor looks the
+    // mask up between two stages.  (The producer lanes walk the full list: they run ahead of the MMA warps anyway.)
+    int* clist = reinterpret_cast<int*>(base + lay.clist) + (warp < TWARPS ? warp : 0) * TMAXST * 2;
+    int n_live = 0, ks_all = 0;
+    if (warp < TWARPS) {
+        const int* cd = sched + 8 + warp * TMAXST * 2;
+        const int cnt = sched[warp];
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+            const int i = i0 + lane;
+            int d0 = 0, d1 = 0;
+            unsigned lv = 0u;
+            if (i < cnt) { d0 = cd[2 * i]; d1 = cd[2 * i + 1]; lv = live_boxes(d1 & 0xffff, d0 >> 16); ks_all += d0 >> 16; }
+            const unsigned bal = __ballot_sync(0xffffffffu, lv != 0u);
+            if (lv != 0u) {
+                const int pos = n_live + __popc(bal & ((1u << lane) - 1u));
+                clist[2 * pos] = (d0 & ~(1 << 13)) | (int)(lv << 20);
+                clist[2 * pos + 1] = d1;
+            }
+            n_live += __popc(bal);
+        }
+        __syncwarp();
+        for (int j = lane; j < n_live; j += 32)
+            if (j == n_live - 1 || ((clist[2 * (j + 1)] ^ clist[2 * j]) & 0xfff) != 0) atomicOr(clist + 2 * j, 1 << 13);
+        __syncwarp();
+    }
     // producer cursors (lanes 0, 1 of the four producer warps: two streams each); the first tiles are requested now
     // so that they land while the panel is evaluated
     constexpr int PL = TWARPS / 4;             // producer lanes per warp of the producer warpgroup
@@ -401,8 +428,8 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
     const int o0 = g * 8 + ((c0 ^ sw) << 1) + (t4 & 1);
     const int o1 = g * 8 + (((c0 | 1) ^ sw) << 1) + (t4 & 1);
     const int cm0 = (t4 & 1) | ((t4 & 2) << 1);          // k-step 0 uses the columns {0,1,4,5} of a box, k-step 1 {2,3,6,7}
-    const int* cdesc = sched + 8 + warp * TMAXST * 2;
-    const int ccount = sched[warp];
+    const int* cdesc = clist;
+    const int ccount = n_live;
     int stage = 0;
     uint32_t par = 0;
     double acc0[2][NJ][2], acc1[2][NJ][2];
@@ -472,16 +499,11 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
             }
         }
     };
-    bool touched = false;          // a stage of the current chunk ran
-    int ks_run = 0, ks_all = 0;
+    int ks_run = 0;
     for (int ck = 0; ck < ccount; ++ck) {
         const int d0 = cdesc[2 * ck], d1 = cdesc[2 * ck + 1];
         const int c_r0 = d0 & 0xfff, c_kcol = d1 & 0xffff, c_col0 = d1 >> 16;
-        ks_all += d0 >> 16;
-        const unsigned live = live_boxes(c_kcol, d0 >> 16);
-        const bool run = live != 0u;
-        if (run) {
-        touched = true;
+        const unsigned live = (unsigned)(d0 >> 20) & 0xfu;
         ks_run += 2 * __popc(live);
         const uint32_t bi = 8 * (warp * TST + stage);
         mbar_wait(full0 + bi, par);
@@ -494,7 +516,7 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
             const int r = c_r0 + i * 8 + g;
             lim[i] = r < n ? min(N - 1, r - c_col0) - c_kcol : -1;
         }
-        const int nst = (p.dbg & 1) ? 0 : (d0 >> 16);                     // k-steps of 4 that carry data (whole boxes)
+        const int nst = (p.dbg & 1) ? 0 : ((d0 >> 16) & 0xf);                  // k-steps of 4 that carry data (whole boxes)
         const bool first = (O == 1 || !(d0 & (1 << 12)));
         auto kstep = [&](int st, double (&acc)[2][NJ][2]) {
             const int q = st >> 1, h = st & 1;
@@ -533,19 +555,19 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + bi);
         if (++stage == TST) { stage = 0; par ^= 1; }
-        }   // run
-        if (d0 & (1 << 13)) {
-            if (touched && !(p.dbg & 8)) {
-                // chunk complete: reduce the V tile over its 16 rows straight from the accumulators
-                if (O == 2 && (d0 & (1 << 14))) reduce(c_r0, std::true_type{});
-                else reduce(c_r0, std::false_type{});
-                zero_acc(acc0);
-                zero_acc(acc1);
-            }
-            touched = false;
+        if ((d0 & (1 << 13)) && !(p.dbg & 8)) {
+            // chunk complete (its last live stage): reduce the V tile over its 16 rows straight from the accumulators
+            if (O == 2 && (d0 & (1 << 14))) reduce(c_r0, std::true_type{});
+            else reduce(c_r0, std::false_type{});
+            zero_acc(acc0);
+            zero_acc(acc1);
         }
     }
-    if (lane == 0 && (p.dbg & 32768)) { atomicAdd(&g_pstats[0], (unsigned long long)ks_run); atomicAdd(&g_pstats[1], (unsigned long long)ks_all); }
+    if (p.dbg & 32768) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ks_all += __shfl_xor_sync(0xffffffffu, ks_all, o);
+        if (lane == 0) { atomicAdd(&g_pstats[0], (unsigned long long)ks_run); atomicAdd(&g_pstats[1], (unsigned long long)ks_all); }
+    }
     if (TWARPS == 8) asm volatile("bar.sync 1, 256;\n" ::: "memory"); else asm volatile("bar.sync 1, 128;\n" ::: "memory");
 
     // ---------------------------------------------------------------- outputs (reference layout, query last)
