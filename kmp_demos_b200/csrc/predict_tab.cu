@@ -350,6 +350,31 @@ __global__ void __launch_bounds__(TWARPS * 32 + 128, TWARPS == 4 ? 2 : 1) k_kmp_
     // clamped and the results selected, and the exponential itself is branch-free (exp_nonpos), so the chains interleave.
     auto fill = [&](auto one_dim) {         // the I == 1 test is hoisted: a branch inside the chain body would serialise the chains
         constexpr bool ONE = decltype(one_dim)::value;
+        if (ONE && s_in_regs && !keep_all && TQT == 4 * FILL_WARPS) {
+            // 32-query tile under the box mask: a warp owns four queries, and only the groups of 32 stored points (four boxes)
+            // with a live box are evaluated - the panel entries of dead boxes are never read.  Four independent chains per group;
+            // the FP64 pipe this shares with the partner CTA's DMMAs is what bounds the panel, so the work saved is time saved.
+            const int pj = (lane & ~6) | ((lane & 2) << 1) | ((lane & 4) >> 1);
+            const unsigned kword = kmask[0];
+            double qv[4];
+            bool lq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int m = warp + k * FILL_WARPS; qv[k] = sqs[m]; lq[k] = m0 + m < p.M; }
+            if (p.dbg & 4) return;
+#pragma unroll
+            for (int u = 0; u < FILL_J; ++u) {
+                if (((kword >> (4 * u)) & 0xfu) == 0u) continue;          // warp-uniform
+                double e[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const double d = fabs(qv[k] - sj[u]); e[k] = exp_tab(-p.sigma_f * (d * d), etab); }
+                const int j = lane + 32 * u;
+                if (j < ldp - 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) panel[(size_t)(warp + k * FILL_WARPS) * ldp + pj + 32 * u] = (j < N && lq[k]) ? e[k] : 0.0;
+                }
+            }
+            return;
+        }
         if (ONE && s_in_regs) {
             // scalar inputs, N <= 224: a lane owns the same FILL_J stored points for every query, so they are loaded once, and
             // two queries are evaluated per batch: 2 FILL_J independent chains per lane (the panel is latency bound: each warp
