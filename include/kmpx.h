@@ -59,6 +59,9 @@ int kmpx_debug_set(int flags);
 /* k-steps executed / scheduled by the table-driven predict kernel since the last reset (out_host[2]), counted while
  * kmpx_debug_set(32768) is on: how much of the dense contraction the 2^-60 kappa-block skipping left. */
 int kmpx_debug_predict_stats(long long* out_host, int reset);
+/* Host only: the (O, N) row of the predict kernel's stage table for 4 or 8 MMA warps (layout in predict_tab.cu); returns the ints per
+ * row (776), 0 when the system is too large for the table (the kernel is then not used), < 0 on a bad argument. */
+int kmpx_debug_predict_schedule(int O, int N, int warps, int* row_out, int row_cap);
 /* y[i] = exp(x[i]) through the branch-free exponentials of the hot kernels (mode 0: exp_nonpos, 1: table-driven exp_tab);
  * accuracy probe for the tests, x and y are device arrays. */
 int kmpx_debug_exp(const double* x, double* y, long long n, int mode, void* stream);

@@ -26,6 +26,7 @@ _SIGNATURES = {
     'kmpx_launch_count': [],
     'kmpx_debug_phases': [_p, _i],
     'kmpx_debug_predict_stats': [_p, _i],
+    'kmpx_debug_predict_schedule': [_i, _i, _i, _p, _i],
     'kmpx_predict_skip_threshold': [_d],
     'kmpx_predict_tile_queries': [_i],
     'kmpx_debug_set': [_i],

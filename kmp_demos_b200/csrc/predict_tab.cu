@@ -674,3 +674,18 @@ int launch_predict_tab(PredictArgs& p, cudaStream_t st) {
 }  // namespace kmpx
 
 extern "C" int kmpx_debug_predict_stats(long long* out_host, int reset) { return kmpx::debug_predict_stats(out_host, reset); }
+
+// Host only (no device call): the stage schedule of the table-driven predict kernel for one (O, N) and `warps` MMA warps (4 or 8).
+// row_out[0 .. warps): stages per warp;  row_out[8 + 2 (w * (768 / 2 / warps) + i)], [... + 1]: descriptor {d0, d1} of stage i of warp w
+// (d0 = r0 | a << 12 | chunk_end << 13 | has_v1 << 14 | k-steps << 16;  d1 = k offset | first column of the block << 16).
+// Returns the ints per row (776), 0 when a warp would need more stages than the table holds, < 0 on a bad argument.
+extern "C" int kmpx_debug_predict_schedule(int O, int N, int warps, int* row_out, int row_cap) {
+    using namespace kmpx;
+    if (O < 1 || O > 2 || N < 1 || N > 1024) return fail_arg(1, "O must be 1 or 2, N in [1, 1024]");
+    if (warps != 4 && warps != 8) return fail_arg(3, "warps must be 4 or 8");
+    if (!row_out || row_cap < TROW) return fail_arg(4, "row_out must hold 776 ints");
+    std::vector<int> row(TROW, 0);
+    const bool ok = tab_schedule_host(O, N, row.data(), warps);
+    std::copy(row.begin(), row.end(), row_out);
+    return ok ? TROW : 0;
+}

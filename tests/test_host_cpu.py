@@ -167,3 +167,63 @@ def test_headless_demos_import_like_main_py():
     assert d1 is demo1 and {c.__name__ for c in (demo1, demo2, demo3)} == {'demo1', 'demo2', 'demo3'}
     with pytest.raises(AttributeError):
         kmp.demo4
+
+
+@pytest.mark.parametrize('warps', [4, 8])
+@pytest.mark.parametrize('O', [1, 2])
+def test_predict_stage_schedule_covers_every_stage_exactly_once(O, warps):
+    """Host side of the table-driven predict kernel (predict_tab.cu): for every (O, N) the stage lists of the MMA warps must be a
+    partition of the lower-triangular contraction V = Linv k*^T (KMP.py:187-190 restated as chunks of 16 rows x blocks of 32
+    columns per component block) - every stage once, the stages of a chunk consecutive in ONE warp's list and in k order, the
+    chunk-end flag on the last of them, the V_1 flag where a chunk reaches the second component block."""
+    from kmp_demos_b200 import _lib
+    lib = _lib.load()
+    row = (ctypes.c_int * 776)()
+    assert lib.kmpx_debug_predict_schedule(3, 10, warps, row, 776) == -1
+    assert lib.kmpx_debug_predict_schedule(O, 10, 6, row, 776) == -3
+    assert lib.kmpx_debug_predict_schedule(O, 10, warps, row, 100) == -4
+    cap = 768 // 2 // warps                                   # stages per warp the table holds
+    for N in (1, 2, 7, 8, 9, 16, 31, 32, 33, 100, 201, 202, 204, 208, 224, 250, 300):
+        rc = lib.kmpx_debug_predict_schedule(O, N, warps, row, 776)
+        assert rc in (0, 776)
+        Ns = (N + 1) & ~1
+        n = O * Ns
+        expect = []                                            # (r0, a, k offset, k-steps, first column of the block)
+        for r0 in range(0, n, 16):
+            for a in range(O):
+                jm = min(max(r0 + 16 - a * Ns, 0), N)
+                for kb in range((jm + 31) // 32):
+                    kv = jm - 32 * kb
+                    expect.append((r0, a, 32 * kb, 8 if kv >= 32 else 2 * ((kv + 7) // 8), a * Ns))
+        if rc == 0:
+            assert len(expect) > cap                          # refused only when it cannot fit
+            continue
+        got, load = [], []
+        for w in range(warps):
+            cnt = row[w]
+            assert 0 <= cnt <= cap
+            stages = []
+            for i in range(cnt):
+                d0, d1 = row[8 + 2 * (w * cap + i)], row[8 + 2 * (w * cap + i) + 1]
+                stages.append(dict(r0=d0 & 0xfff, a=(d0 >> 12) & 1, end=(d0 >> 13) & 1, v1=(d0 >> 14) & 1, nst=d0 >> 16,
+                                   k=d1 & 0xffff, col0=d1 >> 16))
+            # chunks are runs of equal r0; inside a run: component 0 before 1, k ascending, the end flag on the last stage only
+            i = 0
+            seen = set()
+            while i < cnt:
+                j = i
+                while j + 1 < cnt and stages[j + 1]['r0'] == stages[i]['r0']:
+                    j += 1
+                run = stages[i:j + 1]
+                assert stages[i]['r0'] not in seen           # one run per chunk
+                seen.add(stages[i]['r0'])
+                assert [(s['a'], s['k']) for s in run] == sorted((s['a'], s['k']) for s in run)
+                assert [s['end'] for s in run] == [0] * (len(run) - 1) + [1]
+                has_v1 = int(any(s['a'] == 1 for s in run))
+                assert all(s['v1'] == has_v1 for s in run)
+                i = j + 1
+            got += [(s['r0'], s['a'], s['k'], s['nst'], s['col0']) for s in stages]
+            load.append(sum(32 * s['nst'] + 120 for s in stages))
+        assert sorted(got) == sorted(expect), (O, N, warps)
+        if len(expect) >= 8 * warps:                          # the deal is balanced (cycle model of the kernel: 32 per k-step + hand-over)
+            assert max(load) <= 1.25 * (sum(load) / warps), (O, N, warps, load)
